@@ -1,0 +1,58 @@
+"""In-tree build of libfspt_b200.so (nvcc, sm_100a only).  `python -m fspt_b200.build`."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT_DIR = os.path.join(HERE, "lib")
+LIB = os.path.join(OUT_DIR, "libfspt_b200.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+
+# --fmad=false + IEEE div/sqrt + no FTZ: the kernels follow the reference's f32 operation order exactly
+# (DESIGN.md section 4); -lineinfo for ncu source pages.
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
+    "--fmad=false", "--prec-div=true", "--prec-sqrt=true", "--ftz=false",
+    "-Xcompiler", "-fPIC,-ffp-contract=off,-O2", "-Xptxas", "-v",
+]
+CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-pthread"]
+
+
+def sources():
+    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))]
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    inc = os.path.join(HERE, "..", "include", "fspt_b200.h")
+    return any(os.path.getmtime(s) > t for s in sources() + [inc, os.path.abspath(__file__)])
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB
+    os.makedirs(OUT_DIR, exist_ok=True)
+    obj_cu = os.path.join(OUT_DIR, "fspt_api.o")
+    obj_cpp = os.path.join(OUT_DIR, "bvh_builder.o")
+    cmds = [
+        [NVCC] + NVCC_FLAGS + ["-c", os.path.join(CSRC, "fspt_api.cu"), "-o", obj_cu],
+        ["g++"] + CXX_FLAGS + ["-c", os.path.join(CSRC, "bvh_builder.cpp"), "-o", obj_cpp],
+        [NVCC, "-shared", "-o", LIB, obj_cu, obj_cpp, "-Xlinker", "--no-undefined", "-lpthread"],
+    ]
+    for cmd in cmds:
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or r.returncode != 0:
+            sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError("build failed: " + " ".join(cmd))
+        if cmd[0] == NVCC and "-c" in cmd:
+            with open(os.path.join(OUT_DIR, "ptxas.log"), "w") as f:
+                f.write(r.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

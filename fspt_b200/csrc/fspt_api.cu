@@ -1,0 +1,678 @@
+// fspt_api.cu -- context, scene upload (layout repack), wavefront render loop and the extern "C" ABI of
+// libfspt_b200.so (include/fspt_b200.h).  Host side of what main.js does between initBVH() and tick():
+// texImage uploads (main.js:408-437,548-560,170-180), drawCamera/drawTracer/drawQuad (main.js:741-824).
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/fspt_b200.h"
+#include "device_common.cuh"
+#include "shade.cuh"
+#include "traverse.cuh"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Ctx {
+  int device = 0, sm_count = 0;
+  int width = 0, height = 0, n_pixels = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+  std::vector<cudaEvent_t> ev_trace;  // pairs around traversal launches of the last render
+  size_t ev_trace_used = 0;
+  bool render_timed = false;
+  std::string error;
+
+  // scene
+  bool has_scene = false, has_dielectric = false;
+  DeviceScene sc{};
+  void *d_nodes = nullptr, *d_tris = nullptr, *d_shade = nullptr, *d_bins = nullptr;
+  cudaArray_t atlas_arr = nullptr, env_arr = nullptr;
+  size_t scene_bytes = 0;
+
+  // frame state
+  float4* d_fb = nullptr;          // accumulation target (RGBA32F)
+  float4* d_last_color = nullptr;
+  float4* d_sample_color = nullptr;
+  float4* d_cam_pos = nullptr;     // debug_primary only
+  float4* d_cam_dir = nullptr;
+  uchar4* d_rgba8 = nullptr;
+  uint32_t next_tick = 0;
+  uint64_t accum_samples = 0;
+  int accum_mode = 0;
+  int sanitize = 1;
+  int max_refractions = 64;
+
+  // wavefront state
+  int wave_samples = 0;       // samples in flight per wave
+  size_t wave_paths = 0;
+  PathState ps{};
+  int* d_list[3] = {nullptr, nullptr, nullptr};  // two continuation lists (ping-pong) + shadow list
+  int* d_counts = nullptr;    // [0..1] counts A, [2..3] counts B, [4] fetch cursor, [5..7] pad
+  int* d_count_out = nullptr; // per-slot visit count (debug)
+  unsigned long long* d_stats = nullptr;  // rays, nodes, leaves, capped
+  float* d_rb = nullptr;      // rand bases of one render call: [0,cap) camera, [cap,2cap) tracer
+  float* h_rb = nullptr;      // pinned staging
+  int rb_cap = 0;
+  int trace_blocks = 0, trace_blocks_cnt = 0, shade_blocks = 0;
+
+  fspt_stats stats{};
+};
+
+int fail(Ctx* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->error = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CK(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess) return fail(c, FSPT_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+template <class T>
+void dfree(T*& p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+
+void free_scene(Ctx* c) {
+  if (c->sc.atlas) cudaDestroyTextureObject(c->sc.atlas);
+  if (c->sc.env) cudaDestroyTextureObject(c->sc.env);
+  if (c->atlas_arr) cudaFreeArray(c->atlas_arr);
+  if (c->env_arr) cudaFreeArray(c->env_arr);
+  c->atlas_arr = c->env_arr = nullptr;
+  dfree(c->d_nodes); dfree(c->d_tris); dfree(c->d_shade); dfree(c->d_bins);
+  c->sc = DeviceScene{};
+  c->has_scene = false;
+}
+
+int alloc_wave(Ctx* c) {
+  // samples in flight: enough paths to fill the machine several times over, bounded so that the
+  // per-path state (7 x 16 B + lists) stays a few hundred MB of the 180 GB
+  const size_t target_paths = (size_t)4 << 20;
+  int S = (int)std::max<size_t>(1, target_paths / (size_t)c->n_pixels);
+  S = std::min(S, 16);
+  c->wave_samples = S;
+  c->wave_paths = (size_t)S * c->n_pixels;
+  const size_t W = c->wave_paths;
+  CK(cudaMalloc(&c->ps.ro, W * 16)); CK(cudaMalloc(&c->ps.rd, W * 16)); CK(cudaMalloc(&c->ps.sd, W * 16));
+  CK(cudaMalloc(&c->ps.thr, W * 16)); CK(cudaMalloc(&c->ps.bt, W * 16)); CK(cudaMalloc(&c->ps.pend, W * 16));
+  CK(cudaMalloc(&c->ps.col, W * 16));
+  for (int i = 0; i < 3; ++i) CK(cudaMalloc(&c->d_list[i], W * sizeof(int)));
+  CK(cudaMalloc(&c->d_counts, 8 * sizeof(int)));
+  CK(cudaMalloc(&c->d_count_out, W * sizeof(int)));
+  CK(cudaMalloc(&c->d_stats, 8 * sizeof(unsigned long long)));  // [0..3] live, [4..7] snapshot at render start
+  CK(cudaMemset(c->d_stats, 0, 8 * sizeof(unsigned long long)));
+  CK(cudaMalloc(&c->d_sample_color, W * 16));
+  c->rb_cap = 64;
+  CK(cudaMalloc(&c->d_rb, 2 * (size_t)c->rb_cap * sizeof(float)));
+  CK(cudaMallocHost(&c->h_rb, 2 * (size_t)c->rb_cap * sizeof(float)));
+  return FSPT_OK;
+}
+
+// ---- traversal launch helpers ---------------------------------------------------------------------------
+void record_trace_begin(Ctx* c) {
+  if (c->ev_trace_used + 2 > c->ev_trace.size()) {
+    for (int i = 0; i < 2; ++i) { cudaEvent_t e; cudaEventCreate(&e); c->ev_trace.push_back(e); }
+  }
+  cudaEventRecord(c->ev_trace[c->ev_trace_used], c->stream);
+}
+void record_trace_end(Ctx* c) {
+  cudaEventRecord(c->ev_trace[c->ev_trace_used + 1], c->stream);
+  c->ev_trace_used += 2;
+}
+
+// counts at d_counts + 2*which; cursor at d_counts + 4
+int launch_trace(Ctx* c, const int* list_cont, const int* list_shadow, int which, bool write_count) {
+  TraceArgs A;
+  A.nodes = c->sc.nodes; A.tris = c->sc.tris; A.root_ref = c->sc.root_ref;
+  A.ro = c->ps.ro; A.rd = c->ps.rd; A.sd = c->ps.sd;
+  A.list_cont = list_cont; A.list_shadow = list_shadow;
+  A.counts = c->d_counts + 2 * which;
+  A.next = c->d_counts + 4;
+  A.stats = c->d_stats;
+  A.count_out = write_count ? c->d_count_out : nullptr;
+  CK(cudaMemsetAsync(c->d_counts + 4, 0, sizeof(int), c->stream));
+  record_trace_begin(c);
+  if (write_count) k_trace<true><<<c->trace_blocks_cnt, TRACE_THREADS, 0, c->stream>>>(A);
+  else k_trace<false><<<c->trace_blocks, TRACE_THREADS, 0, c->stream>>>(A);
+  record_trace_end(c);
+  c->stats.kernel_launches++;
+  CK(cudaGetLastError());
+  return FSPT_OK;
+}
+
+int set_counts(Ctx* c, int which, int n_cont, int n_shadow) {
+  int h[2] = {n_cont, n_shadow};
+  CK(cudaMemcpyAsync(c->d_counts + 2 * which, h, sizeof h, cudaMemcpyHostToDevice, c->stream));
+  return FSPT_OK;
+}
+
+FrameParams make_frame(const Ctx* c, const fspt_frame_params* f) {
+  FrameParams p;
+  for (int k = 0; k < 3; ++k) { p.eye[k] = f->eye[k]; p.dir[k] = f->dir[k]; }
+  p.fov_scale = f->fov_scale; p.lens0 = f->lens_features[0]; p.lens1 = f->lens_features[1];
+  p.env_theta = f->env_theta;
+  p.width = c->width; p.height = c->height;
+  p.tiled = (c->width % 8 == 0 && c->height % 4 == 0) ? 1 : 0;
+  return p;
+}
+
+int render_wave(Ctx* c, const FrameParams& fp, uint32_t first_tick, int S, const float* rb_cam, const float* rb_trace) {
+  const int P = c->n_pixels;
+  const int n_paths = S * P;
+  k_camera<<<(n_paths + 255) / 256, 256, 0, c->stream>>>(fp, rb_cam, n_paths, P, c->ps, nullptr, nullptr);
+  c->stats.kernel_launches++;
+  int rc = set_counts(c, 0, n_paths, 0);
+  if (rc) return rc;
+  rc = launch_trace(c, nullptr, nullptr, 0, false);  // primary rays, tracer.fs:440
+  if (rc) return rc;
+
+  ShadeArgs A;
+  A.sc = c->sc; A.ps = c->ps; A.f = fp;
+  A.rb_trace = rb_trace;
+  A.sample_color = c->d_sample_color;
+  A.capped = c->d_stats + 3;
+  A.paths_per_sample = P;
+  A.max_refractions = c->max_refractions;
+  int cur = 0;  // which counts/list holds the slots to shade
+  const int hard_cap = FSPT_NUM_BOUNCES + 1 + (c->has_dielectric ? c->max_refractions + 2 : 0);
+  for (int b = 0; b < hard_cap; ++b) {
+    const int nxt = cur ^ 1;
+    CK(cudaMemsetAsync(c->d_counts + 2 * nxt, 0, 2 * sizeof(int), c->stream));
+    A.first = (b == 0);
+    A.list_in = (b == 0) ? nullptr : c->d_list[cur];
+    A.counts_in = c->d_counts + 2 * cur;
+    A.list_cont_out = c->d_list[nxt];
+    A.list_shadow_out = c->d_list[2];
+    A.counts_out = c->d_counts + 2 * nxt;
+    k_shade<<<c->shade_blocks, 128, 0, c->stream>>>(A);
+    c->stats.kernel_launches++;
+    CK(cudaGetLastError());
+    cur = nxt;
+    if (b >= FSPT_NUM_BOUNCES) {
+      if (!c->has_dielectric) break;  // every surviving path has i == NUM_BOUNCES: nothing was appended
+      int h[2];
+      CK(cudaMemcpyAsync(h, c->d_counts + 2 * cur, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      if (h[0] == 0) break;
+    }
+    rc = launch_trace(c, c->d_list[cur], c->d_list[2], cur, false);  // tracer.fs:501,507
+    if (rc) return rc;
+  }
+  k_accumulate<<<(P + 255) / 256, 256, 0, c->stream>>>(c->d_sample_color, c->d_fb, c->d_last_color, P, S, first_tick,
+                                                       c->accum_mode, c->sanitize);
+  c->stats.kernel_launches++;
+  CK(cudaGetLastError());
+  return FSPT_OK;
+}
+
+int pull_stats(Ctx* c) {
+  unsigned long long h[8];
+  CK(cudaMemcpy(h, c->d_stats, sizeof h, cudaMemcpyDeviceToHost));
+  c->stats.rays = h[0]; c->stats.node_visits = h[1]; c->stats.leaf_visits = h[2]; c->stats.capped_paths = h[3];
+  c->stats.last_rays = h[0] - h[4]; c->stats.last_node_visits = h[1] - h[5]; c->stats.last_leaf_visits = h[2] - h[6];
+  return FSPT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fspt_abi_version(void) { return FSPT_ABI_VERSION; }
+
+const char* fspt_last_error(const fspt_ctx* ctx) {
+  if (!ctx) return g_create_error.c_str();
+  return reinterpret_cast<const Ctx*>(ctx)->error.c_str();
+}
+
+int fspt_create(fspt_ctx** out, int32_t width, int32_t height, int32_t device) {
+  Ctx* c = nullptr;
+  if (!out || width <= 0 || height <= 0 || (int64_t)width * height > (1 << 27))
+    return fail(c, FSPT_E_INVALID, "fspt_create: bad arguments (%d x %d)", width, height);
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev <= 0)
+    return fail(c, FSPT_E_CUDA, "no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(e));
+  if (device < 0 || device >= n_dev) return fail(c, FSPT_E_INVALID, "device %d out of range (%d present)", device, n_dev);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10)
+    return fail(c, FSPT_E_CUDA, "device %d is sm_%d%d; kernels are built for sm_100a only", device, prop.major, prop.minor);
+  Ctx* ctx = new Ctx();
+  c = ctx;
+  c->device = device; c->sm_count = prop.multiProcessorCount;
+  c->width = width; c->height = height; c->n_pixels = width * height;
+  cudaError_t err;
+#define CKC(call) if ((err = (call)) != cudaSuccess) { g_create_error = std::string(#call) + ": " + cudaGetErrorString(err); delete ctx; return FSPT_E_CUDA; }
+  CKC(cudaSetDevice(device));
+  CKC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CKC(cudaEventCreate(&c->ev_begin));
+  CKC(cudaEventCreate(&c->ev_end));
+  CKC(cudaMalloc(&c->d_fb, (size_t)c->n_pixels * 16));
+  CKC(cudaMemset(c->d_fb, 0, (size_t)c->n_pixels * 16));
+  CKC(cudaMalloc(&c->d_last_color, (size_t)c->n_pixels * 16));
+  CKC(cudaMalloc(&c->d_cam_pos, (size_t)c->n_pixels * 16));
+  CKC(cudaMalloc(&c->d_cam_dir, (size_t)c->n_pixels * 16));
+  CKC(cudaMalloc(&c->d_rgba8, (size_t)c->n_pixels * 4));
+#undef CKC
+  int rc = alloc_wave(c);
+  if (rc) { g_create_error = c->error; fspt_destroy(reinterpret_cast<fspt_ctx*>(c)); return rc; }
+  // persistent grids: resident CTAs per SM x SM count
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<false>, TRACE_THREADS, 0);
+  c->trace_blocks = std::max(1, per_sm) * c->sm_count;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<true>, TRACE_THREADS, 0);
+  c->trace_blocks_cnt = std::max(1, per_sm) * c->sm_count;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shade, 128, 0);
+  c->shade_blocks = std::max(1, per_sm) * c->sm_count;
+  *out = reinterpret_cast<fspt_ctx*>(c);
+  return FSPT_OK;
+}
+
+void fspt_destroy(fspt_ctx* ctx) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  free_scene(c);
+  dfree(c->d_fb); dfree(c->d_last_color); dfree(c->d_sample_color); dfree(c->d_cam_pos); dfree(c->d_cam_dir); dfree(c->d_rgba8);
+  dfree(c->ps.ro); dfree(c->ps.rd); dfree(c->ps.sd); dfree(c->ps.thr); dfree(c->ps.bt); dfree(c->ps.pend); dfree(c->ps.col);
+  for (int i = 0; i < 3; ++i) dfree(c->d_list[i]);
+  dfree(c->d_counts); dfree(c->d_count_out); dfree(c->d_stats); dfree(c->d_rb);
+  if (c->h_rb) cudaFreeHost(c->h_rb);
+  for (auto e : c->ev_trace) cudaEventDestroy(e);
+  if (c->ev_begin) cudaEventDestroy(c->ev_begin);
+  if (c->ev_end) cudaEventDestroy(c->ev_end);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  if (!c) return FSPT_E_INVALID;
+  if (!s || !s->bvh || !s->triangles || !s->materials || !s->normals || !s->uvs || !s->atlas || !s->env || !s->radiance_bins)
+    return fail(c, FSPT_E_INVALID, "scene_upload: NULL buffer");
+  if (s->n_nodes <= 0 || s->n_triangles <= 0 || s->atlas_res <= 0 || s->atlas_layers <= 0 || s->env_width <= 0 ||
+      s->env_height <= 0 || s->env_bins <= 0)
+    return fail(c, FSPT_E_INVALID, "scene_upload: non-positive size (an environment with >= 1 bin is mandatory, main.js:303-308)");
+  if (s->leaf_size != 4) return fail(c, FSPT_E_INVALID, "scene_upload: LEAF_SIZE must be 4 (main.js:45), got %d", s->leaf_size);
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  free_scene(c);
+
+  const int N = s->n_nodes, T = s->n_triangles;
+  // ---- BVH repack: reference node i = [left,right,triIndex | min | max] -> Node64 per interior node ----
+  std::vector<int32_t> ref((size_t)N);   // child reference of node i
+  std::vector<int32_t> interior_of;      // reference node index of interior record k
+  auto ibits = [&](int node, int k) { int32_t v; memcpy(&v, s->bvh + (size_t)node * 9 + k, 4); return v; };
+  for (int i = 0; i < N; ++i) {
+    const int32_t tri = ibits(i, 2);
+    if (tri > -1) {  // `current.triangles > -1`, tracer.fs:379
+      if (tri >= T) return fail(c, FSPT_E_INVALID, "node %d: triangle index %d out of range", i, tri);
+      ref[i] = ~tri;
+    } else {
+      ref[i] = (int32_t)interior_of.size();
+      interior_of.push_back(i);
+    }
+  }
+  const size_t NI = interior_of.size();
+  std::vector<float> nodes(std::max<size_t>(NI, 1) * 16, 0.0f);
+  for (size_t k = 0; k < NI; ++k) {
+    const int i = interior_of[k];
+    const int32_t l = ibits(i, 0), r = ibits(i, 1);
+    if (l < 0 || l >= N || r < 0 || r >= N || l == i || r == i)
+      return fail(c, FSPT_E_INVALID, "node %d: child index out of range (%d, %d)", i, l, r);
+    const float* lb = s->bvh + (size_t)l * 9 + 3;
+    const float* rb = s->bvh + (size_t)r * 9 + 3;
+    float* o = nodes.data() + k * 16;
+    o[0] = lb[0]; o[1] = lb[1]; o[2] = lb[2]; o[3] = lb[3]; o[4] = lb[4]; o[5] = lb[5];
+    o[6] = rb[0]; o[7] = rb[1]; o[8] = rb[2]; o[9] = rb[3]; o[10] = rb[4]; o[11] = rb[5];
+    const int32_t lr = ref[l], rr = ref[r];
+    memcpy(o + 12, &lr, 4); memcpy(o + 13, &rr, 4);
+  }
+  // depth / stack bound check (the reference has int stack[64], tracer.fs:368): iterative DFS
+  {
+    std::vector<std::pair<int, int>> st;
+    st.push_back({0, 1});
+    int max_depth = 0;
+    size_t visited = 0;
+    while (!st.empty()) {
+      auto [n, d] = st.back(); st.pop_back();
+      if (++visited > (size_t)N) return fail(c, FSPT_E_INVALID, "BVH is not a tree (cycle or shared node)");
+      max_depth = std::max(max_depth, d);
+      if (ibits(n, 2) > -1) continue;
+      st.push_back({ibits(n, 0), d + 1});
+      st.push_back({ibits(n, 1), d + 1});
+    }
+    if (max_depth + 1 > FSPT_STACK)
+      return fail(c, FSPT_E_LIMIT, "BVH depth %d exceeds the traversal stack (%d, as in tracer.fs:368)", max_depth, FSPT_STACK);
+  }
+  // ---- triangles: v1, e1, e2 (tracer.fs:301-302) + LEAF_SIZE-1 padBuffer-style (-1,-1,-1) tail records ----
+  std::vector<float> tris((size_t)(T + 3) * 12, 0.0f);
+  for (int t = 0; t < T + 3; ++t) {
+    float v[9];
+    if (t < T) memcpy(v, s->triangles + (size_t)t * 9, sizeof v);
+    else for (float& x : v) x = -1.0f;
+    float* o = tris.data() + (size_t)t * 12;
+    o[0] = v[0]; o[1] = v[1]; o[2] = v[2];
+    volatile float e;  // keep these as single f32 subtractions
+    e = v[3] - v[0]; o[3] = e; e = v[4] - v[1]; o[4] = e; e = v[5] - v[2]; o[5] = e;
+    e = v[6] - v[0]; o[6] = e; e = v[7] - v[1]; o[7] = e; e = v[8] - v[2]; o[8] = e;
+  }
+  // ---- shading records ------------------------------------------------------------------------------------
+  std::vector<float> shade((size_t)T * 48, 0.0f);
+  bool dielectric = false;
+  for (int t = 0; t < T; ++t) {
+    float* o = shade.data() + (size_t)t * 48;
+    memcpy(o, s->materials + (size_t)t * 12, 48);
+    memcpy(o + 12, s->uvs + (size_t)t * 6, 24);
+    memcpy(o + 20, s->normals + (size_t)t * 27, 108);
+    if (o[10] >= 0.0f) dielectric = true;
+  }
+  std::vector<float> bins((size_t)s->env_bins * 4);
+  for (size_t i = 0; i < bins.size(); ++i) bins[i] = (float)s->radiance_bins[i];  // vec4(radianceBins[idx]), tracer.fs:424
+
+  CK(cudaMalloc(&c->d_nodes, nodes.size() * 4));
+  CK(cudaMalloc(&c->d_tris, tris.size() * 4));
+  CK(cudaMalloc(&c->d_shade, shade.size() * 4));
+  CK(cudaMalloc(&c->d_bins, bins.size() * 4));
+  CK(cudaMemcpyAsync(c->d_nodes, nodes.data(), nodes.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_tris, tris.data(), tris.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_shade, shade.data(), shade.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_bins, bins.data(), bins.size() * 4, cudaMemcpyHostToDevice, c->stream));
+
+  // ---- atlas: 2D layered array, RGBA8 (main.js:548-560) -----------------------------------------------------
+  cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
+  const int R = s->atlas_res, L = s->atlas_layers;
+  CK(cudaMalloc3DArray(&c->atlas_arr, &fmt, make_cudaExtent(R, R, L), cudaArrayLayered));
+  cudaMemcpy3DParms cp = {};
+  cp.srcPtr = make_cudaPitchedPtr(const_cast<uint8_t*>(s->atlas), (size_t)R * 4, R, R);
+  cp.dstArray = c->atlas_arr;
+  cp.extent = make_cudaExtent(R, R, L);
+  cp.kind = cudaMemcpyHostToDevice;
+  CK(cudaMemcpy3DAsync(&cp, c->stream));
+  cudaResourceDesc rd = {};
+  rd.resType = cudaResourceTypeArray;
+  rd.res.array.array = c->atlas_arr;
+  cudaTextureDesc td = {};
+  td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+  td.filterMode = cudaFilterModePoint;
+  td.readMode = cudaReadModeElementType;
+  td.normalizedCoords = 0;
+  CK(cudaCreateTextureObject(&c->sc.atlas, &rd, &td, nullptr));
+  // ---- environment: 2D array, RGBA8 RGBE (main.js:170-180) ----------------------------------------------------
+  CK(cudaMallocArray(&c->env_arr, &fmt, s->env_width, s->env_height));
+  CK(cudaMemcpy2DToArrayAsync(c->env_arr, 0, 0, s->env, (size_t)s->env_width * 4, (size_t)s->env_width * 4,
+                              s->env_height, cudaMemcpyHostToDevice, c->stream));
+  rd.res.array.array = c->env_arr;
+  CK(cudaCreateTextureObject(&c->sc.env, &rd, &td, nullptr));
+  CK(cudaStreamSynchronize(c->stream));
+
+  c->sc.nodes = reinterpret_cast<const float4*>(c->d_nodes);
+  c->sc.tris = reinterpret_cast<const float4*>(c->d_tris);
+  c->sc.shade = reinterpret_cast<const float4*>(c->d_shade);
+  c->sc.bins = reinterpret_cast<const float4*>(c->d_bins);
+  c->sc.root_ref = ref[0];
+  c->sc.n_tris = T; c->sc.n_interior = (int)NI;
+  c->sc.atlas_res = R; c->sc.atlas_layers = L; c->sc.env_w = s->env_width; c->sc.env_h = s->env_height;
+  c->sc.n_bins = s->env_bins;
+  c->has_dielectric = dielectric;
+  c->has_scene = true;
+  c->scene_bytes = (size_t)N * 36 + (size_t)T * (36 + 48 + 108 + 24) + (size_t)R * R * 4 * L +
+                   (size_t)s->env_width * s->env_height * 4 + (size_t)s->env_bins * 8;
+  return FSPT_OK;
+}
+
+int fspt_clear(fspt_ctx* ctx) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  if (!c) return FSPT_E_INVALID;
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemsetAsync(c->d_fb, 0, (size_t)c->n_pixels * 16, c->stream));
+  c->next_tick = 0;
+  c->accum_samples = 0;
+  c->stats.samples = 0;
+  return FSPT_OK;
+}
+
+int fspt_render(fspt_ctx* ctx, const fspt_frame_params* frame, uint32_t first_tick, int32_t n_samples,
+                const float* rand_base_camera, const float* rand_base_tracer) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  if (!c) return FSPT_E_INVALID;
+  if (!frame || n_samples < 0 || (n_samples > 0 && (!rand_base_camera || !rand_base_tracer)))
+    return fail(c, FSPT_E_INVALID, "fspt_render: bad arguments");
+  if (!c->has_scene) return fail(c, FSPT_E_STATE, "fspt_render before fspt_scene_upload");
+  CK(cudaSetDevice(c->device));
+  const FrameParams fp = make_frame(c, frame);
+  c->ev_trace_used = 0;
+  CK(cudaMemcpyAsync(c->d_stats + 4, c->d_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, c->stream));
+  // all rand bases of this call go up in one copy: [0,cap) camera, [cap,2cap) tracer
+  if (n_samples > c->rb_cap) {
+    CK(cudaStreamSynchronize(c->stream));
+    dfree(c->d_rb);
+    if (c->h_rb) cudaFreeHost(c->h_rb);
+    c->h_rb = nullptr;
+    c->rb_cap = std::max(n_samples, 2 * c->rb_cap);
+    CK(cudaMalloc(&c->d_rb, 2 * (size_t)c->rb_cap * sizeof(float)));
+    CK(cudaMallocHost(&c->h_rb, 2 * (size_t)c->rb_cap * sizeof(float)));
+  }
+  if (n_samples > 0) {
+    CK(cudaStreamSynchronize(c->stream));  // previous call may still read the staging buffer
+    memcpy(c->h_rb, rand_base_camera, (size_t)n_samples * sizeof(float));
+    memcpy(c->h_rb + c->rb_cap, rand_base_tracer, (size_t)n_samples * sizeof(float));
+    CK(cudaMemcpyAsync(c->d_rb, c->h_rb, 2 * (size_t)c->rb_cap * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  }
+  CK(cudaEventRecord(c->ev_begin, c->stream));
+  for (int done = 0; done < n_samples;) {
+    const int S = std::min(c->wave_samples, n_samples - done);
+    int rc = render_wave(c, fp, first_tick + (uint32_t)done, S, c->d_rb + done, c->d_rb + c->rb_cap + done);
+    if (rc) return rc;
+    done += S;
+  }
+  CK(cudaEventRecord(c->ev_end, c->stream));
+  c->render_timed = true;
+  c->next_tick = first_tick + (uint32_t)n_samples;
+  c->accum_samples += (uint64_t)n_samples;
+  c->stats.samples += (uint64_t)n_samples * (uint64_t)c->n_pixels;
+  return FSPT_OK;
+}
+
+int fspt_synchronize(fspt_ctx* ctx) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  if (!c) return FSPT_E_INVALID;
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  return FSPT_OK;
+}
+
+int fspt_resolve(fspt_ctx* ctx, const fspt_post_params* post, uint8_t* rgba8_out) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  if (!c) return FSPT_E_INVALID;
+  if (!post || !rgba8_out) return fail(c, FSPT_E_INVALID, "fspt_resolve: NULL argument");
+  CK(cudaSetDevice(c->device));
+  dim3 blk(32, 8), grd((c->width + 31) / 32, (c->height + 7) / 8);
+  const int use_div = c->accum_mode == 1;
+  const float count = (float)std::max<uint64_t>(1, c->accum_samples);
+  k_post<<<grd, blk, 0, c->stream>>>(c->d_fb, c->d_rgba8, c->width, c->height, post->exposure, post->saturation,
+                                     post->denoise ? 1 : 0, post->max_sigma, post->scale, count, use_div);
+  c->stats.kernel_launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(rgba8_out, c->d_rgba8, (size_t)c->n_pixels * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return FSPT_OK;
+}
+
+int fspt_read_accum(fspt_ctx* ctx, float* out) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  if (!c || !out) return FSPT_E_INVALID;
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemcpyAsync(out, c->d_fb, (size_t)c->n_pixels * 16, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return FSPT_OK;
+}
+
+int fspt_write_accum(fspt_ctx* ctx, const float* in, uint32_t next_tick) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  if (!c || !in) return FSPT_E_INVALID;
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemcpyAsync(c->d_fb, in, (size_t)c->n_pixels * 16, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  c->next_tick = next_tick;
+  c->accum_samples = next_tick;
+  return FSPT_OK;
+}
+
+int fspt_set_accum_mode(fspt_ctx* ctx, int32_t mode) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  if (!c || (mode != 0 && mode != 1)) return FSPT_E_INVALID;
+  c->accum_mode = mode;
+  return FSPT_OK;
+}
+
+int fspt_accum_device_ptr(fspt_ctx* ctx, void** dptr, uint64_t* n_floats, uint64_t* n_samples) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  if (!c) return FSPT_E_INVALID;
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  if (dptr) *dptr = c->d_fb;
+  if (n_floats) *n_floats = (uint64_t)c->n_pixels * 4;
+  if (n_samples) *n_samples = c->accum_samples;
+  return FSPT_OK;
+}
+
+int fspt_set_accum_samples(fspt_ctx* ctx, uint64_t n) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  if (!c) return FSPT_E_INVALID;
+  c->accum_samples = n;
+  return FSPT_OK;
+}
+
+int fspt_debug_primary(fspt_ctx* ctx, const fspt_frame_params* frame, float rand_base_camera, int32_t* index_out,
+                       float* t_out, int32_t* count_out, float* pos4_out, float* dir4_out) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  if (!c || !frame) return FSPT_E_INVALID;
+  if (!c->has_scene) return fail(c, FSPT_E_STATE, "fspt_debug_primary before fspt_scene_upload");
+  CK(cudaSetDevice(c->device));
+  const FrameParams fp = make_frame(c, frame);
+  const int P = c->n_pixels;
+  c->h_rb[0] = rand_base_camera;
+  CK(cudaMemcpyAsync(c->d_rb, c->h_rb, sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  k_camera<<<(P + 255) / 256, 256, 0, c->stream>>>(fp, c->d_rb, P, P, c->ps, c->d_cam_pos, c->d_cam_dir);
+  c->stats.kernel_launches++;
+  int rc = set_counts(c, 0, P, 0);
+  if (rc) return rc;
+  c->ev_trace_used = 0;
+  rc = launch_trace(c, nullptr, nullptr, 0, true);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(c->stream));
+  // un-swizzle path slots -> pixels on the host
+  std::vector<float4> ro(P), rdv(P);
+  std::vector<int> cnt(P);
+  CK(cudaMemcpy(ro.data(), c->ps.ro, (size_t)P * 16, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(rdv.data(), c->ps.rd, (size_t)P * 16, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(cnt.data(), c->d_count_out, (size_t)P * 4, cudaMemcpyDeviceToHost));
+  for (int j = 0; j < P; ++j) {
+    int x, y;
+    if (fp.tiled) {
+      const int tiles_x = fp.width >> 3, tile = j >> 5, l = j & 31;
+      x = ((tile % tiles_x) << 3) + (l & 7);
+      y = ((tile / tiles_x) << 2) + (l >> 3);
+    } else { x = j % fp.width; y = j / fp.width; }
+    const size_t px = (size_t)y * fp.width + x;
+    if (t_out) t_out[px] = ro[j].w;
+    if (index_out) memcpy(&index_out[px], &rdv[j].w, 4);
+    if (count_out) count_out[px] = cnt[j];
+  }
+  if (pos4_out) CK(cudaMemcpy(pos4_out, c->d_cam_pos, (size_t)P * 16, cudaMemcpyDeviceToHost));
+  if (dir4_out) CK(cudaMemcpy(dir4_out, c->d_cam_dir, (size_t)P * 16, cudaMemcpyDeviceToHost));
+  return pull_stats(c);
+}
+
+int fspt_debug_trace(fspt_ctx* ctx, const float* pos4, const float* dir4, int32_t n_rays, int32_t* index_out,
+                     float* t_out, int32_t* count_out) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  if (!c || !pos4 || !dir4 || n_rays < 0) return FSPT_E_INVALID;
+  if (!c->has_scene) return fail(c, FSPT_E_STATE, "fspt_debug_trace before fspt_scene_upload");
+  CK(cudaSetDevice(c->device));
+  std::vector<float4> ro, rdv;
+  std::vector<int> cnt;
+  for (int64_t done = 0; done < n_rays;) {
+    const int n = (int)std::min<int64_t>((int64_t)c->wave_paths, n_rays - done);
+    CK(cudaMemcpyAsync(c->ps.ro, pos4 + 4 * done, (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->ps.rd, dir4 + 4 * done, (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
+    int rc = set_counts(c, 0, n, 0);
+    if (rc) return rc;
+    c->ev_trace_used = 0;
+    rc = launch_trace(c, nullptr, nullptr, 0, true);
+    if (rc) return rc;
+    ro.resize(n); rdv.resize(n); cnt.resize(n);
+    CK(cudaMemcpyAsync(ro.data(), c->ps.ro, (size_t)n * 16, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(rdv.data(), c->ps.rd, (size_t)n * 16, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(cnt.data(), c->d_count_out, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < n; ++i) {
+      if (t_out) t_out[done + i] = ro[i].w;
+      if (index_out) memcpy(&index_out[done + i], &rdv[i].w, 4);
+      if (count_out) count_out[done + i] = cnt[i];
+    }
+    done += n;
+  }
+  return pull_stats(c);
+}
+
+int fspt_debug_last_color(fspt_ctx* ctx, float* out) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  if (!c || !out) return FSPT_E_INVALID;
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemcpyAsync(out, c->d_last_color, (size_t)c->n_pixels * 16, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return FSPT_OK;
+}
+
+int fspt_debug_math(fspt_ctx* ctx, int32_t fn, const float* x, const float* y, float* out, int32_t n) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  if (!c || !x || !out || n < 0) return FSPT_E_INVALID;
+  CK(cudaSetDevice(c->device));
+  float *dx = nullptr, *dy = nullptr, *dout = nullptr;
+  CK(cudaMalloc(&dx, (size_t)n * 4 + 4)); CK(cudaMalloc(&dy, (size_t)n * 4 + 4)); CK(cudaMalloc(&dout, (size_t)n * 4 + 4));
+  CK(cudaMemcpy(dx, x, (size_t)n * 4, cudaMemcpyHostToDevice));
+  if (y) CK(cudaMemcpy(dy, y, (size_t)n * 4, cudaMemcpyHostToDevice)); else CK(cudaMemset(dy, 0, (size_t)n * 4));
+  if (n) k_debug_math<<<(n + 255) / 256, 256, 0, c->stream>>>(fn, dx, dy, dout, n);
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaMemcpy(out, dout, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  cudaFree(dx); cudaFree(dy); cudaFree(dout);
+  return FSPT_OK;
+}
+
+int fspt_get_stats(fspt_ctx* ctx, fspt_stats* out) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  if (!c || !out) return FSPT_E_INVALID;
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  int rc = pull_stats(c);
+  if (rc) return rc;
+  float ms = 0.0f;
+  if (c->render_timed && cudaEventElapsedTime(&ms, c->ev_begin, c->ev_end) == cudaSuccess) c->stats.render_ms = ms;
+  double tr = 0.0;
+  for (size_t i = 0; i + 1 < c->ev_trace_used; i += 2) {
+    float t = 0.0f;
+    if (cudaEventElapsedTime(&t, c->ev_trace[i], c->ev_trace[i + 1]) == cudaSuccess) tr += t;
+  }
+  (void)cudaGetLastError();  // event queries must not leave a sticky status for the next launch check
+  c->stats.trace_ms = tr;
+  *out = c->stats;
+  return FSPT_OK;
+}
+
+}  // extern "C"

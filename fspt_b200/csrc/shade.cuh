@@ -1,0 +1,537 @@
+// shade.cuh -- camera ray generation, per-vertex shading (UE4-style GGX / Lambert / refraction + Beer,
+// env-map NEE with MIS) and accumulation, as wavefront stages around the traversal kernel.
+//
+// Replaces camera.fs main (:37-46) and tracer.fs main (:436-518) minus its three intersectScene calls.
+// The reference runs a whole path inside one fragment invocation; here a path is a slot of PathState that
+// alternates between k_shade (one vertex) and k_trace (its shadow + continuation rays).  Per path the
+// floating-point operations and their order are the reference's, so per-sample colours are bit-identical
+// to the CPU oracle; only the scheduling differs.
+#pragma once
+#include "device_common.cuh"
+#include "dm_math.cuh"
+
+struct SampleParams {     // per sample in flight
+  const float* rb_cam;    // randBase of drawCamera (main.js:748), indexed by sample-in-wave
+  const float* rb_trace;  // randBase of drawTracer (main.js:777)
+};
+
+// rnd(), tracer.fs:181 / camera.fs:19
+__device__ __forceinline__ float rnd(float& seed) {
+  seed += 0.211324865405187f;
+  return fractf(dm::sinf_(seed) * 43758.5453123f);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// camera.fs main, :37-46.  One thread per path slot p = s * P + j.
+__global__ void __launch_bounds__(256) k_camera(const FrameParams f, const float* __restrict__ rb_cam, int n_paths,
+                                                int paths_per_sample, PathState ps, float4* cam_pos_out,
+                                                float4* cam_dir_out) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_paths) return;
+  const int s = p / paths_per_sample, j = p - s * paths_per_sample;
+  int x, y;
+  path_to_pixel(f, j, x, y);
+  const float resx = (float)f.width, resy = (float)f.height;
+  const float fx = (float)x + 0.5f, fy = (float)y + 0.5f;  // gl_FragCoord
+  const float uvx = (fx / resx) * 2.0f - 1.0f, uvy = (fy / resy) * 2.0f - 1.0f;  // `uv` varying (camera.vs)
+  float seed = rb_cam[s] + fx * resy + fy;  // :38
+  const v3 P = mk3(f.eye[0], f.eye[1], f.eye[2]), I = mk3(f.dir[0], f.dir[1], f.dir[2]);
+  const v3 basisX = normalize(cross(I, mk3(0.0f, 1.0f, 0.0f)));  // :39
+  const v3 basisY = normalize(cross(basisX, I));                 // :40
+  const float inCamX = uvx * (resx / resy), inCamY = uvy * 1.0f;  // getScreen, :21-24
+  const v3 screen = add(add(add(mul(mul(inCamX, basisX), f.fov_scale), mul(mul(inCamY, basisY), f.fov_scale)), I), P);
+  const float theta = rnd(seed) * 3.14159265f * 2.0f;  // getAA, :26-30
+  const float r = sqrtf(rnd(seed)) * 1.414f;
+  float st, ct;
+  dm::sincosf_(theta, st, ct);
+  v3 aa = mul(r, add(div(mul(basisX, ct), resx), div(mul(basisY, st), resy)));
+  aa = mul(aa, f.fov_scale);  // :42
+  const float theta2 = rnd(seed) * 3.14159265f * 2.0f;  // getDOF, :32-35
+  float st2, ct2;
+  dm::sincosf_(theta2, st2, ct2);
+  const v3 dofDir = add(mul(ct2, basisX), mul(st2, basisY));
+  const v3 dof = mul(mul(dofDir, f.lens1), sqrtf(rnd(seed)));
+  const v3 o = add(P, dof);  // :44
+  const v3 d = normalize(sub(add(add(screen, aa), mul(dof, f.lens0)), add(P, dof)));  // :45
+  ps.ro[p] = make_float4(o.x, o.y, o.z, FSPT_MAX_T);
+  ps.rd[p] = make_float4(d.x, d.y, d.z, __int_as_float(-1));
+  if (cam_pos_out) {
+    cam_pos_out[(size_t)y * f.width + x] = make_float4(o.x, o.y, o.z, 1.0f);
+    cam_dir_out[(size_t)y * f.width + x] = make_float4(d.x, d.y, d.z, 1.0f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Texture units.  The atlas and the environment are CUDA texture objects (block-linear arrays through the
+// texture cache); texels are fetched un-filtered and the GL LINEAR weights (GL ES 3.0 section 3.8.10) are
+// applied in f32 exactly as the oracle does, because hardware filtering uses 8-bit fixed-point weights.
+__device__ __forceinline__ float4 texel8(uchar4 c) {
+  return make_float4((float)c.x / 255.0f, (float)c.y / 255.0f, (float)c.z / 255.0f, (float)c.w / 255.0f);
+}
+__device__ __forceinline__ float4 bilerp(float4 t00, float4 t10, float4 t01, float4 t11, float a, float b) {
+  const float w00 = (1.0f - a) * (1.0f - b), w10 = a * (1.0f - b), w01 = (1.0f - a) * b, w11 = a * b;
+  float4 r;
+  r.x = w00 * t00.x + w10 * t10.x + w01 * t01.x + w11 * t11.x;
+  r.y = w00 * t00.y + w10 * t10.y + w01 * t01.y + w11 * t11.y;
+  r.z = w00 * t00.z + w10 * t10.z + w01 * t01.z + w11 * t11.z;
+  r.w = w00 * t00.w + w10 * t10.w + w01 * t01.w + w11 * t11.w;
+  return r;
+}
+__device__ __forceinline__ int wrap_repeat(long long i, int size) {
+  long long m = i % size;
+  if (m < 0) m += size;
+  return (int)m;
+}
+__device__ __forceinline__ int wrap_clamp(long long i, int size) { return (int)(i < 0 ? 0 : (i >= size ? size - 1 : i)); }
+
+// texture(texArray, vec3(uv, layer)): REPEAT/REPEAT, LINEAR (main.js:551-555)
+__device__ __forceinline__ float4 texture_atlas(const DeviceScene& sc, float u, float v, float layerf) {
+  const int R = sc.atlas_res;
+  const long long Lq = coord_to_int(floorf(layerf + 0.5f));
+  const int L = (int)(Lq < 0 ? 0 : (Lq >= sc.atlas_layers ? sc.atlas_layers - 1 : Lq));
+  const float x = u * (float)R - 0.5f, y = v * (float)R - 0.5f;
+  const float fx = floorf(x), fy = floorf(y);
+  const float a = x - fx, b = y - fy;
+  const long long ixx = coord_to_int(fx), iyy = coord_to_int(fy);
+  const float i0 = (float)wrap_repeat(ixx, R) + 0.5f, i1 = (float)wrap_repeat(ixx + 1, R) + 0.5f;
+  const float j0 = (float)wrap_repeat(iyy, R) + 0.5f, j1 = (float)wrap_repeat(iyy + 1, R) + 0.5f;
+  const uchar4 t00 = tex2DLayered<uchar4>(sc.atlas, i0, j0, L), t10 = tex2DLayered<uchar4>(sc.atlas, i1, j0, L);
+  const uchar4 t01 = tex2DLayered<uchar4>(sc.atlas, i0, j1, L), t11 = tex2DLayered<uchar4>(sc.atlas, i1, j1, L);
+  return bilerp(texel8(t00), texel8(t10), texel8(t01), texel8(t11), a, b);
+}
+// texture(envTex, c): S REPEAT, T CLAMP_TO_EDGE, LINEAR on the ENCODED RGBE texel (main.js:170-180)
+__device__ __forceinline__ float4 texture_env(const DeviceScene& sc, float u, float v) {
+  const int W = sc.env_w, H = sc.env_h;
+  const float x = u * (float)W - 0.5f, y = v * (float)H - 0.5f;
+  const float fx = floorf(x), fy = floorf(y);
+  const float a = x - fx, b = y - fy;
+  const long long ixx = coord_to_int(fx), iyy = coord_to_int(fy);
+  const float i0 = (float)wrap_repeat(ixx, W) + 0.5f, i1 = (float)wrap_repeat(ixx + 1, W) + 0.5f;
+  const float j0 = (float)wrap_clamp(iyy, H) + 0.5f, j1 = (float)wrap_clamp(iyy + 1, H) + 0.5f;
+  const uchar4 t00 = tex2D<uchar4>(sc.env, i0, j0), t10 = tex2D<uchar4>(sc.env, i1, j0);
+  const uchar4 t01 = tex2D<uchar4>(sc.env, i0, j1), t11 = tex2D<uchar4>(sc.env, i1, j1);
+  return bilerp(texel8(t00), texel8(t10), texel8(t01), texel8(t11), a, b);
+}
+// envColor + envSample, tracer.fs:410-419
+__device__ __forceinline__ v3 env_sample(const DeviceScene& sc, v3 dir, float envTheta) {
+  const float cx = envTheta + dm::atan2f_(dir.z, dir.x) / FSPT_TAU;
+  const float cy = dm::asinf_(-dir.y) * FSPT_INV_PI + 0.5f;
+  const float4 rgbe = texture_env(sc, cx, cy);
+  const float p = dm::powf_(2.0f, rgbe.w * 255.0f - 128.0f);
+  return mk3(rgbe.x * p, rgbe.y * p, rgbe.z * p);
+}
+
+// ---- BSDF pieces, tracer.fs:194-298 ---------------------------------------------------------------------
+__device__ __forceinline__ v2 mis_weights(float a, float b) {
+  v2 r;
+  if (a > FSPT_EPSILON && b > FSPT_EPSILON) {
+    const float a2 = a * a, b2 = b * b, a2b2 = a2 + b2;
+    r.x = a2 / a2b2;
+    r.y = b2 / a2b2;
+  } else {
+    r.x = 1.0f;
+    r.y = 0.0f;
+  }
+  return r;
+}
+__device__ __forceinline__ float gtr2(float ndh, float a) {
+  const float a2 = a * a;
+  const float t = 1.0f + (a2 - 1.0f) * ndh * ndh;
+  return a2 / (FSPT_PI * t * t);
+}
+__device__ __forceinline__ float smith_g(float NDotv, float alphaG) {
+  const float a = alphaG * alphaG;
+  const float b = NDotv * NDotv;
+  return 1.0f / (NDotv + sqrtf(a + b - a * b));
+}
+__device__ __forceinline__ float gtr2_pdf(v3 incident, v3 normal, v2 mr, v3 bsdfDir) {
+  const float specularAlpha = fmaxf(0.001f, mr.y);
+  const v3 halfVec = normalize(add(bsdfDir, incident));
+  const float cosTheta = fabsf(dot(halfVec, normal));
+  const float pdfgtr2 = gtr2(cosTheta, specularAlpha) * cosTheta;
+  return pdfgtr2 / (4.0f * fabsf(dot(bsdfDir, halfVec)));
+}
+__device__ __forceinline__ float schlick(v3 incident, v3 normal, v2 ns) {
+  float r0 = (ns.x - ns.y) / (ns.x + ns.y);
+  r0 *= r0;
+  float cosTheta = dot(normal, incident);
+  if (ns.x > ns.y) {
+    const float n = ns.x / ns.y;
+    const float sinTheta2 = n * n * (1.0f - cosTheta * cosTheta);
+    if (sinTheta2 > 1.0f) return 1.0f;
+    cosTheta = sqrtf(1.0f - sinTheta2);
+  }
+  const float x = 1.0f - cosTheta;
+  return r0 + (1.0f - r0) * x * x * x * x * x;
+}
+__device__ __forceinline__ v3 eval_specular(v3 incident, v3 normal, v3 diffuseColor, v2 mr, v3 bsdfDir) {
+  const float ndl = dot(normal, bsdfDir);
+  const float ndv = dot(normal, incident);
+  const v3 H = normalize(add(bsdfDir, incident));
+  const float ndh = dot(normal, H);
+  const float a = fmaxf(0.001f, mr.y);
+  const float Ds = gtr2(ndh, a);
+  const v3 Fs = mix3(mk3(1.0f, 1.0f, 1.0f), diffuseColor, mr.x);
+  float roughg = (mr.y * 0.5f + 0.5f);
+  roughg = roughg * roughg;
+  const float Gs = smith_g(ndl, roughg) * smith_g(ndv, roughg);
+  return mul(mul(Gs, Fs), Ds);
+}
+__device__ __forceinline__ void tangent_frame(v3 normal, v3& tangent, v3& bitangent) {  // tracer.fs:259-261
+  const v3 up = fabsf(normal.z) < 0.999f ? mk3(0.0f, 0.0f, 1.0f) : mk3(1.0f, 0.0f, 0.0f);
+  tangent = normalize(cross(up, normal));
+  bitangent = cross(normal, tangent);
+}
+
+struct ShadeArgs {
+  DeviceScene sc;
+  PathState ps;
+  FrameParams f;
+  const float* rb_trace;      // per sample-in-wave
+  const int* list_in;         // path slots to shade; NULL = identity
+  const int* counts_in;       // counts_in[0] = number of slots in list_in
+  int* list_cont_out;         // continuation rays for the next traversal
+  int* list_shadow_out;
+  int* counts_out;            // [0] continuation, [1] shadow
+  float4* sample_color;       // [sample-in-wave][pixel] final un-clamped path colour
+  unsigned long long* capped; // paths stopped by the refraction cap
+  int paths_per_sample;
+  int first;                  // 1: slots hold fresh primary hits (tracer.fs:440-445)
+  int max_refractions;
+};
+
+// Warp-aggregated append: one atomicAdd per warp per list (ballot + popc prefix)
+__device__ __forceinline__ void append(bool want, int value, int* list, int* counter) {
+  const unsigned m = __ballot_sync(0xffffffffu, want);  // callers keep whole warps in the loop
+  if (!want) return;
+  const unsigned lane = threadIdx.x & 31u;
+  const int leader = __ffs(m) - 1;
+  int base = 0;
+  if ((int)lane == leader) base = atomicAdd(counter, __popc(m));
+  base = __shfl_sync(m, base, leader);
+  list[base + __popc(m & ((1u << lane) - 1u))] = value;
+}
+
+// One loop iteration of tracer.fs main (:446-513), split at the intersectScene calls.
+__global__ void __launch_bounds__(128) k_shade(const ShadeArgs A) {
+  const int n = A.counts_in[0];
+  for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < ((n + 31) & ~31); it += gridDim.x * blockDim.x) {
+    const bool live = it < n;
+    bool cont = false, shadow = false;
+    int slot = 0;
+    if (live) {
+      slot = A.list_in ? A.list_in[it] : it;
+      const DeviceScene& sc = A.sc;
+      const float4 o4 = A.ps.ro[slot], d4 = A.ps.rd[slot];
+      v3 rayOrigin = mk3(o4.x, o4.y, o4.z), rayDir = mk3(d4.x, d4.y, d4.z);
+      const float hit_t = o4.w;
+      const int hit_index = __float_as_int(d4.w);
+      const int s = slot / A.paths_per_sample, j = slot - s * A.paths_per_sample;
+      const float randBase = A.rb_trace[s];
+      const float envTheta = A.f.env_theta;
+      v3 color, reflectance;
+      int i = 0, refractions = 0;
+      bool done = false;
+      if (A.first) {
+        color = mk3(0.0f, 0.0f, 0.0f);
+        reflectance = mk3(1.0f, 1.0f, 1.0f);
+        if (hit_index < 0) {  // :442-443
+          color = add(color, env_sample(sc, rayDir, envTheta));
+          done = true;
+        }
+      } else {
+        const float4 c4 = A.ps.col[slot], t4 = A.ps.thr[slot], b4 = A.ps.bt[slot], s4 = A.ps.sd[slot];
+        color = mk3(c4.x, c4.y, c4.z);
+        reflectance = mk3(t4.x, t4.y, t4.z);
+        const int packed = __float_as_int(b4.w);
+        i = (packed & 0xffff) - 0x100;  // stored biased so that i = -1 survives
+        refractions = packed >> 16;
+        if (__float_as_int(s4.w) == 2) {  // shadow.index == -1, :502-504
+          const float4 p4 = A.ps.pend[slot];
+          color = add(color, mk3(p4.x, p4.y, p4.z));
+        }
+        reflectance = mul(reflectance, mk3(b4.x, b4.y, b4.z));  // :508
+        if (hit_index == -1) {  // :509-512
+          color = add(color, mul(mul(reflectance, env_sample(sc, rayDir, envTheta)), t4.w));
+          done = true;
+        } else {
+          ++i;  // for (...; ++i), :446
+          if (!(i < FSPT_NUM_BOUNCES)) done = true;
+        }
+      }
+      if (!done) {
+        // createMaterial / createTriangle / createTexCoords / createNormals, :447-449,460
+        const float4* rec = sc.shade + 12 * (size_t)hit_index;
+        const float4 m0 = __ldg(rec), m1 = __ldg(rec + 1), m2 = __ldg(rec + 2);
+        const float4 u0 = __ldg(rec + 3), u1 = __ldg(rec + 4);
+        const float mapDiffuse = m0.x, mapSpecular = m0.y, mapNormal = m0.z, mapRoughness = m0.w;
+        const float matIor = m2.y, matDielectric = m2.z;
+        const float4* tp = sc.tris + 3 * (size_t)hit_index;
+        const float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
+        const v3 tv1 = mk3(q0.x, q0.y, q0.z);
+        const v3 origin = add(rayOrigin, mul(rayDir, hit_t));  // :450
+        // barycentricWeights, :339-353 (v0 = v2 - v1 and v1 = v3 - v1 are the stored edges)
+        const v3 e0 = mk3(q0.w, q1.x, q1.y), e1 = mk3(q1.z, q1.w, q2.x), e2 = sub(origin, tv1);
+        const float d00 = dot(e0, e0), d01 = dot(e0, e1), d11 = dot(e1, e1), d20 = dot(e2, e0), d21 = dot(e2, e1);
+        const float invDenom = 1.0f / (d00 * d11 - d01 * d01);
+        const float bv = (d11 * d20 - d01 * d21) * invDenom;
+        const float bw_ = (d00 * d21 - d01 * d20) * invDenom;
+        const float bu = 1.0f - bv - bw_;
+        const float tcx = bu * u0.x + bv * u0.z + bw_ * u1.x;  // barycentricTexCoord, :328-330
+        const float tcy = bu * u0.y + bv * u0.w + bw_ * u1.y;
+        const float4 tD = texture_atlas(sc, tcx, tcy, mapDiffuse);     // :453
+        const float4 tE = texture_atlas(sc, tcx, tcy, mapSpecular);    // :454
+        const float4 tMR = texture_atlas(sc, tcx, tcy, mapRoughness);  // :455
+        const float4 tN = texture_atlas(sc, tcx, tcy, mapNormal);      // :456
+        const v3 texDiffuse = mk3(tD.x, tD.y, tD.z), texEmmissive = mk3(tE.x, tE.y, tE.z);
+        v2 texMR;
+        texMR.x = tMR.x;
+        texMR.y = tMR.y;
+        const v3 texNormal = mul(sub(mk3(tN.x, tN.y, tN.z), mk3(0.5f, 0.5f, 0.0f)), mk3(2.0f, 2.0f, 1.0f));
+        texMR.y *= texMR.y;  // :457
+        float seed = origin.x * randBase * origin.y * 1.396529836f + origin.z * 4761.52835f;  // :458
+        // normals record: [n1 t1 b1 n2 t2 b2 n3 t3 b3] starting at float 20 of the 48-float record
+        float nn[27];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+          const float4 t = __ldg(rec + 5 + k);
+          if (4 * k + 0 < 27) nn[4 * k + 0] = t.x;
+          if (4 * k + 1 < 27) nn[4 * k + 1] = t.y;
+          if (4 * k + 2 < 27) nn[4 * k + 2] = t.z;
+          if (4 * k + 3 < 27) nn[4 * k + 3] = t.w;
+        }
+        const v3 n1 = mk3(nn[0], nn[1], nn[2]), t1 = mk3(nn[3], nn[4], nn[5]), b1 = mk3(nn[6], nn[7], nn[8]);
+        const v3 n2 = mk3(nn[9], nn[10], nn[11]), t2 = mk3(nn[12], nn[13], nn[14]), b2 = mk3(nn[15], nn[16], nn[17]);
+        const v3 n3 = mk3(nn[18], nn[19], nn[20]), t3 = mk3(nn[21], nn[22], nn[23]), b3 = mk3(nn[24], nn[25], nn[26]);
+        const v3 baryNormal = add(add(mul(bu, n1), mul(bv, n2)), mul(bw_, n3));  // :333-336
+        const v3 baryTangent = add(add(mul(bu, t1), mul(bv, t2)), mul(bw_, t3));
+        const v3 baryBiTangent = add(add(mul(bu, b1), mul(bv, b2)), mul(bw_, b3));
+        v3 macroNormal = normalize(add(add(mul(texNormal.x, baryTangent), mul(texNormal.y, baryBiTangent)),
+                                       mul(texNormal.z, baryNormal)));
+        const bool inside = dot(neg(rayDir), baryNormal) < 0.0f;  // :461
+        v2 ns;
+        if (inside) { ns.x = matIor; ns.y = 1.0f; } else { ns.x = 1.0f; ns.y = matIor; }  // :462
+        macroNormal = inside ? neg(macroNormal) : macroNormal;                          // :463
+        rayOrigin = add(origin, mul(mul(macroNormal, FSPT_EPSILON), 2.0f));              // :464
+        color = add(color, mul(mul(mul(reflectance, texEmmissive), texDiffuse), 30.0f));  // :467
+        const v3 incident = neg(rayDir);
+        v3 envThroughput, bsdfThroughput;
+        float bsdfPdf;
+        // sampleMicrofacet, :256-270
+        v3 microNormal;
+        {
+          const float r1 = rnd(seed), r2 = rnd(seed);
+          v3 tangent, bitangent;
+          tangent_frame(macroNormal, tangent, bitangent);
+          const float a = fmaxf(0.001f, texMR.y);
+          const float phi = r1 * FSPT_TAU;
+          const float cosTheta = sqrtf((1.0f - r2) / (1.0f + (a * a - 1.0f) * r2));
+          const float sinTheta = clampf(sqrtf(1.0f - (cosTheta * cosTheta)), 0.0f, 1.0f);
+          float sinPhi, cosPhi;
+          dm::sincosf_(phi, sinPhi, cosPhi);
+          const v3 h = mk3(sinTheta * cosPhi, sinTheta * sinPhi, cosTheta);
+          microNormal = add(add(mul(tangent, h.x), mul(bitangent, h.y)), mul(macroNormal, h.z));
+        }
+        // sampleEnv, :421-434
+        v3 envDir;
+        float envPdf;
+        {
+          int idx = (int)coord_to_int((float)sc.n_bins * rnd(seed));
+          if (idx >= sc.n_bins) idx = sc.n_bins - 1;
+          if (idx < 0) idx = 0;
+          const float4 bin = __ldg(sc.bins + idx);
+          const float dimsx = (float)sc.env_w, dimsy = (float)sc.env_h;
+          const float r1 = rnd(seed);
+          const float r2 = rnd(seed);
+          const float uvx = -envTheta + ((bin.z - bin.x) * r1 + bin.x) / dimsx;
+          const float uvy = 0.0f + ((bin.w - bin.y) * r2 + bin.y) / dimsy;
+          const float theta = uvx * FSPT_TAU;
+          const float phi = uvy * FSPT_PI;
+          float sinPhi, cosPhi, sinTheta, cosTheta;
+          dm::sincosf_(phi, sinPhi, cosPhi);
+          dm::sincosf_(theta, sinTheta, cosTheta);
+          envDir = mk3(cosTheta * sinPhi, cosPhi, sinTheta * sinPhi);
+          const float nominal = (dimsx * dimsy) / (float)sc.n_bins;
+          envPdf = nominal / ((bin.z - bin.x) * (bin.w - bin.y) * FSPT_TAU * FSPT_PI * sinPhi);
+        }
+        const float cosEnv = dot(macroNormal, envDir);  // :474
+        const bool specular = mixf(schlick(incident, microNormal, ns), 1.0f, texMR.x) > rnd(seed);  // :475
+        if (specular) {
+          rayDir = reflect(neg(incident), microNormal);  // :477
+          bsdfPdf = gtr2_pdf(incident, macroNormal, texMR, rayDir);
+          bsdfThroughput = div(mul(eval_specular(incident, macroNormal, texDiffuse, texMR, rayDir),
+                                   clampf(dot(macroNormal, rayDir), 0.0f, 1.0f)), bsdfPdf);
+          envThroughput = div(mul(eval_specular(incident, macroNormal, texDiffuse, texMR, envDir),
+                                  clampf(cosEnv, 0.0f, 1.0f)), envPdf);
+        } else if (matDielectric >= 0.0f) {  // :481-488
+          bsdfPdf = 1.0f;
+          bsdfThroughput = mk3(1.0f, 1.0f, 1.0f);
+          envThroughput = mk3(0.0f, 0.0f, 0.0f);
+          rayOrigin = sub(origin, mul(mul(macroNormal, FSPT_EPSILON), 2.0f));
+          rayDir = refract(neg(incident), microNormal, ns.x / ns.y);
+          i--;
+          if (++refractions > A.max_refractions) {  // safety cap of the reference's unbounded loop
+            i = FSPT_NUM_BOUNCES;
+            atomicAdd(A.capped, 1ull);
+          }
+        } else {  // :489-494
+          {
+            const float r1 = rnd(seed), r2 = rnd(seed);
+            v3 tangent, bitangent;
+            tangent_frame(macroNormal, tangent, bitangent);
+            const float r = sqrtf(r1);
+            const float phi = FSPT_TAU * r2;
+            float sp_, cp_;
+            dm::sincosf_(phi, sp_, cp_);
+            v3 dir;
+            dir.x = r * cp_;
+            dir.y = r * sp_;
+            dir.z = sqrtf(fmaxf(0.0f, 1.0f - dir.x * dir.x - dir.y * dir.y));
+            rayDir = add(add(mul(tangent, dir.x), mul(bitangent, dir.y)), mul(macroNormal, dir.z));
+          }
+          bsdfPdf = fabsf(dot(rayDir, macroNormal)) * FSPT_INV_PI;  // lambertPdf, :235-237
+          const v3 lam = mul(texDiffuse, FSPT_INV_PI);               // evalLambert, :296-298
+          bsdfThroughput = div(mul(lam, clampf(dot(macroNormal, rayDir), 0.0f, 1.0f)), bsdfPdf);
+          envThroughput = div(mul(lam, clampf(cosEnv, 0.0f, 1.0f)), envPdf);
+        }
+        if (inside) {  // Beer's-law override, :497
+          const v3 om_ = sub(mk3(1.0f, 1.0f, 1.0f), texDiffuse);
+          const v3 b = sub(mk3(1.0f, 1.0f, 1.0f), mul(mul(om_, hit_t), matDielectric));
+          bsdfThroughput = mk3(fmaxf(b.x, 0.0f), fmaxf(b.y, 0.0f), fmaxf(b.z, 0.0f));
+        }
+        const v2 weights = mis_weights(envPdf, bsdfPdf);  // :499
+        shadow = (matDielectric < 0.0f && cosEnv > 0.0f);  // :500
+        v3 pend = mk3(0.0f, 0.0f, 0.0f);
+        if (shadow) pend = mul(mul(mul(reflectance, envThroughput), env_sample(sc, envDir, envTheta)), weights.x);  // :503
+        cont = true;
+        A.ps.ro[slot] = make_float4(rayOrigin.x, rayOrigin.y, rayOrigin.z, FSPT_MAX_T);
+        A.ps.rd[slot] = make_float4(rayDir.x, rayDir.y, rayDir.z, __int_as_float(-1));
+        A.ps.sd[slot] = make_float4(envDir.x, envDir.y, envDir.z, __int_as_float(shadow ? 1 : 0));
+        A.ps.thr[slot] = make_float4(reflectance.x, reflectance.y, reflectance.z, weights.y);
+        A.ps.bt[slot] = make_float4(bsdfThroughput.x, bsdfThroughput.y, bsdfThroughput.z,
+                                    __int_as_float(((i + 0x100) & 0xffff) | (refractions << 16)));
+        A.ps.pend[slot] = make_float4(pend.x, pend.y, pend.z, 0.0f);
+        A.ps.col[slot] = make_float4(color.x, color.y, color.z, 0.0f);
+      } else {
+        int x, y;
+        path_to_pixel(A.f, j, x, y);
+        A.sample_color[(size_t)s * ((size_t)A.f.width * A.f.height) + (size_t)y * A.f.width + x] =
+            make_float4(color.x, color.y, color.z, 1.0f);
+      }
+    }
+    append(cont, slot, A.list_cont_out, A.counts_out + 0);
+    append(shadow, slot, A.list_shadow_out, A.counts_out + 1);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// tracer.fs:515-517: clamp, then running mean over ticks (mode 0) or plain sum (mode 1), per pixel in tick
+// order so that the f32 result equals the reference's sequence of passes.
+__global__ void __launch_bounds__(256) k_accumulate(const float4* __restrict__ sample_color, float4* fb, float4* last_color,
+                                                    int n_pixels, int n_samples, unsigned first_tick, int mode, int sanitize) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pixels) return;
+  float4 acc = fb[p];
+  v3 c = mk3(0.0f, 0.0f, 0.0f);
+  for (int s = 0; s < n_samples; ++s) {
+    const float4 c4 = sample_color[(size_t)s * n_pixels + p];
+    c = mk3(c4.x, c4.y, c4.z);
+    if (sanitize) {  // deviation from the reference, which lets NaN stick
+      if (c.x != c.x) c.x = 0.0f;
+      if (c.y != c.y) c.y = 0.0f;
+      if (c.z != c.z) c.z = 0.0f;
+    }
+    c = clamp3(c, 0.0f, 1024.0f);  // :515
+    if (mode == 0) {
+      const float ft = (float)(first_tick + (unsigned)s);
+      const v3 t = mk3(acc.x, acc.y, acc.z);
+      const v3 o = div(add(c, mul(t, ft)), ft + 1.0f);  // :517
+      acc = make_float4(o.x, o.y, o.z, 1.0f);
+    } else {
+      acc = make_float4(acc.x + c.x, acc.y + c.y, acc.z + c.z, 1.0f);
+    }
+  }
+  fb[p] = acc;
+  if (last_color) last_color[p] = make_float4(c.x, c.y, c.z, 1.0f);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// draw.fs main (:82-93) with filterFireflies (:50-80) and ACESFitted (:39-48), fused: one pass RGBA32F -> RGBA8.
+// In sum mode (multi-GPU) the buffer is divided by the sample count on the fly.
+__device__ __forceinline__ v3 fb_fetch(const float4* fb, int W, int H, long long cx, long long cy, float inv_count, int use_div) {
+  if (cx < 0 || cy < 0 || cx >= W || cy >= H) return mk3(0.0f, 0.0f, 0.0f);  // robust texelFetch
+  const float4 v = fb[(size_t)cy * W + (size_t)cx];
+  if (use_div) return mk3(v.x / inv_count, v.y / inv_count, v.z / inv_count);
+  return mk3(v.x, v.y, v.z);
+}
+__device__ __forceinline__ float rrt_odt_fit(float v) {  // draw.fs:32-37
+  const float a = v * (v + 0.0245786f) - 0.000090537f;
+  const float b = v * (0.983729f * v + 0.4329510f) + 0.238081f;
+  return a / b;
+}
+__device__ __forceinline__ unsigned char quant8(float v) {
+  if (!(v > 0.0f)) return 0;
+  if (v >= 1.0f) return 255;
+  return (unsigned char)(int)floorf(v * 255.0f + 0.5f);
+}
+__global__ void __launch_bounds__(256) k_post(const float4* __restrict__ fb, uchar4* out, int W, int H, float exposure,
+                                              float saturation, int denoise, float maxSigma, float scale,
+                                              float count, int use_div) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= W || y >= H) return;
+  const v3 lumaCoefs = mk3(0.2126f, 0.7152f, 0.0722f);
+  const float fx = (float)x + 0.5f, fy = (float)y + 0.5f;
+  const long long bx = coord_to_int(fx * scale), by = coord_to_int(fy * scale);
+  v3 texColor;
+  if (denoise) {
+    float sum = 0.0f, sq_sum = 0.0f;
+    v3 middle = mk3(0.0f, 0.0f, 0.0f);
+    float middleLuma = 0.0f;
+    const float samples = 24.0f;
+    for (int i = 0; i < 5; i++)
+      for (int j = 0; j < 5; j++) {
+        const int osx = i - 2, osy = j - 2;
+        const v3 color = fb_fetch(fb, W, H, bx + osx, by + osy, count, use_div);
+        const float luma = dot(color, lumaCoefs);
+        if (osx == 0 && osy == 0) { middle = color; middleLuma = luma; continue; }
+        sum += luma;
+        sq_sum += luma * luma;
+      }
+    const float mean = sum / samples;
+    const float variance = sq_sum / samples - mean * mean;
+    const float sigma = sqrtf(variance);
+    if (fabsf(middleLuma - mean) > maxSigma * sigma) middle = mul(middle, mean / middleLuma);
+    texColor = mul(middle, exposure);
+  } else {
+    texColor = mul(fb_fetch(fb, W, H, bx, by, count, use_div), exposure);
+  }
+  const v3 c = texColor;
+  v3 a = mk3(c.x * 0.59719f + c.y * 0.35458f + c.z * 0.04823f, c.x * 0.07600f + c.y * 0.90834f + c.z * 0.01566f,
+             c.x * 0.02840f + c.y * 0.13383f + c.z * 0.83777f);
+  a = mk3(rrt_odt_fit(a.x), rrt_odt_fit(a.y), rrt_odt_fit(a.z));
+  const v3 o = mk3(a.x * 1.60475f + a.y * -0.53108f + a.z * -0.07367f, a.x * -0.10208f + a.y * 1.10813f + a.z * -0.00605f,
+                   a.x * -0.00327f + a.y * -0.07276f + a.z * 1.07602f);
+  v3 mapped = clamp3(o, 0.0f, 1.0f);
+  const float l = dot(mapped, lumaCoefs);
+  mapped = mix3(mk3(l, l, l), mapped, saturation);
+  mapped = mk3(dm::powf_(mapped.x, 0.454545f), dm::powf_(mapped.y, 0.454545f), dm::powf_(mapped.z, 0.454545f));
+  out[(size_t)y * W + x] = make_uchar4(quant8(mapped.x), quant8(mapped.y), quant8(mapped.z), 255);
+}
+
+// FSPT-DM1 probes (fspt_debug_math)
+__global__ void k_debug_math(int fn, const float* x, const float* y, float* out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float r = 0.0f;
+  switch (fn) {
+    case 0: r = dm::sinf_(x[i]); break;
+    case 1: r = dm::cosf_(x[i]); break;
+    case 2: r = dm::atan2f_(y[i], x[i]); break;
+    case 3: r = dm::asinf_(x[i]); break;
+    case 4: r = dm::exp2f_(x[i]); break;
+    case 5: r = dm::powf_(x[i], y[i]); break;
+    case 6: { float s, c; dm::sincosf_(x[i], s, c); r = s; break; }
+    case 7: { float s, c; dm::sincosf_(x[i], s, c); r = c; break; }
+  }
+  out[i] = r;
+}

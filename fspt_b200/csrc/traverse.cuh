@@ -1,0 +1,174 @@
+// traverse.cuh -- closest-hit BVH traversal + Moller-Trumbore, persistent warps with dynamic ray fetch.
+//
+// Replaces intersectScene / rayBoxIntersect / processLeaf / rayTriangleIntersect of the reference
+// (tracer.fs:300-326,355-404; counter variant bvh_test.fs:173-221).  Per ray the sequence of visited nodes,
+// the pruning comparisons and the triangle-test order are exactly the reference's, so (index, t, count)
+// are bit-identical:
+//   - near child first, `leftHit > rightHit` sends the ray right (ties go left), far child deferred
+//     (tracer.fs:382-392); deferred nodes are NOT re-tested against result.t when popped (tracer.fs:401);
+//   - a leaf tests exactly LEAF_SIZE = 4 consecutive triangles starting at its first one, over-reading
+//     into the next leaf (tracer.fs:355-364); strict `<` keeps the first hit on ties (tracer.fs:359);
+//   - slab test: (b - o) * (1/d), IEEE division, min/max = minNum/maxNum, `tMax >= tMin && tMax > 0`
+//     (tracer.fs:317-326); no FMA contraction anywhere (file is compiled with --fmad=false).
+// The two box tests the reference also performs on leaf visits (children 0,0 -> root box, tracer.fs:377-378)
+// have no observable effect and are skipped.
+//
+// Execution model: one ray per lane, a warp keeps running until fewer than REFILL lanes still have a ray,
+// then the idle lanes are refilled from a global queue with one atomicAdd per warp (__ballot_sync +
+// popc prefix = the compaction), so short rays do not wait for the longest ray of their warp.
+#pragma once
+#include "device_common.cuh"
+
+struct TraceArgs {
+  const float4* nodes;
+  const float4* tris;
+  int root_ref;
+  float4* ro;             // PathState.ro / rd / sd
+  float4* rd;
+  float4* sd;
+  const int* list_cont;   // path slots of continuation rays; NULL = identity
+  const int* list_shadow; // path slots of shadow rays
+  const int* counts;      // counts[0] = #continuation, counts[1] = #shadow
+  int* next;              // work-fetch cursor (zeroed before launch)
+  unsigned long long* stats;  // [0] rays, [1] node visits, [2] leaf visits
+  int* count_out;         // per-slot visit count (debug / bvh_test mode) or NULL
+};
+
+#define TRACE_THREADS 128
+#define TRACE_REFILL 20
+
+__device__ __forceinline__ float slab(float bminx, float bminy, float bminz, float bmaxx, float bmaxy, float bmaxz,
+                                      float ox, float oy, float oz, float ix, float iy, float iz) {
+  const float t1x = (bminx - ox) * ix, t2x = (bmaxx - ox) * ix;
+  const float t1y = (bminy - oy) * iy, t2y = (bmaxy - oy) * iy;
+  const float t1z = (bminz - oz) * iz, t2z = (bmaxz - oz) * iz;
+  const float tMax = fminf(fminf(fmaxf(t1x, t2x), fmaxf(t1y, t2y)), fmaxf(t1z, t2z));
+  const float tMin = fmaxf(fmaxf(fminf(t1x, t2x), fminf(t1y, t2y)), fminf(t1z, t2z));
+  return (tMax >= tMin && tMax > 0.0f) ? tMin : FSPT_MAX_T;
+}
+
+// rayTriangleIntersect with e1/e2 precomputed; predicates are the reference's conditions, un-negated, so
+// NaN behaves identically (tracer.fs:305,309,312,314)
+__device__ __forceinline__ float tri_test(const float4 q0, const float4 q1, const float4 q2, float ox, float oy,
+                                          float oz, float dx, float dy, float dz) {
+  const float e1x = q0.w, e1y = q1.x, e1z = q1.y, e2x = q1.z, e2y = q1.w, e2z = q2.x;
+  const float px = dy * e2z - e2y * dz, py = dz * e2x - e2z * dx, pz = dx * e2y - e2x * dy;  // cross(dir,e2)
+  const float det = e1x * px + e1y * py + e1z * pz;
+  if (fabsf(det) < FSPT_EPSILON) return FSPT_MAX_T;
+  const float invDet = 1.0f / det;
+  const float tx = ox - q0.x, ty = oy - q0.y, tz = oz - q0.z;
+  const float u = (tx * px + ty * py + tz * pz) * invDet;
+  if (u < 0.0f || u > 1.0f) return FSPT_MAX_T;
+  const float qx = ty * e1z - e1y * tz, qy = tz * e1x - e1z * tx, qz = tx * e1y - e1x * ty;  // cross(t,e1)
+  const float v = (dx * qx + dy * qy + dz * qz) * invDet;
+  if (v < 0.0f || u + v > 1.0f) return FSPT_MAX_T;
+  const float dist = (e2x * qx + e2y * qy + e2z * qz) * invDet;
+  return dist > FSPT_EPSILON ? dist : FSPT_MAX_T;
+}
+
+template <bool WRITE_COUNT>
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace(const TraceArgs A) {
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned FULL = 0xffffffffu;
+  const int n_cont = A.counts[0];
+  const int total = n_cont + A.counts[1];
+
+  int stack[FSPT_STACK];
+  int cur = FSPT_SENTINEL, sp = 0;
+  int slot = -1, kind = 0, cnt = 0;
+  float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0, ix = 0, iy = 0, iz = 0;
+  float tbest = FSPT_MAX_T;
+  int ibest = -1;
+  unsigned long long n_rays = 0, n_nodes = 0, n_leaves = 0;
+  bool drained = false;
+
+  for (;;) {
+    const bool need = (cur == FSPT_SENTINEL);
+    if (need && slot >= 0) {  // retire the finished ray
+      if (kind == 0) {
+        reinterpret_cast<float*>(A.ro)[4 * (size_t)slot + 3] = tbest;
+        reinterpret_cast<int*>(A.rd)[4 * (size_t)slot + 3] = ibest;
+      } else {
+        reinterpret_cast<int*>(A.sd)[4 * (size_t)slot + 3] = (ibest == -1) ? 2 : 3;
+      }
+      if (WRITE_COUNT) A.count_out[slot] = cnt;
+      n_nodes += (unsigned long long)cnt;
+      slot = -1;
+    }
+    if (!drained) {
+      const unsigned m = __ballot_sync(FULL, need);
+      if (m) {
+        const int leader = __ffs(m) - 1;
+        const int want = __popc(m);
+        int base = 0;
+        if ((int)lane == leader) base = atomicAdd(A.next, want);
+        base = __shfl_sync(FULL, base, leader);
+        if (base + want >= total) drained = true;
+        if (need) {
+          const int my = base + __popc(m & ((1u << lane) - 1u));
+          if (my < total) {
+            kind = my >= n_cont;
+            slot = kind ? A.list_shadow[my - n_cont] : (A.list_cont ? A.list_cont[my] : my);
+            const float4 o4 = A.ro[slot];
+            const float4 d4 = kind ? A.sd[slot] : A.rd[slot];
+            ox = o4.x; oy = o4.y; oz = o4.z;
+            dx = d4.x; dy = d4.y; dz = d4.z;
+            ix = 1.0f / dx; iy = 1.0f / dy; iz = 1.0f / dz;  // `vec3 inverse = 1.0 / ray.dir`, tracer.fs:318
+            tbest = FSPT_MAX_T; ibest = -1; cnt = 0;
+            stack[0] = FSPT_SENTINEL; sp = 1;
+            cur = A.root_ref;
+            n_rays++;
+          }
+        }
+      }
+    }
+    if (__ballot_sync(FULL, cur != FSPT_SENTINEL) == 0u) break;
+
+    const int refill = drained ? 1 : TRACE_REFILL;
+    for (;;) {
+      // ---- interior nodes ------------------------------------------------------------------------
+      while (cur >= 0) {
+        cnt++;
+        const float4* np = A.nodes + 4 * (size_t)cur;
+        const float4 a = __ldg(np), b = __ldg(np + 1), c = __ldg(np + 2);
+        const int4 d = __ldg(reinterpret_cast<const int4*>(np + 3));
+        const float lh = slab(a.x, a.y, a.z, a.w, b.x, b.y, ox, oy, oz, ix, iy, iz);
+        const float rh = slab(b.z, b.w, c.x, c.y, c.z, c.w, ox, oy, oz, ix, iy, iz);
+        const bool tl = lh < tbest, tr = rh < tbest;
+        if (tl && tr) {
+          if (lh > rh) { stack[sp++] = d.x; cur = d.y; }
+          else { stack[sp++] = d.y; cur = d.x; }
+        } else if (tl) cur = d.x;
+        else if (tr) cur = d.y;
+        else cur = stack[--sp];
+      }
+      // ---- leaf: 4 consecutive triangles ------------------------------------------------------------
+      if (cur != FSPT_SENTINEL) {
+        cnt++;
+        n_leaves++;
+        const int first = ~cur;
+        const float4* tp = A.tris + 3 * (size_t)first;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float4 q0 = __ldg(tp + 3 * k), q1 = __ldg(tp + 3 * k + 1), q2 = __ldg(tp + 3 * k + 2);
+          const float res = tri_test(q0, q1, q2, ox, oy, oz, dx, dy, dz);
+          if (res < tbest) { ibest = first + k; tbest = res; }
+        }
+        cur = stack[--sp];
+      }
+      if (__popc(__ballot_sync(FULL, cur != FSPT_SENTINEL)) < refill) break;
+    }
+  }
+  // per-warp statistics -> 3 atomics per warp
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    n_rays += __shfl_xor_sync(FULL, n_rays, o);
+    n_nodes += __shfl_xor_sync(FULL, n_nodes, o);
+    n_leaves += __shfl_xor_sync(FULL, n_leaves, o);
+  }
+  if (lane == 0) {
+    atomicAdd(A.stats + 0, n_rays);
+    atomicAdd(A.stats + 1, n_nodes);
+    atomicAdd(A.stats + 2, n_leaves);
+  }
+}

@@ -1,0 +1,136 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Bars (BASELINE.md section 4 / north star):
+  * primary-hit records (index, t, count) of the bvh_test.fs traversal: BIT-EXACT;
+  * camera rays, per-sample radiance, running-mean accumulator and RGBA8 post-pass: the CUDA kernels
+    implement the same FSPT-DM1 arithmetic as the oracle, so these are asserted bit-exact as well
+    (stated tolerance: 0 ulp; a mismatch-rate report is printed if that ever fails).
+"""
+import numpy as np
+import pytest
+
+from fspt_b200 import capi, scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def assert_bit_equal(got, ref, what):
+    got, ref = np.ascontiguousarray(got), np.ascontiguousarray(ref)
+    if got.dtype.kind == "f":
+        same = (bits(got) == bits(ref)) | (np.isnan(got) & np.isnan(ref))
+    else:
+        same = got == ref
+    bad = int((~same).sum())
+    if bad:
+        i = np.argwhere(~same)[0]
+        raise AssertionError("%s: %d of %d differ; first at %s: got %r ref %r" %
+                             (what, bad, same.size, tuple(i), got[tuple(i)], ref[tuple(i)]))
+
+
+@pytest.fixture(scope="module")
+def ctx_small(small_bunny):
+    sa, cam = small_bunny
+    ctx = capi.Context(160, 96)
+    ctx.scene_upload(sa)
+    yield ctx
+    ctx.close()
+
+
+def _frame(ctx, cam):
+    return ctx.frame(cam["eye"], cam["dir"], cam["fov_scale"], scenes.lens_features(cam), cam["env_theta"])
+
+
+def test_dm_math_matches_oracle(ctx_small, oracle_mod):
+    rng = np.random.default_rng(3)
+    x = np.concatenate([rng.uniform(-1e7, 1e7, 100000), rng.uniform(-8, 8, 100000), [0.0, -0.0, 1e-30, 3.4e38]]).astype(np.float32)
+    for fn in ("sin", "cos"):
+        assert_bit_equal(ctx_small.debug_math(fn, x), oracle_mod.dm_eval(fn, x), fn)
+    assert_bit_equal(ctx_small.debug_math("sincos_s", x), oracle_mod.dm_eval("sin", x), "sincos.s")
+    assert_bit_equal(ctx_small.debug_math("sincos_c", x), oracle_mod.dm_eval("cos", x), "sincos.c")
+    a = rng.uniform(-1.01, 1.01, 100000).astype(np.float32)
+    b = rng.uniform(-1, 1, 100000).astype(np.float32)
+    assert_bit_equal(ctx_small.debug_math("atan2", a, b), oracle_mod.dm_eval("atan2", a, b), "atan2")
+    assert_bit_equal(ctx_small.debug_math("asin", a), oracle_mod.dm_eval("asin", a), "asin")
+    e = rng.uniform(-150, 130, 100000).astype(np.float32)
+    assert_bit_equal(ctx_small.debug_math("exp2", e), oracle_mod.dm_eval("exp2", e), "exp2")
+    p = rng.uniform(0, 2, 100000).astype(np.float32)
+    q = rng.uniform(0.1, 3, 100000).astype(np.float32)
+    assert_bit_equal(ctx_small.debug_math("pow", p, q), oracle_mod.dm_eval("pow", p, q), "pow")
+
+
+def test_camera_and_primary_hits_bit_exact(ctx_small, small_bunny, oracle_mod):
+    sa, cam = small_bunny
+    O = oracle_mod.Oracle(sa)
+    for rb in (1234.5, 9876.25):
+        idx, t, cnt, pos, d = ctx_small.debug_primary(_frame(ctx_small, cam), rb)
+        opos, odir = oracle_mod.camera(160, 96, cam["eye"], cam["dir"], cam["fov_scale"], scenes.lens_features(cam), rb)
+        assert_bit_equal(pos, opos, "camera pos")
+        assert_bit_equal(d, odir, "camera dir")
+        oi, ot, oc, st = O.bvh_test(opos, odir)
+        assert_bit_equal(idx, oi, "hit index")
+        assert_bit_equal(t, ot, "hit t")
+        assert_bit_equal(cnt, oc, "visit count")
+        assert (oi >= 0).mean() > 0.3
+
+
+def test_debug_trace_random_rays(ctx_small, small_bunny, oracle_mod):
+    sa, _ = small_bunny
+    O = oracle_mod.Oracle(sa)
+    rng = np.random.default_rng(11)
+    n = 50000
+    pos = np.ones((n, 4), np.float32)
+    pos[:, :3] = rng.uniform(-1.5, 1.5, (n, 3))
+    d = np.ones((n, 4), np.float32)
+    v = rng.normal(size=(n, 3))
+    d[:, :3] = (v / np.linalg.norm(v, axis=1, keepdims=True)).astype(np.float32)
+    d[:100, 0] = 0.0   # axis-parallel components: 1/0 = inf slabs
+    d[100:200, 1] = -0.0
+    idx, t, cnt = ctx_small.debug_trace(pos, d)
+    oi, ot, oc, st = O.bvh_test(pos, d)
+    assert_bit_equal(idx, oi, "hit index")
+    assert_bit_equal(t, ot, "hit t")
+    assert_bit_equal(cnt, oc, "visit count")
+    s = ctx_small.stats()
+    assert s["rays"] >= n
+
+
+def test_radiance_accumulator_bit_exact(ctx_small, small_bunny, oracle_mod):
+    sa, cam = small_bunny
+    O = oracle_mod.Oracle(sa)
+    W, H, N = 160, 96, 6
+    rc, rt = scenes.rand_bases(N, 42)
+    ctx_small.clear()
+    ctx_small.render(_frame(ctx_small, cam), 0, rc, rt)
+    fb = ctx_small.read_accum()
+    last = ctx_small.debug_last_color()
+    ofb = None
+    rays = 0
+    for k in range(N):
+        pos, d = oracle_mod.camera(W, H, cam["eye"], cam["dir"], cam["fov_scale"], scenes.lens_features(cam), rc[k])
+        ofb, ocol, st = O.trace(pos, d, W, H, k, rt[k], cam["env_theta"], fb_prev=ofb, want_color=True)
+        rays += st["rays"]
+    assert_bit_equal(last[..., :3], ocol[..., :3], "last sample colour")
+    assert_bit_equal(fb[..., :3], ofb[..., :3], "accumulator")
+    s = ctx_small.stats()
+    assert s["last_rays"] == rays
+    # split renders continue the same running mean
+    ctx_small.clear()
+    ctx_small.render(_frame(ctx_small, cam), 0, rc[:2], rt[:2])
+    ctx_small.render(_frame(ctx_small, cam), 2, rc[2:], rt[2:])
+    assert_bit_equal(ctx_small.read_accum()[..., :3], ofb[..., :3], "accumulator (split)")
+
+
+def test_post_pass_bit_exact(ctx_small, small_bunny, oracle_mod):
+    sa, cam = small_bunny
+    rc, rt = scenes.rand_bases(3, 5)
+    ctx_small.clear()
+    ctx_small.render(_frame(ctx_small, cam), 0, rc, rt)
+    fb = ctx_small.read_accum()
+    for kw in (dict(), dict(denoise=True, max_sigma=2.0), dict(exposure=1.7, saturation=0.6), dict(denoise=True, exposure=0.5, saturation=1.3)):
+        got = ctx_small.resolve(**kw)
+        ref = oracle_mod.draw(fb, **kw)
+        assert_bit_equal(got, ref, "rgba8 %r" % (kw,))
