@@ -27,8 +27,11 @@ namespace {
 struct Aabb {
   double mn[3], mx[3];
   void reset() { for (int k = 0; k < 3; ++k) { mn[k] = INFINITY; mx[k] = -INFINITY; } }
-  void grow(const Aabb& b) {  // Math.min / Math.max (vector.js:55-61); inputs are never NaN (checked)
-    for (int k = 0; k < 3; ++k) { if (b.mn[k] < mn[k]) mn[k] = b.mn[k]; if (mx[k] < b.mx[k]) mx[k] = b.mx[k]; }
+  // Math.min / Math.max (vector.js:55-61) incl. their signed-zero rule (-0 < +0); inputs are never NaN (checked)
+  static double lo(double a, double b) { return a < b ? a : (b < a ? b : (signbit(a) ? a : b)); }
+  static double hi(double a, double b) { return a < b ? b : (b < a ? a : (signbit(a) ? b : a)); }
+  void grow(const Aabb& b) {
+    for (int k = 0; k < 3; ++k) { mn[k] = lo(mn[k], b.mn[k]); mx[k] = hi(mx[k], b.mx[k]); }
   }
   double area() const {  // BoundingBox.getSurfaceArea, bvh.js:137-142
     double xl = mx[0] - mn[0], yl = mx[1] - mn[1], zl = mx[2] - mn[2];
@@ -156,8 +159,8 @@ extern "C" int fspt_bvh_build(const double* verts, int32_t n_tris, int32_t max_t
       for (int k = 0; k < 3; ++k) {
         double x = verts[(size_t)i * 9 + v * 3 + k];
         if (!(x == x) || isinf(x)) return FSPT_E_INVALID;
-        if (x < b.mn[k]) b.mn[k] = x;
-        if (b.mx[k] < x) b.mx[k] = x;
+        b.mn[k] = Aabb::lo(x, b.mn[k]);
+        b.mx[k] = Aabb::hi(x, b.mx[k]);
       }
     for (int k = 0; k < 3; ++k) cen[k][i] = (b.mn[k] + b.mx[k]) * 0.5;  // centroid, bvh.js:130-135
   }

@@ -34,8 +34,19 @@ struct Box { /* bvh.js:93-143 BoundingBox */
     return (xl * yl + xl * zl + yl * zl) * 2;
   }
   double centroid(int axis) const { return (mn[axis] + mx[axis]) * 0.5; } /* bvh.js:130-135 */
-  static double jsmin(double a, double b) { if (a != a || b != b) return NAN; return b < a ? b : a; }
-  static double jsmax(double a, double b) { if (a != a || b != b) return NAN; return a < b ? b : a; }
+  /* Math.min / Math.max: NaN-propagating, and -0 < +0 (ECMA-262 21.3.2.24-25) */
+  static double jsmin(double a, double b) {
+    if (a != a || b != b) return NAN;
+    if (a < b) return a;
+    if (b < a) return b;
+    return signbit(a) ? a : b;
+  }
+  static double jsmax(double a, double b) {
+    if (a != a || b != b) return NAN;
+    if (a < b) return b;
+    if (b < a) return a;
+    return signbit(a) ? b : a;
+  }
 };
 
 struct Tri { const double* v; Box box; };

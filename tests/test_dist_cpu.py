@@ -1,0 +1,60 @@
+"""Multi-GPU host logic on CPU: world_size-2 gloo.  Sample-set sharding (rank r renders ticks r, r+G, ...) and
+the reduce(sum) of per-rank f32 sum buffers must equal the single-process sum over all ticks."""
+import os
+import sys
+
+import numpy as np
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    import oracle
+    from fspt_b200 import dist as fdist, scenes
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sa, cam = scenes.bunny_class(subdiv=2, atlas_res=16, env_size=(64, 32))
+    O = oracle.Oracle(sa)
+    W, H, N = 32, 24, 6
+    rc, rt = scenes.rand_bases(N, 9)
+    ticks = fdist.shard_ticks(N, rank, world)
+    local = np.zeros((H, W, 4), np.float32)
+    for k in ticks:  # per-rank sum buffer (accumulation mode 1 of the library), colours from the CPU oracle
+        pos, d = oracle.camera(W, H, cam["eye"], cam["dir"], cam["fov_scale"], scenes.lens_features(cam), rc[k], nthreads=1)
+        _, col, _ = O.trace(pos, d, W, H, 0, rt[k], cam["env_theta"], want_color=True, nthreads=1)
+        local += col
+    total = fdist.reduce_arrays_cpu(local, dst=0)
+    if rank == 0:
+        np.save(os.path.join(out_dir, "reduced.npy"), total)
+    np.save(os.path.join(out_dir, "ticks%d.npy" % rank), ticks)
+    dist.destroy_process_group()
+
+
+def test_sample_set_sharding_reduce_matches_single_process(tmp_path, oracle_mod):
+    world, port = 2, 29500 + (os.getpid() % 500)
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    from fspt_b200 import scenes
+    t0, t1 = np.load(tmp_path / "ticks0.npy"), np.load(tmp_path / "ticks1.npy")
+    assert sorted(np.concatenate([t0, t1]).tolist()) == list(range(6)) and not set(t0) & set(t1)
+    sa, cam = scenes.bunny_class(subdiv=2, atlas_res=16, env_size=(64, 32))
+    O = oracle_mod.Oracle(sa)
+    W, H, N = 32, 24, 6
+    rc, rt = scenes.rand_bases(N, 9)
+    cols = []
+    for k in range(N):
+        pos, d = oracle_mod.camera(W, H, cam["eye"], cam["dir"], cam["fov_scale"], scenes.lens_features(cam), rc[k])
+        _, col, _ = O.trace(pos, d, W, H, 0, rt[k], cam["env_theta"], want_color=True)
+        cols.append(col)
+    # same association as the sharded run: (sum of even ticks) + (sum of odd ticks)
+    ref = (cols[0] + cols[2] + cols[4]) + (cols[1] + cols[3] + cols[5])
+    got = np.load(tmp_path / "reduced.npy")
+    assert np.array_equal(got[..., :3], ref[..., :3])
+    # and it is the running mean of the reference up to f32 summation order
+    mean = None
+    for k in range(N):
+        mean = cols[k][..., :3] if mean is None else (cols[k][..., :3] + mean * np.float32(k)) / np.float32(k + 1)
+    assert np.allclose(got[..., :3] / N, mean, rtol=2e-6, atol=1e-7)
