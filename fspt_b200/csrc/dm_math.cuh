@@ -56,17 +56,20 @@ __device__ __forceinline__ double reduce(double x, int& q) {
   q = (int)(((long long)k) & 3);
   return r;
 }
+// both kernels are always evaluated and the quadrant only selects: no divergence inside a warp
 __device__ __forceinline__ float sinf_(float x) {
   int q;
   const double r = reduce((double)x, q);
-  double s = (q & 1) ? kcos(r) : ksin(r);
+  const double a = ksin(r), b = kcos(r);
+  double s = (q & 1) ? b : a;
   if (q & 2) s = -s;
   return (float)s;
 }
 __device__ __forceinline__ float cosf_(float x) {
   int q;
   const double r = reduce((double)x, q);
-  double s = (q & 1) ? ksin(r) : kcos(r);
+  const double a = ksin(r), b = kcos(r);
+  double s = (q & 1) ? a : b;
   if (q == 1 || q == 2) s = -s;
   return (float)s;
 }

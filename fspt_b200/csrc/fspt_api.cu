@@ -24,7 +24,8 @@ struct Ctx {
   int width = 0, height = 0, n_pixels = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
-  std::vector<cudaEvent_t> ev_trace;  // pairs around traversal launches of the last render
+  std::vector<cudaEvent_t> ev_trace;  // pairs around traversal (tag 0) / shading (tag 1) launches of the last render
+  std::vector<int> ev_tag;
   size_t ev_trace_used = 0;
   bool render_timed = false;
   std::string error;
@@ -53,8 +54,8 @@ struct Ctx {
   int wave_samples = 0;       // samples in flight per wave
   size_t wave_paths = 0;
   PathState ps{};
-  int* d_list[3] = {nullptr, nullptr, nullptr};  // two continuation lists (ping-pong) + shadow list
-  int* d_counts = nullptr;    // [0..1] counts A, [2..3] counts B, [4] fetch cursor, [5..7] pad
+  int* d_list[4] = {nullptr, nullptr, nullptr, nullptr};  // continuation, shadow (trace inputs); hit, miss (trace outputs)
+  int* d_counts = nullptr;    // [0] #cont [1] #shadow [2] #hit [3] #miss [4] fetch cursor, [5..7] pad
   int* d_count_out = nullptr; // per-slot visit count (debug)
   unsigned long long* d_stats = nullptr;  // rays, nodes, leaves, capped
   float* d_rb = nullptr;      // rand bases of one render call: [0,cap) camera, [cap,2cap) tracer
@@ -110,7 +111,7 @@ int alloc_wave(Ctx* c) {
   CK(cudaMalloc(&c->ps.ro, W * 16)); CK(cudaMalloc(&c->ps.rd, W * 16)); CK(cudaMalloc(&c->ps.sd, W * 16));
   CK(cudaMalloc(&c->ps.thr, W * 16)); CK(cudaMalloc(&c->ps.bt, W * 16)); CK(cudaMalloc(&c->ps.pend, W * 16));
   CK(cudaMalloc(&c->ps.col, W * 16));
-  for (int i = 0; i < 3; ++i) CK(cudaMalloc(&c->d_list[i], W * sizeof(int)));
+  for (int i = 0; i < 4; ++i) CK(cudaMalloc(&c->d_list[i], W * sizeof(int)));
   CK(cudaMalloc(&c->d_counts, 8 * sizeof(int)));
   CK(cudaMalloc(&c->d_count_out, W * sizeof(int)));
   CK(cudaMalloc(&c->d_stats, 8 * sizeof(unsigned long long)));  // [0..3] live, [4..7] snapshot at render start
@@ -123,10 +124,12 @@ int alloc_wave(Ctx* c) {
 }
 
 // ---- traversal launch helpers ---------------------------------------------------------------------------
-void record_trace_begin(Ctx* c) {
+void record_trace_begin(Ctx* c, int tag = 0) {
   if (c->ev_trace_used + 2 > c->ev_trace.size()) {
     for (int i = 0; i < 2; ++i) { cudaEvent_t e; cudaEventCreate(&e); c->ev_trace.push_back(e); }
   }
+  if (c->ev_tag.size() < c->ev_trace.size() / 2) c->ev_tag.resize(c->ev_trace.size() / 2);
+  c->ev_tag[c->ev_trace_used / 2] = tag;
   cudaEventRecord(c->ev_trace[c->ev_trace_used], c->stream);
 }
 void record_trace_end(Ctx* c) {
@@ -134,17 +137,23 @@ void record_trace_end(Ctx* c) {
   c->ev_trace_used += 2;
 }
 
-// counts at d_counts + 2*which; cursor at d_counts + 4
-int launch_trace(Ctx* c, const int* list_cont, const int* list_shadow, int which, bool write_count) {
+__global__ void k_set_counts(int* counts, int n_cont, int n_shadow) {
+  counts[0] = n_cont; counts[1] = n_shadow; counts[2] = 0; counts[3] = 0; counts[4] = 0;
+}
+
+// Traverses d_counts[0] continuation rays (list_cont, NULL = identity) + d_counts[1] shadow rays and sorts the
+// continuation results into the hit / miss lists (d_counts[2], d_counts[3]).
+int launch_trace(Ctx* c, const int* list_cont, bool classify, bool write_count) {
   TraceArgs A;
   A.nodes = c->sc.nodes; A.tris = c->sc.tris; A.root_ref = c->sc.root_ref;
   A.ro = c->ps.ro; A.rd = c->ps.rd; A.sd = c->ps.sd;
-  A.list_cont = list_cont; A.list_shadow = list_shadow;
-  A.counts = c->d_counts + 2 * which;
+  A.list_cont = list_cont; A.list_shadow = c->d_list[1];
+  A.counts = c->d_counts;
+  A.list_hit = c->d_list[2]; A.list_miss = c->d_list[3];
+  A.counts_out = classify ? c->d_counts + 2 : nullptr;
   A.next = c->d_counts + 4;
   A.stats = c->d_stats;
   A.count_out = write_count ? c->d_count_out : nullptr;
-  CK(cudaMemsetAsync(c->d_counts + 4, 0, sizeof(int), c->stream));
   record_trace_begin(c);
   if (write_count) k_trace<true><<<c->trace_blocks_cnt, TRACE_THREADS, 0, c->stream>>>(A);
   else k_trace<false><<<c->trace_blocks, TRACE_THREADS, 0, c->stream>>>(A);
@@ -154,9 +163,9 @@ int launch_trace(Ctx* c, const int* list_cont, const int* list_shadow, int which
   return FSPT_OK;
 }
 
-int set_counts(Ctx* c, int which, int n_cont, int n_shadow) {
-  int h[2] = {n_cont, n_shadow};
-  CK(cudaMemcpyAsync(c->d_counts + 2 * which, h, sizeof h, cudaMemcpyHostToDevice, c->stream));
+int set_counts(Ctx* c, int n_cont, int n_shadow) {  // also zeroes #hit, #miss and the fetch cursor
+  k_set_counts<<<1, 1, 0, c->stream>>>(c->d_counts, n_cont, n_shadow);
+  CK(cudaGetLastError());
   return FSPT_OK;
 }
 
@@ -175,41 +184,40 @@ int render_wave(Ctx* c, const FrameParams& fp, uint32_t first_tick, int S, const
   const int n_paths = S * P;
   k_camera<<<(n_paths + 255) / 256, 256, 0, c->stream>>>(fp, rb_cam, n_paths, P, c->ps, nullptr, nullptr);
   c->stats.kernel_launches++;
-  int rc = set_counts(c, 0, n_paths, 0);
+  int rc = set_counts(c, n_paths, 0);
   if (rc) return rc;
-  rc = launch_trace(c, nullptr, nullptr, 0, false);  // primary rays, tracer.fs:440
+  rc = launch_trace(c, nullptr, true, false);  // primary rays, tracer.fs:440
   if (rc) return rc;
 
   ShadeArgs A;
   A.sc = c->sc; A.ps = c->ps; A.f = fp;
   A.rb_trace = rb_trace;
+  A.list_hit = c->d_list[2]; A.list_miss = c->d_list[3];
+  A.counts_in = c->d_counts + 2;
+  A.list_cont_out = c->d_list[0]; A.list_shadow_out = c->d_list[1];
+  A.counts_out = c->d_counts;
   A.sample_color = c->d_sample_color;
   A.capped = c->d_stats + 3;
   A.paths_per_sample = P;
   A.max_refractions = c->max_refractions;
-  int cur = 0;  // which counts/list holds the slots to shade
   const int hard_cap = FSPT_NUM_BOUNCES + 1 + (c->has_dielectric ? c->max_refractions + 2 : 0);
   for (int b = 0; b < hard_cap; ++b) {
-    const int nxt = cur ^ 1;
-    CK(cudaMemsetAsync(c->d_counts + 2 * nxt, 0, 2 * sizeof(int), c->stream));
+    CK(cudaMemsetAsync(c->d_counts, 0, 2 * sizeof(int), c->stream));  // #cont = #shadow = 0
     A.first = (b == 0);
-    A.list_in = (b == 0) ? nullptr : c->d_list[cur];
-    A.counts_in = c->d_counts + 2 * cur;
-    A.list_cont_out = c->d_list[nxt];
-    A.list_shadow_out = c->d_list[2];
-    A.counts_out = c->d_counts + 2 * nxt;
-    k_shade<<<c->shade_blocks, 128, 0, c->stream>>>(A);
+    record_trace_begin(c, 1);
+    k_shade<<<c->shade_blocks, SHADE_THREADS, 1024, c->stream>>>(A);
+    record_trace_end(c);
     c->stats.kernel_launches++;
     CK(cudaGetLastError());
-    cur = nxt;
     if (b >= FSPT_NUM_BOUNCES) {
-      if (!c->has_dielectric) break;  // every surviving path has i == NUM_BOUNCES: nothing was appended
+      if (!c->has_dielectric) break;  // every surviving path had i == NUM_BOUNCES: nothing was appended
       int h[2];
-      CK(cudaMemcpyAsync(h, c->d_counts + 2 * cur, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaMemcpyAsync(h, c->d_counts, sizeof h, cudaMemcpyDeviceToHost, c->stream));
       CK(cudaStreamSynchronize(c->stream));
       if (h[0] == 0) break;
     }
-    rc = launch_trace(c, c->d_list[cur], c->d_list[2], cur, false);  // tracer.fs:501,507
+    CK(cudaMemsetAsync(c->d_counts + 2, 0, 3 * sizeof(int), c->stream));  // #hit = #miss = cursor = 0
+    rc = launch_trace(c, c->d_list[0], true, false);  // tracer.fs:501,507
     if (rc) return rc;
   }
   k_accumulate<<<(P + 255) / 256, 256, 0, c->stream>>>(c->d_sample_color, c->d_fb, c->d_last_color, P, S, first_tick,
@@ -275,7 +283,7 @@ int fspt_create(fspt_ctx** out, int32_t width, int32_t height, int32_t device) {
   c->trace_blocks = std::max(1, per_sm) * c->sm_count;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<true>, TRACE_THREADS, 0);
   c->trace_blocks_cnt = std::max(1, per_sm) * c->sm_count;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shade, 128, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shade, SHADE_THREADS, 1024);
   c->shade_blocks = std::max(1, per_sm) * c->sm_count;
   *out = reinterpret_cast<fspt_ctx*>(c);
   return FSPT_OK;
@@ -289,7 +297,7 @@ void fspt_destroy(fspt_ctx* ctx) {
   free_scene(c);
   dfree(c->d_fb); dfree(c->d_last_color); dfree(c->d_sample_color); dfree(c->d_cam_pos); dfree(c->d_cam_dir); dfree(c->d_rgba8);
   dfree(c->ps.ro); dfree(c->ps.rd); dfree(c->ps.sd); dfree(c->ps.thr); dfree(c->ps.bt); dfree(c->ps.pend); dfree(c->ps.col);
-  for (int i = 0; i < 3; ++i) dfree(c->d_list[i]);
+  for (int i = 0; i < 4; ++i) dfree(c->d_list[i]);
   dfree(c->d_counts); dfree(c->d_count_out); dfree(c->d_stats); dfree(c->d_rb);
   if (c->h_rb) cudaFreeHost(c->h_rb);
   for (auto e : c->ev_trace) cudaEventDestroy(e);
@@ -570,10 +578,10 @@ int fspt_debug_primary(fspt_ctx* ctx, const fspt_frame_params* frame, float rand
   CK(cudaMemcpyAsync(c->d_rb, c->h_rb, sizeof(float), cudaMemcpyHostToDevice, c->stream));
   k_camera<<<(P + 255) / 256, 256, 0, c->stream>>>(fp, c->d_rb, P, P, c->ps, c->d_cam_pos, c->d_cam_dir);
   c->stats.kernel_launches++;
-  int rc = set_counts(c, 0, P, 0);
+  int rc = set_counts(c, P, 0);
   if (rc) return rc;
   c->ev_trace_used = 0;
-  rc = launch_trace(c, nullptr, nullptr, 0, true);
+  rc = launch_trace(c, nullptr, false, true);
   if (rc) return rc;
   CK(cudaStreamSynchronize(c->stream));
   // un-swizzle path slots -> pixels on the host
@@ -611,10 +619,10 @@ int fspt_debug_trace(fspt_ctx* ctx, const float* pos4, const float* dir4, int32_
     const int n = (int)std::min<int64_t>((int64_t)c->wave_paths, n_rays - done);
     CK(cudaMemcpyAsync(c->ps.ro, pos4 + 4 * done, (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->ps.rd, dir4 + 4 * done, (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
-    int rc = set_counts(c, 0, n, 0);
+    int rc = set_counts(c, n, 0);
     if (rc) return rc;
     c->ev_trace_used = 0;
-    rc = launch_trace(c, nullptr, nullptr, 0, true);
+    rc = launch_trace(c, nullptr, false, true);
     if (rc) return rc;
     ro.resize(n); rdv.resize(n); cnt.resize(n);
     CK(cudaMemcpyAsync(ro.data(), c->ps.ro, (size_t)n * 16, cudaMemcpyDeviceToHost, c->stream));
@@ -664,11 +672,12 @@ int fspt_get_stats(fspt_ctx* ctx, fspt_stats* out) {
   if (rc) return rc;
   float ms = 0.0f;
   if (c->render_timed && cudaEventElapsedTime(&ms, c->ev_begin, c->ev_end) == cudaSuccess) c->stats.render_ms = ms;
-  double tr = 0.0;
+  double tr = 0.0, sh = 0.0;
   for (size_t i = 0; i + 1 < c->ev_trace_used; i += 2) {
     float t = 0.0f;
-    if (cudaEventElapsedTime(&t, c->ev_trace[i], c->ev_trace[i + 1]) == cudaSuccess) tr += t;
+    if (cudaEventElapsedTime(&t, c->ev_trace[i], c->ev_trace[i + 1]) == cudaSuccess) (c->ev_tag[i / 2] ? sh : tr) += t;
   }
+  c->stats.shade_ms = sh;
   (void)cudaGetLastError();  // event queries must not leave a sticky status for the next launch check
   c->stats.trace_ms = tr;
   *out = c->stats;

@@ -16,9 +16,11 @@ struct SampleParams {     // per sample in flight
 };
 
 // rnd(), tracer.fs:181 / camera.fs:19
+// (kept out of line: the shading kernel calls it ~8 times per vertex and its binary64 body is ~60 instructions)
+__device__ __noinline__ float sin_hash(float seed) { return fractf(dm::sinf_(seed) * 43758.5453123f); }
 __device__ __forceinline__ float rnd(float& seed) {
   seed += 0.211324865405187f;
-  return fractf(dm::sinf_(seed) * 43758.5453123f);
+  return sin_hash(seed);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -65,8 +67,15 @@ __global__ void __launch_bounds__(256) k_camera(const FrameParams f, const float
 // Texture units.  The atlas and the environment are CUDA texture objects (block-linear arrays through the
 // texture cache); texels are fetched un-filtered and the GL LINEAR weights (GL ES 3.0 section 3.8.10) are
 // applied in f32 exactly as the oracle does, because hardware filtering uses 8-bit fixed-point weights.
+// unorm8 -> f32 is (float)c / 255.0f; the 256 possible quotients are computed once per block with IEEE division
+// into shared memory, so a bilinear fetch costs 16 LDS instead of 16 I2F + 16 division sequences (XU pipe).
+extern __shared__ float s_unorm8[];
+__device__ __forceinline__ void init_unorm8_lut() {
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_unorm8[i] = (float)i / 255.0f;
+  __syncthreads();
+}
 __device__ __forceinline__ float4 texel8(uchar4 c) {
-  return make_float4((float)c.x / 255.0f, (float)c.y / 255.0f, (float)c.z / 255.0f, (float)c.w / 255.0f);
+  return make_float4(s_unorm8[c.x], s_unorm8[c.y], s_unorm8[c.z], s_unorm8[c.w]);
 }
 __device__ __forceinline__ float4 bilerp(float4 t00, float4 t10, float4 t01, float4 t11, float a, float b) {
   const float w00 = (1.0f - a) * (1.0f - b), w10 = a * (1.0f - b), w01 = (1.0f - a) * b, w11 = a * b;
@@ -77,48 +86,56 @@ __device__ __forceinline__ float4 bilerp(float4 t00, float4 t10, float4 t01, flo
   r.w = w00 * t00.w + w10 * t10.w + w01 * t01.w + w11 * t11.w;
   return r;
 }
-__device__ __forceinline__ int wrap_repeat(long long i, int size) {
-  long long m = i % size;
+// texel index wrapping.  coord_to_int() bounds |i| by 1e9, so 32-bit arithmetic is exact; power-of-two sizes
+// (every atlas / environment in practice) wrap with a mask, which equals the mathematical modulo for negatives too.
+__device__ __forceinline__ int wrap_repeat(int i, int size) {
+  if ((size & (size - 1)) == 0) return i & (size - 1);
+  int m = i % size;
   if (m < 0) m += size;
-  return (int)m;
+  return m;
 }
-__device__ __forceinline__ int wrap_clamp(long long i, int size) { return (int)(i < 0 ? 0 : (i >= size ? size - 1 : i)); }
+__device__ __forceinline__ int wrap_clamp(int i, int size) { return i < 0 ? 0 : (i >= size ? size - 1 : i); }
 
 // texture(texArray, vec3(uv, layer)): REPEAT/REPEAT, LINEAR (main.js:551-555)
-__device__ __forceinline__ float4 texture_atlas(const DeviceScene& sc, float u, float v, float layerf) {
-  const int R = sc.atlas_res;
+__device__ __noinline__ float4 texture_atlas(cudaTextureObject_t atlas, int R, int n_layers, float u, float v, float layerf) {
   const long long Lq = coord_to_int(floorf(layerf + 0.5f));
-  const int L = (int)(Lq < 0 ? 0 : (Lq >= sc.atlas_layers ? sc.atlas_layers - 1 : Lq));
+  const int L = (int)(Lq < 0 ? 0 : (Lq >= n_layers ? n_layers - 1 : Lq));
   const float x = u * (float)R - 0.5f, y = v * (float)R - 0.5f;
   const float fx = floorf(x), fy = floorf(y);
   const float a = x - fx, b = y - fy;
-  const long long ixx = coord_to_int(fx), iyy = coord_to_int(fy);
+  const int ixx = (int)coord_to_int(fx), iyy = (int)coord_to_int(fy);
   const float i0 = (float)wrap_repeat(ixx, R) + 0.5f, i1 = (float)wrap_repeat(ixx + 1, R) + 0.5f;
   const float j0 = (float)wrap_repeat(iyy, R) + 0.5f, j1 = (float)wrap_repeat(iyy + 1, R) + 0.5f;
-  const uchar4 t00 = tex2DLayered<uchar4>(sc.atlas, i0, j0, L), t10 = tex2DLayered<uchar4>(sc.atlas, i1, j0, L);
-  const uchar4 t01 = tex2DLayered<uchar4>(sc.atlas, i0, j1, L), t11 = tex2DLayered<uchar4>(sc.atlas, i1, j1, L);
+  const uchar4 t00 = tex2DLayered<uchar4>(atlas, i0, j0, L), t10 = tex2DLayered<uchar4>(atlas, i1, j0, L);
+  const uchar4 t01 = tex2DLayered<uchar4>(atlas, i0, j1, L), t11 = tex2DLayered<uchar4>(atlas, i1, j1, L);
   return bilerp(texel8(t00), texel8(t10), texel8(t01), texel8(t11), a, b);
 }
 // texture(envTex, c): S REPEAT, T CLAMP_TO_EDGE, LINEAR on the ENCODED RGBE texel (main.js:170-180)
-__device__ __forceinline__ float4 texture_env(const DeviceScene& sc, float u, float v) {
-  const int W = sc.env_w, H = sc.env_h;
+__device__ __forceinline__ float4 texture_env(cudaTextureObject_t env, int W, int H, float u, float v) {
   const float x = u * (float)W - 0.5f, y = v * (float)H - 0.5f;
   const float fx = floorf(x), fy = floorf(y);
   const float a = x - fx, b = y - fy;
-  const long long ixx = coord_to_int(fx), iyy = coord_to_int(fy);
+  const int ixx = (int)coord_to_int(fx), iyy = (int)coord_to_int(fy);
   const float i0 = (float)wrap_repeat(ixx, W) + 0.5f, i1 = (float)wrap_repeat(ixx + 1, W) + 0.5f;
   const float j0 = (float)wrap_clamp(iyy, H) + 0.5f, j1 = (float)wrap_clamp(iyy + 1, H) + 0.5f;
-  const uchar4 t00 = tex2D<uchar4>(sc.env, i0, j0), t10 = tex2D<uchar4>(sc.env, i1, j0);
-  const uchar4 t01 = tex2D<uchar4>(sc.env, i0, j1), t11 = tex2D<uchar4>(sc.env, i1, j1);
+  const uchar4 t00 = tex2D<uchar4>(env, i0, j0), t10 = tex2D<uchar4>(env, i1, j0);
+  const uchar4 t01 = tex2D<uchar4>(env, i0, j1), t11 = tex2D<uchar4>(env, i1, j1);
   return bilerp(texel8(t00), texel8(t10), texel8(t01), texel8(t11), a, b);
 }
 // envColor + envSample, tracer.fs:410-419
-__device__ __forceinline__ v3 env_sample(const DeviceScene& sc, v3 dir, float envTheta) {
-  const float cx = envTheta + dm::atan2f_(dir.z, dir.x) / FSPT_TAU;
-  const float cy = dm::asinf_(-dir.y) * FSPT_INV_PI + 0.5f;
-  const float4 rgbe = texture_env(sc, cx, cy);
-  const float p = dm::powf_(2.0f, rgbe.w * 255.0f - 128.0f);
+__device__ __noinline__ v3 env_sample_(cudaTextureObject_t env, int W, int H, float dx, float dy, float dz, float envTheta) {
+  const float cx = envTheta + dm::atan2f_(dz, dx) / FSPT_TAU;
+  const float cy = dm::asinf_(-dy) * FSPT_INV_PI + 0.5f;
+  const float4 rgbe = texture_env(env, W, H, cx, cy);
+  // pow(2.0, e), tracer.fs:412: in FSPT-DM1 log2(2.0) evaluates to exactly 1.0, so this is exp2(e) bit for bit
+  const float p = dm::exp2f_(rgbe.w * 255.0f - 128.0f);
   return mk3(rgbe.x * p, rgbe.y * p, rgbe.z * p);
+}
+__device__ __forceinline__ v3 env_sample(const DeviceScene& sc, v3 dir, float envTheta) {
+  return env_sample_(sc.env, sc.env_w, sc.env_h, dir.x, dir.y, dir.z, envTheta);
+}
+__device__ __forceinline__ float4 texture_atlas(const DeviceScene& sc, float u, float v, float layerf) {
+  return texture_atlas(sc.atlas, sc.atlas_res, sc.atlas_layers, u, v, layerf);
 }
 
 // ---- BSDF pieces, tracer.fs:194-298 ---------------------------------------------------------------------
@@ -188,21 +205,22 @@ struct ShadeArgs {
   PathState ps;
   FrameParams f;
   const float* rb_trace;      // per sample-in-wave
-  const int* list_in;         // path slots to shade; NULL = identity
-  const int* counts_in;       // counts_in[0] = number of slots in list_in
+  const int* list_hit;        // path slots whose continuation/primary ray hit a triangle (from k_trace)
+  const int* list_miss;       // path slots whose ray left the scene
+  const int* counts_in;       // [0] = #hit, [1] = #miss
   int* list_cont_out;         // continuation rays for the next traversal
   int* list_shadow_out;
   int* counts_out;            // [0] continuation, [1] shadow
   float4* sample_color;       // [sample-in-wave][pixel] final un-clamped path colour
   unsigned long long* capped; // paths stopped by the refraction cap
   int paths_per_sample;
-  int first;                  // 1: slots hold fresh primary hits (tracer.fs:440-445)
+  int first;                  // 1: slots hold fresh primary rays (tracer.fs:440-445)
   int max_refractions;
 };
 
-// Warp-aggregated append: one atomicAdd per warp per list (ballot + popc prefix)
+// Warp-aggregated append: one atomicAdd per warp per list (ballot + popc prefix); call with all 32 lanes
 __device__ __forceinline__ void append(bool want, int value, int* list, int* counter) {
-  const unsigned m = __ballot_sync(0xffffffffu, want);  // callers keep whole warps in the loop
+  const unsigned m = __ballot_sync(0xffffffffu, want);
   if (!want) return;
   const unsigned lane = threadIdx.x & 31u;
   const int leader = __ffs(m) - 1;
@@ -212,216 +230,241 @@ __device__ __forceinline__ void append(bool want, int value, int* list, int* cou
   list[base + __popc(m & ((1u << lane) - 1u))] = value;
 }
 
-// One loop iteration of tracer.fs main (:446-513), split at the intersectScene calls.
-__global__ void __launch_bounds__(128) k_shade(const ShadeArgs A) {
-  const int n = A.counts_in[0];
-  for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < ((n + 31) & ~31); it += gridDim.x * blockDim.x) {
-    const bool live = it < n;
+__device__ __forceinline__ void write_sample(const ShadeArgs& A, int slot, v3 color) {
+  const int s = slot / A.paths_per_sample, j = slot - s * A.paths_per_sample;
+  int x, y;
+  path_to_pixel(A.f, j, x, y);
+  A.sample_color[(size_t)s * ((size_t)A.f.width * A.f.height) + (size_t)y * A.f.width + x] =
+      make_float4(color.x, color.y, color.z, 1.0f);
+}
+
+// The tail of the previous loop iteration for a path whose ray MISSED: tracer.fs:442-443 (primary) or
+// :502-504 + :508-512 (bounce).  Ends the path.
+__device__ __forceinline__ void shade_miss(const ShadeArgs& A, int slot) {
+  const float4 d4 = A.ps.rd[slot];
+  const v3 rayDir = mk3(d4.x, d4.y, d4.z);
+  const v3 env = env_sample(A.sc, rayDir, A.f.env_theta);
+  v3 color;
+  if (A.first) {
+    color = add(mk3(0.0f, 0.0f, 0.0f), env);  // :443
+  } else {
+    const float4 c4 = A.ps.col[slot], t4 = A.ps.thr[slot], b4 = A.ps.bt[slot], s4 = A.ps.sd[slot];
+    color = mk3(c4.x, c4.y, c4.z);
+    if (__float_as_int(s4.w) == 2) {  // shadow.index == -1, :502-504
+      const float4 p4 = A.ps.pend[slot];
+      color = add(color, mk3(p4.x, p4.y, p4.z));
+    }
+    const v3 reflectance = mul(mk3(t4.x, t4.y, t4.z), mk3(b4.x, b4.y, b4.z));  // :508
+    color = add(color, mul(mul(reflectance, env), t4.w));                      // :510
+  }
+  write_sample(A, slot, color);
+}
+
+// One loop iteration of tracer.fs main (:446-513) for a path whose ray HIT, split at the intersectScene calls.
+// Returns true when the path continues (a continuation ray, and maybe a shadow ray, were written).
+__device__ __forceinline__ bool shade_hit(const ShadeArgs& A, int slot, bool& shadow) {
+  const DeviceScene& sc = A.sc;
+  const float4 o4 = A.ps.ro[slot], d4 = A.ps.rd[slot];
+  v3 rayOrigin = mk3(o4.x, o4.y, o4.z), rayDir = mk3(d4.x, d4.y, d4.z);
+  const float hit_t = o4.w;
+  const int hit_index = __float_as_int(d4.w);
+  const int s = slot / A.paths_per_sample;
+  const float randBase = A.rb_trace[s];
+  const float envTheta = A.f.env_theta;
+  v3 color, reflectance;
+  int i = 0, refractions = 0;
+  shadow = false;
+  if (A.first) {
+    color = mk3(0.0f, 0.0f, 0.0f);
+    reflectance = mk3(1.0f, 1.0f, 1.0f);
+  } else {
+    const float4 c4 = A.ps.col[slot], t4 = A.ps.thr[slot], b4 = A.ps.bt[slot], s4 = A.ps.sd[slot];
+    color = mk3(c4.x, c4.y, c4.z);
+    reflectance = mk3(t4.x, t4.y, t4.z);
+    const int packed = __float_as_int(b4.w);
+    i = (packed & 0xffff) - 0x100;  // stored biased so that i = -1 survives
+    refractions = packed >> 16;
+    if (__float_as_int(s4.w) == 2) {  // shadow.index == -1, :502-504
+      const float4 p4 = A.ps.pend[slot];
+      color = add(color, mk3(p4.x, p4.y, p4.z));
+    }
+    reflectance = mul(reflectance, mk3(b4.x, b4.y, b4.z));  // :508
+    ++i;                                                    // for (...; ++i), :446
+    if (!(i < FSPT_NUM_BOUNCES)) {
+      write_sample(A, slot, color);
+      return false;
+    }
+  }
+  // createMaterial / createTriangle / createTexCoords / createNormals, :447-449,460
+  const float4* rec = sc.shade + 12 * (size_t)hit_index;
+  const float4 m0 = __ldg(rec), m2 = __ldg(rec + 2);
+  const float4 u0 = __ldg(rec + 3), u1 = __ldg(rec + 4);
+  const float mapDiffuse = m0.x, mapSpecular = m0.y, mapNormal = m0.z, mapRoughness = m0.w;
+  const float matIor = m2.y, matDielectric = m2.z;
+  const float4* tp = sc.tris + 3 * (size_t)hit_index;
+  const float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
+  const v3 tv1 = mk3(q0.x, q0.y, q0.z);
+  const v3 origin = add(rayOrigin, mul(rayDir, hit_t));  // :450
+  // barycentricWeights, :339-353 (v0 = v2 - v1 and v1 = v3 - v1 are the stored edges)
+  const v3 e0 = mk3(q0.w, q1.x, q1.y), e1 = mk3(q1.z, q1.w, q2.x), e2 = sub(origin, tv1);
+  const float d00 = dot(e0, e0), d01 = dot(e0, e1), d11 = dot(e1, e1), d20 = dot(e2, e0), d21 = dot(e2, e1);
+  const float invDenom = 1.0f / (d00 * d11 - d01 * d01);
+  const float bv = (d11 * d20 - d01 * d21) * invDenom;
+  const float bw_ = (d00 * d21 - d01 * d20) * invDenom;
+  const float bu = 1.0f - bv - bw_;
+  const float tcx = bu * u0.x + bv * u0.z + bw_ * u1.x;  // barycentricTexCoord, :328-330
+  const float tcy = bu * u0.y + bv * u0.w + bw_ * u1.y;
+  const float4 tD = texture_atlas(sc, tcx, tcy, mapDiffuse);     // :453
+  const float4 tE = texture_atlas(sc, tcx, tcy, mapSpecular);    // :454
+  const float4 tMR = texture_atlas(sc, tcx, tcy, mapRoughness);  // :455
+  const float4 tN = texture_atlas(sc, tcx, tcy, mapNormal);      // :456
+  const v3 texDiffuse = mk3(tD.x, tD.y, tD.z), texEmmissive = mk3(tE.x, tE.y, tE.z);
+  v2 texMR;
+  texMR.x = tMR.x;
+  texMR.y = tMR.y;
+  const v3 texNormal = mul(sub(mk3(tN.x, tN.y, tN.z), mk3(0.5f, 0.5f, 0.0f)), mk3(2.0f, 2.0f, 1.0f));
+  texMR.y *= texMR.y;  // :457
+  float seed = origin.x * randBase * origin.y * 1.396529836f + origin.z * 4761.52835f;  // :458
+  // normals record: [n1 t1 b1 n2 t2 b2 n3 t3 b3] = floats 20..46 of the 48-float record
+  float nn[28];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    const float4 t = __ldg(rec + 5 + k);
+    nn[4 * k + 0] = t.x; nn[4 * k + 1] = t.y; nn[4 * k + 2] = t.z; nn[4 * k + 3] = t.w;
+  }
+  const v3 n1 = mk3(nn[0], nn[1], nn[2]), t1 = mk3(nn[3], nn[4], nn[5]), b1 = mk3(nn[6], nn[7], nn[8]);
+  const v3 n2 = mk3(nn[9], nn[10], nn[11]), t2 = mk3(nn[12], nn[13], nn[14]), b2 = mk3(nn[15], nn[16], nn[17]);
+  const v3 n3 = mk3(nn[18], nn[19], nn[20]), t3 = mk3(nn[21], nn[22], nn[23]), b3 = mk3(nn[24], nn[25], nn[26]);
+  const v3 baryNormal = add(add(mul(bu, n1), mul(bv, n2)), mul(bw_, n3));  // :333-336
+  const v3 baryTangent = add(add(mul(bu, t1), mul(bv, t2)), mul(bw_, t3));
+  const v3 baryBiTangent = add(add(mul(bu, b1), mul(bv, b2)), mul(bw_, b3));
+  v3 macroNormal = normalize(add(add(mul(texNormal.x, baryTangent), mul(texNormal.y, baryBiTangent)),
+                                 mul(texNormal.z, baryNormal)));
+  const bool inside = dot(neg(rayDir), baryNormal) < 0.0f;  // :461
+  v2 ns;
+  if (inside) { ns.x = matIor; ns.y = 1.0f; } else { ns.x = 1.0f; ns.y = matIor; }  // :462
+  macroNormal = inside ? neg(macroNormal) : macroNormal;                          // :463
+  rayOrigin = add(origin, mul(mul(macroNormal, FSPT_EPSILON), 2.0f));              // :464
+  color = add(color, mul(mul(mul(reflectance, texEmmissive), texDiffuse), 30.0f));  // :467
+  const v3 incident = neg(rayDir);
+  v3 envThroughput, bsdfThroughput;
+  float bsdfPdf;
+  // sampleMicrofacet, :256-270
+  v3 microNormal;
+  {
+    const float r1 = rnd(seed), r2 = rnd(seed);
+    v3 tangent, bitangent;
+    tangent_frame(macroNormal, tangent, bitangent);
+    const float a = fmaxf(0.001f, texMR.y);
+    const float phi = r1 * FSPT_TAU;
+    const float cosTheta = sqrtf((1.0f - r2) / (1.0f + (a * a - 1.0f) * r2));
+    const float sinTheta = clampf(sqrtf(1.0f - (cosTheta * cosTheta)), 0.0f, 1.0f);
+    float sinPhi, cosPhi;
+    dm::sincosf_(phi, sinPhi, cosPhi);
+    const v3 h = mk3(sinTheta * cosPhi, sinTheta * sinPhi, cosTheta);
+    microNormal = add(add(mul(tangent, h.x), mul(bitangent, h.y)), mul(macroNormal, h.z));
+  }
+  // sampleEnv, :421-434
+  v3 envDir;
+  float envPdf;
+  {
+    int idx = (int)coord_to_int((float)sc.n_bins * rnd(seed));
+    if (idx >= sc.n_bins) idx = sc.n_bins - 1;
+    if (idx < 0) idx = 0;
+    const float4 bin = __ldg(sc.bins + idx);
+    const float dimsx = (float)sc.env_w, dimsy = (float)sc.env_h;
+    const float r1 = rnd(seed);
+    const float r2 = rnd(seed);
+    const float uvx = -envTheta + ((bin.z - bin.x) * r1 + bin.x) / dimsx;
+    const float uvy = 0.0f + ((bin.w - bin.y) * r2 + bin.y) / dimsy;
+    const float theta = uvx * FSPT_TAU;
+    const float phi = uvy * FSPT_PI;
+    float sinPhi, cosPhi, sinTheta, cosTheta;
+    dm::sincosf_(phi, sinPhi, cosPhi);
+    dm::sincosf_(theta, sinTheta, cosTheta);
+    envDir = mk3(cosTheta * sinPhi, cosPhi, sinTheta * sinPhi);
+    const float nominal = (dimsx * dimsy) / (float)sc.n_bins;
+    envPdf = nominal / ((bin.z - bin.x) * (bin.w - bin.y) * FSPT_TAU * FSPT_PI * sinPhi);
+  }
+  const float cosEnv = dot(macroNormal, envDir);  // :474
+  const bool specular = mixf(schlick(incident, microNormal, ns), 1.0f, texMR.x) > rnd(seed);  // :475
+  if (specular) {
+    rayDir = reflect(neg(incident), microNormal);  // :477
+    bsdfPdf = gtr2_pdf(incident, macroNormal, texMR, rayDir);
+    bsdfThroughput = div(mul(eval_specular(incident, macroNormal, texDiffuse, texMR, rayDir),
+                             clampf(dot(macroNormal, rayDir), 0.0f, 1.0f)), bsdfPdf);
+    envThroughput = div(mul(eval_specular(incident, macroNormal, texDiffuse, texMR, envDir),
+                            clampf(cosEnv, 0.0f, 1.0f)), envPdf);
+  } else if (matDielectric >= 0.0f) {  // :481-488
+    bsdfPdf = 1.0f;
+    bsdfThroughput = mk3(1.0f, 1.0f, 1.0f);
+    envThroughput = mk3(0.0f, 0.0f, 0.0f);
+    rayOrigin = sub(origin, mul(mul(macroNormal, FSPT_EPSILON), 2.0f));
+    rayDir = refract(neg(incident), microNormal, ns.x / ns.y);
+    i--;
+    if (++refractions > A.max_refractions) {  // safety cap of the reference's unbounded loop
+      i = FSPT_NUM_BOUNCES;
+      atomicAdd(A.capped, 1ull);
+    }
+  } else {  // :489-494
+    {
+      const float r1 = rnd(seed), r2 = rnd(seed);
+      v3 tangent, bitangent;
+      tangent_frame(macroNormal, tangent, bitangent);
+      const float r = sqrtf(r1);
+      const float phi = FSPT_TAU * r2;
+      float sp_, cp_;
+      dm::sincosf_(phi, sp_, cp_);
+      v3 dir;
+      dir.x = r * cp_;
+      dir.y = r * sp_;
+      dir.z = sqrtf(fmaxf(0.0f, 1.0f - dir.x * dir.x - dir.y * dir.y));
+      rayDir = add(add(mul(tangent, dir.x), mul(bitangent, dir.y)), mul(macroNormal, dir.z));
+    }
+    bsdfPdf = fabsf(dot(rayDir, macroNormal)) * FSPT_INV_PI;  // lambertPdf, :235-237
+    const v3 lam = mul(texDiffuse, FSPT_INV_PI);               // evalLambert, :296-298
+    bsdfThroughput = div(mul(lam, clampf(dot(macroNormal, rayDir), 0.0f, 1.0f)), bsdfPdf);
+    envThroughput = div(mul(lam, clampf(cosEnv, 0.0f, 1.0f)), envPdf);
+  }
+  if (inside) {  // Beer's-law override, :497
+    const v3 om_ = sub(mk3(1.0f, 1.0f, 1.0f), texDiffuse);
+    const v3 b = sub(mk3(1.0f, 1.0f, 1.0f), mul(mul(om_, hit_t), matDielectric));
+    bsdfThroughput = mk3(fmaxf(b.x, 0.0f), fmaxf(b.y, 0.0f), fmaxf(b.z, 0.0f));
+  }
+  const v2 weights = mis_weights(envPdf, bsdfPdf);  // :499
+  shadow = (matDielectric < 0.0f && cosEnv > 0.0f);  // :500
+  v3 pend = mk3(0.0f, 0.0f, 0.0f);
+  if (shadow) pend = mul(mul(mul(reflectance, envThroughput), env_sample(sc, envDir, envTheta)), weights.x);  // :503
+  A.ps.ro[slot] = make_float4(rayOrigin.x, rayOrigin.y, rayOrigin.z, FSPT_MAX_T);
+  A.ps.rd[slot] = make_float4(rayDir.x, rayDir.y, rayDir.z, __int_as_float(-1));
+  A.ps.sd[slot] = make_float4(envDir.x, envDir.y, envDir.z, __int_as_float(shadow ? 1 : 0));
+  A.ps.thr[slot] = make_float4(reflectance.x, reflectance.y, reflectance.z, weights.y);
+  A.ps.bt[slot] = make_float4(bsdfThroughput.x, bsdfThroughput.y, bsdfThroughput.z,
+                              __int_as_float(((i + 0x100) & 0xffff) | (refractions << 16)));
+  A.ps.pend[slot] = make_float4(pend.x, pend.y, pend.z, 0.0f);
+  A.ps.col[slot] = make_float4(color.x, color.y, color.z, 0.0f);
+  return true;
+}
+
+#define SHADE_THREADS 128
+// The traversal kernel sorts finished rays into a hit list and a miss list, so a warp here is all-hit (full
+// vertex shading) or all-miss (one env lookup): the reference's per-fragment `if (result.index < 0)` branches
+// (tracer.fs:442,509) never diverge inside a warp.
+__global__ void __launch_bounds__(SHADE_THREADS) k_shade(const ShadeArgs A) {
+  init_unorm8_lut();
+  const int n_hit = A.counts_in[0], n_miss = A.counts_in[1];
+  const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int it = t0; it < ((n_hit + 31) & ~31); it += stride) {
     bool cont = false, shadow = false;
     int slot = 0;
-    if (live) {
-      slot = A.list_in ? A.list_in[it] : it;
-      const DeviceScene& sc = A.sc;
-      const float4 o4 = A.ps.ro[slot], d4 = A.ps.rd[slot];
-      v3 rayOrigin = mk3(o4.x, o4.y, o4.z), rayDir = mk3(d4.x, d4.y, d4.z);
-      const float hit_t = o4.w;
-      const int hit_index = __float_as_int(d4.w);
-      const int s = slot / A.paths_per_sample, j = slot - s * A.paths_per_sample;
-      const float randBase = A.rb_trace[s];
-      const float envTheta = A.f.env_theta;
-      v3 color, reflectance;
-      int i = 0, refractions = 0;
-      bool done = false;
-      if (A.first) {
-        color = mk3(0.0f, 0.0f, 0.0f);
-        reflectance = mk3(1.0f, 1.0f, 1.0f);
-        if (hit_index < 0) {  // :442-443
-          color = add(color, env_sample(sc, rayDir, envTheta));
-          done = true;
-        }
-      } else {
-        const float4 c4 = A.ps.col[slot], t4 = A.ps.thr[slot], b4 = A.ps.bt[slot], s4 = A.ps.sd[slot];
-        color = mk3(c4.x, c4.y, c4.z);
-        reflectance = mk3(t4.x, t4.y, t4.z);
-        const int packed = __float_as_int(b4.w);
-        i = (packed & 0xffff) - 0x100;  // stored biased so that i = -1 survives
-        refractions = packed >> 16;
-        if (__float_as_int(s4.w) == 2) {  // shadow.index == -1, :502-504
-          const float4 p4 = A.ps.pend[slot];
-          color = add(color, mk3(p4.x, p4.y, p4.z));
-        }
-        reflectance = mul(reflectance, mk3(b4.x, b4.y, b4.z));  // :508
-        if (hit_index == -1) {  // :509-512
-          color = add(color, mul(mul(reflectance, env_sample(sc, rayDir, envTheta)), t4.w));
-          done = true;
-        } else {
-          ++i;  // for (...; ++i), :446
-          if (!(i < FSPT_NUM_BOUNCES)) done = true;
-        }
-      }
-      if (!done) {
-        // createMaterial / createTriangle / createTexCoords / createNormals, :447-449,460
-        const float4* rec = sc.shade + 12 * (size_t)hit_index;
-        const float4 m0 = __ldg(rec), m1 = __ldg(rec + 1), m2 = __ldg(rec + 2);
-        const float4 u0 = __ldg(rec + 3), u1 = __ldg(rec + 4);
-        const float mapDiffuse = m0.x, mapSpecular = m0.y, mapNormal = m0.z, mapRoughness = m0.w;
-        const float matIor = m2.y, matDielectric = m2.z;
-        const float4* tp = sc.tris + 3 * (size_t)hit_index;
-        const float4 q0 = __ldg(tp), q1 = __ldg(tp + 1), q2 = __ldg(tp + 2);
-        const v3 tv1 = mk3(q0.x, q0.y, q0.z);
-        const v3 origin = add(rayOrigin, mul(rayDir, hit_t));  // :450
-        // barycentricWeights, :339-353 (v0 = v2 - v1 and v1 = v3 - v1 are the stored edges)
-        const v3 e0 = mk3(q0.w, q1.x, q1.y), e1 = mk3(q1.z, q1.w, q2.x), e2 = sub(origin, tv1);
-        const float d00 = dot(e0, e0), d01 = dot(e0, e1), d11 = dot(e1, e1), d20 = dot(e2, e0), d21 = dot(e2, e1);
-        const float invDenom = 1.0f / (d00 * d11 - d01 * d01);
-        const float bv = (d11 * d20 - d01 * d21) * invDenom;
-        const float bw_ = (d00 * d21 - d01 * d20) * invDenom;
-        const float bu = 1.0f - bv - bw_;
-        const float tcx = bu * u0.x + bv * u0.z + bw_ * u1.x;  // barycentricTexCoord, :328-330
-        const float tcy = bu * u0.y + bv * u0.w + bw_ * u1.y;
-        const float4 tD = texture_atlas(sc, tcx, tcy, mapDiffuse);     // :453
-        const float4 tE = texture_atlas(sc, tcx, tcy, mapSpecular);    // :454
-        const float4 tMR = texture_atlas(sc, tcx, tcy, mapRoughness);  // :455
-        const float4 tN = texture_atlas(sc, tcx, tcy, mapNormal);      // :456
-        const v3 texDiffuse = mk3(tD.x, tD.y, tD.z), texEmmissive = mk3(tE.x, tE.y, tE.z);
-        v2 texMR;
-        texMR.x = tMR.x;
-        texMR.y = tMR.y;
-        const v3 texNormal = mul(sub(mk3(tN.x, tN.y, tN.z), mk3(0.5f, 0.5f, 0.0f)), mk3(2.0f, 2.0f, 1.0f));
-        texMR.y *= texMR.y;  // :457
-        float seed = origin.x * randBase * origin.y * 1.396529836f + origin.z * 4761.52835f;  // :458
-        // normals record: [n1 t1 b1 n2 t2 b2 n3 t3 b3] starting at float 20 of the 48-float record
-        float nn[27];
-#pragma unroll
-        for (int k = 0; k < 7; ++k) {
-          const float4 t = __ldg(rec + 5 + k);
-          if (4 * k + 0 < 27) nn[4 * k + 0] = t.x;
-          if (4 * k + 1 < 27) nn[4 * k + 1] = t.y;
-          if (4 * k + 2 < 27) nn[4 * k + 2] = t.z;
-          if (4 * k + 3 < 27) nn[4 * k + 3] = t.w;
-        }
-        const v3 n1 = mk3(nn[0], nn[1], nn[2]), t1 = mk3(nn[3], nn[4], nn[5]), b1 = mk3(nn[6], nn[7], nn[8]);
-        const v3 n2 = mk3(nn[9], nn[10], nn[11]), t2 = mk3(nn[12], nn[13], nn[14]), b2 = mk3(nn[15], nn[16], nn[17]);
-        const v3 n3 = mk3(nn[18], nn[19], nn[20]), t3 = mk3(nn[21], nn[22], nn[23]), b3 = mk3(nn[24], nn[25], nn[26]);
-        const v3 baryNormal = add(add(mul(bu, n1), mul(bv, n2)), mul(bw_, n3));  // :333-336
-        const v3 baryTangent = add(add(mul(bu, t1), mul(bv, t2)), mul(bw_, t3));
-        const v3 baryBiTangent = add(add(mul(bu, b1), mul(bv, b2)), mul(bw_, b3));
-        v3 macroNormal = normalize(add(add(mul(texNormal.x, baryTangent), mul(texNormal.y, baryBiTangent)),
-                                       mul(texNormal.z, baryNormal)));
-        const bool inside = dot(neg(rayDir), baryNormal) < 0.0f;  // :461
-        v2 ns;
-        if (inside) { ns.x = matIor; ns.y = 1.0f; } else { ns.x = 1.0f; ns.y = matIor; }  // :462
-        macroNormal = inside ? neg(macroNormal) : macroNormal;                          // :463
-        rayOrigin = add(origin, mul(mul(macroNormal, FSPT_EPSILON), 2.0f));              // :464
-        color = add(color, mul(mul(mul(reflectance, texEmmissive), texDiffuse), 30.0f));  // :467
-        const v3 incident = neg(rayDir);
-        v3 envThroughput, bsdfThroughput;
-        float bsdfPdf;
-        // sampleMicrofacet, :256-270
-        v3 microNormal;
-        {
-          const float r1 = rnd(seed), r2 = rnd(seed);
-          v3 tangent, bitangent;
-          tangent_frame(macroNormal, tangent, bitangent);
-          const float a = fmaxf(0.001f, texMR.y);
-          const float phi = r1 * FSPT_TAU;
-          const float cosTheta = sqrtf((1.0f - r2) / (1.0f + (a * a - 1.0f) * r2));
-          const float sinTheta = clampf(sqrtf(1.0f - (cosTheta * cosTheta)), 0.0f, 1.0f);
-          float sinPhi, cosPhi;
-          dm::sincosf_(phi, sinPhi, cosPhi);
-          const v3 h = mk3(sinTheta * cosPhi, sinTheta * sinPhi, cosTheta);
-          microNormal = add(add(mul(tangent, h.x), mul(bitangent, h.y)), mul(macroNormal, h.z));
-        }
-        // sampleEnv, :421-434
-        v3 envDir;
-        float envPdf;
-        {
-          int idx = (int)coord_to_int((float)sc.n_bins * rnd(seed));
-          if (idx >= sc.n_bins) idx = sc.n_bins - 1;
-          if (idx < 0) idx = 0;
-          const float4 bin = __ldg(sc.bins + idx);
-          const float dimsx = (float)sc.env_w, dimsy = (float)sc.env_h;
-          const float r1 = rnd(seed);
-          const float r2 = rnd(seed);
-          const float uvx = -envTheta + ((bin.z - bin.x) * r1 + bin.x) / dimsx;
-          const float uvy = 0.0f + ((bin.w - bin.y) * r2 + bin.y) / dimsy;
-          const float theta = uvx * FSPT_TAU;
-          const float phi = uvy * FSPT_PI;
-          float sinPhi, cosPhi, sinTheta, cosTheta;
-          dm::sincosf_(phi, sinPhi, cosPhi);
-          dm::sincosf_(theta, sinTheta, cosTheta);
-          envDir = mk3(cosTheta * sinPhi, cosPhi, sinTheta * sinPhi);
-          const float nominal = (dimsx * dimsy) / (float)sc.n_bins;
-          envPdf = nominal / ((bin.z - bin.x) * (bin.w - bin.y) * FSPT_TAU * FSPT_PI * sinPhi);
-        }
-        const float cosEnv = dot(macroNormal, envDir);  // :474
-        const bool specular = mixf(schlick(incident, microNormal, ns), 1.0f, texMR.x) > rnd(seed);  // :475
-        if (specular) {
-          rayDir = reflect(neg(incident), microNormal);  // :477
-          bsdfPdf = gtr2_pdf(incident, macroNormal, texMR, rayDir);
-          bsdfThroughput = div(mul(eval_specular(incident, macroNormal, texDiffuse, texMR, rayDir),
-                                   clampf(dot(macroNormal, rayDir), 0.0f, 1.0f)), bsdfPdf);
-          envThroughput = div(mul(eval_specular(incident, macroNormal, texDiffuse, texMR, envDir),
-                                  clampf(cosEnv, 0.0f, 1.0f)), envPdf);
-        } else if (matDielectric >= 0.0f) {  // :481-488
-          bsdfPdf = 1.0f;
-          bsdfThroughput = mk3(1.0f, 1.0f, 1.0f);
-          envThroughput = mk3(0.0f, 0.0f, 0.0f);
-          rayOrigin = sub(origin, mul(mul(macroNormal, FSPT_EPSILON), 2.0f));
-          rayDir = refract(neg(incident), microNormal, ns.x / ns.y);
-          i--;
-          if (++refractions > A.max_refractions) {  // safety cap of the reference's unbounded loop
-            i = FSPT_NUM_BOUNCES;
-            atomicAdd(A.capped, 1ull);
-          }
-        } else {  // :489-494
-          {
-            const float r1 = rnd(seed), r2 = rnd(seed);
-            v3 tangent, bitangent;
-            tangent_frame(macroNormal, tangent, bitangent);
-            const float r = sqrtf(r1);
-            const float phi = FSPT_TAU * r2;
-            float sp_, cp_;
-            dm::sincosf_(phi, sp_, cp_);
-            v3 dir;
-            dir.x = r * cp_;
-            dir.y = r * sp_;
-            dir.z = sqrtf(fmaxf(0.0f, 1.0f - dir.x * dir.x - dir.y * dir.y));
-            rayDir = add(add(mul(tangent, dir.x), mul(bitangent, dir.y)), mul(macroNormal, dir.z));
-          }
-          bsdfPdf = fabsf(dot(rayDir, macroNormal)) * FSPT_INV_PI;  // lambertPdf, :235-237
-          const v3 lam = mul(texDiffuse, FSPT_INV_PI);               // evalLambert, :296-298
-          bsdfThroughput = div(mul(lam, clampf(dot(macroNormal, rayDir), 0.0f, 1.0f)), bsdfPdf);
-          envThroughput = div(mul(lam, clampf(cosEnv, 0.0f, 1.0f)), envPdf);
-        }
-        if (inside) {  // Beer's-law override, :497
-          const v3 om_ = sub(mk3(1.0f, 1.0f, 1.0f), texDiffuse);
-          const v3 b = sub(mk3(1.0f, 1.0f, 1.0f), mul(mul(om_, hit_t), matDielectric));
-          bsdfThroughput = mk3(fmaxf(b.x, 0.0f), fmaxf(b.y, 0.0f), fmaxf(b.z, 0.0f));
-        }
-        const v2 weights = mis_weights(envPdf, bsdfPdf);  // :499
-        shadow = (matDielectric < 0.0f && cosEnv > 0.0f);  // :500
-        v3 pend = mk3(0.0f, 0.0f, 0.0f);
-        if (shadow) pend = mul(mul(mul(reflectance, envThroughput), env_sample(sc, envDir, envTheta)), weights.x);  // :503
-        cont = true;
-        A.ps.ro[slot] = make_float4(rayOrigin.x, rayOrigin.y, rayOrigin.z, FSPT_MAX_T);
-        A.ps.rd[slot] = make_float4(rayDir.x, rayDir.y, rayDir.z, __int_as_float(-1));
-        A.ps.sd[slot] = make_float4(envDir.x, envDir.y, envDir.z, __int_as_float(shadow ? 1 : 0));
-        A.ps.thr[slot] = make_float4(reflectance.x, reflectance.y, reflectance.z, weights.y);
-        A.ps.bt[slot] = make_float4(bsdfThroughput.x, bsdfThroughput.y, bsdfThroughput.z,
-                                    __int_as_float(((i + 0x100) & 0xffff) | (refractions << 16)));
-        A.ps.pend[slot] = make_float4(pend.x, pend.y, pend.z, 0.0f);
-        A.ps.col[slot] = make_float4(color.x, color.y, color.z, 0.0f);
-      } else {
-        int x, y;
-        path_to_pixel(A.f, j, x, y);
-        A.sample_color[(size_t)s * ((size_t)A.f.width * A.f.height) + (size_t)y * A.f.width + x] =
-            make_float4(color.x, color.y, color.z, 1.0f);
-      }
+    if (it < n_hit) {
+      slot = A.list_hit[it];
+      cont = shade_hit(A, slot, shadow);
     }
     append(cont, slot, A.list_cont_out, A.counts_out + 0);
     append(shadow, slot, A.list_shadow_out, A.counts_out + 1);
   }
+  for (int it = t0; it < n_miss; it += stride) shade_miss(A, A.list_miss[it]);
 }
 
 // ---------------------------------------------------------------------------------------------------------

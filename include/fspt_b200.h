@@ -90,6 +90,7 @@ typedef struct fspt_stats {
   double render_ms;       /* CUDA-event time of the last fspt_render (camera+trace+shade+accumulate) */
   uint64_t last_rays, last_node_visits, last_leaf_visits; /* of the last fspt_render only            */
   uint64_t capped_paths;  /* paths stopped by the refraction safety cap                              */
+  double shade_ms;        /* CUDA-event time spent in shading kernels during the last fspt_render    */
 } fspt_stats;
 
 int fspt_abi_version(void);
