@@ -31,16 +31,19 @@ def needs_build():
     return any(os.path.getmtime(s) > t for s in sources() + [inc, os.path.abspath(__file__)])
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines/out: build an A/B variant (e.g. defines=["-DTRACE_REFILL=24"], out="lib/variants/x.so")."""
+    lib = LIB if out is None else os.path.join(HERE, out)
+    if out is None and not force and not needs_build():
         return LIB
-    os.makedirs(OUT_DIR, exist_ok=True)
-    obj_cu = os.path.join(OUT_DIR, "fspt_api.o")
+    os.makedirs(os.path.dirname(lib), exist_ok=True)
+    tag = "" if out is None else "_" + os.path.basename(out).replace(".so", "")
+    obj_cu = os.path.join(OUT_DIR, "fspt_api%s.o" % tag)
     obj_cpp = os.path.join(OUT_DIR, "bvh_builder.o")
     cmds = [
-        [NVCC] + NVCC_FLAGS + ["-c", os.path.join(CSRC, "fspt_api.cu"), "-o", obj_cu],
+        [NVCC] + NVCC_FLAGS + list(defines) + ["-c", os.path.join(CSRC, "fspt_api.cu"), "-o", obj_cu],
         ["g++"] + CXX_FLAGS + ["-c", os.path.join(CSRC, "bvh_builder.cpp"), "-o", obj_cpp],
-        [NVCC, "-shared", "-o", LIB, obj_cu, obj_cpp, "-Xlinker", "--no-undefined", "-lpthread"],
+        [NVCC, "-shared", "-o", lib, obj_cu, obj_cpp, "-Xlinker", "--no-undefined", "-lpthread"],
     ]
     for cmd in cmds:
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -48,10 +51,10 @@ def build(force=False, verbose=False):
             sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
         if r.returncode != 0:
             raise RuntimeError("build failed: " + " ".join(cmd))
-        if cmd[0] == NVCC and "-c" in cmd:
+        if cmd[0] == NVCC and "-c" in cmd and out is None:
             with open(os.path.join(OUT_DIR, "ptxas.log"), "w") as f:
                 f.write(r.stderr)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":

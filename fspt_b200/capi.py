@@ -67,11 +67,12 @@ def load(build_if_needed=True):
     global _lib
     if _lib is not None:
         return _lib
-    if build_if_needed and os.path.exists(_build.NVCC):
+    path = os.environ.get("FSPT_LIB") or _build.LIB  # FSPT_LIB: A/B kernel variants (tools/quick.py)
+    if path == _build.LIB and build_if_needed and os.path.exists(_build.NVCC):
         _build.build()
-    if not os.path.exists(_build.LIB):
-        raise FsptError(-2, "libfspt_b200.so is not built (run `python -m fspt_b200.build`); there is no CPU fallback")
-    lib = C.CDLL(_build.LIB)
+    if not os.path.exists(path):
+        raise FsptError(-2, "%s is not built (run `python -m fspt_b200.build`); there is no CPU fallback" % path)
+    lib = C.CDLL(path)
     lib.fspt_last_error.restype = C.c_char_p
     lib.fspt_last_error.argtypes = [C.c_void_p]
     lib.fspt_destroy.restype = None

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -102,15 +103,14 @@ void free_scene(Ctx* c) {
 int alloc_wave(Ctx* c) {
   // samples in flight: enough paths to fill the machine several times over, bounded so that the
   // per-path state (7 x 16 B + lists) stays a few hundred MB of the 180 GB
-  const size_t target_paths = (size_t)4 << 20;
+  const size_t target_paths = (size_t)16 << 20;
   int S = (int)std::max<size_t>(1, target_paths / (size_t)c->n_pixels);
   S = std::min(S, 16);
+  if (const char* e = getenv("FSPT_WAVE_SAMPLES")) S = std::max(1, std::min(64, atoi(e)));  // tuning knob
   c->wave_samples = S;
   c->wave_paths = (size_t)S * c->n_pixels;
   const size_t W = c->wave_paths;
-  CK(cudaMalloc(&c->ps.ro, W * 16)); CK(cudaMalloc(&c->ps.rd, W * 16)); CK(cudaMalloc(&c->ps.sd, W * 16));
-  CK(cudaMalloc(&c->ps.thr, W * 16)); CK(cudaMalloc(&c->ps.bt, W * 16)); CK(cudaMalloc(&c->ps.pend, W * 16));
-  CK(cudaMalloc(&c->ps.col, W * 16));
+  CK(cudaMalloc(&c->ps.rec, W * 16 * FSPT_PATH_WORDS));
   for (int i = 0; i < 4; ++i) CK(cudaMalloc(&c->d_list[i], W * sizeof(int)));
   CK(cudaMalloc(&c->d_counts, 8 * sizeof(int)));
   CK(cudaMalloc(&c->d_count_out, W * sizeof(int)));
@@ -146,7 +146,7 @@ __global__ void k_set_counts(int* counts, int n_cont, int n_shadow) {
 int launch_trace(Ctx* c, const int* list_cont, bool classify, bool write_count) {
   TraceArgs A;
   A.nodes = c->sc.nodes; A.tris = c->sc.tris; A.root_ref = c->sc.root_ref;
-  A.ro = c->ps.ro; A.rd = c->ps.rd; A.sd = c->ps.sd;
+  A.ps = c->ps;
   A.list_cont = list_cont; A.list_shadow = c->d_list[1];
   A.counts = c->d_counts;
   A.list_hit = c->d_list[2]; A.list_miss = c->d_list[3];
@@ -296,7 +296,7 @@ void fspt_destroy(fspt_ctx* ctx) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   free_scene(c);
   dfree(c->d_fb); dfree(c->d_last_color); dfree(c->d_sample_color); dfree(c->d_cam_pos); dfree(c->d_cam_dir); dfree(c->d_rgba8);
-  dfree(c->ps.ro); dfree(c->ps.rd); dfree(c->ps.sd); dfree(c->ps.thr); dfree(c->ps.bt); dfree(c->ps.pend); dfree(c->ps.col);
+  dfree(c->ps.rec);
   for (int i = 0; i < 4; ++i) dfree(c->d_list[i]);
   dfree(c->d_counts); dfree(c->d_count_out); dfree(c->d_stats); dfree(c->d_rb);
   if (c->h_rb) cudaFreeHost(c->h_rb);
@@ -587,8 +587,8 @@ int fspt_debug_primary(fspt_ctx* ctx, const fspt_frame_params* frame, float rand
   // un-swizzle path slots -> pixels on the host
   std::vector<float4> ro(P), rdv(P);
   std::vector<int> cnt(P);
-  CK(cudaMemcpy(ro.data(), c->ps.ro, (size_t)P * 16, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(rdv.data(), c->ps.rd, (size_t)P * 16, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy2D(ro.data(), 16, c->ps.rec + 0, 16 * FSPT_PATH_WORDS, 16, P, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy2D(rdv.data(), 16, c->ps.rec + 1, 16 * FSPT_PATH_WORDS, 16, P, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(cnt.data(), c->d_count_out, (size_t)P * 4, cudaMemcpyDeviceToHost));
   for (int j = 0; j < P; ++j) {
     int x, y;
@@ -617,16 +617,16 @@ int fspt_debug_trace(fspt_ctx* ctx, const float* pos4, const float* dir4, int32_
   std::vector<int> cnt;
   for (int64_t done = 0; done < n_rays;) {
     const int n = (int)std::min<int64_t>((int64_t)c->wave_paths, n_rays - done);
-    CK(cudaMemcpyAsync(c->ps.ro, pos4 + 4 * done, (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(c->ps.rd, dir4 + 4 * done, (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpy2DAsync(c->ps.rec + 0, 16 * FSPT_PATH_WORDS, pos4 + 4 * done, 16, 16, n, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpy2DAsync(c->ps.rec + 1, 16 * FSPT_PATH_WORDS, dir4 + 4 * done, 16, 16, n, cudaMemcpyHostToDevice, c->stream));
     int rc = set_counts(c, n, 0);
     if (rc) return rc;
     c->ev_trace_used = 0;
     rc = launch_trace(c, nullptr, false, true);
     if (rc) return rc;
     ro.resize(n); rdv.resize(n); cnt.resize(n);
-    CK(cudaMemcpyAsync(ro.data(), c->ps.ro, (size_t)n * 16, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(rdv.data(), c->ps.rd, (size_t)n * 16, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpy2DAsync(ro.data(), 16, c->ps.rec + 0, 16 * FSPT_PATH_WORDS, 16, n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpy2DAsync(rdv.data(), 16, c->ps.rec + 1, 16 * FSPT_PATH_WORDS, 16, n, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(cnt.data(), c->d_count_out, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     for (int i = 0; i < n; ++i) {

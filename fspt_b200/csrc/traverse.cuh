@@ -24,9 +24,7 @@ struct TraceArgs {
   const float4* nodes;
   const float4* tris;
   int root_ref;
-  float4* ro;             // PathState.ro / rd / sd
-  float4* rd;
-  float4* sd;
+  PathState ps;           // rays in, hits out (words 0..2 of the path record)
   const int* list_cont;   // path slots of continuation rays; NULL = identity
   const int* list_shadow; // path slots of shadow rays
   const int* counts;      // counts[0] = #continuation, counts[1] = #shadow
@@ -39,7 +37,9 @@ struct TraceArgs {
 };
 
 #define TRACE_THREADS 128
-#define TRACE_REFILL 20
+#ifndef TRACE_REFILL
+#define TRACE_REFILL 12
+#endif
 #ifndef TRACE_INT_WEIGHT
 #define TRACE_INT_WEIGHT 1
 #define TRACE_LEAF_WEIGHT 1
@@ -95,10 +95,10 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(const TraceArgs A) {
     const bool retire = need && slot >= 0;
     if (retire) {  // retire the finished ray
       if (kind == 0) {
-        reinterpret_cast<float*>(A.ro)[4 * (size_t)slot + 3] = tbest;
-        reinterpret_cast<int*>(A.rd)[4 * (size_t)slot + 3] = ibest;
+        A.ps.ro(slot).w = tbest;
+        A.ps.rd(slot).w = __int_as_float(ibest);
       } else {
-        reinterpret_cast<int*>(A.sd)[4 * (size_t)slot + 3] = (ibest == -1) ? 2 : 3;
+        A.ps.sd(slot).w = __int_as_float((ibest == -1) ? 2 : 3);
       }
       if (WRITE_COUNT) A.count_out[slot] = cnt;
       n_nodes += (unsigned long long)cnt;
@@ -136,8 +136,8 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(const TraceArgs A) {
           if (my < total) {
             kind = my >= n_cont;
             slot = kind ? A.list_shadow[my - n_cont] : (A.list_cont ? A.list_cont[my] : my);
-            const float4 o4 = A.ro[slot];
-            const float4 d4 = kind ? A.sd[slot] : A.rd[slot];
+            const float4 o4 = A.ps.ro(slot);
+            const float4 d4 = kind ? A.ps.sd(slot) : A.ps.rd(slot);
             ox = o4.x; oy = o4.y; oz = o4.z;
             dx = d4.x; dy = d4.y; dz = d4.z;
             ix = 1.0f / dx; iy = 1.0f / dy; iz = 1.0f / dz;  // `vec3 inverse = 1.0 / ray.dir`, tracer.fs:318
