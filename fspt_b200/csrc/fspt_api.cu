@@ -277,6 +277,11 @@ int fspt_create(fspt_ctx** out, int32_t width, int32_t height, int32_t device) {
 #undef CKC
   int rc = alloc_wave(c);
   if (rc) { g_create_error = c->error; fspt_destroy(reinterpret_cast<fspt_ctx*>(c)); return rc; }
+  // traversal uses no shared memory: give the whole unified array to L1 (BVH nodes + triangles live there)
+  if (!getenv("FSPT_NO_CARVEOUT")) {
+    cudaFuncSetAttribute(k_trace<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(k_trace<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+  }
   // persistent grids: resident CTAs per SM x SM count
   int per_sm = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<false>, TRACE_THREADS, 0);
