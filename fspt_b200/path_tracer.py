@@ -26,6 +26,19 @@ class PathTracer:
         self._seed = seed
         self._rand = scenes.rand_bases
 
+    @classmethod
+    def from_scene(cls, scene_path, resolution, asset_root=None, device=0, seed=1, autofocus=True, **kw):
+        """PathTracer(scenePath, ...) (main.js:915-950 -> start(), :879-913): compile the scene JSON, upload,
+        shoot the autofocus ray."""
+        from . import scene_json
+        sa, cam = scene_json.load_scene(scene_path, asset_root)
+        pt = cls(sa, resolution, cam, device=device, seed=seed, exposure=cam.get("exposure", 1.0),
+                 max_samples=cam.get("samples", 2000), **kw)
+        if autofocus:
+            dist = scene_json.autofocus_distance(sa.tris.astype(np.float64), pt.eye, pt.dir)
+            pt.lensFeatures[0] = 1.0 - 1.0 / dist   # main.js:543-544
+        return pt
+
     # -- main.js:826-836
     def clear(self):
         self.ctx.clear()
