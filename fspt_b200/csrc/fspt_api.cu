@@ -34,8 +34,9 @@ struct Ctx {
   // scene
   bool has_scene = false, has_dielectric = false;
   DeviceScene sc{};
-  void *d_nodes = nullptr, *d_tris = nullptr, *d_shade = nullptr, *d_bins = nullptr;
+  void *d_nodes = nullptr, *d_tris = nullptr, *d_shade = nullptr, *d_bins = nullptr, *d_layer_info = nullptr;
   cudaArray_t atlas_arr = nullptr, env_arr = nullptr;
+  cudaTextureObject_t nodes_tex = 0, tris_tex = 0;
   size_t scene_bytes = 0;
 
   // frame state
@@ -95,7 +96,7 @@ void free_scene(Ctx* c) {
   if (c->atlas_arr) cudaFreeArray(c->atlas_arr);
   if (c->env_arr) cudaFreeArray(c->env_arr);
   c->atlas_arr = c->env_arr = nullptr;
-  dfree(c->d_nodes); dfree(c->d_tris); dfree(c->d_shade); dfree(c->d_bins);
+  dfree(c->d_nodes); dfree(c->d_tris); dfree(c->d_shade); dfree(c->d_bins); dfree(c->d_layer_info);
   c->sc = DeviceScene{};
   c->has_scene = false;
 }
@@ -145,7 +146,7 @@ __global__ void k_set_counts(int* counts, int n_cont, int n_shadow) {
 // continuation results into the hit / miss lists (d_counts[2], d_counts[3]).
 int launch_trace(Ctx* c, const int* list_cont, bool classify, bool write_count) {
   TraceArgs A;
-  A.nodes = c->sc.nodes; A.tris = c->sc.tris; A.root_ref = c->sc.root_ref;
+  A.nodes = c->sc.nodes; A.tris = c->sc.tris; A.root_ref = c->sc.root_ref; A.nodes_tex = c->nodes_tex; A.tris_tex = c->tris_tex;
   A.ps = c->ps;
   A.list_cont = list_cont; A.list_shadow = c->d_list[1];
   A.counts = c->d_counts;
@@ -350,8 +351,8 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
     const float* lb = s->bvh + (size_t)l * 9 + 3;
     const float* rb = s->bvh + (size_t)r * 9 + 3;
     float* o = nodes.data() + k * 16;
-    o[0] = lb[0]; o[1] = lb[1]; o[2] = lb[2]; o[3] = lb[3]; o[4] = lb[4]; o[5] = lb[5];
-    o[6] = rb[0]; o[7] = rb[1]; o[8] = rb[2]; o[9] = rb[3]; o[10] = rb[4]; o[11] = rb[5];
+    // (left, right) pairs per component, the operand layout of the packed f32x2 slab test (traverse.cuh)
+    for (int k = 0; k < 6; ++k) { o[2 * k] = lb[k]; o[2 * k + 1] = rb[k]; }
     const int32_t lr = ref[l], rr = ref[r];
     memcpy(o + 12, &lr, 4); memcpy(o + 13, &rr, 4);
   }
@@ -397,6 +398,19 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
   std::vector<float> bins((size_t)s->env_bins * 4);
   for (size_t i = 0; i < bins.size(); ++i) bins[i] = (float)s->radiance_bins[i];  // vec4(radianceBins[idx]), tracer.fs:424
 
+  // constant-colour layers
+  std::vector<uint32_t> layer_info((size_t)s->atlas_layers * 2);
+  for (int l = 0; l < s->atlas_layers; ++l) {
+    const uint32_t* px = reinterpret_cast<const uint32_t*>(s->atlas) + (size_t)l * s->atlas_res * s->atlas_res;
+    uint32_t first;
+    memcpy(&first, px, 4);
+    bool same = true;
+    for (size_t i = 1, n = (size_t)s->atlas_res * s->atlas_res; i < n && same; ++i) same = (px[i] == first);
+    layer_info[2 * l] = same ? 1u : 0u;
+    layer_info[2 * l + 1] = first;
+  }
+  CK(cudaMalloc(&c->d_layer_info, layer_info.size() * 4));
+  CK(cudaMemcpyAsync(c->d_layer_info, layer_info.data(), layer_info.size() * 4, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMalloc(&c->d_nodes, nodes.size() * 4));
   CK(cudaMalloc(&c->d_tris, tris.size() * 4));
   CK(cudaMalloc(&c->d_shade, shade.size() * 4));
@@ -431,12 +445,28 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
                               s->env_height, cudaMemcpyHostToDevice, c->stream));
   rd.res.array.array = c->env_arr;
   CK(cudaCreateTextureObject(&c->sc.env, &rd, &td, nullptr));
+  {
+    cudaResourceDesc nr = {};
+    nr.resType = cudaResourceTypeLinear;
+    nr.res.linear.devPtr = c->d_nodes;
+    nr.res.linear.desc = cudaCreateChannelDesc<float4>();
+    nr.res.linear.sizeInBytes = nodes.size() * 4;
+    cudaTextureDesc nt = {};
+    nt.readMode = cudaReadModeElementType;
+    if (c->nodes_tex) cudaDestroyTextureObject(c->nodes_tex);
+    CK(cudaCreateTextureObject(&c->nodes_tex, &nr, &nt, nullptr));
+    nr.res.linear.devPtr = c->d_tris;
+    nr.res.linear.sizeInBytes = tris.size() * 4;
+    if (c->tris_tex) cudaDestroyTextureObject(c->tris_tex);
+    CK(cudaCreateTextureObject(&c->tris_tex, &nr, &nt, nullptr));
+  }
   CK(cudaStreamSynchronize(c->stream));
 
   c->sc.nodes = reinterpret_cast<const float4*>(c->d_nodes);
   c->sc.tris = reinterpret_cast<const float4*>(c->d_tris);
   c->sc.shade = reinterpret_cast<const float4*>(c->d_shade);
   c->sc.bins = reinterpret_cast<const float4*>(c->d_bins);
+  c->sc.layer_info = reinterpret_cast<const uint2*>(c->d_layer_info);
   c->sc.root_ref = ref[0];
   c->sc.n_tris = T; c->sc.n_interior = (int)NI;
   c->sc.atlas_res = R; c->sc.atlas_layers = L; c->sc.env_w = s->env_width; c->sc.env_h = s->env_height;

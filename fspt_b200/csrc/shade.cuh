@@ -97,9 +97,21 @@ __device__ __forceinline__ int wrap_repeat(int i, int size) {
 __device__ __forceinline__ int wrap_clamp(int i, int size) { return i < 0 ? 0 : (i >= size ? size - 1 : i); }
 
 // texture(texArray, vec3(uv, layer)): REPEAT/REPEAT, LINEAR (main.js:551-555)
-__device__ __noinline__ float4 texture_atlas(cudaTextureObject_t atlas, int R, int n_layers, float u, float v, float layerf) {
+__device__ __noinline__ float4 texture_atlas(cudaTextureObject_t atlas, const uint2* __restrict__ layer_info, int R, int n_layers,
+                                             float u, float v, float layerf) {
   const long long Lq = coord_to_int(floorf(layerf + 0.5f));
   const int L = (int)(Lq < 0 ? 0 : (Lq >= n_layers ? n_layers - 1 : Lq));
+  // Colour layers (TexturePacker.addColor, texture_packer.js:25-34,152-157) are res x res copies of one texel:
+  // the four taps are known without touching the 16.8 MB layer; the filter arithmetic below still runs, so
+  // the result is the same f32 value the fetches would give.
+  const uint2 info = __ldg(layer_info + L);
+  if (info.x) {
+    const uchar4 t = make_uchar4(info.y & 0xff, (info.y >> 8) & 0xff, (info.y >> 16) & 0xff, info.y >> 24);
+    const float x = u * (float)R - 0.5f, y = v * (float)R - 0.5f;
+    const float a = x - floorf(x), b = y - floorf(y);
+    const float4 tf = texel8(t);
+    return bilerp(tf, tf, tf, tf, a, b);
+  }
   const float x = u * (float)R - 0.5f, y = v * (float)R - 0.5f;
   const float fx = floorf(x), fy = floorf(y);
   const float a = x - fx, b = y - fy;
@@ -135,7 +147,7 @@ __device__ __forceinline__ v3 env_sample(const DeviceScene& sc, v3 dir, float en
   return env_sample_(sc.env, sc.env_w, sc.env_h, dir.x, dir.y, dir.z, envTheta);
 }
 __device__ __forceinline__ float4 texture_atlas(const DeviceScene& sc, float u, float v, float layerf) {
-  return texture_atlas(sc.atlas, sc.atlas_res, sc.atlas_layers, u, v, layerf);
+  return texture_atlas(sc.atlas, sc.layer_info, sc.atlas_res, sc.atlas_layers, u, v, layerf);
 }
 
 // ---- BSDF pieces, tracer.fs:194-298 ---------------------------------------------------------------------

@@ -23,6 +23,8 @@
 struct TraceArgs {
   const float4* nodes;
   const float4* tris;
+  cudaTextureObject_t nodes_tex;  // the node / triangle arrays again as linear textures (second L1 data pipe)
+  cudaTextureObject_t tris_tex;
   int root_ref;
   PathState ps;           // rays in, hits out (words 0..2 of the path record)
   const int* list_cont;   // path slots of continuation rays; NULL = identity
@@ -37,6 +39,12 @@ struct TraceArgs {
 };
 
 #define TRACE_THREADS 128
+#ifndef TRACE_NODE_TEX
+#define TRACE_NODE_TEX 15  /* bit k: word k of the node record comes through the texture pipe */
+#endif
+#ifndef TRACE_TRI_TEX
+#define TRACE_TRI_TEX 0    /* bit k: word k of a triangle record comes through the texture pipe */
+#endif
 #ifndef TRACE_REFILL
 #define TRACE_REFILL 12
 #endif
@@ -53,6 +61,31 @@ __device__ __forceinline__ float slab(float bminx, float bminy, float bminz, flo
   const float tMax = fminf(fminf(fmaxf(t1x, t2x), fmaxf(t1y, t2y)), fmaxf(t1z, t2z));
   const float tMin = fmaxf(fmaxf(fminf(t1x, t2x), fminf(t1y, t2y)), fminf(t1z, t2z));
   return (tMax >= tMin && tMax > 0.0f) ? tMin : FSPT_MAX_T;
+}
+
+// Both child boxes at once with Blackwell's packed f32x2 pipe: FADD2 / FMUL2 perform two independent IEEE
+// round-to-nearest f32 operations per instruction (lane 0 = left child, lane 1 = right child), so the 24
+// subtract/multiply operations of the two slab tests issue as 12 instructions.  Bitwise identical to slab().
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ void slab_pair(const float4 w0, const float4 w1, const float4 w2, f32x2 ox2, f32x2 oy2, f32x2 oz2,
+                                          f32x2 ix2, f32x2 iy2, f32x2 iz2, float& lh, float& rh) {
+  // record words: w0 = (lmin.x rmin.x lmin.y rmin.y)  w1 = (lmin.z rmin.z lmax.x rmax.x)  w2 = (lmax.y rmax.y lmax.z rmax.z)
+  const f32x2 t1x = mul2(sub2(pack2(w0.x, w0.y), ox2), ix2), t1y = mul2(sub2(pack2(w0.z, w0.w), oy2), iy2);
+  const f32x2 t1z = mul2(sub2(pack2(w1.x, w1.y), oz2), iz2), t2x = mul2(sub2(pack2(w1.z, w1.w), ox2), ix2);
+  const f32x2 t2y = mul2(sub2(pack2(w2.x, w2.y), oy2), iy2), t2z = mul2(sub2(pack2(w2.z, w2.w), oz2), iz2);
+  float a1x, b1x, a1y, b1y, a1z, b1z, a2x, b2x, a2y, b2y, a2z, b2z;
+  unpack2(t1x, a1x, b1x); unpack2(t1y, a1y, b1y); unpack2(t1z, a1z, b1z);
+  unpack2(t2x, a2x, b2x); unpack2(t2y, a2y, b2y); unpack2(t2z, a2z, b2z);
+  const float lMax = fminf(fminf(fmaxf(a1x, a2x), fmaxf(a1y, a2y)), fmaxf(a1z, a2z));
+  const float lMin = fmaxf(fmaxf(fminf(a1x, a2x), fminf(a1y, a2y)), fminf(a1z, a2z));
+  const float rMax = fminf(fminf(fmaxf(b1x, b2x), fmaxf(b1y, b2y)), fmaxf(b1z, b2z));
+  const float rMin = fmaxf(fmaxf(fminf(b1x, b2x), fminf(b1y, b2y)), fminf(b1z, b2z));
+  lh = (lMax >= lMin && lMax > 0.0f) ? lMin : FSPT_MAX_T;
+  rh = (rMax >= rMin && rMax > 0.0f) ? rMin : FSPT_MAX_T;
 }
 
 // rayTriangleIntersect with e1/e2 precomputed; predicates are the reference's conditions, un-negated, so
@@ -84,7 +117,8 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(const TraceArgs A) {
   int stack[FSPT_STACK];
   int cur = FSPT_SENTINEL, sp = 0;
   int slot = -1, kind = 0, cnt = 0;
-  float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0, ix = 0, iy = 0, iz = 0;
+  float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0;
+  f32x2 ox2 = 0, oy2 = 0, oz2 = 0, ix2 = 0, iy2 = 0, iz2 = 0;  // (v, v) pairs for the packed slab test
   float tbest = FSPT_MAX_T;
   int ibest = -1;
   unsigned long long n_rays = 0, n_nodes = 0, n_leaves = 0;
@@ -140,7 +174,9 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(const TraceArgs A) {
             const float4 d4 = kind ? A.ps.sd(slot) : A.ps.rd(slot);
             ox = o4.x; oy = o4.y; oz = o4.z;
             dx = d4.x; dy = d4.y; dz = d4.z;
-            ix = 1.0f / dx; iy = 1.0f / dy; iz = 1.0f / dz;  // `vec3 inverse = 1.0 / ray.dir`, tracer.fs:318
+            const float ix = 1.0f / dx, iy = 1.0f / dy, iz = 1.0f / dz;  // `vec3 inverse = 1.0 / ray.dir`, tracer.fs:318
+            ox2 = pack2(ox, ox); oy2 = pack2(oy, oy); oz2 = pack2(oz, oz);
+            ix2 = pack2(ix, ix); iy2 = pack2(iy, iy); iz2 = pack2(iz, iz);
             tbest = FSPT_MAX_T; ibest = -1; cnt = 0;
             stack[0] = FSPT_SENTINEL; sp = 1;
             cur = A.root_ref;
@@ -164,11 +200,16 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(const TraceArgs A) {
         // ---- interior node: both child boxes from one 64-byte record --------------------------------
         if (is_int) {
           cnt++;
+          // The record's four words are split between the two L1 data pipes (texture fetch / LSU load): the
+          // kernel is bound by L1 wavefronts (ncu: l1tex data-pipe ~60 % busy), not by issue slots.
           const float4* np = A.nodes + 4 * (size_t)cur;
-          const float4 a = __ldg(np), b = __ldg(np + 1), c = __ldg(np + 2);
-          const int4 d = __ldg(reinterpret_cast<const int4*>(np + 3));
-          const float lh = slab(a.x, a.y, a.z, a.w, b.x, b.y, ox, oy, oz, ix, iy, iz);
-          const float rh = slab(b.z, b.w, c.x, c.y, c.z, c.w, ox, oy, oz, ix, iy, iz);
+          const float4 a = (TRACE_NODE_TEX & 1) ? tex1Dfetch<float4>(A.nodes_tex, 4 * cur) : __ldg(np);
+          const float4 b = (TRACE_NODE_TEX & 2) ? tex1Dfetch<float4>(A.nodes_tex, 4 * cur + 1) : __ldg(np + 1);
+          const float4 c = (TRACE_NODE_TEX & 4) ? tex1Dfetch<float4>(A.nodes_tex, 4 * cur + 2) : __ldg(np + 2);
+          const float4 df = (TRACE_NODE_TEX & 8) ? tex1Dfetch<float4>(A.nodes_tex, 4 * cur + 3) : __ldg(np + 3);
+          const int4 d = make_int4(__float_as_int(df.x), __float_as_int(df.y), 0, 0);
+          float lh, rh;
+          slab_pair(a, b, c, ox2, oy2, oz2, ix2, iy2, iz2, lh, rh);
           const bool tl = lh < tbest, tr = rh < tbest;
           const bool right_first = lh > rh;                   // tracer.fs:384 (ties go left)
           if (tl && tr) {
@@ -189,7 +230,9 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(const TraceArgs A) {
           const float4* tp = A.tris + 3 * (size_t)first;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const float4 q0 = __ldg(tp + 3 * k), q1 = __ldg(tp + 3 * k + 1), q2 = __ldg(tp + 3 * k + 2);
+            const float4 q0 = (TRACE_TRI_TEX & 1) ? tex1Dfetch<float4>(A.tris_tex, 3 * (first + k)) : __ldg(tp + 3 * k);
+            const float4 q1 = (TRACE_TRI_TEX & 2) ? tex1Dfetch<float4>(A.tris_tex, 3 * (first + k) + 1) : __ldg(tp + 3 * k + 1);
+            const float4 q2 = (TRACE_TRI_TEX & 4) ? tex1Dfetch<float4>(A.tris_tex, 3 * (first + k) + 2) : __ldg(tp + 3 * k + 2);
             const float res = tri_test(q0, q1, q2, ox, oy, oz, dx, dy, dz);
             if (res < tbest) { ibest = first + k; tbest = res; }
           }

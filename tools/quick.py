@@ -19,6 +19,10 @@ elif a.scene == "soup":
     sa, cam = scenes.sphere_soup()
 elif a.scene == "pbr":
     sa, cam = scenes.pbr_scene()
+elif a.scene == "soup10m":
+    t0 = time.time()
+    sa, cam = scenes.sphere_soup(subdiv=8, n_soup=10000000 - 1310720, seed=4321)
+    print("compiled %d tris, %d nodes, depth %d in %.1f s" % (sa.n_tris, sa.bvh.shape[0], sa.depth, time.time() - t0))
 pt = PathTracer(sa, (W, H), cam)
 rc, rt = scenes.rand_bases(a.spp, 1)
 for r in range(a.reps + 1):
