@@ -96,31 +96,45 @@ __device__ __forceinline__ int wrap_repeat(int i, int size) {
 }
 __device__ __forceinline__ int wrap_clamp(int i, int size) { return i < 0 ? 0 : (i >= size ? size - 1 : i); }
 
-// texture(texArray, vec3(uv, layer)): REPEAT/REPEAT, LINEAR (main.js:551-555)
-__device__ __noinline__ float4 texture_atlas(cudaTextureObject_t atlas, const uint2* __restrict__ layer_info, int R, int n_layers,
-                                             float u, float v, float layerf) {
+// The four texture(texArray, vec3(uv, layer)) lookups of one vertex (tracer.fs:453-456): REPEAT/REPEAT, LINEAR
+// (main.js:551-555).  All four maps share the texel footprint, so the coordinates are computed once and the 16
+// fetches are issued back to back (one memory round trip instead of four).
+// Colour layers (TexturePacker.addColor, texture_packer.js:25-34,152-157) are res x res copies of one texel: their
+// taps are known without touching the 16.8 MB layer; the filter arithmetic still runs, so the f32 result is the
+// one the fetches would give.
+__device__ __forceinline__ int atlas_layer(float layerf, int n_layers) {
   const long long Lq = coord_to_int(floorf(layerf + 0.5f));
-  const int L = (int)(Lq < 0 ? 0 : (Lq >= n_layers ? n_layers - 1 : Lq));
-  // Colour layers (TexturePacker.addColor, texture_packer.js:25-34,152-157) are res x res copies of one texel:
-  // the four taps are known without touching the 16.8 MB layer; the filter arithmetic below still runs, so
-  // the result is the same f32 value the fetches would give.
-  const uint2 info = __ldg(layer_info + L);
-  if (info.x) {
-    const uchar4 t = make_uchar4(info.y & 0xff, (info.y >> 8) & 0xff, (info.y >> 16) & 0xff, info.y >> 24);
-    const float x = u * (float)R - 0.5f, y = v * (float)R - 0.5f;
-    const float a = x - floorf(x), b = y - floorf(y);
-    const float4 tf = texel8(t);
-    return bilerp(tf, tf, tf, tf, a, b);
-  }
+  return (int)(Lq < 0 ? 0 : (Lq >= n_layers ? n_layers - 1 : Lq));
+}
+__device__ __forceinline__ uchar4 as_uchar4(unsigned v) { return make_uchar4(v & 0xff, (v >> 8) & 0xff, (v >> 16) & 0xff, v >> 24); }
+__device__ __forceinline__ void texture_atlas4(const DeviceScene& sc, float u, float v, const float (&layerf)[4], float4 (&out)[4]) {
+  const int R = sc.atlas_res;
   const float x = u * (float)R - 0.5f, y = v * (float)R - 0.5f;
   const float fx = floorf(x), fy = floorf(y);
   const float a = x - fx, b = y - fy;
   const int ixx = (int)coord_to_int(fx), iyy = (int)coord_to_int(fy);
   const float i0 = (float)wrap_repeat(ixx, R) + 0.5f, i1 = (float)wrap_repeat(ixx + 1, R) + 0.5f;
   const float j0 = (float)wrap_repeat(iyy, R) + 0.5f, j1 = (float)wrap_repeat(iyy + 1, R) + 0.5f;
-  const uchar4 t00 = tex2DLayered<uchar4>(atlas, i0, j0, L), t10 = tex2DLayered<uchar4>(atlas, i1, j0, L);
-  const uchar4 t01 = tex2DLayered<uchar4>(atlas, i0, j1, L), t11 = tex2DLayered<uchar4>(atlas, i1, j1, L);
-  return bilerp(texel8(t00), texel8(t10), texel8(t01), texel8(t11), a, b);
+  int L[4];
+  uint2 info[4];
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    L[m] = atlas_layer(layerf[m], sc.atlas_layers);
+    info[m] = __ldg(sc.layer_info + L[m]);
+  }
+  uchar4 t[4][4];
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    t[m][0] = t[m][1] = t[m][2] = t[m][3] = as_uchar4(info[m].y);
+    if (!info[m].x) {
+      t[m][0] = tex2DLayered<uchar4>(sc.atlas, i0, j0, L[m]);
+      t[m][1] = tex2DLayered<uchar4>(sc.atlas, i1, j0, L[m]);
+      t[m][2] = tex2DLayered<uchar4>(sc.atlas, i0, j1, L[m]);
+      t[m][3] = tex2DLayered<uchar4>(sc.atlas, i1, j1, L[m]);
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < 4; ++m) out[m] = bilerp(texel8(t[m][0]), texel8(t[m][1]), texel8(t[m][2]), texel8(t[m][3]), a, b);
 }
 // texture(envTex, c): S REPEAT, T CLAMP_TO_EDGE, LINEAR on the ENCODED RGBE texel (main.js:170-180)
 __device__ __forceinline__ float4 texture_env(cudaTextureObject_t env, int W, int H, float u, float v) {
@@ -145,9 +159,6 @@ __device__ __noinline__ v3 env_sample_(cudaTextureObject_t env, int W, int H, fl
 }
 __device__ __forceinline__ v3 env_sample(const DeviceScene& sc, v3 dir, float envTheta) {
   return env_sample_(sc.env, sc.env_w, sc.env_h, dir.x, dir.y, dir.z, envTheta);
-}
-__device__ __forceinline__ float4 texture_atlas(const DeviceScene& sc, float u, float v, float layerf) {
-  return texture_atlas(sc.atlas, sc.layer_info, sc.atlas_res, sc.atlas_layers, u, v, layerf);
 }
 
 // ---- BSDF pieces, tracer.fs:194-298 ---------------------------------------------------------------------
@@ -326,10 +337,10 @@ __device__ __forceinline__ bool shade_hit(const ShadeArgs& A, int slot, bool& sh
   const float bu = 1.0f - bv - bw_;
   const float tcx = bu * u0.x + bv * u0.z + bw_ * u1.x;  // barycentricTexCoord, :328-330
   const float tcy = bu * u0.y + bv * u0.w + bw_ * u1.y;
-  const float4 tD = texture_atlas(sc, tcx, tcy, mapDiffuse);     // :453
-  const float4 tE = texture_atlas(sc, tcx, tcy, mapSpecular);    // :454
-  const float4 tMR = texture_atlas(sc, tcx, tcy, mapRoughness);  // :455
-  const float4 tN = texture_atlas(sc, tcx, tcy, mapNormal);      // :456
+  const float layers[4] = {mapDiffuse, mapSpecular, mapRoughness, mapNormal};
+  float4 tex[4];
+  texture_atlas4(sc, tcx, tcy, layers, tex);  // :453-456
+  const float4 tD = tex[0], tE = tex[1], tMR = tex[2], tN = tex[3];
   const v3 texDiffuse = mk3(tD.x, tD.y, tD.z), texEmmissive = mk3(tE.x, tE.y, tE.z);
   v2 texMR;
   texMR.x = tMR.x;

@@ -134,3 +134,57 @@ def test_post_pass_bit_exact(ctx_small, small_bunny, oracle_mod):
         got = ctx_small.resolve(**kw)
         ref = oracle_mod.draw(fb, **kw)
         assert_bit_equal(got, ref, "rgba8 %r" % (kw,))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# BASELINE.json full sizes: whole frames against the oracle, bit for bit
+def _full_frame_check(oracle_mod, sa, cam, W, H, n, seed):
+    O = oracle_mod.Oracle(sa)
+    ctx = capi.Context(W, H)
+    try:
+        ctx.scene_upload(sa)
+        fr = _frame(ctx, cam)
+        rc, rt = scenes.rand_bases(n, seed)
+        idx, t, cnt, pos, d = ctx.debug_primary(fr, rc[0])
+        opos, odir = oracle_mod.camera(W, H, cam["eye"], cam["dir"], cam["fov_scale"], scenes.lens_features(cam), rc[0])
+        assert_bit_equal(pos, opos, "camera pos")
+        assert_bit_equal(d, odir, "camera dir")
+        oi, ot, oc, st = O.bvh_test(opos, odir)
+        assert_bit_equal(idx, oi, "hit index")
+        assert_bit_equal(t, ot, "hit t")
+        assert_bit_equal(cnt, oc, "visit count")
+        ctx.clear()
+        ctx.render(fr, 0, rc, rt)
+        fb = ctx.read_accum()
+        ofb, rays, nodes, leaves = None, 0, 0, 0
+        for k in range(n):
+            p, dd = oracle_mod.camera(W, H, cam["eye"], cam["dir"], cam["fov_scale"], scenes.lens_features(cam), rc[k])
+            ofb, s2 = O.trace(p, dd, W, H, k, rt[k], cam["env_theta"], fb_prev=ofb)
+            rays += s2["rays"]; nodes += s2["node_visits"]; leaves += s2["leaf_visits"]
+        assert_bit_equal(fb[..., :3], ofb[..., :3], "accumulator")
+        s = ctx.stats()
+        # the device-side V / L counters that feed bench.py's algorithmic bytes equal the oracle's
+        assert (s["last_rays"], s["last_node_visits"], s["last_leaf_visits"]) == (rays, nodes, leaves)
+        assert_bit_equal(ctx.resolve(denoise=True), oracle_mod.draw(ofb, denoise=True), "rgba8")
+    finally:
+        ctx.close()
+
+
+def test_full_size_bunny_frame_bit_exact(oracle_mod):
+    """BASELINE configs[1] geometry and resolution (1280x720, 81,920-triangle bunny-class mesh + textured quads)."""
+    sa, cam = scenes.bunny_class(subdiv=6, atlas_res=512)
+    _full_frame_check(oracle_mod, sa, cam, 1280, 720, 2, 3)
+
+
+def test_million_triangle_soup_bit_exact(oracle_mod):
+    """BASELINE configs[2]: 1 M triangles (icosphere + soup), 1280x720, primary + 4 bounces."""
+    sa, cam = scenes.sphere_soup()
+    assert sa.n_tris == 1000000
+    _full_frame_check(oracle_mod, sa, cam, 1280, 720, 1, 5)
+
+
+def test_refractive_pbr_scene_bit_exact(oracle_mod):
+    """BASELINE configs[3] features: four texture maps per prop + a refractive prop (dielectric >= 0, free bounces)."""
+    sa, cam = scenes.pbr_scene(atlas_res=256, subdiv=4)
+    _full_frame_check(oracle_mod, sa, cam, 480, 270, 3, 9)
+    assert (sa.mats[:, 10] >= 0).any()
