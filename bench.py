@@ -44,8 +44,8 @@ def workload_config(args, sa, n_gpus):
                                      args.height, args.spp),
         "resolution": [args.width, args.height], "spp_per_gpu": args.spp, "triangles": int(sa.n_tris),
         "bvh_nodes": int(sa.bvh.shape[0]), "parallelism": "sample-set sharding x%d + NCCL reduce(sum)" % n_gpus,
-        "l2": "L2 flushed (512 MB write) between timed steps; per-wave path state (~470 MB) exceeds the 126 MB L2; "
-              "BVH+triangles (~7 MB) stay L2-resident inside a step by design",
+        "l2": "L2 flushed (512 MB write) between timed steps; per-wave path state (16 samples x 0.92 M paths x 128 B = 1.9 GB) "
+              "and the 184 MB atlas exceed the 126 MB L2; BVH+triangles (~7 MB) stay L2-resident inside a step by design",
     }
 
 
@@ -161,7 +161,7 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--width", type=int, default=WIDTH)

@@ -8,6 +8,10 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -37,6 +41,10 @@ struct Ctx {
   void *d_nodes = nullptr, *d_tris = nullptr, *d_shade = nullptr, *d_bins = nullptr, *d_layer_info = nullptr;
   cudaArray_t atlas_arr = nullptr, env_arr = nullptr;
   cudaTextureObject_t nodes_tex = 0, tris_tex = 0;
+  int atlas_R = 0, atlas_L = 0, env_W = 0, env_H = 0;       // dims of the resident arrays (reused across uploads)
+  size_t cap_nodes = 0, cap_tris = 0, cap_shade = 0, cap_bins = 0, cap_layer_info = 0;
+  uint8_t* h_stage = nullptr;                               // pinned staging for the atlas (one slot per layer)
+  size_t stage_bytes = 0;
   size_t scene_bytes = 0;
 
   // frame state
@@ -93,12 +101,29 @@ void dfree(T*& p) {
 void free_scene(Ctx* c) {
   if (c->sc.atlas) cudaDestroyTextureObject(c->sc.atlas);
   if (c->sc.env) cudaDestroyTextureObject(c->sc.env);
+  if (c->nodes_tex) cudaDestroyTextureObject(c->nodes_tex);
+  if (c->tris_tex) cudaDestroyTextureObject(c->tris_tex);
+  c->nodes_tex = c->tris_tex = 0;
   if (c->atlas_arr) cudaFreeArray(c->atlas_arr);
   if (c->env_arr) cudaFreeArray(c->env_arr);
   c->atlas_arr = c->env_arr = nullptr;
+  c->atlas_R = c->atlas_L = c->env_W = c->env_H = 0;
   dfree(c->d_nodes); dfree(c->d_tris); dfree(c->d_shade); dfree(c->d_bins); dfree(c->d_layer_info);
+  c->cap_nodes = c->cap_tris = c->cap_shade = c->cap_bins = c->cap_layer_info = 0;
+  if (c->h_stage) cudaFreeHost(c->h_stage);
+  c->h_stage = nullptr; c->stage_bytes = 0;
   c->sc = DeviceScene{};
   c->has_scene = false;
+}
+
+// device buffer that is only re-allocated when it has to grow
+int ensure(Ctx* c, void*& p, size_t& cap, size_t bytes) {
+  if (p && cap >= bytes) return FSPT_OK;
+  if (p) cudaFree(p);
+  p = nullptr; cap = 0;
+  CK(cudaMalloc(&p, bytes));
+  cap = bytes;
+  return FSPT_OK;
 }
 
 int alloc_wave(Ctx* c) {
@@ -315,6 +340,14 @@ void fspt_destroy(fspt_ctx* ctx) {
 
 int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  const bool timing = getenv("FSPT_TIMING") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[fspt upload] %-28s %7.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+    t_prev = now;
+  };
   if (!c) return FSPT_E_INVALID;
   if (!s || !s->bvh || !s->triangles || !s->materials || !s->normals || !s->uvs || !s->atlas || !s->env || !s->radiance_bins)
     return fail(c, FSPT_E_INVALID, "scene_upload: NULL buffer");
@@ -324,8 +357,8 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
   if (s->leaf_size != 4) return fail(c, FSPT_E_INVALID, "scene_upload: LEAF_SIZE must be 4 (main.js:45), got %d", s->leaf_size);
   CK(cudaSetDevice(c->device));
   CK(cudaStreamSynchronize(c->stream));
-  free_scene(c);
-
+  c->has_scene = false;  // device buffers, arrays and texture objects of the previous scene are reused when they fit
+  lap("sync");
   const int N = s->n_nodes, T = s->n_triangles;
   // ---- BVH repack: reference node i = [left,right,triIndex | min | max] -> Node64 per interior node ----
   std::vector<int32_t> ref((size_t)N);   // child reference of node i
@@ -373,6 +406,7 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
     if (max_depth + 1 > FSPT_STACK)
       return fail(c, FSPT_E_LIMIT, "BVH depth %d exceeds the traversal stack (%d, as in tracer.fs:368)", max_depth, FSPT_STACK);
   }
+  lap("bvh repack + depth check");
   // ---- triangles: v1, e1, e2 (tracer.fs:301-302) + LEAF_SIZE-1 padBuffer-style (-1,-1,-1) tail records ----
   std::vector<float> tris((size_t)(T + 3) * 12, 0.0f);
   for (int t = 0; t < T + 3; ++t) {
@@ -398,53 +432,98 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
   std::vector<float> bins((size_t)s->env_bins * 4);
   for (size_t i = 0; i < bins.size(); ++i) bins[i] = (float)s->radiance_bins[i];  // vec4(radianceBins[idx]), tracer.fs:424
 
-  // constant-colour layers
-  std::vector<uint32_t> layer_info((size_t)s->atlas_layers * 2);
-  for (int l = 0; l < s->atlas_layers; ++l) {
-    const uint32_t* px = reinterpret_cast<const uint32_t*>(s->atlas) + (size_t)l * s->atlas_res * s->atlas_res;
-    uint32_t first;
-    memcpy(&first, px, 4);
-    bool same = true;
-    for (size_t i = 1, n = (size_t)s->atlas_res * s->atlas_res; i < n && same; ++i) same = (px[i] == first);
-    layer_info[2 * l] = same ? 1u : 0u;
-    layer_info[2 * l + 1] = first;
-  }
-  CK(cudaMalloc(&c->d_layer_info, layer_info.size() * 4));
-  CK(cudaMemcpyAsync(c->d_layer_info, layer_info.data(), layer_info.size() * 4, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMalloc(&c->d_nodes, nodes.size() * 4));
-  CK(cudaMalloc(&c->d_tris, tris.size() * 4));
-  CK(cudaMalloc(&c->d_shade, shade.size() * 4));
-  CK(cudaMalloc(&c->d_bins, bins.size() * 4));
-  CK(cudaMemcpyAsync(c->d_nodes, nodes.data(), nodes.size() * 4, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->d_tris, tris.data(), tris.size() * 4, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->d_shade, shade.data(), shade.size() * 4, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->d_bins, bins.data(), bins.size() * 4, cudaMemcpyHostToDevice, c->stream));
-
-  // ---- atlas: 2D layered array, RGBA8 (main.js:548-560) -----------------------------------------------------
-  cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
+  lap("tri + shade records");
+  // constant-colour layers (one host thread per layer; exact: every texel compared)
   const int R = s->atlas_res, L = s->atlas_layers;
-  CK(cudaMalloc3DArray(&c->atlas_arr, &fmt, make_cudaExtent(R, R, L), cudaArrayLayered));
-  cudaMemcpy3DParms cp = {};
-  cp.srcPtr = make_cudaPitchedPtr(const_cast<uint8_t*>(s->atlas), (size_t)R * 4, R, R);
-  cp.dstArray = c->atlas_arr;
-  cp.extent = make_cudaExtent(R, R, L);
-  cp.kind = cudaMemcpyHostToDevice;
-  CK(cudaMemcpy3DAsync(&cp, c->stream));
+  const size_t layer_bytes = (size_t)R * R * 4;
+  std::vector<uint32_t> layer_info((size_t)L * 2);
+  // ---- atlas: 2D layered array, RGBA8 (main.js:548-560).  Layers are staged into pinned memory by a few host
+  // threads (a pageable cudaMemcpy tops out near 9 GB/s on this box) and DMA'd layer by layer as they land.
+  cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
   cudaResourceDesc rd = {};
   rd.resType = cudaResourceTypeArray;
-  rd.res.array.array = c->atlas_arr;
   cudaTextureDesc td = {};
   td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
   td.filterMode = cudaFilterModePoint;
   td.readMode = cudaReadModeElementType;
   td.normalizedCoords = 0;
-  CK(cudaCreateTextureObject(&c->sc.atlas, &rd, &td, nullptr));
+  if (!c->atlas_arr || c->atlas_R != R || c->atlas_L != L) {
+    if (c->sc.atlas) cudaDestroyTextureObject(c->sc.atlas);
+    c->sc.atlas = 0;
+    if (c->atlas_arr) cudaFreeArray(c->atlas_arr);
+    c->atlas_arr = nullptr;
+    CK(cudaMalloc3DArray(&c->atlas_arr, &fmt, make_cudaExtent(R, R, L), cudaArrayLayered));
+    rd.res.array.array = c->atlas_arr;
+    CK(cudaCreateTextureObject(&c->sc.atlas, &rd, &td, nullptr));
+    c->atlas_R = R; c->atlas_L = L;
+  }
+  if (c->stage_bytes < layer_bytes * L) {
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    c->h_stage = nullptr; c->stage_bytes = 0;
+    CK(cudaMallocHost(&c->h_stage, layer_bytes * L));
+    c->stage_bytes = layer_bytes * L;
+  }
+  {
+    std::atomic<int> next_layer(0);
+    std::atomic<int> cuda_err(0);
+    std::mutex mu;
+    const int n_workers = std::max(1, std::min(L, 6));
+    std::vector<std::thread> workers;
+    for (int w = 0; w < n_workers; ++w)
+      workers.emplace_back([&]() {
+        cudaSetDevice(c->device);
+        for (;;) {
+          const int l = next_layer.fetch_add(1);
+          if (l >= L) break;
+          const uint8_t* src = s->atlas + (size_t)l * layer_bytes;
+          uint8_t* dst = c->h_stage + (size_t)l * layer_bytes;
+          memcpy(dst, src, layer_bytes);
+          const uint32_t* px = reinterpret_cast<const uint32_t*>(dst);
+          const uint32_t first = px[0];
+          bool same = true;
+          for (size_t i = 1, n = (size_t)R * R; i < n && same; ++i) same = (px[i] == first);
+          layer_info[2 * l] = same ? 1u : 0u;
+          layer_info[2 * l + 1] = first;
+          cudaMemcpy3DParms cp = {};
+          cp.srcPtr = make_cudaPitchedPtr(dst, (size_t)R * 4, R, R);
+          cp.dstArray = c->atlas_arr;
+          cp.dstPos = make_cudaPos(0, 0, l);
+          cp.extent = make_cudaExtent(R, R, 1);
+          cp.kind = cudaMemcpyHostToDevice;
+          std::lock_guard<std::mutex> g(mu);
+          cudaError_t e = cudaMemcpy3DAsync(&cp, c->stream);
+          if (e != cudaSuccess) cuda_err.store((int)e);
+        }
+      });
+    for (auto& t : workers) t.join();
+    if (cuda_err.load()) return fail(c, FSPT_E_CUDA, "atlas upload failed: %s", cudaGetErrorString((cudaError_t)cuda_err.load()));
+  }
+  lap("atlas stage + scan + enqueue");
+  int rc_;
+  if ((rc_ = ensure(c, c->d_layer_info, c->cap_layer_info, layer_info.size() * 4))) return rc_;
+  if ((rc_ = ensure(c, c->d_nodes, c->cap_nodes, nodes.size() * 4))) return rc_;
+  if ((rc_ = ensure(c, c->d_tris, c->cap_tris, tris.size() * 4))) return rc_;
+  if ((rc_ = ensure(c, c->d_shade, c->cap_shade, shade.size() * 4))) return rc_;
+  if ((rc_ = ensure(c, c->d_bins, c->cap_bins, bins.size() * 4))) return rc_;
+  CK(cudaMemcpyAsync(c->d_layer_info, layer_info.data(), layer_info.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_nodes, nodes.data(), nodes.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_tris, tris.data(), tris.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_shade, shade.data(), shade.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_bins, bins.data(), bins.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  lap("malloc + enqueue geometry");
   // ---- environment: 2D array, RGBA8 RGBE (main.js:170-180) ----------------------------------------------------
-  CK(cudaMallocArray(&c->env_arr, &fmt, s->env_width, s->env_height));
+  if (!c->env_arr || c->env_W != s->env_width || c->env_H != s->env_height) {
+    if (c->sc.env) cudaDestroyTextureObject(c->sc.env);
+    c->sc.env = 0;
+    if (c->env_arr) cudaFreeArray(c->env_arr);
+    c->env_arr = nullptr;
+    CK(cudaMallocArray(&c->env_arr, &fmt, s->env_width, s->env_height));
+    rd.res.array.array = c->env_arr;
+    CK(cudaCreateTextureObject(&c->sc.env, &rd, &td, nullptr));
+    c->env_W = s->env_width; c->env_H = s->env_height;
+  }
   CK(cudaMemcpy2DToArrayAsync(c->env_arr, 0, 0, s->env, (size_t)s->env_width * 4, (size_t)s->env_width * 4,
                               s->env_height, cudaMemcpyHostToDevice, c->stream));
-  rd.res.array.array = c->env_arr;
-  CK(cudaCreateTextureObject(&c->sc.env, &rd, &td, nullptr));
   {
     cudaResourceDesc nr = {};
     nr.resType = cudaResourceTypeLinear;
@@ -461,7 +540,7 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
     CK(cudaCreateTextureObject(&c->tris_tex, &nr, &nt, nullptr));
   }
   CK(cudaStreamSynchronize(c->stream));
-
+  lap("env + textures + sync");
   c->sc.nodes = reinterpret_cast<const float4*>(c->d_nodes);
   c->sc.tris = reinterpret_cast<const float4*>(c->d_tris);
   c->sc.shade = reinterpret_cast<const float4*>(c->d_shade);
@@ -469,11 +548,11 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
   c->sc.layer_info = reinterpret_cast<const uint2*>(c->d_layer_info);
   c->sc.root_ref = ref[0];
   c->sc.n_tris = T; c->sc.n_interior = (int)NI;
-  c->sc.atlas_res = R; c->sc.atlas_layers = L; c->sc.env_w = s->env_width; c->sc.env_h = s->env_height;
+  c->sc.atlas_res = s->atlas_res; c->sc.atlas_layers = s->atlas_layers; c->sc.env_w = s->env_width; c->sc.env_h = s->env_height;
   c->sc.n_bins = s->env_bins;
   c->has_dielectric = dielectric;
   c->has_scene = true;
-  c->scene_bytes = (size_t)N * 36 + (size_t)T * (36 + 48 + 108 + 24) + (size_t)R * R * 4 * L +
+  c->scene_bytes = (size_t)N * 36 + (size_t)T * (36 + 48 + 108 + 24) + (size_t)s->atlas_res * s->atlas_res * 4 * s->atlas_layers +
                    (size_t)s->env_width * s->env_height * 4 + (size_t)s->env_bins * 8;
   return FSPT_OK;
 }

@@ -1,0 +1,15 @@
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from fspt_b200 import scenes, capi
+sa, cam = scenes.bunny_class(subdiv=6, atlas_res=2048)
+ctx = capi.Context(1280, 720)
+for i in range(4):
+    t0 = time.perf_counter(); n = ctx.scene_upload(sa); ctx.synchronize(); dt = time.perf_counter() - t0
+    print("upload %.1f ms for %.1f MB -> %.1f GB/s" % (dt * 1e3, n / 1e6, n / dt / 1e9))
+import numpy as np
+out = np.empty((720, 1280, 4), np.uint8)
+rc, rt = scenes.rand_bases(1, 1)
+ctx.render(ctx.frame(cam["eye"], cam["dir"], cam["fov_scale"], scenes.lens_features(cam), cam["env_theta"]), 0, rc, rt)
+for i in range(3):
+    t0 = time.perf_counter(); ctx.resolve(out=out); dt = time.perf_counter() - t0
+    print("resolve+readback %.2f ms" % (dt * 1e3))
