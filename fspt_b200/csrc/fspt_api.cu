@@ -533,11 +533,13 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
     cudaTextureDesc nt = {};
     nt.readMode = cudaReadModeElementType;
     if (c->nodes_tex) cudaDestroyTextureObject(c->nodes_tex);
-    CK(cudaCreateTextureObject(&c->nodes_tex, &nr, &nt, nullptr));
+    if (c->tris_tex) cudaDestroyTextureObject(c->tris_tex);
+    c->nodes_tex = c->tris_tex = 0;
+    const size_t max_texels = (size_t)1 << 27;  // linear-texture limit; beyond it the kernels use plain loads
+    if (nodes.size() / 4 <= max_texels) CK(cudaCreateTextureObject(&c->nodes_tex, &nr, &nt, nullptr));
     nr.res.linear.devPtr = c->d_tris;
     nr.res.linear.sizeInBytes = tris.size() * 4;
-    if (c->tris_tex) cudaDestroyTextureObject(c->tris_tex);
-    CK(cudaCreateTextureObject(&c->tris_tex, &nr, &nt, nullptr));
+    if (tris.size() / 4 <= max_texels) CK(cudaCreateTextureObject(&c->tris_tex, &nr, &nt, nullptr));
   }
   CK(cudaStreamSynchronize(c->stream));
   lap("env + textures + sync");

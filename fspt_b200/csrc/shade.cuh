@@ -55,8 +55,8 @@ __global__ void __launch_bounds__(256) k_camera(const FrameParams f, const float
   const v3 dof = mul(mul(dofDir, f.lens1), sqrtf(rnd(seed)));
   const v3 o = add(P, dof);  // :44
   const v3 d = normalize(sub(add(add(screen, aa), mul(dof, f.lens0)), add(P, dof)));  // :45
-  ps.ro(p) = make_float4(o.x, o.y, o.z, FSPT_MAX_T);
-  ps.rd(p) = make_float4(d.x, d.y, d.z, __int_as_float(-1));
+  st_path(ps.ro(p), make_float4(o.x, o.y, o.z, FSPT_MAX_T));
+  st_path(ps.rd(p), make_float4(d.x, d.y, d.z, __int_as_float(-1)));
   if (cam_pos_out) {
     cam_pos_out[(size_t)y * f.width + x] = make_float4(o.x, o.y, o.z, 1.0f);
     cam_dir_out[(size_t)y * f.width + x] = make_float4(d.x, d.y, d.z, 1.0f);
@@ -264,17 +264,17 @@ __device__ __forceinline__ void write_sample(const ShadeArgs& A, int slot, v3 co
 // The tail of the previous loop iteration for a path whose ray MISSED: tracer.fs:442-443 (primary) or
 // :502-504 + :508-512 (bounce).  Ends the path.
 __device__ __forceinline__ void shade_miss(const ShadeArgs& A, int slot) {
-  const float4 d4 = A.ps.rd(slot);
+  const float4 d4 = ld_path(A.ps.rd(slot));
   const v3 rayDir = mk3(d4.x, d4.y, d4.z);
   const v3 env = env_sample(A.sc, rayDir, A.f.env_theta);
   v3 color;
   if (A.first) {
     color = add(mk3(0.0f, 0.0f, 0.0f), env);  // :443
   } else {
-    const float4 c4 = A.ps.col(slot), t4 = A.ps.thr(slot), b4 = A.ps.bt(slot), s4 = A.ps.sd(slot);
+    const float4 c4 = ld_path(A.ps.col(slot)), t4 = ld_path(A.ps.thr(slot)), b4 = ld_path(A.ps.bt(slot)), s4 = ld_path(A.ps.sd(slot));
     color = mk3(c4.x, c4.y, c4.z);
     if (__float_as_int(s4.w) == 2) {  // shadow.index == -1, :502-504
-      const float4 p4 = A.ps.pend(slot);
+      const float4 p4 = ld_path(A.ps.pend(slot));
       color = add(color, mk3(p4.x, p4.y, p4.z));
     }
     const v3 reflectance = mul(mk3(t4.x, t4.y, t4.z), mk3(b4.x, b4.y, b4.z));  // :508
@@ -287,7 +287,7 @@ __device__ __forceinline__ void shade_miss(const ShadeArgs& A, int slot) {
 // Returns true when the path continues (a continuation ray, and maybe a shadow ray, were written).
 __device__ __forceinline__ bool shade_hit(const ShadeArgs& A, int slot, bool& shadow) {
   const DeviceScene& sc = A.sc;
-  const float4 o4 = A.ps.ro(slot), d4 = A.ps.rd(slot);
+  const float4 o4 = ld_path(A.ps.ro(slot)), d4 = ld_path(A.ps.rd(slot));
   v3 rayOrigin = mk3(o4.x, o4.y, o4.z), rayDir = mk3(d4.x, d4.y, d4.z);
   const float hit_t = o4.w;
   const int hit_index = __float_as_int(d4.w);
@@ -301,14 +301,14 @@ __device__ __forceinline__ bool shade_hit(const ShadeArgs& A, int slot, bool& sh
     color = mk3(0.0f, 0.0f, 0.0f);
     reflectance = mk3(1.0f, 1.0f, 1.0f);
   } else {
-    const float4 c4 = A.ps.col(slot), t4 = A.ps.thr(slot), b4 = A.ps.bt(slot), s4 = A.ps.sd(slot);
+    const float4 c4 = ld_path(A.ps.col(slot)), t4 = ld_path(A.ps.thr(slot)), b4 = ld_path(A.ps.bt(slot)), s4 = ld_path(A.ps.sd(slot));
     color = mk3(c4.x, c4.y, c4.z);
     reflectance = mk3(t4.x, t4.y, t4.z);
     const int packed = __float_as_int(b4.w);
     i = (packed & 0xffff) - 0x100;  // stored biased so that i = -1 survives
     refractions = packed >> 16;
     if (__float_as_int(s4.w) == 2) {  // shadow.index == -1, :502-504
-      const float4 p4 = A.ps.pend(slot);
+      const float4 p4 = ld_path(A.ps.pend(slot));
       color = add(color, mk3(p4.x, p4.y, p4.z));
     }
     reflectance = mul(reflectance, mk3(b4.x, b4.y, b4.z));  // :508
@@ -458,14 +458,14 @@ __device__ __forceinline__ bool shade_hit(const ShadeArgs& A, int slot, bool& sh
   shadow = (matDielectric < 0.0f && cosEnv > 0.0f);  // :500
   v3 pend = mk3(0.0f, 0.0f, 0.0f);
   if (shadow) pend = mul(mul(mul(reflectance, envThroughput), env_sample(sc, envDir, envTheta)), weights.x);  // :503
-  A.ps.ro(slot) = make_float4(rayOrigin.x, rayOrigin.y, rayOrigin.z, FSPT_MAX_T);
-  A.ps.rd(slot) = make_float4(rayDir.x, rayDir.y, rayDir.z, __int_as_float(-1));
-  A.ps.sd(slot) = make_float4(envDir.x, envDir.y, envDir.z, __int_as_float(shadow ? 1 : 0));
-  A.ps.thr(slot) = make_float4(reflectance.x, reflectance.y, reflectance.z, weights.y);
-  A.ps.bt(slot) = make_float4(bsdfThroughput.x, bsdfThroughput.y, bsdfThroughput.z,
-                              __int_as_float(((i + 0x100) & 0xffff) | (refractions << 16)));
-  A.ps.pend(slot) = make_float4(pend.x, pend.y, pend.z, 0.0f);
-  A.ps.col(slot) = make_float4(color.x, color.y, color.z, 0.0f);
+  st_path(A.ps.ro(slot), make_float4(rayOrigin.x, rayOrigin.y, rayOrigin.z, FSPT_MAX_T));
+  st_path(A.ps.rd(slot), make_float4(rayDir.x, rayDir.y, rayDir.z, __int_as_float(-1)));
+  st_path(A.ps.sd(slot), make_float4(envDir.x, envDir.y, envDir.z, __int_as_float(shadow ? 1 : 0)));
+  st_path(A.ps.thr(slot), make_float4(reflectance.x, reflectance.y, reflectance.z, weights.y));
+  st_path(A.ps.bt(slot), make_float4(bsdfThroughput.x, bsdfThroughput.y, bsdfThroughput.z,
+                                     __int_as_float(((i + 0x100) & 0xffff) | (refractions << 16))));
+  st_path(A.ps.pend(slot), make_float4(pend.x, pend.y, pend.z, 0.0f));
+  st_path(A.ps.col(slot), make_float4(color.x, color.y, color.z, 0.0f));
   return true;
 }
 
@@ -486,13 +486,13 @@ __global__ void __launch_bounds__(SHADE_THREADS, SHADE_MIN_BLOCKS) k_shade(const
     bool cont = false, shadow = false;
     int slot = 0;
     if (it < n_hit) {
-      slot = A.list_hit[it];
+      slot = ld_list(A.list_hit + it);
       cont = shade_hit(A, slot, shadow);
     }
     append(cont, slot, A.list_cont_out, A.counts_out + 0);
     append(shadow, slot, A.list_shadow_out, A.counts_out + 1);
   }
-  for (int it = t0; it < n_miss; it += stride) shade_miss(A, A.list_miss[it]);
+  for (int it = t0; it < n_miss; it += stride) shade_miss(A, ld_list(A.list_miss + it));
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -129,10 +129,10 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(const TraceArgs A) {
     const bool retire = need && slot >= 0;
     if (retire) {  // retire the finished ray
       if (kind == 0) {
-        A.ps.ro(slot).w = tbest;
-        A.ps.rd(slot).w = __int_as_float(ibest);
+        st_path_w(A.ps.ro(slot), tbest);
+        st_path_w(A.ps.rd(slot), __int_as_float(ibest));
       } else {
-        A.ps.sd(slot).w = __int_as_float((ibest == -1) ? 2 : 3);
+        st_path_w(A.ps.sd(slot), __int_as_float((ibest == -1) ? 2 : 3));
       }
       if (WRITE_COUNT) A.count_out[slot] = cnt;
       n_nodes += (unsigned long long)cnt;
@@ -169,9 +169,9 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(const TraceArgs A) {
           const int my = base + __popc(m & ((1u << lane) - 1u));
           if (my < total) {
             kind = my >= n_cont;
-            slot = kind ? A.list_shadow[my - n_cont] : (A.list_cont ? A.list_cont[my] : my);
-            const float4 o4 = A.ps.ro(slot);
-            const float4 d4 = kind ? A.ps.sd(slot) : A.ps.rd(slot);
+            slot = kind ? ld_list(A.list_shadow + (my - n_cont)) : (A.list_cont ? ld_list(A.list_cont + my) : my);
+            const float4 o4 = ld_path(A.ps.ro(slot));
+            const float4 d4 = ld_path(kind ? A.ps.sd(slot) : A.ps.rd(slot));
             ox = o4.x; oy = o4.y; oz = o4.z;
             dx = d4.x; dy = d4.y; dz = d4.z;
             const float ix = 1.0f / dx, iy = 1.0f / dy, iz = 1.0f / dz;  // `vec3 inverse = 1.0 / ray.dir`, tracer.fs:318
@@ -203,10 +203,11 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(const TraceArgs A) {
           // The record's four words are split between the two L1 data pipes (texture fetch / LSU load): the
           // kernel is bound by L1 wavefronts (ncu: l1tex data-pipe ~60 % busy), not by issue slots.
           const float4* np = A.nodes + 4 * (size_t)cur;
-          const float4 a = (TRACE_NODE_TEX & 1) ? tex1Dfetch<float4>(A.nodes_tex, 4 * cur) : __ldg(np);
-          const float4 b = (TRACE_NODE_TEX & 2) ? tex1Dfetch<float4>(A.nodes_tex, 4 * cur + 1) : __ldg(np + 1);
-          const float4 c = (TRACE_NODE_TEX & 4) ? tex1Dfetch<float4>(A.nodes_tex, 4 * cur + 2) : __ldg(np + 2);
-          const float4 df = (TRACE_NODE_TEX & 8) ? tex1Dfetch<float4>(A.nodes_tex, 4 * cur + 3) : __ldg(np + 3);
+          const bool tex_ok = A.nodes_tex != 0;  // 0: array too large for a linear texture (2^27 texels)
+          const float4 a = ((TRACE_NODE_TEX & 1) && tex_ok) ? tex1Dfetch<float4>(A.nodes_tex, 4 * cur) : __ldg(np);
+          const float4 b = ((TRACE_NODE_TEX & 2) && tex_ok) ? tex1Dfetch<float4>(A.nodes_tex, 4 * cur + 1) : __ldg(np + 1);
+          const float4 c = ((TRACE_NODE_TEX & 4) && tex_ok) ? tex1Dfetch<float4>(A.nodes_tex, 4 * cur + 2) : __ldg(np + 2);
+          const float4 df = ((TRACE_NODE_TEX & 8) && tex_ok) ? tex1Dfetch<float4>(A.nodes_tex, 4 * cur + 3) : __ldg(np + 3);
           const int4 d = make_int4(__float_as_int(df.x), __float_as_int(df.y), 0, 0);
           float lh, rh;
           slab_pair(a, b, c, ox2, oy2, oz2, ix2, iy2, iz2, lh, rh);
