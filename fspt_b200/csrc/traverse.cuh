@@ -45,6 +45,9 @@ struct TraceArgs {
 #ifndef TRACE_TRI_TEX
 #define TRACE_TRI_TEX 0    /* bit k: word k of a triangle record comes through the texture pipe */
 #endif
+#ifndef TRACE_DUP_LOADS
+#define TRACE_DUP_LOADS 0
+#endif
 #ifndef TRACE_REFILL
 #define TRACE_REFILL 12
 #endif
@@ -208,7 +211,17 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(const TraceArgs A) {
           const float4 b = ((TRACE_NODE_TEX & 2) && tex_ok) ? tex1Dfetch<float4>(A.nodes_tex, 4 * cur + 1) : __ldg(np + 1);
           const float4 c = ((TRACE_NODE_TEX & 4) && tex_ok) ? tex1Dfetch<float4>(A.nodes_tex, 4 * cur + 2) : __ldg(np + 2);
           const float4 df = ((TRACE_NODE_TEX & 8) && tex_ok) ? tex1Dfetch<float4>(A.nodes_tex, 4 * cur + 3) : __ldg(np + 3);
-          const int4 d = make_int4(__float_as_int(df.x), __float_as_int(df.y), 0, 0);
+          int4 d = make_int4(__float_as_int(df.x), __float_as_int(df.y), 0, 0);
+#if TRACE_DUP_LOADS  /* sensitivity experiment: issue the record's loads a second time through the LSU pipe */
+          {
+            float4 e0, e1, e2, e3;
+            asm volatile("ld.global.ca.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(e0.x), "=f"(e0.y), "=f"(e0.z), "=f"(e0.w) : "l"(np));
+            asm volatile("ld.global.ca.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(e1.x), "=f"(e1.y), "=f"(e1.z), "=f"(e1.w) : "l"(np + 1));
+            asm volatile("ld.global.ca.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(e2.x), "=f"(e2.y), "=f"(e2.z), "=f"(e2.w) : "l"(np + 2));
+            asm volatile("ld.global.ca.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(e3.x), "=f"(e3.y), "=f"(e3.z), "=f"(e3.w) : "l"(np + 3));
+            if (e0.x + e1.x + e2.x + e3.x == 12345.678f) d.x = 0;  // keep the loads alive
+          }
+#endif
           float lh, rh;
           slab_pair(a, b, c, ox2, oy2, oz2, ix2, iy2, iz2, lh, rh);
           const bool tl = lh < tbest, tr = rh < tbest;
