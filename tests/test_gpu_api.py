@@ -1,0 +1,126 @@
+"""C-ABI behaviour on the GPU: error convention, checkpoint/resume, odd resolutions, sum mode."""
+import types
+
+import numpy as np
+import pytest
+
+from fspt_b200 import capi, scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def _frame(ctx, cam):
+    return ctx.frame(cam["eye"], cam["dir"], cam["fov_scale"], scenes.lens_features(cam), cam["env_theta"])
+
+
+def test_error_convention(small_bunny):
+    sa, cam = small_bunny
+    ctx = capi.Context(64, 48)
+    try:
+        with pytest.raises(capi.FsptError) as e:  # render before scene upload
+            ctx.render(_frame(ctx, cam), 0, [1.0], [2.0])
+        assert e.value.code == -3 and "scene_upload" in str(e.value)
+        bad = types.SimpleNamespace(**{k: getattr(sa, k) for k in ("bvh", "tris", "mats", "norms", "uvs", "atlas", "env", "bins")})
+        bad.leaf_size = 8
+        with pytest.raises(capi.FsptError) as e:
+            ctx.scene_upload(bad)
+        assert e.value.code == -1 and "LEAF_SIZE" in str(e.value)
+        # a chain deeper than the reference's int stack[64] (tracer.fs:368) is refused, not silently truncated
+        n = 70
+        bvh = np.zeros((2 * n + 1, 9), np.float32)
+        hdr = bvh.view(np.int32)
+        for i in range(n):            # interior i: left = leaf 2i+1 ... laid out as [interior, leaf, interior, leaf ...]
+            hdr[2 * i, 0], hdr[2 * i, 1], hdr[2 * i, 2] = 2 * i + 1, 2 * i + 2, -1
+            hdr[2 * i + 1, 2] = 0
+        hdr[2 * n, 2] = 0
+        bvh[:, 3:6], bvh[:, 6:9] = -1.0, 1.0
+        deep = types.SimpleNamespace(bvh=bvh, tris=sa.tris[:4], mats=sa.mats[:4], norms=sa.norms[:4], uvs=sa.uvs[:4],
+                                     atlas=sa.atlas, env=sa.env, bins=sa.bins, leaf_size=4)
+        with pytest.raises(capi.FsptError) as e:
+            ctx.scene_upload(deep)
+        assert e.value.code == -4 and "stack" in str(e.value)
+        cyc = bvh[:3].copy()
+        cyc.view(np.int32)[0, :3] = (0, 0, -1)  # node 0 is its own child
+        with pytest.raises(capi.FsptError):
+            ctx.scene_upload(types.SimpleNamespace(bvh=cyc, tris=sa.tris[:4], mats=sa.mats[:4], norms=sa.norms[:4],
+                                                   uvs=sa.uvs[:4], atlas=sa.atlas, env=sa.env, bins=sa.bins, leaf_size=4))
+        ctx.scene_upload(sa)  # the context is still usable after errors
+        ctx.render(_frame(ctx, cam), 0, [1.0], [2.0])
+        assert np.isfinite(ctx.read_accum()).all()
+    finally:
+        ctx.close()
+    with pytest.raises(capi.FsptError):
+        capi.Context(64, 48, device=99)
+
+
+def test_checkpoint_resume_and_scene_swap(small_bunny, oracle_mod):
+    sa, cam = small_bunny
+    W, H, N = 72, 40, 5  # 40 rows / 72 columns: tiled path ordering
+    rc, rt = scenes.rand_bases(N, 8)
+    a = capi.Context(W, H)
+    b = capi.Context(W, H)
+    try:
+        a.scene_upload(sa)
+        a.render(_frame(a, cam), 0, rc, rt)
+        full = a.read_accum()
+        # stop after 2 samples, move the accumulator to another context, continue there
+        a.clear()
+        a.render(_frame(a, cam), 0, rc[:2], rt[:2])
+        b.scene_upload(sa)
+        b.write_accum(a.read_accum(), 2)
+        b.render(_frame(b, cam), 2, rc[2:], rt[2:])
+        assert np.array_equal(b.read_accum().view(np.uint32), full.view(np.uint32))
+        # uploading a different scene into the same context reuses buffers and gives that scene's image
+        sb, camb = scenes.quad_scene()
+        a.scene_upload(sb)
+        a.clear()
+        a.render(_frame(a, camb), 0, rc[:1], rt[:1])
+        O = oracle_mod.Oracle(sb)
+        pos, d = oracle_mod.camera(W, H, camb["eye"], camb["dir"], camb["fov_scale"], scenes.lens_features(camb), rc[0])
+        ref, _ = O.trace(pos, d, W, H, 0, rt[0], camb["env_theta"])
+        assert np.array_equal(a.read_accum()[..., :3].view(np.uint32), ref[..., :3].view(np.uint32))
+    finally:
+        a.close()
+        b.close()
+
+
+@pytest.mark.parametrize("res", [(50, 37), (8, 4), (1, 1), (33, 64)])
+def test_odd_resolutions_bit_exact(small_bunny, oracle_mod, res):
+    sa, cam = small_bunny
+    W, H = res
+    O = oracle_mod.Oracle(sa)
+    rc, rt = scenes.rand_bases(2, 4)
+    ctx = capi.Context(W, H)
+    try:
+        ctx.scene_upload(sa)
+        ctx.render(_frame(ctx, cam), 0, rc, rt)
+        fb = None
+        for k in range(2):
+            pos, d = oracle_mod.camera(W, H, cam["eye"], cam["dir"], cam["fov_scale"], scenes.lens_features(cam), rc[k])
+            fb, _ = O.trace(pos, d, W, H, k, rt[k], cam["env_theta"], fb_prev=fb)
+        assert np.array_equal(ctx.read_accum()[..., :3].view(np.uint32), fb[..., :3].view(np.uint32))
+        assert np.array_equal(ctx.resolve(denoise=True), oracle_mod.draw(fb, denoise=True))
+    finally:
+        ctx.close()
+
+
+def test_sum_mode_single_gpu(small_bunny, oracle_mod):
+    sa, cam = small_bunny
+    W, H, N = 64, 48, 4
+    O = oracle_mod.Oracle(sa)
+    rc, rt = scenes.rand_bases(N, 6)
+    ctx = capi.Context(W, H)
+    try:
+        ctx.scene_upload(sa)
+        ctx.set_accum_mode(1)
+        ctx.render(_frame(ctx, cam), 0, rc, rt)
+        ref = np.zeros((H, W, 3), np.float32)
+        for k in range(N):
+            pos, d = oracle_mod.camera(W, H, cam["eye"], cam["dir"], cam["fov_scale"], scenes.lens_features(cam), rc[k])
+            _, col, _ = O.trace(pos, d, W, H, 0, rt[k], cam["env_theta"], want_color=True)
+            ref = ref + col[..., :3]
+        assert np.array_equal(ctx.read_accum()[..., :3].view(np.uint32), ref.view(np.uint32))
+        ptr, n, s = ctx.accum_device_ptr()
+        assert ptr and n == W * H * 4 and s == N
+    finally:
+        ctx.close()
