@@ -51,7 +51,7 @@ EXPORTS = [
     "fspt_abi_version", "fspt_create", "fspt_destroy", "fspt_last_error", "fspt_scene_upload", "fspt_clear",
     "fspt_render", "fspt_resolve", "fspt_read_accum", "fspt_write_accum", "fspt_set_accum_mode",
     "fspt_accum_device_ptr", "fspt_set_accum_samples", "fspt_debug_primary", "fspt_debug_trace",
-    "fspt_debug_last_color", "fspt_debug_math", "fspt_get_stats", "fspt_synchronize", "fspt_bvh_build",
+    "fspt_debug_last_color", "fspt_debug_math", "fspt_get_stats", "fspt_synchronize", "fspt_bvh_build", "fspt_bvh_build2",
     "fspt_env_bins",
 ]
 
@@ -91,17 +91,21 @@ def f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 
 
-def bvh_build(verts, max_tris=4, n_threads=0):
-    """fspt_bvh_build: bvh.js + serializeTree + flatten.  Returns (nodes[N,9] f32 masked, order[T] i32, depth)."""
+def bvh_build(verts, max_tris=4, n_threads=0, box_verts=None):
+    """fspt_bvh_build(2): bvh.js + serializeTree + flatten.  Returns (nodes[N,9] f32 masked, order[T] i32, depth).
+    box_verts: vertices the stale Triangle.boundingBox was computed from (scene.normalize), default = verts."""
     lib = load()
     verts = np.ascontiguousarray(verts, dtype=np.float64).reshape(-1, 9)
     T = verts.shape[0]
+    if box_verts is not None:
+        box_verts = np.ascontiguousarray(box_verts, dtype=np.float64).reshape(-1, 9)
+        assert box_verts.shape == verts.shape
     nodes = np.empty((2 * T + 1, 9), np.float32)
     order = np.empty(T, np.int32)
     n = C.c_int32(0)
     depth = C.c_int32(0)
-    rc = lib.fspt_bvh_build(ptr(verts), C.c_int32(T), C.c_int32(max_tris), ptr(nodes), ptr(order), C.byref(n),
-                            C.byref(depth), C.c_int32(n_threads))
+    rc = lib.fspt_bvh_build2(ptr(verts), ptr(box_verts), C.c_int32(T), C.c_int32(max_tris), ptr(nodes), ptr(order),
+                             C.byref(n), C.byref(depth), C.c_int32(n_threads))
     if rc != FSPT_OK:
         raise FsptError(rc, "fspt_bvh_build failed (degenerate input: the JavaScript builder would not terminate)")
     return nodes[: n.value].copy(), order, int(depth.value)

@@ -42,7 +42,8 @@ struct Aabb {
 struct BuildNode { Aabb box; int32_t left, right, lo, hi; };  // left < 0 => leaf over idx[0][lo,hi)
 
 struct Ctx {
-  const Aabb* tb;             // per-triangle boxes
+  const Aabb* tb;             // per-triangle boxes seen by the presorts and the SAH sweeps (Triangle.boundingBox)
+  const Aabb* nb;             // per-triangle boxes of the current vertices (node boxes, BoundingBox.addNode)
   int32_t* idx[3];            // centroid-sorted triangle ids, partitioned in place
   int32_t* tmp;               // partition scratch, indexed by position
   double* sback;              // suffix surface areas, indexed by position
@@ -63,7 +64,7 @@ int32_t build(Ctx& c, int32_t lo, int32_t hi, int d) {
   while (d > prev && !c.depth.compare_exchange_weak(prev, d)) {}
   const int32_t n = hi - lo;
   nd.box.reset();
-  for (int32_t i = lo; i < hi; ++i) nd.box.grow(c.tb[c.idx[0][i]]);  // BoundingBox.addNode, bvh.js:122-128
+  for (int32_t i = lo; i < hi; ++i) nd.box.grow(c.nb[c.idx[0][i]]);  // BoundingBox.addNode, bvh.js:122-128
   if (n <= c.max_tris) { c.nodes[self] = nd; return self; }          // bvh.js:22 (split of a leaf is unused)
   // Node.setSplit, bvh.js:168-197
   double best = INFINITY;
@@ -149,20 +150,41 @@ void flatten(const Ctx& c, int32_t root, float* out, int32_t* order, int32_t* n_
 
 extern "C" int fspt_bvh_build(const double* verts, int32_t n_tris, int32_t max_tris, float* nodes_out,
                               int32_t* order_out, int32_t* n_nodes_out, int32_t* depth_out, int32_t n_threads) {
+  return fspt_bvh_build2(verts, nullptr, n_tris, max_tris, nodes_out, order_out, n_nodes_out, depth_out, n_threads);
+}
+
+// box_verts != NULL reproduces `scene.normalize` (main.js:337-348): Triangle.boundingBox is computed when the
+// triangle is created (bvh.js:208) and NOT refreshed when normalize rescales the vertices, so the presorts and
+// the SAH sweeps see the old boxes (box_verts) while node boxes are built from the new vertices (verts).
+extern "C" int fspt_bvh_build2(const double* verts, const double* box_verts, int32_t n_tris, int32_t max_tris,
+                               float* nodes_out, int32_t* order_out, int32_t* n_nodes_out, int32_t* depth_out,
+                               int32_t n_threads) {
   if (!verts || !nodes_out || !order_out || n_tris <= 0 || max_tris <= 0) return FSPT_E_INVALID;
-  std::vector<Aabb> tb((size_t)n_tris);
+  const double* bv = box_verts ? box_verts : verts;
+  std::vector<Aabb> tb((size_t)n_tris), nb;
+  if (box_verts) nb.resize((size_t)n_tris);
   std::vector<double> cen[3];
   for (int a = 0; a < 3; ++a) cen[a].resize((size_t)n_tris);
   for (int32_t i = 0; i < n_tris; ++i) {  // Triangle.boundingBox, bvh.js:208
     Aabb& b = tb[i]; b.reset();
     for (int v = 0; v < 3; ++v)
       for (int k = 0; k < 3; ++k) {
-        double x = verts[(size_t)i * 9 + v * 3 + k];
+        double x = bv[(size_t)i * 9 + v * 3 + k];
         if (!(x == x) || isinf(x)) return FSPT_E_INVALID;
         b.mn[k] = Aabb::lo(x, b.mn[k]);
         b.mx[k] = Aabb::hi(x, b.mx[k]);
       }
     for (int k = 0; k < 3; ++k) cen[k][i] = (b.mn[k] + b.mx[k]) * 0.5;  // centroid, bvh.js:130-135
+    if (box_verts) {
+      Aabb& n = nb[i]; n.reset();
+      for (int v = 0; v < 3; ++v)
+        for (int k = 0; k < 3; ++k) {
+          double x = verts[(size_t)i * 9 + v * 3 + k];
+          if (!(x == x) || isinf(x)) return FSPT_E_INVALID;
+          n.mn[k] = Aabb::lo(x, n.mn[k]);
+          n.mx[k] = Aabb::hi(x, n.mx[k]);
+        }
+    }
   }
   std::vector<int32_t> ix[3], tmp((size_t)n_tris);
   std::vector<double> sback((size_t)n_tris);
@@ -181,6 +203,7 @@ extern "C" int fspt_bvh_build(const double* verts, int32_t n_tris, int32_t max_t
   }
   Ctx c;
   c.tb = tb.data();
+  c.nb = box_verts ? nb.data() : tb.data();
   for (int a = 0; a < 3; ++a) c.idx[a] = ix[a].data();
   c.tmp = tmp.data(); c.sback = sback.data(); c.side = side.data();
   c.nodes.resize((size_t)2 * n_tris + 1);

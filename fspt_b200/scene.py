@@ -115,9 +115,9 @@ def flatten(triangle_sets, atlas, env, bins, normalize=None, n_threads=0, builde
         centroid = (mn + mx) * 0.5
         verts = (verts - centroid) * (2 * normalize / longest)
     builder = builder or capi.bvh_build
-    nodes, order, depth = builder(build_verts, 4, n_threads) if builder is capi.bvh_build else builder(build_verts, 4)
-    if normalize:
-        raise NotImplementedError("scene.normalize leaves node boxes stale in the reference; not supported")
+    box = build_verts if normalize else None
+    nodes, order, depth = (builder(verts, 4, n_threads, box_verts=box) if builder is capi.bvh_build
+                           else builder(verts, 4, box_verts=box))
     normals = np.concatenate([t.normals for t in triangle_sets], axis=0)
     tangents = np.concatenate([t.tangents for t in triangle_sets], axis=0)
     bitangents = np.concatenate([t.bitangents for t in triangle_sets], axis=0)

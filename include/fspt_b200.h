@@ -161,6 +161,11 @@ int fspt_synchronize(fspt_ctx* ctx);
 int fspt_bvh_build(const double* verts, int32_t n_tris, int32_t max_tris, float* nodes_out, int32_t* order_out,
                    int32_t* n_nodes_out, int32_t* depth_out, int32_t n_threads);
 
+/* Same, for scenes with `normalize` (main.js:337-348): box_verts = the vertices BEFORE the rescale, which is what
+ * Triangle.boundingBox still holds (presorts + SAH sweeps), verts = the rescaled vertices (node boxes).  NULL = verts. */
+int fspt_bvh_build2(const double* verts, const double* box_verts, int32_t n_tris, int32_t max_tris, float* nodes_out,
+                    int32_t* order_out, int32_t* n_nodes_out, int32_t* depth_out, int32_t n_threads);
+
 /* ProcessEnvRadiance(img) (env_sampler.js:1-74) on an RGBA8 RGBE image; bins_out capacity in u16. */
 int fspt_env_bins(const uint8_t* rgba8, int32_t width, int32_t height, uint16_t* bins_out, int32_t capacity,
                   int32_t* n_u16_out);

@@ -50,6 +50,7 @@ def lib():
     if _lib is None:
         _lib = C.CDLL(build())
         _lib.oracle_bvh_build.restype = C.c_int
+        _lib.oracle_bvh_build2.restype = C.c_int
         _lib.oracle_env_bins.restype = C.c_int
     return _lib
 
@@ -137,12 +138,14 @@ def dm_eval(fn, x, y=None):
     return out
 
 
-def bvh_build(verts, max_tris=4):
+def bvh_build(verts, max_tris=4, box_verts=None):
     """bvh.js + main.js flatten.  verts: (T,3,3) float64.  Returns (nodes[N,9] f32 masked, order[T] i32, depth)."""
     verts = np.ascontiguousarray(verts, dtype=np.float64).reshape(-1, 9)
+    if box_verts is not None:
+        box_verts = np.ascontiguousarray(box_verts, dtype=np.float64).reshape(-1, 9)
     T = verts.shape[0]
     nodes = np.empty((2 * T + 1, 9), np.float32); order = np.empty(T, np.int32); depth = C.c_int32(0)
-    n = lib().oracle_bvh_build(_p(verts), C.c_int(T), C.c_int(max_tris), _p(nodes), _p(order), C.byref(depth))
+    n = lib().oracle_bvh_build2(_p(verts), _p(box_verts), C.c_int(T), C.c_int(max_tris), _p(nodes), _p(order), C.byref(depth))
     if n < 0:
         raise RuntimeError("bvh.js would crash / recurse forever on this input")
     return nodes[:n].copy(), order, int(depth.value)

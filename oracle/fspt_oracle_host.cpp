@@ -49,7 +49,7 @@ struct Box { /* bvh.js:93-143 BoundingBox */
   }
 };
 
-struct Tri { const double* v; Box box; };
+struct Tri { const double* v; Box box; };  /* v: current verts; box: Triangle.boundingBox (may be stale) */
 
 struct BNode { /* bvh.js:145-198 Node */
   std::vector<int> idx[3];
@@ -155,14 +155,23 @@ extern "C" {
  * verts: n_tris*9 doubles (post-transform world space, as in Triangle.verts).
  * nodes_out: capacity 2*n_tris*9 floats; order_out: n_tris ints (source triangle of each triTex slot).
  * Returns node count, or -1 where the JS would crash / recurse forever. */
+int oracle_bvh_build2(const double* verts, const double* box_verts, int n_tris, int max_tris, float* nodes_out,
+                      int32_t* order_out, int32_t* depth_out);
 int oracle_bvh_build(const double* verts, int n_tris, int max_tris, float* nodes_out, int32_t* order_out,
                      int32_t* depth_out) {
+  return oracle_bvh_build2(verts, nullptr, n_tris, max_tris, nodes_out, order_out, depth_out);
+}
+/* box_verts: the vertices Triangle.boundingBox was computed from (bvh.js:208); main.js:337-348 (`normalize`)
+ * rescales Triangle.verts afterwards and leaves the boxes stale.  NULL = same as verts. */
+int oracle_bvh_build2(const double* verts, const double* box_verts, int n_tris, int max_tris, float* nodes_out,
+                      int32_t* order_out, int32_t* depth_out) {
+  const double* bv = box_verts ? box_verts : verts;
   Builder b;
   b.maxTris = max_tris;
   b.tris.resize(n_tris);
   for (int i = 0; i < n_tris; ++i) {
     b.tris[i].v = verts + (size_t)i * 9;
-    for (int k = 0; k < 3; ++k) b.tris[i].box.addVertex(verts + (size_t)i * 9 + 3 * k); /* bvh.js:208 */
+    for (int k = 0; k < 3; ++k) b.tris[i].box.addVertex(bv + (size_t)i * 9 + 3 * k); /* bvh.js:208 */
   }
   std::vector<int> idx[3];
   for (int a = 0; a < 3; ++a) {

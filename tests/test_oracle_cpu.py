@@ -330,3 +330,74 @@ def test_smooth_normals_and_tangent_frames():
     assert cosang.min() > 0.95
     assert np.abs((ts.tangents * ts.normals).sum(axis=2)).max() < 1e-9
     assert np.all(ts.uvs[:, 1] - ts.uvs[:, 0] != 0) or True
+
+
+# ---------------------------------------------------------------- scene.normalize (stale Triangle.boundingBox)
+def test_normalize_uses_stale_triangle_boxes(oracle_mod):
+    v, f = pr.icosphere(3)
+    verts = pr.lumpy(v)[f] * 3.0 + np.array([5.0, 1.0, -2.0])
+    # a NON-uniform "old" space makes the stale boxes matter: the presorts / SAH see box_verts, node boxes see verts
+    old = verts * np.array([1.0, 7.0, 0.2])
+    a = capi.bvh_build(verts, 4, 4, box_verts=old)
+    b = oracle_mod.bvh_build(verts, 4, box_verts=old)
+    c = capi.bvh_build(verts, 4, 4)
+    assert np.array_equal(a[0].view(np.int32), b[0].view(np.int32)) and np.array_equal(a[1], b[1])
+    assert not np.array_equal(a[1], c[1])  # different tree than with fresh boxes
+    # node boxes still bound the CURRENT vertices
+    lo, hi = verts.reshape(-1, 3).min(0), verts.reshape(-1, 3).max(0)
+    assert np.allclose(a[0][0, 3:6], lo.astype(np.float32)) and np.allclose(a[0][0, 6:9], hi.astype(np.float32))
+
+
+def test_flatten_with_normalize(oracle_mod):
+    from fspt_b200.geometry import mesh_to_triangles
+    from fspt_b200.scene import flatten
+    v, f = pr.icosphere(2)
+    ts = mesh_to_triangles(v * 10.0, f, {"scale": 1, "rotate": [], "translate": [3, 0, 0], "normals": "flat"})
+    ts.material = dict(diffuseIndex=0, specularIndex=0, normalIndex=0, roughnessIndex=0, ior=1.4, dielectric=-1, emittance=[0, 0, 0])
+    env = pr.constant_environment(8, 4, 1.0)
+    sa = flatten([ts], np.zeros((1, 1, 1, 4), np.uint8), env, capi.env_bins(env), normalize=1.0)
+    ext = sa.tris.reshape(-1, 3).max(0) - sa.tris.reshape(-1, 3).min(0)
+    assert abs(ext.max() - 2.0) < 1e-5  # longest side scaled to 2*normalize (main.js:341)
+    assert np.allclose((sa.tris.reshape(-1, 3).max(0) + sa.tris.reshape(-1, 3).min(0)) * 0.5, 0, atol=1e-6)
+    n2, o2, _ = oracle_mod.bvh_build(((ts.verts - (ts.verts.reshape(-1, 3).min(0) + ts.verts.reshape(-1, 3).max(0)) * 0.5)
+                                      * (2 * 1.0 / float((ts.verts.reshape(-1, 3).max(0) - ts.verts.reshape(-1, 3).min(0)).max()))),
+                                     4, box_verts=ts.verts)
+    assert np.array_equal(sa.bvh.view(np.int32), n2.view(np.int32)) and np.array_equal(sa.order, o2)
+
+
+# ---------------------------------------------------------------- property test (hypothesis): BVH == brute force
+def test_property_traversal_vs_brute_force(oracle_mod):
+    from hypothesis import given, settings, strategies as st
+
+    class SA:
+        pass
+
+    @settings(max_examples=25, deadline=None)
+    @given(seed=st.integers(0, 2 ** 31 - 1), n=st.integers(1, 200), flat=st.booleans())
+    def check(seed, n, flat):
+        rng = np.random.default_rng(seed)
+        soup = pr.triangle_soup(n, seed=seed, extent=1.0, edge=(0.02, 0.6))
+        if flat:
+            soup[:, :, 1] = np.round(soup[:, :, 1] * 2) / 2  # coplanar sheets: zero-thickness boxes, many ties
+        try:
+            nodes, order, _ = oracle_mod.bvh_build(soup)
+        except RuntimeError:
+            return  # inputs bvh.js itself cannot build
+        sa = SA()
+        sa.bvh, sa.tris = nodes, soup[order].reshape(-1, 9).astype(np.float32)
+        sa.mats, sa.norms, sa.uvs = np.zeros((n, 12), np.float32), np.zeros((n, 27), np.float32), np.zeros((n, 6), np.float32)
+        sa.atlas, sa.env, sa.bins = np.zeros((1, 1, 1, 4), np.uint8), np.zeros((2, 2, 4), np.uint8), np.array([[0, 0, 2, 2]], np.uint16)
+        O = oracle_mod.Oracle(sa)
+        m = 400
+        o = np.ones((m, 4), np.float32)
+        d = np.ones((m, 4), np.float32)
+        o[:, :3] = rng.uniform(-2, 2, (m, 3))
+        dd = rng.normal(size=(m, 3))
+        d[:, :3] = dd / np.linalg.norm(dd, axis=1, keepdims=True)
+        idx, t, cnt, stt = O.bvh_test(o, d)
+        bi, bt = O.brute_force(o, d)
+        assert np.array_equal(t, bt)
+        diff = idx != bi
+        assert not diff.any() or np.all(t[diff] == bt[diff])
+        assert stt["stack_overflow"] == 0
+    check()
