@@ -1,179 +1,151 @@
-// dm_math.cuh -- device implementation of the "FSPT-DM1" arithmetic model.
+// dm_math.cuh -- device implementation of the "FSPT-DM2" arithmetic model.
 //
 // The reference shaders leave sin/cos/atan/asin/pow to the GLSL platform (tracer.fs:181,412,417,429-430,
-// camera.fs:19,27-34, draw.fs:92).  To make the CUDA path reproducible against the CPU oracle, these built-ins
-// are evaluated here in IEEE binary64 with explicitly rounded, never-contracted operations (__dmul_rn /
-// __dadd_rn / __ddiv_rn / __dsqrt_rn) and rounded once to binary32.  B200 issues 64 FP64 ops/clk/SM, so the
-// cost is a few percent of a shading pass and nothing in traversal.
+// camera.fs:19,27-34, draw.fs:92).  To make the CUDA path reproducible against the CPU oracle these built-ins are
+// evaluated by fixed binary32 operation sequences: explicitly rounded add/mul/div/sqrt (never contracted) and
+// explicit single-rounded FMAs (__fmaf_rn), which x86 FMA3 reproduces bit for bit on the oracle side.
+// (DM1, the first version, evaluated them in binary64: 46 % of the shading kernel's instructions.)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace dm {
 
-__device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
-__device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
-__device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
-__device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ float fma_(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ float mul_(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add_(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub_(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float div_(float a, float b) { return __fdiv_rn(a, b); }
 
-#define DM_TWO_OVER_PI 0x1.45f306dc9c883p-1
-#define DM_PIO2_A 0x1.921fb54000000p+0
-#define DM_PIO2_B 0x1.10b4610000000p-30
-#define DM_PIO2_C 0x1.a62633145c06ep-58
-#define DM_PI 0x1.921fb54442d18p+1
-#define DM_PIO2 0x1.921fb54442d18p+0
-#define DM_PIO4 0x1.921fb54442d18p-1
-#define DM_LN2 0x1.62e42fefa39efp-1
-#define DM_LOG2E 0x1.71547652b82fep+0
+#define DM_TWO_OVER_PI 0x1.45f306p-1f
+#define DM_PIO2_1 0x1.921fb6p+0f
+#define DM_PIO2_2 -0x1.777a5cp-25f
+#define DM_PIO2_3 -0x1.ee59dap-50f
+#define DM_PI 0x1.921fb6p+1f
+#define DM_PIO2 0x1.921fb6p+0f
+#define DM_PIO4 0x1.921fb6p-1f
+#define DM_LN2 0x1.62e430p-1f
+#define DM_LOG2E 0x1.715476p+0f
 
-// Horner step  c + z*p  with separately rounded multiply and add
-__device__ __forceinline__ double hs(double c, double z, double p) { return add(c, mul(z, p)); }
-
-__device__ __forceinline__ double ksin(double r) {
-  const double z = mul(r, r);
-  const double v = mul(z, r);
-  double p = hs(-2.50507602534068634195e-08, z, 1.58969099521155010221e-10);
-  p = hs(2.75573137070700676789e-06, z, p);
-  p = hs(-1.98412698298579493134e-04, z, p);
-  p = hs(8.33333333332248946124e-03, z, p);
-  return add(r, mul(v, hs(-1.66666666666666324348e-01, z, p)));
-}
-__device__ __forceinline__ double kcos(double r) {
-  const double z = mul(r, r);
-  double p = hs(2.08757232129817482790e-09, z, -1.13596475577881948265e-11);
-  p = hs(-2.75573143513906633035e-07, z, p);
-  p = hs(2.48015872894767294178e-05, z, p);
-  p = hs(-1.38888888888741095749e-03, z, p);
-  p = hs(4.16666666666666019037e-02, z, p);
-  p = mul(z, p);
-  return sub(1.0, sub(mul(0.5, z), mul(z, p)));
-}
-// r = x - k*pi/2 with a 27+27+53-bit split of pi/2 (k*A and k*B exact for |k| < 2^26)
-__device__ __forceinline__ double reduce(double x, int& q) {
-  const double k = rint(mul(x, DM_TWO_OVER_PI));
-  const double r = sub(sub(sub(x, mul(k, DM_PIO2_A)), mul(k, DM_PIO2_B)), mul(k, DM_PIO2_C));
-  if (!(k > -9.0e15 && k < 9.0e15)) { q = 0; return 0.0; }
-  q = (int)(((long long)k) & 3);
+// r = x - k*pi/2: three-term Cody-Waite with exact products inside the FMAs, then one more fold because the f32
+// product x*2/pi can miss the nearest integer by one for |x| > ~1e5 (the sin-hash RNG reaches 1e7)
+__device__ __forceinline__ float reduce(float x, int& q) {
+  if (!(fabsf(x) <= 1.0e9f)) { q = 0; return 0.0f; }
+  const float k = rintf(mul_(x, DM_TWO_OVER_PI));
+  float r = fma_(-k, DM_PIO2_1, x);
+  r = fma_(-k, DM_PIO2_2, r);
+  r = fma_(-k, DM_PIO2_3, r);
+  const float k2 = rintf(mul_(r, DM_TWO_OVER_PI));
+  r = fma_(-k2, DM_PIO2_1, r);
+  r = fma_(-k2, DM_PIO2_2, r);
+  q = ((int)k + (int)k2) & 3;
   return r;
+}
+__device__ __forceinline__ float ksin(float r) {
+  const float z = mul_(r, r);
+  float p = fma_(2.7234684694121825e-06f, z, -0.00019839966262225062f);
+  p = fma_(p, z, 0.008333331905305386f);
+  p = fma_(p, z, -0.1666666716337204f);
+  return fma_(mul_(r, z), p, r);
+}
+__device__ __forceinline__ float kcos(float r) {
+  const float z = mul_(r, r);
+  float p = fma_(2.453538400004618e-05f, z, -0.001388824312016368f);
+  p = fma_(p, z, 0.0416666641831398f);
+  return fma_(mul_(z, z), p, fma_(-0.5f, z, 1.0f));
 }
 // both kernels are always evaluated and the quadrant only selects: no divergence inside a warp
 __device__ __forceinline__ float sinf_(float x) {
   int q;
-  const double r = reduce((double)x, q);
-  const double a = ksin(r), b = kcos(r);
-  double s = (q & 1) ? b : a;
-  if (q & 2) s = -s;
-  return (float)s;
+  const float r = reduce(x, q);
+  const float a = ksin(r), b = kcos(r);
+  const float s = (q & 1) ? b : a;
+  return (q & 2) ? -s : s;
 }
 __device__ __forceinline__ float cosf_(float x) {
   int q;
-  const double r = reduce((double)x, q);
-  const double a = ksin(r), b = kcos(r);
-  double s = (q & 1) ? a : b;
-  if (q == 1 || q == 2) s = -s;
-  return (float)s;
+  const float r = reduce(x, q);
+  const float a = ksin(r), b = kcos(r);
+  const float s = (q & 1) ? a : b;
+  return (q == 1 || q == 2) ? -s : s;
 }
 // both at once (sampleMicrofacet, sampleLambert, sampleEnv, camera use the pair on one angle)
 __device__ __forceinline__ void sincosf_(float x, float& sn, float& cs) {
   int q;
-  const double r = reduce((double)x, q);
-  const double a = ksin(r), b = kcos(r);
-  double s = (q & 1) ? b : a;
-  double c = (q & 1) ? a : b;
-  if (q & 2) s = -s;
-  if (q == 1 || q == 2) c = -c;
-  sn = (float)s;
-  cs = (float)c;
+  const float r = reduce(x, q);
+  const float a = ksin(r), b = kcos(r);
+  const float s = (q & 1) ? b : a;
+  const float c = (q & 1) ? a : b;
+  sn = (q & 2) ? -s : s;
+  cs = (q == 1 || q == 2) ? -c : c;
 }
 
-__device__ __forceinline__ double atan01(double a) {
-  double base = 0.0;
-  if (a > 0.41421356237309503) {
-    a = div(sub(a, 1.0), add(a, 1.0));
+__device__ __forceinline__ float atan01(float a) {
+  float base = 0.0f;
+  if (a > 0.4142135679721832f) {
+    a = div_(sub_(a, 1.0f), add_(a, 1.0f));
     base = DM_PIO4;
   }
-  const double z = mul(a, a);
-  double p = 1.0 / 21.0;
-  p = hs(-1.0 / 19.0, z, p);
-  p = hs(1.0 / 17.0, z, p);
-  p = hs(-1.0 / 15.0, z, p);
-  p = hs(1.0 / 13.0, z, p);
-  p = hs(-1.0 / 11.0, z, p);
-  p = hs(1.0 / 9.0, z, p);
-  p = hs(-1.0 / 7.0, z, p);
-  p = hs(1.0 / 5.0, z, p);
-  p = hs(-1.0 / 3.0, z, p);
-  p = hs(1.0, z, p);
-  return add(base, mul(a, p));
+  const float z = mul_(a, a);
+  float p = fma_(-0.06418270617723465f, z, 0.10733865201473236f);
+  p = fma_(p, z, -0.14263083040714264f);
+  p = fma_(p, z, 0.19999517500400543f);
+  p = fma_(p, z, -0.3333333134651184f);
+  return add_(base, fma_(mul_(a, z), p, a));
 }
-__device__ __forceinline__ double atan2d(double y, double x) {
-  const double ax = fabs(x), ay = fabs(y);
-  const double hi = ax > ay ? ax : ay;
-  const double lo = ax > ay ? ay : ax;
-  if (!(hi > 0.0)) return 0.0;
-  double r = atan01(div(lo, hi));
-  if (ay > ax) r = sub(DM_PIO2, r);
-  if (x < 0.0) r = sub(DM_PI, r);
-  if (y < 0.0) r = -r;
+__device__ __forceinline__ float atan2f_(float y, float x) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float hi = ax > ay ? ax : ay;
+  const float lo = ax > ay ? ay : ax;
+  if (!(hi > 0.0f)) return 0.0f;
+  float r = atan01(div_(lo, hi));
+  if (ay > ax) r = sub_(DM_PIO2, r);
+  if (x < 0.0f) r = sub_(DM_PI, r);
+  if (y < 0.0f) r = -r;
   return r;
 }
-__device__ __forceinline__ float atan2f_(float y, float x) { return (float)atan2d((double)y, (double)x); }
 __device__ __forceinline__ float asinf_(float x) {
-  double xd = (double)x;
-  if (xd > 1.0) xd = 1.0;
-  if (xd < -1.0) xd = -1.0;
-  return (float)atan2d(xd, __dsqrt_rn(mul(sub(1.0, xd), add(1.0, xd))));
+  if (x > 1.0f) x = 1.0f;
+  if (x < -1.0f) x = -1.0f;
+  return atan2f_(x, __fsqrt_rn(mul_(sub_(1.0f, x), add_(1.0f, x))));
 }
 
-__device__ __forceinline__ double exp2d(double x) {
+__device__ __forceinline__ float exp2f_(float x) {
   if (x != x) return x;
-  if (x > 1000.0) x = 1000.0;
-  if (x < -1100.0) x = -1100.0;
-  const double n = rint(x);
-  const double t = mul(sub(x, n), DM_LN2);
-  double p = 1.0 / 479001600.0;
-  p = hs(1.0 / 39916800.0, t, p);
-  p = hs(1.0 / 3628800.0, t, p);
-  p = hs(1.0 / 362880.0, t, p);
-  p = hs(1.0 / 40320.0, t, p);
-  p = hs(1.0 / 5040.0, t, p);
-  p = hs(1.0 / 720.0, t, p);
-  p = hs(1.0 / 120.0, t, p);
-  p = hs(1.0 / 24.0, t, p);
-  p = hs(1.0 / 6.0, t, p);
-  p = hs(0.5, t, p);
-  p = hs(1.0, t, p);
-  p = hs(1.0, t, p);
+  if (x > 130.0f) x = 130.0f;
+  if (x < -160.0f) x = -160.0f;
+  const float n = rintf(x);
+  const float f = sub_(x, n);
+  float p = fma_(0.0001545316627016291f, f, 0.00133813067805022f);
+  p = fma_(p, f, 0.009618083015084267f);
+  p = fma_(p, f, 0.055503811687231064f);
+  p = fma_(p, f, 0.24022650718688965f);
+  const float r = fma_(mul_(f, f), p, fma_(f, DM_LN2, 1.0f));
   const int ni = (int)n;
   const int n1 = ni / 2, n2 = ni - n1;
-  const double s1 = __longlong_as_double((long long)(n1 + 1023) << 52);
-  const double s2 = __longlong_as_double((long long)(n2 + 1023) << 52);
-  return mul(mul(p, s1), s2);
+  const float s1 = __int_as_float((n1 + 127) << 23), s2 = __int_as_float((n2 + 127) << 23);
+  return mul_(mul_(r, s1), s2);
 }
-__device__ __forceinline__ double log2d(double x) {
-  long long b = __double_as_longlong(x);
-  int e = (int)((b >> 52) & 0x7ff) - 1023;
-  b = (b & 0x000fffffffffffffLL) | 0x3ff0000000000000LL;
-  double m = __longlong_as_double(b);
-  if (m > 1.4142135623730951) { m = mul(m, 0.5); e += 1; }
-  const double s = div(sub(m, 1.0), add(m, 1.0));
-  const double z = mul(s, s);
-  double p = 1.0 / 17.0;
-  p = hs(1.0 / 15.0, z, p);
-  p = hs(1.0 / 13.0, z, p);
-  p = hs(1.0 / 11.0, z, p);
-  p = hs(1.0 / 9.0, z, p);
-  p = hs(1.0 / 7.0, z, p);
-  p = hs(1.0 / 5.0, z, p);
-  p = hs(1.0 / 3.0, z, p);
-  p = hs(1.0, z, p);
-  return add((double)e, mul(mul(mul(2.0, s), p), DM_LOG2E));
+__device__ __forceinline__ float log2f_(float x) {
+  int e = 0;
+  if (x < 1.17549435e-38f) { x = mul_(x, 16777216.0f); e = -24; }
+  unsigned b = __float_as_uint(x);
+  e += (int)((b >> 23) & 0xffu) - 127;
+  b = (b & 0x007fffffu) | 0x3f800000u;
+  float m = __uint_as_float(b);
+  if (m > 1.4142135381698608f) { m = mul_(m, 0.5f); e += 1; }
+  const float s = div_(sub_(m, 1.0f), add_(m, 1.0f));
+  const float z = mul_(s, s);
+  float p = fma_(0.233596533536911f, z, 0.2855019271373749f);
+  p = fma_(p, z, 0.4000011682510376f);
+  p = fma_(p, z, 0.6666666865348816f);
+  const float lnm = fma_(mul_(s, z), p, mul_(2.0f, s));
+  return fma_(lnm, DM_LOG2E, (float)e);
 }
-__device__ __forceinline__ float exp2f_(float x) { return (float)exp2d((double)x); }
 __device__ __forceinline__ float powf_(float x, float y) {
   if (!(x > 0.0f)) return 0.0f;
   if (x > 3.0e38f) return x;
-  return (float)exp2d(mul((double)y, log2d((double)x)));
+  return exp2f_(mul_(y, log2f_(x)));
 }
 
 }  // namespace dm

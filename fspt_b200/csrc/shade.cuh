@@ -16,7 +16,7 @@ struct SampleParams {     // per sample in flight
 };
 
 // rnd(), tracer.fs:181 / camera.fs:19
-// (kept out of line: the shading kernel calls it ~8 times per vertex and its binary64 body is ~60 instructions)
+// (kept out of line: the shading kernel calls it ~8 times per vertex)
 __device__ __noinline__ float sin_hash(float seed) { return fractf(dm::sinf_(seed) * 43758.5453123f); }
 __device__ __forceinline__ float rnd(float& seed) {
   seed += 0.211324865405187f;
@@ -153,7 +153,7 @@ __device__ __noinline__ v3 env_sample_(cudaTextureObject_t env, int W, int H, fl
   const float cx = envTheta + dm::atan2f_(dz, dx) / FSPT_TAU;
   const float cy = dm::asinf_(-dy) * FSPT_INV_PI + 0.5f;
   const float4 rgbe = texture_env(env, W, H, cx, cy);
-  // pow(2.0, e), tracer.fs:412: in FSPT-DM1 log2(2.0) evaluates to exactly 1.0, so this is exp2(e) bit for bit
+  // pow(2.0, e), tracer.fs:412: in FSPT-DM2 log2(2.0) evaluates to exactly 1.0, so this is exp2(e) bit for bit
   const float p = dm::exp2f_(rgbe.w * 255.0f - 128.0f);
   return mk3(rgbe.x * p, rgbe.y * p, rgbe.z * p);
 }
@@ -589,7 +589,7 @@ __global__ void __launch_bounds__(256) k_post(const float4* __restrict__ fb, uch
   out[(size_t)y * W + x] = make_uchar4(quant8(mapped.x), quant8(mapped.y), quant8(mapped.z), 255);
 }
 
-// FSPT-DM1 probes (fspt_debug_math)
+// FSPT-DM2 probes (fspt_debug_math)
 __global__ void k_debug_math(int fn, const float* x, const float* y, float* out, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;

@@ -145,7 +145,7 @@ int fspt_debug_trace(fspt_ctx* ctx, const float* pos4, const float* dir4, int32_
  * tracer.fs:515), RGBA32F; parity aid. */
 int fspt_debug_last_color(fspt_ctx* ctx, float* rgba32f_out);
 
-/* FSPT-DM1 arithmetic probes evaluated ON THE DEVICE (fn: 0 sin, 1 cos, 2 atan2(y,x), 3 asin, 4 exp2,
+/* FSPT-DM2 arithmetic probes evaluated ON THE DEVICE (fn: 0 sin, 1 cos, 2 atan2(y,x), 3 asin, 4 exp2,
  * 5 pow(x,y)); parity aid for the platform built-ins the shaders rely on (tracer.fs:181,412,417). */
 int fspt_debug_math(fspt_ctx* ctx, int32_t fn, const float* x, const float* y, float* out, int32_t n);
 

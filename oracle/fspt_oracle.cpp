@@ -11,7 +11,7 @@
  * legs may load this library.  The product (fspt_b200/) never does.
  *
  * Every function cites the reference file:line it follows (paths relative to the
- * reference root).  Arithmetic model: oracle_math.h ("FSPT-DM1").
+ * reference root).  Arithmetic model: oracle_math.h ("FSPT-DM2").
  * Build: g++ -O2 -ffp-contract=off -fno-fast-math (see oracle/Makefile).
  */
 #include <stdint.h>
@@ -510,7 +510,7 @@ extern "C" {
 
 int oracle_abi_version() { return 1; }
 
-/* ---- det-math probes (so tests can pin FSPT-DM1 against libm and the GPU) ---- */
+/* ---- det-math probes (so tests can pin FSPT-DM2 against libm and the GPU) ---- */
 void oracle_dm_eval(int fn, const float* x, const float* y, float* out, int n) {
   for (int i = 0; i < n; ++i) {
     switch (fn) {

@@ -5,13 +5,14 @@
  *
  * The reference (apbodnar/FSPT) leaves sin/cos/atan/asin/pow/min/max/normalize
  * to whatever GLSL ES 3.00 implementation runs the shaders.  Nothing in the
- * reference pins them, so the oracle pins them itself, as spec "FSPT-DM1":
+ * reference pins them, so the oracle pins them itself, as spec "FSPT-DM2":
  *
  *   - every f32 operation is a single IEEE-754 binary32 round-to-nearest-even
  *     operation, no contraction (compile with -ffp-contract=off, no fast-math);
- *   - transcendental built-ins are evaluated in IEEE binary64 by the fixed
- *     operation sequences below (only + - * / sqrt rint on doubles) and rounded
- *     ONCE to binary32;
+ *   - transcendental built-ins are evaluated in binary32 by the fixed operation
+ *     sequences below (+ - * / sqrt rint and single-rounded fmaf), i.e. what a GPU
+ *     does natively (DM1, the first version, used binary64: 46 % of the shading
+ *     kernel's instructions, and FP64 is vestigial on some Blackwell parts);
  *   - min/max are IEEE-754 minNum/maxNum (what GPU FMNMX does; GLSL leaves the
  *     NaN case undefined);
  *   - vector built-ins follow the formulas printed in the GLSL ES 3.00 spec
@@ -44,166 +45,141 @@ static inline float clampf(float x, float lo, float hi) { return fminN(fmaxN(x, 
 static inline float fractf(float x) { return x - floorf(x); }
 static inline float mixf(float x, float y, float a) { return x * (1.0f - a) + y * a; }
 
-/* ---- FSPT-DM1 transcendental kernels (binary64) ------------------------ */
-static const double DM_TWO_OVER_PI = 0x1.45f306dc9c883p-1;
-static const double DM_PIO2_A = 0x1.921fb54000000p+0;  /* top 27 bits of pi/2 */
-static const double DM_PIO2_B = 0x1.10b4610000000p-30; /* next 27 bits        */
-static const double DM_PIO2_C = 0x1.a62633145c06ep-58; /* remainder           */
-static const double DM_PI = 0x1.921fb54442d18p+1;
-static const double DM_PIO2 = 0x1.921fb54442d18p+0;
-static const double DM_PIO4 = 0x1.921fb54442d18p-1;
-static const double DM_LN2 = 0x1.62e42fefa39efp-1;
-static const double DM_LOG2E = 0x1.71547652b82fep+0;
+/* ---- FSPT-DM2 transcendental kernels ------------------------------------------------------------
+ * All binary32.  fmaf() is a single-rounded fused multiply-add (x86 FMA3 / glibc fmaf; GPU FFMA.RN via
+ * __fmaf_rn); every other operation is a separately rounded IEEE operation.  The operation sequences below ARE
+ * the specification; the CUDA side (fspt_b200/csrc/dm_math.cuh) restates them with explicit intrinsics.
+ * Accuracy against libm (tests/test_oracle_cpu.py): sin/cos <= 2 ulp for |x| <= 64 and an absolute error below
+ * 4e-7 up to |x| = 1e7 (the sin-hash RNG range); atan2/asin/exp2 <= 3 ulp. */
+static inline float dm_fma(float a, float b, float c) { return __builtin_fmaf(a, b, c); }
 
-/* sin/cos on |r| <= pi/4 : fdlibm k_sin/k_cos minimax coefficients, Horner */
-static inline double dm_ksin(double r) {
-  const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03,
-               S3 = -1.98412698298579493134e-04, S4 = 2.75573137070700676789e-06,
-               S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
-  double z = r * r;
-  double v = z * r;
-  double p = S2 + z * (S3 + z * (S4 + z * (S5 + z * S6)));
-  return r + v * (S1 + z * p);
-}
-static inline double dm_kcos(double r) {
-  const double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03,
-               C3 = 2.48015872894767294178e-05, C4 = -2.75573143513906633035e-07,
-               C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
-  double z = r * r;
-  double p = z * (C1 + z * (C2 + z * (C3 + z * (C4 + z * (C5 + z * C6)))));
-  return 1.0 - (0.5 * z - z * p);
-}
-/* range reduction: r = x - k*pi/2, k = rint(x*2/pi); accurate for |x| < 2^26 */
-static inline double dm_reduce(double x, int64_t* kq) {
-  double k = rint(x * DM_TWO_OVER_PI);
-  double r = ((x - k * DM_PIO2_A) - k * DM_PIO2_B) - k * DM_PIO2_C;
-  /* beyond the accurate domain keep the result bounded and deterministic */
-  if (!(k > -9.0e15 && k < 9.0e15)) { *kq = 0; return 0.0; }
-  *kq = (int64_t)k;
+static const float DM_TWO_OVER_PI = 0x1.45f306p-1f;
+static const float DM_PIO2_1 = 0x1.921fb6p+0f;   /* pi/2 rounded to f32            */
+static const float DM_PIO2_2 = -0x1.777a5cp-25f; /* pi/2 - P1 rounded to f32       */
+static const float DM_PIO2_3 = -0x1.ee59dap-50f; /* pi/2 - P1 - P2 rounded to f32  */
+static const float DM_PI = 0x1.921fb6p+1f;
+static const float DM_PIO2 = 0x1.921fb6p+0f;
+static const float DM_PIO4 = 0x1.921fb6p-1f;
+static const float DM_LN2 = 0x1.62e430p-1f;
+static const float DM_LOG2E = 0x1.715476p+0f;
+
+/* r = x - k*pi/2 with a three-term Cody-Waite reduction; the products k*P are exact inside the FMAs */
+static inline float dm_reduce(float x, int* q) {
+  if (!(fabsf(x) <= 1.0e9f)) { *q = 0; return 0.0f; } /* NaN / inf / huge: defined as angle 0 */
+  float k = __builtin_rintf(x * DM_TWO_OVER_PI);
+  float r = dm_fma(-k, DM_PIO2_1, x);
+  r = dm_fma(-k, DM_PIO2_2, r);
+  r = dm_fma(-k, DM_PIO2_3, r);
+  /* for |x| > ~1e5 the f32 product x*2/pi can miss the nearest integer by one: fold the residue once more */
+  float k2 = __builtin_rintf(r * DM_TWO_OVER_PI);
+  r = dm_fma(-k2, DM_PIO2_1, r);
+  r = dm_fma(-k2, DM_PIO2_2, r);
+  *q = ((int)k + (int)k2) & 3;
   return r;
+}
+/* sin(r) = r + r z (S0 + S1 z + S2 z^2 + S3 z^3), z = r^2, |r| <= pi/4 (least-squares fit at Chebyshev nodes) */
+static inline float dm_ksin(float r) {
+  float z = r * r;
+  float p = dm_fma(2.7234684694121825e-06f, z, -0.00019839966262225062f);
+  p = dm_fma(p, z, 0.008333331905305386f);
+  p = dm_fma(p, z, -0.1666666716337204f);
+  return dm_fma(r * z, p, r);
+}
+/* cos(r) = 1 - z/2 + z^2 (C0 + C1 z + C2 z^2) */
+static inline float dm_kcos(float r) {
+  float z = r * r;
+  float p = dm_fma(2.453538400004618e-05f, z, -0.001388824312016368f);
+  p = dm_fma(p, z, 0.0416666641831398f);
+  return dm_fma(z * z, p, dm_fma(-0.5f, z, 1.0f));
 }
 static inline float dm_sin(float x) {
-  int64_t k;
-  double r = dm_reduce((double)x, &k);
-  double s;
-  switch ((int)(k & 3)) {
-    case 0: s = dm_ksin(r); break;
-    case 1: s = dm_kcos(r); break;
-    case 2: s = -dm_ksin(r); break;
-    default: s = -dm_kcos(r); break;
-  }
-  return (float)s;
+  int q;
+  float r = dm_reduce(x, &q);
+  float a = dm_ksin(r), b = dm_kcos(r);
+  float s = (q & 1) ? b : a;
+  return (q & 2) ? -s : s;
 }
 static inline float dm_cos(float x) {
-  int64_t k;
-  double r = dm_reduce((double)x, &k);
-  double s;
-  switch ((int)(k & 3)) {
-    case 0: s = dm_kcos(r); break;
-    case 1: s = -dm_ksin(r); break;
-    case 2: s = -dm_kcos(r); break;
-    default: s = dm_ksin(r); break;
-  }
-  return (float)s;
+  int q;
+  float r = dm_reduce(x, &q);
+  float a = dm_ksin(r), b = dm_kcos(r);
+  float s = (q & 1) ? a : b;
+  return (q == 1 || q == 2) ? -s : s;
 }
-
-/* atan on [0,1]: one reduction about tan(pi/8), then odd Taylor to a^21 */
-static inline double dm_atan01(double a) {
-  double base = 0.0;
-  if (a > 0.41421356237309503) { /* tan(pi/8) */
-    a = (a - 1.0) / (a + 1.0);
+/* atan on [0,1]: one reduction about tan(pi/8), then a + a z (A0 + A1 z + ... + A4 z^4) */
+static inline float dm_atan01(float a) {
+  float base = 0.0f;
+  if (a > 0.4142135679721832f) {
+    a = (a - 1.0f) / (a + 1.0f);
     base = DM_PIO4;
   }
-  double z = a * a;
-  double p = 1.0 / 21.0;
-  p = -1.0 / 19.0 + z * p;
-  p = 1.0 / 17.0 + z * p;
-  p = -1.0 / 15.0 + z * p;
-  p = 1.0 / 13.0 + z * p;
-  p = -1.0 / 11.0 + z * p;
-  p = 1.0 / 9.0 + z * p;
-  p = -1.0 / 7.0 + z * p;
-  p = 1.0 / 5.0 + z * p;
-  p = -1.0 / 3.0 + z * p;
-  p = 1.0 + z * p;
-  return base + a * p;
+  float z = a * a;
+  float p = dm_fma(-0.06418270617723465f, z, 0.10733865201473236f);
+  p = dm_fma(p, z, -0.14263083040714264f);
+  p = dm_fma(p, z, 0.19999517500400543f);
+  p = dm_fma(p, z, -0.3333333134651184f);
+  return base + dm_fma(a * z, p, a);
 }
-static inline double dm_atan2d(double y, double x) {
-  double ax = fabs(x), ay = fabs(y);
-  double hi = ax > ay ? ax : ay;
-  double lo = ax > ay ? ay : ax;
-  if (!(hi > 0.0)) return 0.0; /* atan(0,0) and NaN inputs: defined as 0 */
-  double r = dm_atan01(lo / hi);
+static inline float dm_atan2(float y, float x) {
+  float ax = fabsf(x), ay = fabsf(y);
+  float hi = ax > ay ? ax : ay;
+  float lo = ax > ay ? ay : ax;
+  if (!(hi > 0.0f)) return 0.0f; /* atan(0,0) and NaN inputs: defined as 0 */
+  float r = dm_atan01(lo / hi);
   if (ay > ax) r = DM_PIO2 - r;
-  if (x < 0.0) r = DM_PI - r;
-  if (y < 0.0) r = -r;
+  if (x < 0.0f) r = DM_PI - r;
+  if (y < 0.0f) r = -r;
   return r;
 }
-static inline float dm_atan2(float y, float x) { return (float)dm_atan2d((double)y, (double)x); }
 static inline float dm_asin(float x) {
-  double xd = (double)x;
-  if (xd > 1.0) xd = 1.0;   /* |x| may exceed 1 by an ulp after normalize() */
-  if (xd < -1.0) xd = -1.0;
-  return (float)dm_atan2d(xd, sqrt((1.0 - xd) * (1.0 + xd)));
+  if (x > 1.0f) x = 1.0f; /* |x| may exceed 1 by an ulp after normalize() */
+  if (x < -1.0f) x = -1.0f;
+  return dm_atan2(x, sqrtf((1.0f - x) * (1.0f + x)));
 }
-
-/* 2^x for double x; Taylor of e^t, t = f*ln2, |f| <= 0.5, to t^12 */
-static inline double dm_exp2d(double x) {
+/* 2^x: n = rint(x), f = x - n, 2^f = 1 + f ln2 + f^2 (E0 + E1 f + ... + E4 f^4), scaled by 2^n in two exact steps */
+static inline float dm_exp2(float x) {
   if (x != x) return x;
-  if (x > 1000.0) x = 1000.0;
-  if (x < -1100.0) x = -1100.0;
-  double n = rint(x);
-  double t = (x - n) * DM_LN2;
-  double p = 1.0 / 479001600.0;
-  p = 1.0 / 39916800.0 + t * p;
-  p = 1.0 / 3628800.0 + t * p;
-  p = 1.0 / 362880.0 + t * p;
-  p = 1.0 / 40320.0 + t * p;
-  p = 1.0 / 5040.0 + t * p;
-  p = 1.0 / 720.0 + t * p;
-  p = 1.0 / 120.0 + t * p;
-  p = 1.0 / 24.0 + t * p;
-  p = 1.0 / 6.0 + t * p;
-  p = 0.5 + t * p;
-  p = 1.0 + t * p;
-  p = 1.0 + t * p;
-  /* scale by 2^n in two exact steps (n in [-1100,1000]) */
+  if (x > 130.0f) x = 130.0f;
+  if (x < -160.0f) x = -160.0f;
+  float n = __builtin_rintf(x);
+  float f = x - n;
+  float p = dm_fma(0.0001545316627016291f, f, 0.00133813067805022f);
+  p = dm_fma(p, f, 0.009618083015084267f);
+  p = dm_fma(p, f, 0.055503811687231064f);
+  p = dm_fma(p, f, 0.24022650718688965f);
+  float r = dm_fma(f * f, p, dm_fma(f, DM_LN2, 1.0f));
   int ni = (int)n;
   int n1 = ni / 2, n2 = ni - n1;
-  uint64_t b1 = (uint64_t)(int64_t)(n1 + 1023) << 52, b2 = (uint64_t)(int64_t)(n2 + 1023) << 52;
-  double s1, s2;
-  memcpy(&s1, &b1, 8);
-  memcpy(&s2, &b2, 8);
-  return (p * s1) * s2;
+  uint32_t b1 = (uint32_t)(n1 + 127) << 23, b2 = (uint32_t)(n2 + 127) << 23;
+  float s1, s2;
+  memcpy(&s1, &b1, 4);
+  memcpy(&s2, &b2, 4);
+  return (r * s1) * s2;
 }
-/* log2 for double x > 0 (normal): atanh series to s^17 */
-static inline double dm_log2d(double x) {
-  uint64_t b;
-  memcpy(&b, &x, 8);
-  int e = (int)((b >> 52) & 0x7ff) - 1023;
-  b = (b & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL;
-  double m;
-  memcpy(&m, &b, 8);
-  if (m > 1.4142135623730951) { m = m * 0.5; e += 1; }
-  double s = (m - 1.0) / (m + 1.0);
-  double z = s * s;
-  double p = 1.0 / 17.0;
-  p = 1.0 / 15.0 + z * p;
-  p = 1.0 / 13.0 + z * p;
-  p = 1.0 / 11.0 + z * p;
-  p = 1.0 / 9.0 + z * p;
-  p = 1.0 / 7.0 + z * p;
-  p = 1.0 / 5.0 + z * p;
-  p = 1.0 / 3.0 + z * p;
-  p = 1.0 + z * p;
-  return (double)e + (2.0 * s * p) * DM_LOG2E;
+/* log2(x), x > 0: x = m 2^e, m in (sqrt(.5), sqrt(2)], ln m = 2s + s z (L0 + L1 z + L2 z^2 + L3 z^3), s = (m-1)/(m+1) */
+static inline float dm_log2(float x) {
+  int e = 0;
+  if (x < 1.17549435e-38f) { x = x * 16777216.0f; e = -24; } /* subnormal */
+  uint32_t b;
+  memcpy(&b, &x, 4);
+  e += (int)((b >> 23) & 0xff) - 127;
+  b = (b & 0x007fffffu) | 0x3f800000u;
+  float m;
+  memcpy(&m, &b, 4);
+  if (m > 1.4142135381698608f) { m = m * 0.5f; e += 1; }
+  float s = (m - 1.0f) / (m + 1.0f);
+  float z = s * s;
+  float p = dm_fma(0.233596533536911f, z, 0.2855019271373749f);
+  p = dm_fma(p, z, 0.4000011682510376f);
+  p = dm_fma(p, z, 0.6666666865348816f);
+  float lnm = dm_fma(s * z, p, 2.0f * s);
+  return dm_fma(lnm, DM_LOG2E, (float)e);
 }
-static inline float dm_exp2(float x) { return (float)dm_exp2d((double)x); }
-/* pow(x,y) = exp2(y*log2(x)) (GLSL ES 3.00 8.2); x <= 0 or NaN -> 0 (GLSL: undefined) */
+/* pow(x,y) = exp2(y*log2(x)) (GLSL ES 3.00 8.2); x <= 0 or NaN -> 0 (GLSL: undefined).  log2(2) is exactly 1. */
 static inline float dm_pow(float x, float y) {
   if (!(x > 0.0f)) return 0.0f;
   if (x > 3.0e38f) return x;
-  return (float)dm_exp2d((double)y * dm_log2d((double)x));
+  return dm_exp2(y * dm_log2(x));
 }
 
 /* ---- vec types ---------------------------------------------------------- */

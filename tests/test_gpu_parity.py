@@ -3,7 +3,7 @@
 Bars (BASELINE.md section 4 / north star):
   * primary-hit records (index, t, count) of the bvh_test.fs traversal: BIT-EXACT;
   * camera rays, per-sample radiance, running-mean accumulator and RGBA8 post-pass: the CUDA kernels
-    implement the same FSPT-DM1 arithmetic as the oracle, so these are asserted bit-exact as well
+    implement the same FSPT-DM2 arithmetic as the oracle, so these are asserted bit-exact as well
     (stated tolerance: 0 ulp; a mismatch-rate report is printed if that ever fails).
 """
 import numpy as np

@@ -1,4 +1,4 @@
-"""CPU suite: pins the oracle (hand-derived KATs, brute force, analytic furnace), the FSPT-DM1 arithmetic,
+"""CPU suite: pins the oracle (hand-derived KATs, brute force, analytic furnace), the FSPT-DM2 arithmetic,
 the native host-side compilers against the oracle's literal restatements, and the C ABI surface.
 No GPU needed.  PARITY UNPINNED against the reference itself (it ships no vectors and cannot run here)."""
 import ctypes as C
@@ -23,28 +23,37 @@ def rays(origins, dirs):
     return o, d
 
 
-# ---------------------------------------------------------------- FSPT-DM1 built-ins vs libm
+# ---------------------------------------------------------------- FSPT-DM2 built-ins vs libm
 def test_dm_math_is_faithful(oracle_mod):
+    """FSPT-DM2 (binary32 + FMA) against libm in binary64: a few ulp where the shaders need accuracy, bounded
+    absolute error over the sin-hash RNG's argument range."""
     rng = np.random.default_rng(0)
 
     def ulps(got, ref64):
         ref32 = ref64.astype(np.float32)
         return np.abs(got.astype(np.float64) - ref64) / np.maximum(np.spacing(np.abs(ref32)).astype(np.float64), 1e-45)
-    x = np.concatenate([rng.uniform(-1e7, 1e7, 100000), rng.uniform(-10, 10, 100000)]).astype(np.float32)
-    assert ulps(oracle_mod.dm_eval("sin", x), np.sin(x.astype(np.float64))).max() < 0.51
-    assert ulps(oracle_mod.dm_eval("cos", x), np.cos(x.astype(np.float64))).max() < 0.51
-    a, b = rng.uniform(-1, 1, 100000).astype(np.float32), rng.uniform(-1, 1, 100000).astype(np.float32)
-    assert ulps(oracle_mod.dm_eval("atan2", a, b), np.arctan2(b.astype(np.float64), a.astype(np.float64))).max() < 0.51
-    assert ulps(oracle_mod.dm_eval("asin", a), np.arcsin(a.astype(np.float64))).max() < 0.51
-    e = rng.uniform(-120, 120, 100000).astype(np.float32)
-    assert ulps(oracle_mod.dm_eval("exp2", e), np.exp2(e.astype(np.float64))).max() < 0.51
-    p, q = rng.uniform(0.001, 2, 100000).astype(np.float32), rng.uniform(0.1, 3, 100000).astype(np.float32)
-    assert ulps(oracle_mod.dm_eval("pow", p, q), np.power(p.astype(np.float64), q.astype(np.float64))).max() < 0.51
+    x = rng.uniform(-64, 64, 200000).astype(np.float32)
+    xb = rng.uniform(-1e7, 1e7, 200000).astype(np.float32)
+    for fn, ref in (("sin", np.sin), ("cos", np.cos)):
+        assert ulps(oracle_mod.dm_eval(fn, x), ref(x.astype(np.float64))).max() < 2.0
+        assert np.abs(oracle_mod.dm_eval(fn, xb) - ref(xb.astype(np.float64))).max() < 4e-7
+    a, b = rng.uniform(-1, 1, 200000).astype(np.float32), rng.uniform(-1, 1, 200000).astype(np.float32)
+    assert ulps(oracle_mod.dm_eval("atan2", a, b), np.arctan2(b.astype(np.float64), a.astype(np.float64))).max() < 3.5
+    assert ulps(oracle_mod.dm_eval("asin", a), np.arcsin(a.astype(np.float64))).max() < 4.0
+    e = rng.uniform(-120, 120, 200000).astype(np.float32)
+    assert ulps(oracle_mod.dm_eval("exp2", e), np.exp2(e.astype(np.float64))).max() < 1.5
+    # pow = exp2(y*log2(x)) in f32 as GLSL defines it: relative error, and the post-pass gamma to well below 1 LSB
+    p, q = rng.uniform(0.001, 2, 200000).astype(np.float32), rng.uniform(0.1, 3, 200000).astype(np.float32)
+    ref = np.power(p.astype(np.float64), q.astype(np.float64))
+    assert (np.abs(oracle_mod.dm_eval("pow", p, q) - ref) / ref).max() < 3e-6
+    m = rng.uniform(0, 1, 100000).astype(np.float32)
+    assert (np.abs(oracle_mod.dm_eval("pow", m, np.full_like(m, 0.454545)) - np.power(m.astype(np.float64), 0.454545)) * 255).max() < 1e-3
     # exact cases the shaders rely on: RGBE exponent decode pow(2, integer) (tracer.fs:412)
     ints = np.arange(-126, 127, dtype=np.float32)
     assert np.array_equal(oracle_mod.dm_eval("pow", np.full_like(ints, 2.0), ints), np.exp2(ints.astype(np.float64)).astype(np.float32))
     assert oracle_mod.dm_eval("atan2", [0.0], [0.0])[0] == 0.0
     assert oracle_mod.dm_eval("asin", [1.0000001])[0] == np.float32(np.pi / 2)
+    assert list(oracle_mod.dm_eval("sin", [np.inf, np.nan, 3e9])) == [0.0, 0.0, 0.0]
 
 
 # ---------------------------------------------------------------- KAT: top_mono.obj quad (root is a leaf)
