@@ -208,7 +208,7 @@ FrameParams make_frame(const Ctx* c, const fspt_frame_params* f) {
 int render_wave(Ctx* c, const FrameParams& fp, uint32_t first_tick, int S, const float* rb_cam, const float* rb_trace) {
   const int P = c->n_pixels;
   const int n_paths = S * P;
-  k_camera<<<(n_paths + 255) / 256, 256, 0, c->stream>>>(fp, rb_cam, n_paths, P, c->ps, nullptr, nullptr);
+  k_camera<<<(n_paths + 255) / 256, 256, 0, c->stream>>>(fp, rb_cam, n_paths, S, c->ps, nullptr, nullptr);
   c->stats.kernel_launches++;
   int rc = set_counts(c, n_paths, 0);
   if (rc) return rc;
@@ -224,7 +224,7 @@ int render_wave(Ctx* c, const FrameParams& fp, uint32_t first_tick, int S, const
   A.counts_out = c->d_counts;
   A.sample_color = c->d_sample_color;
   A.capped = c->d_stats + 3;
-  A.paths_per_sample = P;
+  A.n_samples = S;
   A.max_refractions = c->max_refractions;
   const int hard_cap = FSPT_NUM_BOUNCES + 1 + (c->has_dielectric ? c->max_refractions + 2 : 0);
   for (int b = 0; b < hard_cap; ++b) {
@@ -692,7 +692,7 @@ int fspt_debug_primary(fspt_ctx* ctx, const fspt_frame_params* frame, float rand
   const int P = c->n_pixels;
   c->h_rb[0] = rand_base_camera;
   CK(cudaMemcpyAsync(c->d_rb, c->h_rb, sizeof(float), cudaMemcpyHostToDevice, c->stream));
-  k_camera<<<(P + 255) / 256, 256, 0, c->stream>>>(fp, c->d_rb, P, P, c->ps, c->d_cam_pos, c->d_cam_dir);
+  k_camera<<<(P + 255) / 256, 256, 0, c->stream>>>(fp, c->d_rb, P, 1, c->ps, c->d_cam_pos, c->d_cam_dir);
   c->stats.kernel_launches++;
   int rc = set_counts(c, P, 0);
   if (rc) return rc;

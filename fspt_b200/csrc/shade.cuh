@@ -26,11 +26,13 @@ __device__ __forceinline__ float rnd(float& seed) {
 // ---------------------------------------------------------------------------------------------------------
 // camera.fs main, :37-46.  One thread per path slot p = s * P + j.
 __global__ void __launch_bounds__(256) k_camera(const FrameParams f, const float* __restrict__ rb_cam, int n_paths,
-                                                int paths_per_sample, PathState ps, float4* cam_pos_out,
+                                                int n_samples, PathState ps, float4* cam_pos_out,
                                                 float4* cam_dir_out) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_paths) return;
-  const int s = p / paths_per_sample, j = p - s * paths_per_sample;
+  // slot = pixel * S + sample: the S samples of one pixel sit in adjacent slots (adjacent lanes), so their primary
+  // rays, hit records and texel footprints coincide and are served once per warp instead of once per sample
+  const int j = p / n_samples, s = p - j * n_samples;
   int x, y;
   path_to_pixel(f, j, x, y);
   const float resx = (float)f.width, resy = (float)f.height;
@@ -236,7 +238,7 @@ struct ShadeArgs {
   int* counts_out;            // [0] continuation, [1] shadow
   float4* sample_color;       // [sample-in-wave][pixel] final un-clamped path colour
   unsigned long long* capped; // paths stopped by the refraction cap
-  int paths_per_sample;
+  int n_samples;              // samples in flight in this wave (slot = pixel * n_samples + sample)
   int first;                  // 1: slots hold fresh primary rays (tracer.fs:440-445)
   int max_refractions;
 };
@@ -254,7 +256,7 @@ __device__ __forceinline__ void append(bool want, int value, int* list, int* cou
 }
 
 __device__ __forceinline__ void write_sample(const ShadeArgs& A, int slot, v3 color) {
-  const int s = slot / A.paths_per_sample, j = slot - s * A.paths_per_sample;
+  const int j = slot / A.n_samples, s = slot - j * A.n_samples;
   int x, y;
   path_to_pixel(A.f, j, x, y);
   A.sample_color[(size_t)s * ((size_t)A.f.width * A.f.height) + (size_t)y * A.f.width + x] =
@@ -291,7 +293,7 @@ __device__ __forceinline__ bool shade_hit(const ShadeArgs& A, int slot, bool& sh
   v3 rayOrigin = mk3(o4.x, o4.y, o4.z), rayDir = mk3(d4.x, d4.y, d4.z);
   const float hit_t = o4.w;
   const int hit_index = __float_as_int(d4.w);
-  const int s = slot / A.paths_per_sample;
+  const int s = slot % A.n_samples;
   const float randBase = A.rb_trace[s];
   const float envTheta = A.f.env_theta;
   v3 color, reflectance;
