@@ -39,12 +39,11 @@ def build(force=False, verbose=False, defines=(), out=None):
     os.makedirs(os.path.dirname(lib), exist_ok=True)
     tag = "" if out is None else "_" + os.path.basename(out).replace(".so", "")
     obj_cu = os.path.join(OUT_DIR, "fspt_api%s.o" % tag)
-    obj_cpp = os.path.join(OUT_DIR, "bvh_builder.o")
-    cmds = [
-        [NVCC] + NVCC_FLAGS + list(defines) + ["-c", os.path.join(CSRC, "fspt_api.cu"), "-o", obj_cu],
-        ["g++"] + CXX_FLAGS + ["-c", os.path.join(CSRC, "bvh_builder.cpp"), "-o", obj_cpp],
-        [NVCC, "-shared", "-o", lib, obj_cu, obj_cpp, "-Xlinker", "--no-undefined", "-lpthread"],
-    ]
+    host = ["bvh_builder", "atlas_packer"]
+    objs = [os.path.join(OUT_DIR, h + ".o") for h in host]
+    cmds = [[NVCC] + NVCC_FLAGS + list(defines) + ["-c", os.path.join(CSRC, "fspt_api.cu"), "-o", obj_cu]]
+    cmds += [["g++"] + CXX_FLAGS + ["-c", os.path.join(CSRC, h + ".cpp"), "-o", o] for h, o in zip(host, objs)]
+    cmds += [[NVCC, "-shared", "-o", lib, obj_cu] + objs + ["-Xlinker", "--no-undefined", "-lpthread"]]
     for cmd in cmds:
         r = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or r.returncode != 0:

@@ -52,7 +52,7 @@ EXPORTS = [
     "fspt_render", "fspt_resolve", "fspt_read_accum", "fspt_write_accum", "fspt_set_accum_mode",
     "fspt_accum_device_ptr", "fspt_set_accum_samples", "fspt_debug_primary", "fspt_debug_trace",
     "fspt_debug_last_color", "fspt_debug_math", "fspt_get_stats", "fspt_synchronize", "fspt_bvh_build", "fspt_bvh_build2",
-    "fspt_env_bins",
+    "fspt_env_bins", "fspt_pack_layer",
 ]
 
 _lib = None
@@ -123,6 +123,20 @@ def env_bins(rgba8):
     if rc != FSPT_OK:
         raise FsptError(rc, "fspt_env_bins failed")
     return out[: n.value].reshape(-1, 4).copy()
+
+
+def pack_layer(pixels, res, corrected=False, swizzle=None, n_threads=0):
+    """fspt_pack_layer: one image layer of the atlas.  pixels (h,w,4) uint8, row 0 = image top -> (res,res,4) uint8."""
+    lib = load()
+    pixels = np.ascontiguousarray(pixels, dtype=np.uint8)
+    h, w = pixels.shape[0], pixels.shape[1]
+    out = np.empty((res, res, 4), np.uint8)
+    sw = np.asarray(swizzle, np.int32) if swizzle is not None else None
+    rc = lib.fspt_pack_layer(ptr(pixels), C.c_int32(w), C.c_int32(h), C.c_int32(res), C.c_int32(1 if corrected else 0),
+                             ptr(sw), ptr(out), C.c_int32(n_threads))
+    if rc != FSPT_OK:
+        raise FsptError(rc, "fspt_pack_layer failed (bad size or swizzle)")
+    return out
 
 
 class Context:

@@ -170,6 +170,13 @@ int fspt_bvh_build2(const double* verts, const double* box_verts, int32_t n_tris
 int fspt_env_bins(const uint8_t* rgba8, int32_t width, int32_t height, uint16_t* bins_out, int32_t capacity,
                   int32_t* n_u16_out);
 
+/* One image layer of TexturePacker.getPixels() (texture_packer.js:44-62): the WebGLTextureWriter blit
+ * (:103-121,159-184) -- bilinear resample to res x res, y flip, sRGB decode when `corrected` (base-colour maps),
+ * swizzle, premultiply by alpha, 8-bit quantise.  rgba8: w*h*4, row 0 = image top.  out: res*res*4, row 0 = GL row 0.
+ * swizzle: 4 channel indices or NULL.  Host code, multi-threaded. */
+int fspt_pack_layer(const uint8_t* rgba8, int32_t w, int32_t h, int32_t res, int32_t corrected, const int32_t* swizzle,
+                    uint8_t* out, int32_t n_threads);
+
 #ifdef __cplusplus
 }
 #endif

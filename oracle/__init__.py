@@ -158,3 +158,13 @@ def env_bins(rgba8):
     out = np.empty(cap, np.uint16)
     n = lib().oracle_env_bins(_p(rgba8), C.c_int(W), C.c_int(H), _p(out), C.c_int(cap))
     return out[:n].reshape(-1, 4).copy()
+
+
+def pack_layer(pixels, res, corrected=False, swizzle=None):
+    """texture_packer.js blit, literal per-fragment restatement."""
+    pixels = np.ascontiguousarray(pixels, dtype=np.uint8)
+    h, w = pixels.shape[0], pixels.shape[1]
+    out = np.empty((res, res, 4), np.uint8)
+    sw = np.asarray(swizzle, np.int32) if swizzle is not None else None
+    lib().oracle_pack_layer(_p(pixels), C.c_int(w), C.c_int(h), C.c_int(res), C.c_int(1 if corrected else 0), _p(sw), _p(out))
+    return out

@@ -410,3 +410,21 @@ def test_property_traversal_vs_brute_force(oracle_mod):
         assert not diff.any() or np.all(t[diff] == bt[diff])
         assert stt["stack_overflow"] == 0
     check()
+
+
+# ---------------------------------------------------------------- atlas packer blit (row f2)
+def test_native_pack_layer_matches_blit_restatement(oracle_mod):
+    rng = np.random.default_rng(2)
+    img = rng.integers(0, 256, (37, 53, 4), dtype=np.uint8)  # odd, non-square, with alpha
+    for res, corrected, sw in ((64, True, None), (37, False, [2, 1, 0, 3]), (16, False, None), (128, True, [0, 0, 0, 3])):
+        got = capi.pack_layer(img, res, corrected, sw)
+        ref = oracle_mod.pack_layer(img, res, corrected, sw)
+        assert np.array_equal(got, ref), (res, corrected, sw)
+    # identity-size blit of an opaque image: y flip only (atlas row 0 = image bottom), values preserved
+    op = img.copy()
+    op[..., 3] = 255
+    sq = op[:37, :37]
+    out = capi.pack_layer(sq, 37, False)
+    assert np.array_equal(out[::-1, :, :3], sq[..., :3])
+    with pytest.raises(capi.FsptError):
+        capi.pack_layer(img, 8, False, [0, 1, 2, 7])
