@@ -71,7 +71,7 @@ struct Ctx {
   float* d_rb = nullptr;      // rand bases of one render call: [0,cap) camera, [cap,2cap) tracer
   float* h_rb = nullptr;      // pinned staging
   int rb_cap = 0;
-  int trace_blocks = 0, trace_blocks_cnt = 0, shade_blocks = 0;
+  int trace_blocks = 0, trace_blocks_cnt = 0, trace_blocks_cam = 0, shade_blocks = 0;
 
   fspt_stats stats{};
 };
@@ -169,8 +169,11 @@ __global__ void k_set_counts(int* counts, int n_cont, int n_shadow) {
 
 // Traverses d_counts[0] continuation rays (list_cont, NULL = identity) + d_counts[1] shadow rays and sorts the
 // continuation results into the hit / miss lists (d_counts[2], d_counts[3]).
-int launch_trace(Ctx* c, const int* list_cont, bool classify, bool write_count) {
+int launch_trace(Ctx* c, const int* list_cont, bool classify, bool write_count, const FrameParams* cam = nullptr,
+                 const float* rb_cam = nullptr, int n_samples = 1) {
   TraceArgs A;
+  if (cam) A.f = *cam; else memset(&A.f, 0, sizeof A.f);
+  A.rb_cam = rb_cam; A.n_samples = n_samples;
   A.nodes = c->sc.nodes; A.tris = c->sc.tris; A.root_ref = c->sc.root_ref; A.nodes_tex = c->nodes_tex; A.tris_tex = c->tris_tex;
   A.ps = c->ps;
   A.list_cont = list_cont; A.list_shadow = c->d_list[1];
@@ -181,8 +184,9 @@ int launch_trace(Ctx* c, const int* list_cont, bool classify, bool write_count) 
   A.stats = c->d_stats;
   A.count_out = write_count ? c->d_count_out : nullptr;
   record_trace_begin(c);
-  if (write_count) k_trace<true><<<c->trace_blocks_cnt, TRACE_THREADS, 0, c->stream>>>(A);
-  else k_trace<false><<<c->trace_blocks, TRACE_THREADS, 0, c->stream>>>(A);
+  if (cam) k_trace<false, true><<<c->trace_blocks_cam, TRACE_THREADS, 0, c->stream>>>(A);
+  else if (write_count) k_trace<true, false><<<c->trace_blocks_cnt, TRACE_THREADS, 0, c->stream>>>(A);
+  else k_trace<false, false><<<c->trace_blocks, TRACE_THREADS, 0, c->stream>>>(A);
   record_trace_end(c);
   c->stats.kernel_launches++;
   CK(cudaGetLastError());
@@ -208,11 +212,9 @@ FrameParams make_frame(const Ctx* c, const fspt_frame_params* f) {
 int render_wave(Ctx* c, const FrameParams& fp, uint32_t first_tick, int S, const float* rb_cam, const float* rb_trace) {
   const int P = c->n_pixels;
   const int n_paths = S * P;
-  k_camera<<<(n_paths + 255) / 256, 256, 0, c->stream>>>(fp, rb_cam, n_paths, S, c->ps, nullptr, nullptr);
-  c->stats.kernel_launches++;
   int rc = set_counts(c, n_paths, 0);
   if (rc) return rc;
-  rc = launch_trace(c, nullptr, true, false);  // primary rays, tracer.fs:440
+  rc = launch_trace(c, nullptr, true, false, &fp, rb_cam, S);  // camera.fs + primary rays (tracer.fs:440), fused
   if (rc) return rc;
 
   ShadeArgs A;
@@ -305,15 +307,18 @@ int fspt_create(fspt_ctx** out, int32_t width, int32_t height, int32_t device) {
   if (rc) { g_create_error = c->error; fspt_destroy(reinterpret_cast<fspt_ctx*>(c)); return rc; }
   // traversal uses no shared memory: give the whole unified array to L1 (BVH nodes + triangles live there)
   if (!getenv("FSPT_NO_CARVEOUT")) {
-    cudaFuncSetAttribute(k_trace<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-    cudaFuncSetAttribute(k_trace<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(k_trace<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(k_trace<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(k_trace<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
   }
   // persistent grids: resident CTAs per SM x SM count
   int per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<false>, TRACE_THREADS, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<false, false>, TRACE_THREADS, 0);
   c->trace_blocks = std::max(1, per_sm) * c->sm_count;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<true>, TRACE_THREADS, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<true, false>, TRACE_THREADS, 0);
   c->trace_blocks_cnt = std::max(1, per_sm) * c->sm_count;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<false, true>, TRACE_THREADS, 0);
+  c->trace_blocks_cam = std::max(1, per_sm) * c->sm_count;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shade, SHADE_THREADS, 1024);
   c->shade_blocks = std::max(1, per_sm) * c->sm_count;
   *out = reinterpret_cast<fspt_ctx*>(c);

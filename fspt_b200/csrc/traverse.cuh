@@ -18,6 +18,7 @@
 // popc prefix = the compaction), so short rays do not wait for the longest ray of their warp.  Inside the
 // loop the warp votes each iteration whether to run an interior step or a leaf step (majority of lanes).
 #pragma once
+#include "camera.cuh"
 #include "device_common.cuh"
 
 struct TraceArgs {
@@ -36,6 +37,9 @@ struct TraceArgs {
   int* next;              // work-fetch cursor (zeroed before launch)
   unsigned long long* stats;  // [0] rays, [1] node visits, [2] leaf visits
   int* count_out;         // per-slot visit count (debug / bvh_test mode) or NULL
+  FrameParams f;          // CAMERA mode: primary rays are generated in the fetch instead of being read
+  const float* rb_cam;
+  int n_samples;
 };
 
 #define TRACE_THREADS 128
@@ -110,7 +114,10 @@ __device__ __forceinline__ float tri_test(const float4 q0, const float4 q1, cons
   return dist > FSPT_EPSILON ? dist : FSPT_MAX_T;
 }
 
-template <bool WRITE_COUNT>
+// CAMERA = the primary launch of a render wave: the ray of slot `my` is generated on the fly (camera.fs) and the whole
+// ray + hit record is written at retirement, so the camera pass, its 32 B/path of writes and this launch's 128-byte
+// record reads disappear.
+template <bool WRITE_COUNT, bool CAMERA>
 __global__ void __launch_bounds__(TRACE_THREADS) k_trace(const TraceArgs A) {
   const unsigned lane = threadIdx.x & 31u;
   const unsigned FULL = 0xffffffffu;
@@ -131,7 +138,10 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(const TraceArgs A) {
     const bool need = (cur == FSPT_SENTINEL);
     const bool retire = need && slot >= 0;
     if (retire) {  // retire the finished ray
-      if (kind == 0) {
+      if (CAMERA) {
+        st_path(A.ps.ro(slot), make_float4(ox, oy, oz, tbest));
+        st_path(A.ps.rd(slot), make_float4(dx, dy, dz, __int_as_float(ibest)));
+      } else if (kind == 0) {
         st_path_w(A.ps.ro(slot), tbest);
         st_path_w(A.ps.rd(slot), __int_as_float(ibest));
       } else {
@@ -171,12 +181,22 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(const TraceArgs A) {
         if (need) {
           const int my = base + __popc(m & ((1u << lane) - 1u));
           if (my < total) {
-            kind = my >= n_cont;
-            slot = kind ? ld_list(A.list_shadow + (my - n_cont)) : (A.list_cont ? ld_list(A.list_cont + my) : my);
-            const float4 o4 = ld_path(A.ps.ro(slot));
-            const float4 d4 = ld_path(kind ? A.ps.sd(slot) : A.ps.rd(slot));
-            ox = o4.x; oy = o4.y; oz = o4.z;
-            dx = d4.x; dy = d4.y; dz = d4.z;
+            if (CAMERA) {
+              kind = 0;
+              slot = my;
+              v3 o, d;
+              int px, py;
+              camera_ray(A.f, A.rb_cam, A.n_samples, my, o, d, px, py);
+              ox = o.x; oy = o.y; oz = o.z;
+              dx = d.x; dy = d.y; dz = d.z;
+            } else {
+              kind = my >= n_cont;
+              slot = kind ? ld_list(A.list_shadow + (my - n_cont)) : (A.list_cont ? ld_list(A.list_cont + my) : my);
+              const float4 o4 = ld_path(A.ps.ro(slot));
+              const float4 d4 = ld_path(kind ? A.ps.sd(slot) : A.ps.rd(slot));
+              ox = o4.x; oy = o4.y; oz = o4.z;
+              dx = d4.x; dy = d4.y; dz = d4.z;
+            }
             const float ix = 1.0f / dx, iy = 1.0f / dy, iz = 1.0f / dz;  // `vec3 inverse = 1.0 / ray.dir`, tracer.fs:318
             ox2 = pack2(ox, ox); oy2 = pack2(oy, oy); oz2 = pack2(oz, oz);
             ix2 = pack2(ix, ix); iy2 = pack2(iy, iy); iz2 = pack2(iz, iz);
