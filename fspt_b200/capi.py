@@ -52,8 +52,9 @@ EXPORTS = [
     "fspt_render", "fspt_resolve", "fspt_read_accum", "fspt_write_accum", "fspt_set_accum_mode",
     "fspt_accum_device_ptr", "fspt_set_accum_samples", "fspt_debug_primary", "fspt_debug_trace",
     "fspt_debug_last_color", "fspt_debug_math", "fspt_get_stats", "fspt_synchronize", "fspt_bvh_build", "fspt_bvh_build2",
-    "fspt_env_bins", "fspt_pack_layer",
+    "fspt_env_bins", "fspt_pack_layer", "fspt_set_param",
 ]
+PARAM_ANYHIT, PARAM_MAX_REFRACTIONS, PARAM_SANITIZE_NAN = 1, 2, 3
 
 _lib = None
 
@@ -201,6 +202,9 @@ class Context:
         f.lens_features[:] = [float(x) for x in lens_features]
         f.env_theta = float(env_theta)
         return f
+
+    def set_param(self, key, value):
+        self._ck(self.lib.fspt_set_param(self.h, C.c_int32(key), C.c_int32(value)))
 
     def clear(self):
         self._ck(self.lib.fspt_clear(self.h))

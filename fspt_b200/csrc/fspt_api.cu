@@ -59,6 +59,7 @@ struct Ctx {
   int accum_mode = 0;
   int sanitize = 1;
   int max_refractions = 64;
+  int anyhit = 1;
 
   // wavefront state
   int wave_samples = 0;       // samples in flight per wave
@@ -174,6 +175,7 @@ int launch_trace(Ctx* c, const int* list_cont, bool classify, bool write_count, 
   TraceArgs A;
   if (cam) A.f = *cam; else memset(&A.f, 0, sizeof A.f);
   A.rb_cam = rb_cam; A.n_samples = n_samples;
+  A.anyhit = c->anyhit;
   A.nodes = c->sc.nodes; A.tris = c->sc.tris; A.root_ref = c->sc.root_ref; A.nodes_tex = c->nodes_tex; A.tris_tex = c->tris_tex;
   A.ps = c->ps;
   A.list_cont = list_cont; A.list_shadow = c->d_list[1];
@@ -228,6 +230,7 @@ int render_wave(Ctx* c, const FrameParams& fp, uint32_t first_tick, int S, const
   A.capped = c->d_stats + 3;
   A.n_samples = S;
   A.max_refractions = c->max_refractions;
+  A.anyhit = c->anyhit;
   const int hard_cap = FSPT_NUM_BOUNCES + 1 + (c->has_dielectric ? c->max_refractions + 2 : 0);
   for (int b = 0; b < hard_cap; ++b) {
     CK(cudaMemsetAsync(c->d_counts, 0, 2 * sizeof(int), c->stream));  // #cont = #shadow = 0
@@ -782,6 +785,19 @@ int fspt_debug_math(fspt_ctx* ctx, int32_t fn, const float* x, const float* y, f
   CK(cudaMemcpy(out, dout, (size_t)n * 4, cudaMemcpyDeviceToHost));
   cudaFree(dx); cudaFree(dy); cudaFree(dout);
   return FSPT_OK;
+}
+
+int fspt_set_param(fspt_ctx* ctx, int32_t key, int32_t value) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  if (!c) return FSPT_E_INVALID;
+  switch (key) {
+    case FSPT_PARAM_ANYHIT: c->anyhit = value ? 1 : 0; return FSPT_OK;
+    case FSPT_PARAM_MAX_REFRACTIONS:
+      if (value < 0 || value > 30000) return fail(c, FSPT_E_INVALID, "max_refractions out of range");
+      c->max_refractions = value; return FSPT_OK;
+    case FSPT_PARAM_SANITIZE_NAN: c->sanitize = value ? 1 : 0; return FSPT_OK;
+  }
+  return fail(c, FSPT_E_INVALID, "fspt_set_param: unknown key %d", key);
 }
 
 int fspt_get_stats(fspt_ctx* ctx, fspt_stats* out) {

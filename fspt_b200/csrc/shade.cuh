@@ -207,6 +207,7 @@ struct ShadeArgs {
   int n_samples;              // samples in flight in this wave (slot = pixel * n_samples + sample)
   int first;                  // 1: slots hold fresh primary rays (tracer.fs:440-445)
   int max_refractions;
+  int anyhit;
 };
 
 // Warp-aggregated append: one atomicAdd per warp per list (ballot + popc prefix); call with all 32 lanes
@@ -427,7 +428,10 @@ __device__ __forceinline__ bool shade_hit(const ShadeArgs& A, int slot, bool& sh
   v3 pend = mk3(0.0f, 0.0f, 0.0f);
   if (shadow) pend = mul(mul(mul(reflectance, envThroughput), env_sample(sc, envDir, envTheta)), weights.x);  // :503
   st_path(A.ps.ro(slot), make_float4(rayOrigin.x, rayOrigin.y, rayOrigin.z, FSPT_MAX_T));
-  st_path(A.ps.rd(slot), make_float4(rayDir.x, rayDir.y, rayDir.z, __int_as_float(-1)));
+  // last bounce: the loop ends after this continuation ray whatever it hits (:446 with ++i), only hit-or-miss
+  // matters (:509), so the traversal may stop at the first intersection (index word -2 = "boolean ray")
+  const bool last_bounce = A.anyhit && (i + 1 >= FSPT_NUM_BOUNCES);
+  st_path(A.ps.rd(slot), make_float4(rayDir.x, rayDir.y, rayDir.z, __int_as_float(last_bounce ? -2 : -1)));
   st_path(A.ps.sd(slot), make_float4(envDir.x, envDir.y, envDir.z, __int_as_float(shadow ? 1 : 0)));
   st_path(A.ps.thr(slot), make_float4(reflectance.x, reflectance.y, reflectance.z, weights.y));
   st_path(A.ps.bt(slot), make_float4(bsdfThroughput.x, bsdfThroughput.y, bsdfThroughput.z,

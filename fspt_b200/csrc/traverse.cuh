@@ -40,6 +40,7 @@ struct TraceArgs {
   FrameParams f;          // CAMERA mode: primary rays are generated in the fetch instead of being read
   const float* rb_cam;
   int n_samples;
+  int anyhit;             // 1: hit-or-miss rays (shadow rays, marked last-bounce rays) stop at their first intersection
 };
 
 #define TRACE_THREADS 128
@@ -133,6 +134,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(const TraceArgs A) {
   int ibest = -1;
   unsigned long long n_rays = 0, n_nodes = 0, n_leaves = 0;
   bool drained = false;
+  bool boolean_ray = false;  // only hit-or-miss is consumed (tracer.fs:502, :509 at the last bounce)
 
   for (;;) {
     const bool need = (cur == FSPT_SENTINEL);
@@ -196,6 +198,8 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(const TraceArgs A) {
               const float4 d4 = ld_path(kind ? A.ps.sd(slot) : A.ps.rd(slot));
               ox = o4.x; oy = o4.y; oz = o4.z;
               dx = d4.x; dy = d4.y; dz = d4.z;
+              // shadow rays always; continuation rays when k_shade marked the path's last bounce (index word = -2)
+              boolean_ray = A.anyhit && (kind == 1 || __float_as_int(d4.w) == -2);
             }
             const float ix = 1.0f / dx, iy = 1.0f / dy, iz = 1.0f / dz;  // `vec3 inverse = 1.0 / ray.dir`, tracer.fs:318
             ox2 = pack2(ox, ox); oy2 = pack2(oy, oy); oz2 = pack2(oz, oz);
@@ -271,6 +275,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(const TraceArgs A) {
             if (res < tbest) { ibest = first + k; tbest = res; }
           }
           cur = stack[--sp];
+          if (!CAMERA && boolean_ray && ibest != -1) cur = FSPT_SENTINEL;  // any hit settles it
         }
       }
     }

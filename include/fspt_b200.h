@@ -149,6 +149,18 @@ int fspt_debug_last_color(fspt_ctx* ctx, float* rgba32f_out);
  * 5 pow(x,y)); parity aid for the platform built-ins the shaders rely on (tracer.fs:181,412,417). */
 int fspt_debug_math(fspt_ctx* ctx, int32_t fn, const float* x, const float* y, float* out, int32_t n);
 
+/* Tuning / behaviour switches (none changes an image).  Unknown keys return FSPT_E_INVALID. */
+enum {
+  FSPT_PARAM_ANYHIT = 1,          /* 1 (default): rays whose outcome is only tested for hit-or-miss -- every shadow ray
+                                     (tracer.fs:501-502) and the continuation ray of a path's last bounce (:507-512 with
+                                     i == NUM_BOUNCES-1) -- stop at their first intersection.  Same image bit for bit, fewer
+                                     node visits than the reference's full traversal; 0 = full closest-hit traversal for
+                                     every ray (the visit counters then equal the reference's). */
+  FSPT_PARAM_MAX_REFRACTIONS = 2, /* safety cap of the unbounded refraction loop (tracer.fs:488), default 64 */
+  FSPT_PARAM_SANITIZE_NAN = 3     /* default 1; no effect in practice: clamp() already maps NaN to 0 */
+};
+int fspt_set_param(fspt_ctx* ctx, int32_t key, int32_t value);
+
 int fspt_get_stats(fspt_ctx* ctx, fspt_stats* out);
 int fspt_synchronize(fspt_ctx* ctx);
 

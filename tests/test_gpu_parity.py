@@ -153,6 +153,7 @@ def _full_frame_check(oracle_mod, sa, cam, W, H, n, seed):
         assert_bit_equal(idx, oi, "hit index")
         assert_bit_equal(t, ot, "hit t")
         assert_bit_equal(cnt, oc, "visit count")
+        ctx.set_param(capi.PARAM_ANYHIT, 0)  # full closest-hit traversal for every ray, like the reference
         ctx.clear()
         ctx.render(fr, 0, rc, rt)
         fb = ctx.read_accum()
@@ -166,6 +167,13 @@ def _full_frame_check(oracle_mod, sa, cam, W, H, n, seed):
         # the device-side V / L counters that feed bench.py's algorithmic bytes equal the oracle's
         assert (s["last_rays"], s["last_node_visits"], s["last_leaf_visits"]) == (rays, nodes, leaves)
         assert_bit_equal(ctx.resolve(denoise=True), oracle_mod.draw(ofb, denoise=True), "rgba8")
+        # default mode: hit-or-miss rays stop at their first intersection -- same image, same ray count, fewer visits
+        ctx.set_param(capi.PARAM_ANYHIT, 1)
+        ctx.clear()
+        ctx.render(fr, 0, rc, rt)
+        assert_bit_equal(ctx.read_accum()[..., :3], ofb[..., :3], "accumulator (any-hit)")
+        s = ctx.stats()
+        assert s["last_rays"] == rays and s["last_node_visits"] <= nodes and s["last_leaf_visits"] <= leaves
     finally:
         ctx.close()
 
