@@ -8,8 +8,11 @@
 #include <string.h>
 
 #include <algorithm>
+#include <array>
 #include <atomic>
+#include <map>
 #include <chrono>
+#include <functional>
 #include <mutex>
 #include <thread>
 #include <string>
@@ -39,7 +42,10 @@ struct Ctx {
   bool has_scene = false, has_dielectric = false;
   DeviceScene sc{};
   void *d_nodes = nullptr, *d_tris = nullptr, *d_shade = nullptr, *d_bins = nullptr, *d_layer_info = nullptr;
-  cudaArray_t atlas_arr = nullptr, env_arr = nullptr;
+  cudaArray_t atlas_arr = nullptr, env_arr = nullptr, mat_arr = nullptr;
+  int mat_R = 0, mat_L = 0;
+  void* d_mat_info = nullptr;
+  size_t cap_mat_info = 0;
   cudaTextureObject_t nodes_tex = 0, tris_tex = 0;
   int atlas_R = 0, atlas_L = 0, env_W = 0, env_H = 0;       // dims of the resident arrays (reused across uploads)
   size_t cap_nodes = 0, cap_tris = 0, cap_shade = 0, cap_bins = 0, cap_layer_info = 0;
@@ -105,9 +111,13 @@ void free_scene(Ctx* c) {
   if (c->nodes_tex) cudaDestroyTextureObject(c->nodes_tex);
   if (c->tris_tex) cudaDestroyTextureObject(c->tris_tex);
   c->nodes_tex = c->tris_tex = 0;
+  if (c->sc.mat_tex) cudaDestroyTextureObject(c->sc.mat_tex);
   if (c->atlas_arr) cudaFreeArray(c->atlas_arr);
   if (c->env_arr) cudaFreeArray(c->env_arr);
-  c->atlas_arr = c->env_arr = nullptr;
+  if (c->mat_arr) cudaFreeArray(c->mat_arr);
+  c->atlas_arr = c->env_arr = c->mat_arr = nullptr;
+  c->mat_R = c->mat_L = 0;
+  dfree(c->d_mat_info); c->cap_mat_info = 0;
   c->atlas_R = c->atlas_L = c->env_W = c->env_H = 0;
   dfree(c->d_nodes); dfree(c->d_tris); dfree(c->d_shade); dfree(c->d_bins); dfree(c->d_layer_info);
   c->cap_nodes = c->cap_tris = c->cap_shade = c->cap_bins = c->cap_layer_info = 0;
@@ -430,23 +440,44 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
   // ---- shading records ------------------------------------------------------------------------------------
   std::vector<float> shade((size_t)T * 48, 0.0f);
   bool dielectric = false;
-  for (int t = 0; t < T; ++t) {
-    float* o = shade.data() + (size_t)t * 48;
-    memcpy(o, s->materials + (size_t)t * 12, 48);
-    memcpy(o + 12, s->uvs + (size_t)t * 6, 24);
-    memcpy(o + 20, s->normals + (size_t)t * 27, 108);
-    if (o[10] >= 0.0f) dielectric = true;
+  // materials = distinct quadruples of atlas layers (diffuse, emission, metallic-roughness, normal), tracer.fs:453-456
+  std::vector<std::array<int, 4>> mats;
+  {
+    std::map<std::array<int, 4>, int> ids;
+    std::array<int, 4> last = {-1, -1, -1, -1};
+    int last_id = -1;
+    auto layer_of = [&](float lf) {  // texture(texArray, vec3(uv, layer)): layer = clamp(floor(l + 0.5), 0, d - 1)
+      float f = floorf(lf + 0.5f);
+      if (!(f >= -1.0e9f && f <= 1.0e9f)) f = 0.0f;
+      long long q = (long long)f;
+      return (int)(q < 0 ? 0 : (q >= s->atlas_layers ? s->atlas_layers - 1 : q));
+    };
+    for (int t = 0; t < T; ++t) {
+      float* o = shade.data() + (size_t)t * 48;
+      memcpy(o, s->materials + (size_t)t * 12, 48);
+      memcpy(o + 12, s->uvs + (size_t)t * 6, 24);
+      memcpy(o + 20, s->normals + (size_t)t * 27, 108);
+      if (o[10] >= 0.0f) dielectric = true;
+      const std::array<int, 4> key = {layer_of(o[0]), layer_of(o[1]), layer_of(o[3]), layer_of(o[2])};
+      if (key != last) {
+        auto it = ids.find(key);
+        if (it == ids.end()) { it = ids.emplace(key, (int)mats.size()).first; mats.push_back(key); }
+        last = key; last_id = it->second;
+      }
+      memcpy(o + 18, &last_id, 4);  // material id in the record's padding
+    }
   }
   std::vector<float> bins((size_t)s->env_bins * 4);
   for (size_t i = 0; i < bins.size(); ++i) bins[i] = (float)s->radiance_bins[i];  // vec4(radianceBins[idx]), tracer.fs:424
 
   lap("tri + shade records");
-  // constant-colour layers (one host thread per layer; exact: every texel compared)
+  // ---- atlas (main.js:548-560).  Constant-colour layers are detected (exact: every texel compared), then the atlas
+  // is re-interleaved per material into 16-byte texels (device_common.cuh "MatTexel") in pinned memory by a few host
+  // threads and DMA'd layer by layer as the layers land; a scene with so many layer combinations that this would not
+  // fit falls back to the plain RGBA8 layered array.
   const int R = s->atlas_res, L = s->atlas_layers;
-  const size_t layer_bytes = (size_t)R * R * 4;
+  const size_t layer_texels = (size_t)R * R, layer_bytes = layer_texels * 4;
   std::vector<uint32_t> layer_info((size_t)L * 2);
-  // ---- atlas: 2D layered array, RGBA8 (main.js:548-560).  Layers are staged into pinned memory by a few host
-  // threads (a pageable cudaMemcpy tops out near 9 GB/s on this box) and DMA'd layer by layer as they land.
   cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
   cudaResourceDesc rd = {};
   rd.resType = cudaResourceTypeArray;
@@ -455,65 +486,130 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
   td.filterMode = cudaFilterModePoint;
   td.readMode = cudaReadModeElementType;
   td.normalizedCoords = 0;
-  if (!c->atlas_arr || c->atlas_R != R || c->atlas_L != L) {
-    if (c->sc.atlas) cudaDestroyTextureObject(c->sc.atlas);
-    c->sc.atlas = 0;
-    if (c->atlas_arr) cudaFreeArray(c->atlas_arr);
-    c->atlas_arr = nullptr;
-    CK(cudaMalloc3DArray(&c->atlas_arr, &fmt, make_cudaExtent(R, R, L), cudaArrayLayered));
-    rd.res.array.array = c->atlas_arr;
-    CK(cudaCreateTextureObject(&c->sc.atlas, &rd, &td, nullptr));
-    c->atlas_R = R; c->atlas_L = L;
-  }
-  if (c->stage_bytes < layer_bytes * L) {
-    if (c->h_stage) cudaFreeHost(c->h_stage);
-    c->h_stage = nullptr; c->stage_bytes = 0;
-    CK(cudaMallocHost(&c->h_stage, layer_bytes * L));
-    c->stage_bytes = layer_bytes * L;
-  }
-  {
-    std::atomic<int> next_layer(0);
-    std::atomic<int> cuda_err(0);
-    std::mutex mu;
-    const int n_workers = std::max(1, std::min(L, 6));
+  auto parallel = [&](int n_items, const std::function<void(int)>& fn) {
+    std::atomic<int> next_item(0);
+    const int n_workers = std::max(1, std::min(n_items, 8));
     std::vector<std::thread> workers;
     for (int w = 0; w < n_workers; ++w)
       workers.emplace_back([&]() {
         cudaSetDevice(c->device);
-        for (;;) {
-          const int l = next_layer.fetch_add(1);
-          if (l >= L) break;
-          const uint8_t* src = s->atlas + (size_t)l * layer_bytes;
-          uint8_t* dst = c->h_stage + (size_t)l * layer_bytes;
-          memcpy(dst, src, layer_bytes);
-          const uint32_t* px = reinterpret_cast<const uint32_t*>(dst);
-          const uint32_t first = px[0];
-          bool same = true;
-          for (size_t i = 1, n = (size_t)R * R; i < n && same; ++i) same = (px[i] == first);
-          layer_info[2 * l] = same ? 1u : 0u;
-          layer_info[2 * l + 1] = first;
-          cudaMemcpy3DParms cp = {};
-          cp.srcPtr = make_cudaPitchedPtr(dst, (size_t)R * 4, R, R);
-          cp.dstArray = c->atlas_arr;
-          cp.dstPos = make_cudaPos(0, 0, l);
-          cp.extent = make_cudaExtent(R, R, 1);
-          cp.kind = cudaMemcpyHostToDevice;
-          std::lock_guard<std::mutex> g(mu);
-          cudaError_t e = cudaMemcpy3DAsync(&cp, c->stream);
-          if (e != cudaSuccess) cuda_err.store((int)e);
-        }
+        for (;;) { const int i = next_item.fetch_add(1); if (i >= n_items) break; fn(i); }
       });
     for (auto& t : workers) t.join();
-    if (cuda_err.load()) return fail(c, FSPT_E_CUDA, "atlas upload failed: %s", cudaGetErrorString((cudaError_t)cuda_err.load()));
+  };
+  parallel(L, [&](int l) {
+    const uint32_t* px = reinterpret_cast<const uint32_t*>(s->atlas) + (size_t)l * layer_texels;
+    uint32_t first;
+    memcpy(&first, px, 4);
+    bool same = true;
+    for (size_t i = 1; i < layer_texels && same; ++i) same = (px[i] == first);
+    layer_info[2 * l] = same ? 1u : 0u;
+    layer_info[2 * l + 1] = first;
+  });
+  lap("constant-layer scan");
+  std::vector<int32_t> mat_info(mats.size() * 8, 0);
+  int n_tex_mats = 0;
+  for (size_t m = 0; m < mats.size(); ++m) {
+    bool all_const = true;
+    for (int k = 0; k < 4; ++k) all_const = all_const && layer_info[2 * mats[m][k]];
+    mat_info[8 * m] = all_const ? -1 : n_tex_mats++;
+    for (int k = 0; k < 4; ++k) mat_info[8 * m + 1 + k] = (int32_t)layer_info[2 * mats[m][k] + 1];
   }
+  const bool use_mat_tex = (size_t)n_tex_mats * layer_texels * 16 <= ((size_t)48 << 30) && !getenv("FSPT_PLAIN_ATLAS");
+  std::atomic<int> cuda_err(0);
+  std::mutex mu;
+  if (use_mat_tex) {
+    if (c->sc.atlas) { cudaDestroyTextureObject(c->sc.atlas); c->sc.atlas = 0; }
+    if (c->atlas_arr) { cudaFreeArray(c->atlas_arr); c->atlas_arr = nullptr; c->atlas_R = c->atlas_L = 0; }
+    const int ML = std::max(1, n_tex_mats);
+    if (!c->mat_arr || c->mat_R != R || c->mat_L != ML) {
+      if (c->sc.mat_tex) cudaDestroyTextureObject(c->sc.mat_tex);
+      c->sc.mat_tex = 0;
+      if (c->mat_arr) cudaFreeArray(c->mat_arr);
+      c->mat_arr = nullptr;
+      cudaChannelFormatDesc fmt4 = cudaCreateChannelDesc<uint4>();
+      CK(cudaMalloc3DArray(&c->mat_arr, &fmt4, make_cudaExtent(R, R, ML), cudaArrayLayered));
+      rd.res.array.array = c->mat_arr;
+      CK(cudaCreateTextureObject(&c->sc.mat_tex, &rd, &td, nullptr));
+      c->mat_R = R; c->mat_L = ML;
+    }
+    const size_t need = layer_texels * 16 * (size_t)ML;
+    if (c->stage_bytes < need) {
+      if (c->h_stage) cudaFreeHost(c->h_stage);
+      c->h_stage = nullptr; c->stage_bytes = 0;
+      CK(cudaMallocHost(&c->h_stage, need));
+      c->stage_bytes = need;
+    }
+    // work item = (textured material, band of rows): interleave the four source layers, DMA the band
+    const int bands = std::max(1, std::min(R, 8));
+    std::vector<int> tex_mat_ids;
+    for (size_t m = 0; m < mats.size(); ++m) if (mat_info[8 * m] >= 0) tex_mat_ids.push_back((int)m);
+    parallel((int)tex_mat_ids.size() * bands, [&](int item) {
+      const int m = tex_mat_ids[item / bands], band = item % bands;
+      const int tl = mat_info[8 * m];
+      const int y0 = (int)((long long)R * band / bands), y1 = (int)((long long)R * (band + 1) / bands);
+      const uint32_t* src[4];
+      for (int k = 0; k < 4; ++k) src[k] = reinterpret_cast<const uint32_t*>(s->atlas) + (size_t)mats[m][k] * layer_texels;
+      uint32_t* dst = reinterpret_cast<uint32_t*>(c->h_stage) + ((size_t)tl * layer_texels + (size_t)y0 * R) * 4;
+      const size_t i0 = (size_t)y0 * R, n = (size_t)(y1 - y0) * R;
+      for (size_t i = 0; i < n; ++i) {
+        dst[4 * i + 0] = src[0][i0 + i]; dst[4 * i + 1] = src[1][i0 + i];
+        dst[4 * i + 2] = src[2][i0 + i]; dst[4 * i + 3] = src[3][i0 + i];
+      }
+      cudaMemcpy3DParms cp = {};
+      cp.srcPtr = make_cudaPitchedPtr(dst, (size_t)R * 16, R, y1 - y0);
+      cp.dstArray = c->mat_arr;
+      cp.dstPos = make_cudaPos(0, y0, tl);
+      cp.extent = make_cudaExtent(R, y1 - y0, 1);
+      cp.kind = cudaMemcpyHostToDevice;
+      std::lock_guard<std::mutex> g(mu);
+      cudaError_t e = cudaMemcpy3DAsync(&cp, c->stream);
+      if (e != cudaSuccess) cuda_err.store((int)e);
+    });
+  } else {
+    if (c->sc.mat_tex) { cudaDestroyTextureObject(c->sc.mat_tex); c->sc.mat_tex = 0; }
+    if (c->mat_arr) { cudaFreeArray(c->mat_arr); c->mat_arr = nullptr; c->mat_R = c->mat_L = 0; }
+    if (!c->atlas_arr || c->atlas_R != R || c->atlas_L != L) {
+      if (c->sc.atlas) cudaDestroyTextureObject(c->sc.atlas);
+      c->sc.atlas = 0;
+      if (c->atlas_arr) cudaFreeArray(c->atlas_arr);
+      c->atlas_arr = nullptr;
+      CK(cudaMalloc3DArray(&c->atlas_arr, &fmt, make_cudaExtent(R, R, L), cudaArrayLayered));
+      rd.res.array.array = c->atlas_arr;
+      CK(cudaCreateTextureObject(&c->sc.atlas, &rd, &td, nullptr));
+      c->atlas_R = R; c->atlas_L = L;
+    }
+    if (c->stage_bytes < layer_bytes * L) {
+      if (c->h_stage) cudaFreeHost(c->h_stage);
+      c->h_stage = nullptr; c->stage_bytes = 0;
+      CK(cudaMallocHost(&c->h_stage, layer_bytes * L));
+      c->stage_bytes = layer_bytes * L;
+    }
+    parallel(L, [&](int l) {
+      uint8_t* dst = c->h_stage + (size_t)l * layer_bytes;
+      memcpy(dst, s->atlas + (size_t)l * layer_bytes, layer_bytes);
+      cudaMemcpy3DParms cp = {};
+      cp.srcPtr = make_cudaPitchedPtr(dst, (size_t)R * 4, R, R);
+      cp.dstArray = c->atlas_arr;
+      cp.dstPos = make_cudaPos(0, 0, l);
+      cp.extent = make_cudaExtent(R, R, 1);
+      cp.kind = cudaMemcpyHostToDevice;
+      std::lock_guard<std::mutex> g(mu);
+      cudaError_t e = cudaMemcpy3DAsync(&cp, c->stream);
+      if (e != cudaSuccess) cuda_err.store((int)e);
+    });
+  }
+  if (cuda_err.load()) return fail(c, FSPT_E_CUDA, "atlas upload failed: %s", cudaGetErrorString((cudaError_t)cuda_err.load()));
   lap("atlas stage + scan + enqueue");
   int rc_;
   if ((rc_ = ensure(c, c->d_layer_info, c->cap_layer_info, layer_info.size() * 4))) return rc_;
+  if ((rc_ = ensure(c, c->d_mat_info, c->cap_mat_info, std::max<size_t>(32, mat_info.size() * 4)))) return rc_;
   if ((rc_ = ensure(c, c->d_nodes, c->cap_nodes, nodes.size() * 4))) return rc_;
   if ((rc_ = ensure(c, c->d_tris, c->cap_tris, tris.size() * 4))) return rc_;
   if ((rc_ = ensure(c, c->d_shade, c->cap_shade, shade.size() * 4))) return rc_;
   if ((rc_ = ensure(c, c->d_bins, c->cap_bins, bins.size() * 4))) return rc_;
   CK(cudaMemcpyAsync(c->d_layer_info, layer_info.data(), layer_info.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_mat_info, mat_info.data(), mat_info.size() * 4, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->d_nodes, nodes.data(), nodes.size() * 4, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->d_tris, tris.data(), tris.size() * 4, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->d_shade, shade.data(), shade.size() * 4, cudaMemcpyHostToDevice, c->stream));
@@ -556,6 +652,7 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
   c->sc.shade = reinterpret_cast<const float4*>(c->d_shade);
   c->sc.bins = reinterpret_cast<const float4*>(c->d_bins);
   c->sc.layer_info = reinterpret_cast<const uint2*>(c->d_layer_info);
+  c->sc.mat_info = reinterpret_cast<const int4*>(c->d_mat_info);
   c->sc.root_ref = ref[0];
   c->sc.n_tris = T; c->sc.n_interior = (int)NI;
   c->sc.atlas_res = s->atlas_res; c->sc.atlas_layers = s->atlas_layers; c->sc.env_w = s->env_width; c->sc.env_h = s->env_height;

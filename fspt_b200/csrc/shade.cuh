@@ -104,6 +104,33 @@ __device__ __forceinline__ void texture_atlas4(const DeviceScene& sc, float u, f
 #pragma unroll
   for (int m = 0; m < 4; ++m) out[m] = bilerp(texel8(t[m][0]), texel8(t[m][1]), texel8(t[m][2]), texel8(t[m][3]), a, b);
 }
+// Same four lookups from the material-interleaved atlas (device_common.cuh "MatTexel"): one 16-byte fetch per tap
+// carries the texel of all four maps.  All-constant materials (four colour layers) need no fetch at all.
+__device__ __forceinline__ void texture_material(const DeviceScene& sc, float u, float v, int mat, float4 (&out)[4]) {
+  const int R = sc.atlas_res;
+  const float x = u * (float)R - 0.5f, y = v * (float)R - 0.5f;
+  const float fx = floorf(x), fy = floorf(y);
+  const float a = x - fx, b = y - fy;
+  const int4 info = __ldg(sc.mat_info + 2 * mat);
+  uint4 t00, t10, t01, t11;
+  if (info.x >= 0) {
+    const int ixx = (int)coord_to_int(fx), iyy = (int)coord_to_int(fy);
+    const float i0 = (float)wrap_repeat(ixx, R) + 0.5f, i1 = (float)wrap_repeat(ixx + 1, R) + 0.5f;
+    const float j0 = (float)wrap_repeat(iyy, R) + 0.5f, j1 = (float)wrap_repeat(iyy + 1, R) + 0.5f;
+    t00 = tex2DLayered<uint4>(sc.mat_tex, i0, j0, info.x);
+    t10 = tex2DLayered<uint4>(sc.mat_tex, i1, j0, info.x);
+    t01 = tex2DLayered<uint4>(sc.mat_tex, i0, j1, info.x);
+    t11 = tex2DLayered<uint4>(sc.mat_tex, i1, j1, info.x);
+  } else {
+    const int4 info2 = __ldg(sc.mat_info + 2 * mat + 1);
+    t00 = make_uint4((unsigned)info.y, (unsigned)info.z, (unsigned)info.w, (unsigned)info2.x);
+    t10 = t01 = t11 = t00;
+  }
+  out[0] = bilerp(texel8(as_uchar4(t00.x)), texel8(as_uchar4(t10.x)), texel8(as_uchar4(t01.x)), texel8(as_uchar4(t11.x)), a, b);
+  out[1] = bilerp(texel8(as_uchar4(t00.y)), texel8(as_uchar4(t10.y)), texel8(as_uchar4(t01.y)), texel8(as_uchar4(t11.y)), a, b);
+  out[2] = bilerp(texel8(as_uchar4(t00.z)), texel8(as_uchar4(t10.z)), texel8(as_uchar4(t01.z)), texel8(as_uchar4(t11.z)), a, b);
+  out[3] = bilerp(texel8(as_uchar4(t00.w)), texel8(as_uchar4(t10.w)), texel8(as_uchar4(t01.w)), texel8(as_uchar4(t11.w)), a, b);
+}
 // texture(envTex, c): S REPEAT, T CLAMP_TO_EDGE, LINEAR on the ENCODED RGBE texel (main.js:170-180)
 __device__ __forceinline__ float4 texture_env(cudaTextureObject_t env, int W, int H, float u, float v) {
   const float x = u * (float)W - 0.5f, y = v * (float)H - 0.5f;
@@ -308,7 +335,8 @@ __device__ __forceinline__ bool shade_hit(const ShadeArgs& A, int slot, bool& sh
   const float tcy = bu * u0.y + bv * u0.w + bw_ * u1.y;
   const float layers[4] = {mapDiffuse, mapSpecular, mapRoughness, mapNormal};
   float4 tex[4];
-  texture_atlas4(sc, tcx, tcy, layers, tex);  // :453-456
+  if (sc.mat_tex) texture_material(sc, tcx, tcy, __float_as_int(u1.z), tex);  // :453-456
+  else texture_atlas4(sc, tcx, tcy, layers, tex);
   const float4 tD = tex[0], tE = tex[1], tMR = tex[2], tN = tex[3];
   const v3 texDiffuse = mk3(tD.x, tD.y, tD.z), texEmmissive = mk3(tE.x, tE.y, tE.z);
   v2 texMR;
