@@ -267,14 +267,14 @@ __device__ __forceinline__ void shade_miss(const ShadeArgs& A, int slot) {
   if (A.first) {
     color = add(mk3(0.0f, 0.0f, 0.0f), env);  // :443
   } else {
-    const float4 c4 = ld_path(A.ps.col(slot)), t4 = ld_path(A.ps.thr(slot)), b4 = ld_path(A.ps.bt(slot)), s4 = ld_path(A.ps.sd(slot));
+    const float4 c4 = ld_path(A.ps.col(slot)), t4 = ld_path(A.ps.thr(slot)), s4 = ld_path(A.ps.sd(slot));
     color = mk3(c4.x, c4.y, c4.z);
     if (__float_as_int(s4.w) == 2) {  // shadow.index == -1, :502-504
       const float4 p4 = ld_path(A.ps.pend(slot));
       color = add(color, mk3(p4.x, p4.y, p4.z));
     }
-    const v3 reflectance = mul(mk3(t4.x, t4.y, t4.z), mk3(b4.x, b4.y, b4.z));  // :508
-    color = add(color, mul(mul(reflectance, env), t4.w));                      // :510
+    const v3 reflectance = mk3(t4.x, t4.y, t4.z);                 // accumulatedReflectance *= bsdfThroughput (:508) was
+    color = add(color, mul(mul(reflectance, env), t4.w));         // folded into the stored value; :510
   }
   write_sample(A, slot, color);
 }
@@ -297,17 +297,14 @@ __device__ __forceinline__ bool shade_hit(const ShadeArgs& A, int slot, bool& sh
     color = mk3(0.0f, 0.0f, 0.0f);
     reflectance = mk3(1.0f, 1.0f, 1.0f);
   } else {
-    const float4 c4 = ld_path(A.ps.col(slot)), t4 = ld_path(A.ps.thr(slot)), b4 = ld_path(A.ps.bt(slot)), s4 = ld_path(A.ps.sd(slot));
+    const float4 c4 = ld_path(A.ps.col(slot)), t4 = ld_path(A.ps.thr(slot)), s4 = ld_path(A.ps.sd(slot));
+    const float4 p4 = ld_path(A.ps.pend(slot));
     color = mk3(c4.x, c4.y, c4.z);
-    reflectance = mk3(t4.x, t4.y, t4.z);
-    const int packed = __float_as_int(b4.w);
+    reflectance = mk3(t4.x, t4.y, t4.z);  // already multiplied by the previous bsdfThroughput (:508), see the store below
+    const int packed = __float_as_int(p4.w);
     i = (packed & 0xffff) - 0x100;  // stored biased so that i = -1 survives
     refractions = packed >> 16;
-    if (__float_as_int(s4.w) == 2) {  // shadow.index == -1, :502-504
-      const float4 p4 = ld_path(A.ps.pend(slot));
-      color = add(color, mk3(p4.x, p4.y, p4.z));
-    }
-    reflectance = mul(reflectance, mk3(b4.x, b4.y, b4.z));  // :508
+    if (__float_as_int(s4.w) == 2) color = add(color, mk3(p4.x, p4.y, p4.z));  // shadow.index == -1, :502-504
     ++i;                                                    // for (...; ++i), :446
     if (!(i < FSPT_NUM_BOUNCES)) {
       write_sample(A, slot, color);
@@ -461,10 +458,11 @@ __device__ __forceinline__ bool shade_hit(const ShadeArgs& A, int slot, bool& sh
   const bool last_bounce = A.anyhit && (i + 1 >= FSPT_NUM_BOUNCES);
   st_path(A.ps.rd(slot), make_float4(rayDir.x, rayDir.y, rayDir.z, __int_as_float(last_bounce ? -2 : -1)));
   st_path(A.ps.sd(slot), make_float4(envDir.x, envDir.y, envDir.z, __int_as_float(shadow ? 1 : 0)));
-  st_path(A.ps.thr(slot), make_float4(reflectance.x, reflectance.y, reflectance.z, weights.y));
-  st_path(A.ps.bt(slot), make_float4(bsdfThroughput.x, bsdfThroughput.y, bsdfThroughput.z,
-                                     __int_as_float(((i + 0x100) & 0xffff) | (refractions << 16))));
-  st_path(A.ps.pend(slot), make_float4(pend.x, pend.y, pend.z, 0.0f));
+  // accumulatedReflectance *= bsdfThroughput (:508) is a pure product of two values known here: storing it now gives
+  // the same f32 bits as multiplying in the next pass and keeps the record at six words = three 32-byte sectors
+  const v3 next_reflectance = mul(reflectance, bsdfThroughput);
+  st_path(A.ps.thr(slot), make_float4(next_reflectance.x, next_reflectance.y, next_reflectance.z, weights.y));
+  st_path(A.ps.pend(slot), make_float4(pend.x, pend.y, pend.z, __int_as_float(((i + 0x100) & 0xffff) | (refractions << 16))));
   st_path(A.ps.col(slot), make_float4(color.x, color.y, color.z, 0.0f));
   return true;
 }
