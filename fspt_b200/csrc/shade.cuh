@@ -229,7 +229,7 @@ struct ShadeArgs {
   int* list_cont_out;         // continuation rays for the next traversal
   int* list_shadow_out;
   int* counts_out;            // [0] continuation, [1] shadow
-  float4* sample_color;       // [sample-in-wave][pixel] final un-clamped path colour
+  float4* sample_color;       // [pixel][sample-in-wave] final un-clamped path colour
   unsigned long long* capped; // paths stopped by the refraction cap
   int n_samples;              // samples in flight in this wave (slot = pixel * n_samples + sample)
   int first;                  // 1: slots hold fresh primary rays (tracer.fs:440-445)
@@ -253,8 +253,8 @@ __device__ __forceinline__ void write_sample(const ShadeArgs& A, int slot, v3 co
   const int j = slot / A.n_samples, s = slot - j * A.n_samples;
   int x, y;
   path_to_pixel(A.f, j, x, y);
-  A.sample_color[(size_t)s * ((size_t)A.f.width * A.f.height) + (size_t)y * A.f.width + x] =
-      make_float4(color.x, color.y, color.z, 1.0f);
+  // [pixel][sample]: the samples of a pixel finish in adjacent lanes and land in adjacent 16-byte entries
+  A.sample_color[((size_t)y * A.f.width + x) * A.n_samples + s] = make_float4(color.x, color.y, color.z, 1.0f);
 }
 
 // The tail of the previous loop iteration for a path whose ray MISSED: tracer.fs:442-443 (primary) or
@@ -503,7 +503,7 @@ __global__ void __launch_bounds__(256) k_accumulate(const float4* __restrict__ s
   float4 acc = fb[p];
   v3 c = mk3(0.0f, 0.0f, 0.0f);
   for (int s = 0; s < n_samples; ++s) {
-    const float4 c4 = sample_color[(size_t)s * n_pixels + p];
+    const float4 c4 = sample_color[(size_t)p * n_samples + s];
     c = mk3(c4.x, c4.y, c4.z);
     if (sanitize) {  // deviation from the reference, which lets NaN stick
       if (c.x != c.x) c.x = 0.0f;
