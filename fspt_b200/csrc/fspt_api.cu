@@ -71,9 +71,10 @@ struct Ctx {
   int wave_samples = 0;       // samples in flight per wave
   size_t wave_paths = 0;
   PathState ps{};
-  int* d_list[4] = {nullptr, nullptr, nullptr, nullptr};  // continuation, shadow (trace inputs); hit, miss (trace outputs)
-  int* d_counts = nullptr;    // [0] #cont [1] #shadow [2] #hit [3] #miss [4] fetch cursor, [5..7] pad
+  int* d_list[3] = {nullptr, nullptr, nullptr};  // continuation lists (ping-pong) and the shadow list
+  int* d_counts = nullptr;    // set k at [2k, 2k+1] = (#continuation, #shadow), [4] fetch cursor, [5..7] pad
   int* d_count_out = nullptr; // per-slot visit count (debug)
+  unsigned char* d_hit_flag = nullptr;  // per list position (ordered mode)
   unsigned long long* d_stats = nullptr;  // rays, nodes, leaves, capped
   float* d_rb = nullptr;      // rand bases of one render call: [0,cap) camera, [cap,2cap) tracer
   float* h_rb = nullptr;      // pinned staging
@@ -148,9 +149,10 @@ int alloc_wave(Ctx* c) {
   c->wave_paths = (size_t)S * c->n_pixels;
   const size_t W = c->wave_paths;
   CK(cudaMalloc(&c->ps.rec, W * 16 * FSPT_PATH_WORDS));
-  for (int i = 0; i < 4; ++i) CK(cudaMalloc(&c->d_list[i], W * sizeof(int)));
+  for (int i = 0; i < 3; ++i) CK(cudaMalloc(&c->d_list[i], W * sizeof(int)));
   CK(cudaMalloc(&c->d_counts, 8 * sizeof(int)));
   CK(cudaMalloc(&c->d_count_out, W * sizeof(int)));
+  CK(cudaMalloc(&c->d_hit_flag, W));
   CK(cudaMalloc(&c->d_stats, 8 * sizeof(unsigned long long)));  // [0..3] live, [4..7] snapshot at render start
   CK(cudaMemset(c->d_stats, 0, 8 * sizeof(unsigned long long)));
   CK(cudaMalloc(&c->d_sample_color, W * 16));
@@ -178,23 +180,22 @@ __global__ void k_set_counts(int* counts, int n_cont, int n_shadow) {
   counts[0] = n_cont; counts[1] = n_shadow; counts[2] = 0; counts[3] = 0; counts[4] = 0;
 }
 
-// Traverses d_counts[0] continuation rays (list_cont, NULL = identity) + d_counts[1] shadow rays and sorts the
-// continuation results into the hit / miss lists (d_counts[2], d_counts[3]).
-int launch_trace(Ctx* c, const int* list_cont, bool classify, bool write_count, const FrameParams* cam = nullptr,
-                 const float* rb_cam = nullptr, int n_samples = 1) {
+// Traverses counts[0] continuation rays (list_cont, NULL = identity) + counts[1] shadow rays; results go into the path
+// records, plus one hit/miss byte per continuation-list position when hit_flags is set (read by k_shade).
+int launch_trace(Ctx* c, const int* list_cont, bool hit_flags, bool write_count, const FrameParams* cam = nullptr,
+                 const float* rb_cam = nullptr, int n_samples = 1, const int* list_shadow = nullptr, const int* counts = nullptr) {
   TraceArgs A;
   if (cam) A.f = *cam; else memset(&A.f, 0, sizeof A.f);
   A.rb_cam = rb_cam; A.n_samples = n_samples;
   A.anyhit = c->anyhit;
   A.nodes = c->sc.nodes; A.tris = c->sc.tris; A.root_ref = c->sc.root_ref; A.nodes_tex = c->nodes_tex; A.tris_tex = c->tris_tex;
   A.ps = c->ps;
-  A.list_cont = list_cont; A.list_shadow = c->d_list[1];
-  A.counts = c->d_counts;
-  A.list_hit = c->d_list[2]; A.list_miss = c->d_list[3];
-  A.counts_out = classify ? c->d_counts + 2 : nullptr;
+  A.list_cont = list_cont; A.list_shadow = list_shadow ? list_shadow : c->d_list[2];
+  A.counts = counts ? counts : c->d_counts;
   A.next = c->d_counts + 4;
   A.stats = c->d_stats;
   A.count_out = write_count ? c->d_count_out : nullptr;
+  A.hit_flag = hit_flags ? c->d_hit_flag : nullptr;
   record_trace_begin(c);
   if (cam) k_trace<false, true><<<c->trace_blocks_cam, TRACE_THREADS, 0, c->stream>>>(A);
   else if (write_count) k_trace<true, false><<<c->trace_blocks_cnt, TRACE_THREADS, 0, c->stream>>>(A);
@@ -221,6 +222,8 @@ FrameParams make_frame(const Ctx* c, const fspt_frame_params* f) {
   return p;
 }
 
+// One wave.  Continuation lists ping-pong between d_list[0] / d_list[1], shadow
+// list in d_list[2]; counts: set k at d_counts[2k .. 2k+1] = (#continuation, #shadow), fetch cursor at d_counts[4].
 int render_wave(Ctx* c, const FrameParams& fp, uint32_t first_tick, int S, const float* rb_cam, const float* rb_trace) {
   const int P = c->n_pixels;
   const int n_paths = S * P;
@@ -228,37 +231,41 @@ int render_wave(Ctx* c, const FrameParams& fp, uint32_t first_tick, int S, const
   if (rc) return rc;
   rc = launch_trace(c, nullptr, true, false, &fp, rb_cam, S);  // camera.fs + primary rays (tracer.fs:440), fused
   if (rc) return rc;
-
   ShadeArgs A;
   A.sc = c->sc; A.ps = c->ps; A.f = fp;
   A.rb_trace = rb_trace;
-  A.list_hit = c->d_list[2]; A.list_miss = c->d_list[3];
-  A.counts_in = c->d_counts + 2;
-  A.list_cont_out = c->d_list[0]; A.list_shadow_out = c->d_list[1];
-  A.counts_out = c->d_counts;
+  A.hit_flag = c->d_hit_flag;
+  A.list_shadow_out = c->d_list[2];
   A.sample_color = c->d_sample_color;
   A.capped = c->d_stats + 3;
   A.n_samples = S;
   A.max_refractions = c->max_refractions;
   A.anyhit = c->anyhit;
   const int hard_cap = FSPT_NUM_BOUNCES + 1 + (c->has_dielectric ? c->max_refractions + 2 : 0);
+  int cur = 0;
   for (int b = 0; b < hard_cap; ++b) {
-    CK(cudaMemsetAsync(c->d_counts, 0, 2 * sizeof(int), c->stream));  // #cont = #shadow = 0
+    const int nxt = cur ^ 1;
+    CK(cudaMemsetAsync(c->d_counts + 2 * nxt, 0, 2 * sizeof(int), c->stream));
     A.first = (b == 0);
+    A.list_in = (b == 0) ? nullptr : c->d_list[cur];  // the list the last traversal consumed
+    A.counts_in = c->d_counts + 2 * cur;
+    A.list_cont_out = c->d_list[nxt];
+    A.counts_out = c->d_counts + 2 * nxt;
     record_trace_begin(c, 1);
     k_shade<<<c->shade_blocks, SHADE_THREADS, 1024, c->stream>>>(A);
     record_trace_end(c);
     c->stats.kernel_launches++;
     CK(cudaGetLastError());
+    cur = nxt;
     if (b >= FSPT_NUM_BOUNCES) {
-      if (!c->has_dielectric) break;  // every surviving path had i == NUM_BOUNCES: nothing was appended
+      if (!c->has_dielectric) break;
       int h[2];
-      CK(cudaMemcpyAsync(h, c->d_counts, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaMemcpyAsync(h, c->d_counts + 2 * cur, sizeof h, cudaMemcpyDeviceToHost, c->stream));
       CK(cudaStreamSynchronize(c->stream));
       if (h[0] == 0) break;
     }
-    CK(cudaMemsetAsync(c->d_counts + 2, 0, 3 * sizeof(int), c->stream));  // #hit = #miss = cursor = 0
-    rc = launch_trace(c, c->d_list[0], true, false);  // tracer.fs:501,507
+    CK(cudaMemsetAsync(c->d_counts + 4, 0, sizeof(int), c->stream));  // fetch cursor
+    rc = launch_trace(c, c->d_list[cur], true, false, nullptr, nullptr, 1, c->d_list[2], c->d_counts + 2 * cur);
     if (rc) return rc;
   }
   k_accumulate<<<(P + 255) / 256, 256, 0, c->stream>>>(c->d_sample_color, c->d_fb, c->d_last_color, P, S, first_tick,
@@ -346,8 +353,8 @@ void fspt_destroy(fspt_ctx* ctx) {
   free_scene(c);
   dfree(c->d_fb); dfree(c->d_last_color); dfree(c->d_sample_color); dfree(c->d_cam_pos); dfree(c->d_cam_dir); dfree(c->d_rgba8);
   dfree(c->ps.rec);
-  for (int i = 0; i < 4; ++i) dfree(c->d_list[i]);
-  dfree(c->d_counts); dfree(c->d_count_out); dfree(c->d_stats); dfree(c->d_rb);
+  for (int i = 0; i < 3; ++i) dfree(c->d_list[i]);
+  dfree(c->d_counts); dfree(c->d_count_out); dfree(c->d_hit_flag); dfree(c->d_stats); dfree(c->d_rb);
   if (c->h_rb) cudaFreeHost(c->h_rb);
   for (auto e : c->ev_trace) cudaEventDestroy(e);
   if (c->ev_begin) cudaEventDestroy(c->ev_begin);

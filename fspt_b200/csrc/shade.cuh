@@ -223,9 +223,8 @@ struct ShadeArgs {
   PathState ps;
   FrameParams f;
   const float* rb_trace;      // per sample-in-wave
-  const int* list_hit;        // path slots whose continuation/primary ray hit a triangle (from k_trace)
-  const int* list_miss;       // path slots whose ray left the scene
-  const int* counts_in;       // [0] = #hit, [1] = #miss
+  const int* list_in;         // path slots whose continuation ray was just traced (NULL = identity: primary rays)
+  const int* counts_in;       // [0] = number of entries of list_in
   int* list_cont_out;         // continuation rays for the next traversal
   int* list_shadow_out;
   int* counts_out;            // [0] continuation, [1] shadow
@@ -235,6 +234,7 @@ struct ShadeArgs {
   int first;                  // 1: slots hold fresh primary rays (tracer.fs:440-445)
   int max_refractions;
   int anyhit;
+  const unsigned char* hit_flag;  // hit / miss per position of list_in, written by k_trace
 };
 
 // Warp-aggregated append: one atomicAdd per warp per list (ballot + popc prefix); call with all 32 lanes
@@ -473,24 +473,64 @@ __device__ __forceinline__ bool shade_hit(const ShadeArgs& A, int slot, bool& sh
 #ifndef SHADE_MIN_BLOCKS
 #define SHADE_MIN_BLOCKS 6
 #endif
-// The traversal kernel sorts finished rays into a hit list and a miss list, so a warp here is all-hit (full
-// vertex shading) or all-miss (one env lookup): the reference's per-fragment `if (result.index < 0)` branches
-// (tracer.fs:442,509) never diverge inside a warp.
+// Iterates the SAME list the traversal kernel consumed (identity for primary rays), so slots stay in roughly
+// ascending order from bounce to bounce and path records are streamed rather than gathered; the traversal kernel
+// only leaves a hit/miss byte per list position.  The reference's per-fragment `if (result.index < 0)` branches
+// (tracer.fs:442,509) are resolved per block: every 128-item tile pushes its hits and its misses into two block-local
+// queues and work starts only on full groups of one kind, so hit shading and miss shading never share a warp.
 __global__ void __launch_bounds__(SHADE_THREADS, SHADE_MIN_BLOCKS) k_shade(const ShadeArgs A) {
   init_unorm8_lut();
-  const int n_hit = A.counts_in[0], n_miss = A.counts_in[1];
-  const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
-  for (int it = t0; it < ((n_hit + 31) & ~31); it += stride) {
-    bool cont = false, shadow = false;
-    int slot = 0;
-    if (it < n_hit) {
-      slot = ld_list(A.list_hit + it);
-      cont = shade_hit(A, slot, shadow);
+  // block-local queues: every tile pushes its hits and misses, and work is only started on FULL groups of
+  // SHADE_THREADS items of one kind, so hit shading and miss shading never share a warp (or a block)
+  __shared__ int q_hit[2 * SHADE_THREADS], q_miss[2 * SHADE_THREADS];
+  __shared__ int s_hits[SHADE_THREADS / 32], s_miss[SHADE_THREADS / 32];
+  const int n = A.counts_in[0];
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  int nh = 0, nm = 0;  // queue fill, block-uniform
+  const int n_tiles = (n + SHADE_THREADS - 1) / SHADE_THREADS;
+  for (int tile = blockIdx.x;; tile += gridDim.x) {
+    const bool last = tile >= n_tiles;  // one extra round drains the partial groups
+    if (!last) {
+      const int it = tile * SHADE_THREADS + threadIdx.x;
+      const bool live = it < n;
+      const int slot = live ? (A.list_in ? ld_list(A.list_in + it) : it) : 0;
+      const bool hit = live && A.hit_flag[it] != 0;  // written by k_trace per list position: a coalesced read
+      const unsigned mh = __ballot_sync(0xffffffffu, hit), mm = __ballot_sync(0xffffffffu, live && !hit);
+      if (lane == 0) { s_hits[warp] = __popc(mh); s_miss[warp] = __popc(mm); }
+      __syncthreads();
+      int hits_before = 0, miss_before = 0, t_hit = 0, t_miss = 0;
+#pragma unroll
+      for (int w = 0; w < SHADE_THREADS / 32; ++w) {
+        if (w < (int)warp) { hits_before += s_hits[w]; miss_before += s_miss[w]; }
+        t_hit += s_hits[w]; t_miss += s_miss[w];
+      }
+      const unsigned lt = (1u << lane) - 1u;
+      if (hit) q_hit[nh + hits_before + __popc(mh & lt)] = slot;
+      else if (live) q_miss[nm + miss_before + __popc(mm & lt)] = slot;
+      nh += t_hit; nm += t_miss;
+      __syncthreads();
     }
-    append(cont, slot, A.list_cont_out, A.counts_out + 0);
-    append(shadow, slot, A.list_shadow_out, A.counts_out + 1);
+    while (nh >= SHADE_THREADS || (last && nh > 0)) {
+      const int take = nh < SHADE_THREADS ? nh : SHADE_THREADS;
+      bool cont = false, shadow = false;
+      int my = 0;
+      if ((int)threadIdx.x < take) {
+        my = q_hit[nh - take + threadIdx.x];
+        cont = shade_hit(A, my, shadow);
+      }
+      append(cont, my, A.list_cont_out, A.counts_out + 0);
+      append(shadow, my, A.list_shadow_out, A.counts_out + 1);
+      nh -= take;
+      __syncthreads();
+    }
+    while (nm >= SHADE_THREADS || (last && nm > 0)) {
+      const int take = nm < SHADE_THREADS ? nm : SHADE_THREADS;
+      if ((int)threadIdx.x < take) shade_miss(A, q_miss[nm - take + threadIdx.x]);
+      nm -= take;
+      __syncthreads();
+    }
+    if (last) break;
   }
-  for (int it = t0; it < n_miss; it += stride) shade_miss(A, ld_list(A.list_miss + it));
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -17,6 +17,7 @@
 // then the idle lanes are refilled from a global queue with one atomicAdd per warp (__ballot_sync +
 // popc prefix = the compaction), so short rays do not wait for the longest ray of their warp.  Inside the
 // loop the warp votes each iteration whether to run an interior step or a leaf step (majority of lanes).
+// Results go back into the path record plus one hit/miss byte per list position for the shading kernel.
 #pragma once
 #include "camera.cuh"
 #include "device_common.cuh"
@@ -31,12 +32,10 @@ struct TraceArgs {
   const int* list_cont;   // path slots of continuation rays; NULL = identity
   const int* list_shadow; // path slots of shadow rays
   const int* counts;      // counts[0] = #continuation, counts[1] = #shadow
-  int* list_hit;          // out: slots whose continuation ray hit / missed (sorted for the shading kernel)
-  int* list_miss;
-  int* counts_out;        // [0] = #hit, [1] = #miss (zeroed before launch); NULL = do not classify
   int* next;              // work-fetch cursor (zeroed before launch)
   unsigned long long* stats;  // [0] rays, [1] node visits, [2] leaf visits
   int* count_out;         // per-slot visit count (debug / bvh_test mode) or NULL
+  unsigned char* hit_flag;  // per continuation-list position: 1 = hit (read coalesced by k_shade) or NULL
   FrameParams f;          // CAMERA mode: primary rays are generated in the fetch instead of being read
   const float* rb_cam;
   int n_samples;
@@ -127,7 +126,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(const TraceArgs A) {
 
   int stack[FSPT_STACK];
   int cur = FSPT_SENTINEL, sp = 0;
-  int slot = -1, kind = 0, cnt = 0;
+  int slot = -1, kind = 0, cnt = 0, item = 0;
   float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0;
   f32x2 ox2 = 0, oy2 = 0, oz2 = 0, ix2 = 0, iy2 = 0, iz2 = 0;  // (v, v) pairs for the packed slab test
   float tbest = FSPT_MAX_T;
@@ -150,25 +149,8 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(const TraceArgs A) {
         st_path_w(A.ps.sd(slot), __int_as_float((ibest == -1) ? 2 : 3));
       }
       if (WRITE_COUNT) A.count_out[slot] = cnt;
+      if (A.hit_flag && kind == 0) A.hit_flag[item] = (ibest != -1);
       n_nodes += (unsigned long long)cnt;
-    }
-    if (A.counts_out) {  // compaction by outcome: one atomicAdd per warp per list (all 32 lanes are converged here)
-      const bool hit = retire && kind == 0 && ibest != -1, miss = retire && kind == 0 && ibest == -1;
-      const unsigned mh = __ballot_sync(FULL, hit), mm = __ballot_sync(FULL, miss);
-      if (mh) {
-        const int leader = __ffs(mh) - 1;
-        int base = 0;
-        if ((int)lane == leader) base = atomicAdd(A.counts_out + 0, __popc(mh));
-        base = __shfl_sync(FULL, base, leader);
-        if (hit) A.list_hit[base + __popc(mh & ((1u << lane) - 1u))] = slot;
-      }
-      if (mm) {
-        const int leader = __ffs(mm) - 1;
-        int base = 0;
-        if ((int)lane == leader) base = atomicAdd(A.counts_out + 1, __popc(mm));
-        base = __shfl_sync(FULL, base, leader);
-        if (miss) A.list_miss[base + __popc(mm & ((1u << lane) - 1u))] = slot;
-      }
     }
     if (retire) slot = -1;
     if (!drained) {
@@ -183,6 +165,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(const TraceArgs A) {
         if (need) {
           const int my = base + __popc(m & ((1u << lane) - 1u));
           if (my < total) {
+            item = my;
             if (CAMERA) {
               kind = 0;
               slot = my;
