@@ -70,8 +70,9 @@ struct Ctx {
   // wavefront state
   int wave_samples = 0;       // samples in flight per wave
   size_t wave_paths = 0;
-  PathState ps{};
-  int* d_list[3] = {nullptr, nullptr, nullptr};  // continuation lists (ping-pong) and the shadow list
+  PathState ps{};             // = ps2[0] (debug entry points)
+  PathState ps2[2]{};         // dense path-record arrays, ping-pong: shade reads one, compacts survivors into the other
+  int* d_list = nullptr;      // shadow list: record positions
   int* d_counts = nullptr;    // set k at [2k, 2k+1] = (#continuation, #shadow), [4] fetch cursor, [5..7] pad
   int* d_count_out = nullptr; // per-slot visit count (debug)
   unsigned char* d_hit_flag = nullptr;  // per list position (ordered mode)
@@ -148,8 +149,9 @@ int alloc_wave(Ctx* c) {
   c->wave_samples = S;
   c->wave_paths = (size_t)S * c->n_pixels;
   const size_t W = c->wave_paths;
-  CK(cudaMalloc(&c->ps.rec, W * 16 * FSPT_PATH_WORDS));
-  for (int i = 0; i < 3; ++i) CK(cudaMalloc(&c->d_list[i], W * sizeof(int)));
+  for (int k = 0; k < 2; ++k) CK(cudaMalloc(&c->ps2[k].rec, W * 16 * FSPT_PATH_WORDS));
+  c->ps = c->ps2[0];
+  CK(cudaMalloc(&c->d_list, W * sizeof(int)));
   CK(cudaMalloc(&c->d_counts, 8 * sizeof(int)));
   CK(cudaMalloc(&c->d_count_out, W * sizeof(int)));
   CK(cudaMalloc(&c->d_hit_flag, W));
@@ -180,18 +182,18 @@ __global__ void k_set_counts(int* counts, int n_cont, int n_shadow) {
   counts[0] = n_cont; counts[1] = n_shadow; counts[2] = 0; counts[3] = 0; counts[4] = 0;
 }
 
-// Traverses counts[0] continuation rays (list_cont, NULL = identity) + counts[1] shadow rays; results go into the path
-// records, plus one hit/miss byte per continuation-list position when hit_flags is set (read by k_shade).
-int launch_trace(Ctx* c, const int* list_cont, bool hit_flags, bool write_count, const FrameParams* cam = nullptr,
-                 const float* rb_cam = nullptr, int n_samples = 1, const int* list_shadow = nullptr, const int* counts = nullptr) {
+// Traverses the continuation ray of every record of array `which` (d_counts[2*which] of them) + d_counts[2*which+1]
+// shadow rays (positions in d_list); results go into the records, plus one hit/miss byte per position (for k_shade).
+int launch_trace(Ctx* c, int which, bool hit_flags, bool write_count, const FrameParams* cam = nullptr,
+                 const float* rb_cam = nullptr, int n_samples = 1) {
   TraceArgs A;
   if (cam) A.f = *cam; else memset(&A.f, 0, sizeof A.f);
   A.rb_cam = rb_cam; A.n_samples = n_samples;
   A.anyhit = c->anyhit;
   A.nodes = c->sc.nodes; A.tris = c->sc.tris; A.root_ref = c->sc.root_ref; A.nodes_tex = c->nodes_tex; A.tris_tex = c->tris_tex;
-  A.ps = c->ps;
-  A.list_cont = list_cont; A.list_shadow = list_shadow ? list_shadow : c->d_list[2];
-  A.counts = counts ? counts : c->d_counts;
+  A.ps = c->ps2[which];
+  A.list_shadow = c->d_list;
+  A.counts = c->d_counts + 2 * which;
   A.next = c->d_counts + 4;
   A.stats = c->d_stats;
   A.count_out = write_count ? c->d_count_out : nullptr;
@@ -222,20 +224,20 @@ FrameParams make_frame(const Ctx* c, const fspt_frame_params* f) {
   return p;
 }
 
-// One wave.  Continuation lists ping-pong between d_list[0] / d_list[1], shadow
-// list in d_list[2]; counts: set k at d_counts[2k .. 2k+1] = (#continuation, #shadow), fetch cursor at d_counts[4].
+// One wave.  Path records are dense arrays that ping-pong: set k = (array ps2[k], counts d_counts[2k .. 2k+1] =
+// #records, #shadow rays); the shadow list holds record positions; fetch cursor at d_counts[4].
 int render_wave(Ctx* c, const FrameParams& fp, uint32_t first_tick, int S, const float* rb_cam, const float* rb_trace) {
   const int P = c->n_pixels;
   const int n_paths = S * P;
   int rc = set_counts(c, n_paths, 0);
   if (rc) return rc;
-  rc = launch_trace(c, nullptr, true, false, &fp, rb_cam, S);  // camera.fs + primary rays (tracer.fs:440), fused
+  rc = launch_trace(c, 0, true, false, &fp, rb_cam, S);  // camera.fs + primary rays (tracer.fs:440), fused
   if (rc) return rc;
   ShadeArgs A;
-  A.sc = c->sc; A.ps = c->ps; A.f = fp;
+  A.sc = c->sc; A.f = fp;
   A.rb_trace = rb_trace;
   A.hit_flag = c->d_hit_flag;
-  A.list_shadow_out = c->d_list[2];
+  A.list_shadow_out = c->d_list;
   A.sample_color = c->d_sample_color;
   A.capped = c->d_stats + 3;
   A.n_samples = S;
@@ -247,9 +249,9 @@ int render_wave(Ctx* c, const FrameParams& fp, uint32_t first_tick, int S, const
     const int nxt = cur ^ 1;
     CK(cudaMemsetAsync(c->d_counts + 2 * nxt, 0, 2 * sizeof(int), c->stream));
     A.first = (b == 0);
-    A.list_in = (b == 0) ? nullptr : c->d_list[cur];  // the list the last traversal consumed
+    A.ps = c->ps2[cur];
+    A.ps_out = c->ps2[nxt];
     A.counts_in = c->d_counts + 2 * cur;
-    A.list_cont_out = c->d_list[nxt];
     A.counts_out = c->d_counts + 2 * nxt;
     record_trace_begin(c, 1);
     k_shade<<<c->shade_blocks, SHADE_THREADS, 1024, c->stream>>>(A);
@@ -258,14 +260,14 @@ int render_wave(Ctx* c, const FrameParams& fp, uint32_t first_tick, int S, const
     CK(cudaGetLastError());
     cur = nxt;
     if (b >= FSPT_NUM_BOUNCES) {
-      if (!c->has_dielectric) break;
+      if (!c->has_dielectric) break;  // every surviving path had i == NUM_BOUNCES: nothing was appended
       int h[2];
       CK(cudaMemcpyAsync(h, c->d_counts + 2 * cur, sizeof h, cudaMemcpyDeviceToHost, c->stream));
       CK(cudaStreamSynchronize(c->stream));
       if (h[0] == 0) break;
     }
     CK(cudaMemsetAsync(c->d_counts + 4, 0, sizeof(int), c->stream));  // fetch cursor
-    rc = launch_trace(c, c->d_list[cur], true, false, nullptr, nullptr, 1, c->d_list[2], c->d_counts + 2 * cur);
+    rc = launch_trace(c, cur, true, false);  // tracer.fs:501,507
     if (rc) return rc;
   }
   k_accumulate<<<(P + 255) / 256, 256, 0, c->stream>>>(c->d_sample_color, c->d_fb, c->d_last_color, P, S, first_tick,
@@ -352,8 +354,8 @@ void fspt_destroy(fspt_ctx* ctx) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   free_scene(c);
   dfree(c->d_fb); dfree(c->d_last_color); dfree(c->d_sample_color); dfree(c->d_cam_pos); dfree(c->d_cam_dir); dfree(c->d_rgba8);
-  dfree(c->ps.rec);
-  for (int i = 0; i < 3; ++i) dfree(c->d_list[i]);
+  dfree(c->ps2[0].rec); dfree(c->ps2[1].rec);
+  dfree(c->d_list);
   dfree(c->d_counts); dfree(c->d_count_out); dfree(c->d_hit_flag); dfree(c->d_stats); dfree(c->d_rb);
   if (c->h_rb) cudaFreeHost(c->h_rb);
   for (auto e : c->ev_trace) cudaEventDestroy(e);
@@ -809,7 +811,7 @@ int fspt_debug_primary(fspt_ctx* ctx, const fspt_frame_params* frame, float rand
   int rc = set_counts(c, P, 0);
   if (rc) return rc;
   c->ev_trace_used = 0;
-  rc = launch_trace(c, nullptr, false, true);
+  rc = launch_trace(c, 0, false, true);
   if (rc) return rc;
   CK(cudaStreamSynchronize(c->stream));
   // un-swizzle path slots -> pixels on the host
@@ -850,7 +852,7 @@ int fspt_debug_trace(fspt_ctx* ctx, const float* pos4, const float* dir4, int32_
     int rc = set_counts(c, n, 0);
     if (rc) return rc;
     c->ev_trace_used = 0;
-    rc = launch_trace(c, nullptr, false, true);
+    rc = launch_trace(c, 0, false, true);
     if (rc) return rc;
     ro.resize(n); rdv.resize(n); cnt.resize(n);
     CK(cudaMemcpy2DAsync(ro.data(), 16, c->ps.rec + 0, 16 * FSPT_PATH_WORDS, 16, n, cudaMemcpyDeviceToHost, c->stream));

@@ -220,13 +220,12 @@ __device__ __forceinline__ void tangent_frame(v3 normal, v3& tangent, v3& bitang
 
 struct ShadeArgs {
   DeviceScene sc;
-  PathState ps;
+  PathState ps;               // records of the paths to shade, dense: position 0 .. counts_in[0]-1
+  PathState ps_out;           // compacted records of the paths that continue (position = append order)
   FrameParams f;
   const float* rb_trace;      // per sample-in-wave
-  const int* list_in;         // path slots whose continuation ray was just traced (NULL = identity: primary rays)
-  const int* counts_in;       // [0] = number of entries of list_in
-  int* list_cont_out;         // continuation rays for the next traversal
-  int* list_shadow_out;
+  const int* counts_in;       // [0] = number of records in ps
+  int* list_shadow_out;       // positions (in ps_out) of the paths that also cast a shadow ray
   int* counts_out;            // [0] continuation, [1] shadow
   float4* sample_color;       // [pixel][sample-in-wave] final un-clamped path colour
   unsigned long long* capped; // paths stopped by the refraction cap
@@ -234,7 +233,7 @@ struct ShadeArgs {
   int first;                  // 1: slots hold fresh primary rays (tracer.fs:440-445)
   int max_refractions;
   int anyhit;
-  const unsigned char* hit_flag;  // hit / miss per position of list_in, written by k_trace
+  const unsigned char* hit_flag;  // hit / miss per record position, written by k_trace
 };
 
 // Warp-aggregated append: one atomicAdd per warp per list (ballot + popc prefix); call with all 32 lanes
@@ -249,6 +248,18 @@ __device__ __forceinline__ void append(bool want, int value, int* list, int* cou
   list[base + __popc(m & ((1u << lane) - 1u))] = value;
 }
 
+// position of this lane's element when the lanes with `want` append to a dense array (one atomicAdd per warp)
+__device__ __forceinline__ int append_pos(bool want, int* counter) {
+  const unsigned m = __ballot_sync(0xffffffffu, want);
+  if (m == 0u) return 0;
+  const unsigned lane = threadIdx.x & 31u;
+  const int leader = __ffs(m) - 1;
+  int base = 0;
+  if ((int)lane == leader) base = atomicAdd(counter, __popc(m));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  return base + __popc(m & ((1u << lane) - 1u));
+}
+
 __device__ __forceinline__ void write_sample(const ShadeArgs& A, int slot, v3 color) {
   const int j = slot / A.n_samples, s = slot - j * A.n_samples;
   int x, y;
@@ -259,18 +270,21 @@ __device__ __forceinline__ void write_sample(const ShadeArgs& A, int slot, v3 co
 
 // The tail of the previous loop iteration for a path whose ray MISSED: tracer.fs:442-443 (primary) or
 // :502-504 + :508-512 (bounce).  Ends the path.
-__device__ __forceinline__ void shade_miss(const ShadeArgs& A, int slot) {
-  const float4 d4 = ld_path(A.ps.rd(slot));
+__device__ __forceinline__ void shade_miss(const ShadeArgs& A, int pos) {
+  const int slot_in = pos;  // record position in A.ps
+  int slot = pos;           // path identity (pixel * S + sample); equals the position only in the first pass
+  const float4 d4 = ld_path(A.ps.rd(slot_in));
   const v3 rayDir = mk3(d4.x, d4.y, d4.z);
   const v3 env = env_sample(A.sc, rayDir, A.f.env_theta);
   v3 color;
   if (A.first) {
     color = add(mk3(0.0f, 0.0f, 0.0f), env);  // :443
   } else {
-    const float4 c4 = ld_path(A.ps.col(slot)), t4 = ld_path(A.ps.thr(slot)), s4 = ld_path(A.ps.sd(slot));
+    const float4 c4 = ld_path(A.ps.col(slot_in)), t4 = ld_path(A.ps.thr(slot_in)), s4 = ld_path(A.ps.sd(slot_in));
+    slot = __float_as_int(c4.w);
     color = mk3(c4.x, c4.y, c4.z);
     if (__float_as_int(s4.w) == 2) {  // shadow.index == -1, :502-504
-      const float4 p4 = ld_path(A.ps.pend(slot));
+      const float4 p4 = ld_path(A.ps.pend(slot_in));
       color = add(color, mk3(p4.x, p4.y, p4.z));
     }
     const v3 reflectance = mk3(t4.x, t4.y, t4.z);                 // accumulatedReflectance *= bsdfThroughput (:508) was
@@ -280,15 +294,15 @@ __device__ __forceinline__ void shade_miss(const ShadeArgs& A, int slot) {
 }
 
 // One loop iteration of tracer.fs main (:446-513) for a path whose ray HIT, split at the intersectScene calls.
-// Returns true when the path continues (a continuation ray, and maybe a shadow ray, were written).
-__device__ __forceinline__ bool shade_hit(const ShadeArgs& A, int slot, bool& shadow) {
+// Returns true when the path continues; `out` then holds its new 6-word record (continuation ray, shadow ray, state).
+struct PathRecord { float4 w[6]; };
+__device__ __forceinline__ bool shade_hit(const ShadeArgs& A, int pos, bool& shadow, PathRecord& out) {
   const DeviceScene& sc = A.sc;
-  const float4 o4 = ld_path(A.ps.ro(slot)), d4 = ld_path(A.ps.rd(slot));
+  int slot = pos;  // path identity; equals the record position only in the first pass
+  const float4 o4 = ld_path(A.ps.ro(pos)), d4 = ld_path(A.ps.rd(pos));
   v3 rayOrigin = mk3(o4.x, o4.y, o4.z), rayDir = mk3(d4.x, d4.y, d4.z);
   const float hit_t = o4.w;
   const int hit_index = __float_as_int(d4.w);
-  const int s = slot % A.n_samples;
-  const float randBase = A.rb_trace[s];
   const float envTheta = A.f.env_theta;
   v3 color, reflectance;
   int i = 0, refractions = 0;
@@ -297,8 +311,9 @@ __device__ __forceinline__ bool shade_hit(const ShadeArgs& A, int slot, bool& sh
     color = mk3(0.0f, 0.0f, 0.0f);
     reflectance = mk3(1.0f, 1.0f, 1.0f);
   } else {
-    const float4 c4 = ld_path(A.ps.col(slot)), t4 = ld_path(A.ps.thr(slot)), s4 = ld_path(A.ps.sd(slot));
-    const float4 p4 = ld_path(A.ps.pend(slot));
+    const float4 c4 = ld_path(A.ps.col(pos)), t4 = ld_path(A.ps.thr(pos)), s4 = ld_path(A.ps.sd(pos));
+    const float4 p4 = ld_path(A.ps.pend(pos));
+    slot = __float_as_int(c4.w);
     color = mk3(c4.x, c4.y, c4.z);
     reflectance = mk3(t4.x, t4.y, t4.z);  // already multiplied by the previous bsdfThroughput (:508), see the store below
     const int packed = __float_as_int(p4.w);
@@ -311,6 +326,7 @@ __device__ __forceinline__ bool shade_hit(const ShadeArgs& A, int slot, bool& sh
       return false;
     }
   }
+  const float randBase = A.rb_trace[slot % A.n_samples];
   // createMaterial / createTriangle / createTexCoords / createNormals, :447-449,460
   const float4* rec = sc.shade + 12 * (size_t)hit_index;
   const float4 m0 = __ldg(rec), m2 = __ldg(rec + 2);
@@ -452,18 +468,18 @@ __device__ __forceinline__ bool shade_hit(const ShadeArgs& A, int slot, bool& sh
   shadow = (matDielectric < 0.0f && cosEnv > 0.0f);  // :500
   v3 pend = mk3(0.0f, 0.0f, 0.0f);
   if (shadow) pend = mul(mul(mul(reflectance, envThroughput), env_sample(sc, envDir, envTheta)), weights.x);  // :503
-  st_path(A.ps.ro(slot), make_float4(rayOrigin.x, rayOrigin.y, rayOrigin.z, FSPT_MAX_T));
+  out.w[0] = make_float4(rayOrigin.x, rayOrigin.y, rayOrigin.z, FSPT_MAX_T);
   // last bounce: the loop ends after this continuation ray whatever it hits (:446 with ++i), only hit-or-miss
   // matters (:509), so the traversal may stop at the first intersection (index word -2 = "boolean ray")
   const bool last_bounce = A.anyhit && (i + 1 >= FSPT_NUM_BOUNCES);
-  st_path(A.ps.rd(slot), make_float4(rayDir.x, rayDir.y, rayDir.z, __int_as_float(last_bounce ? -2 : -1)));
-  st_path(A.ps.sd(slot), make_float4(envDir.x, envDir.y, envDir.z, __int_as_float(shadow ? 1 : 0)));
+  out.w[1] = make_float4(rayDir.x, rayDir.y, rayDir.z, __int_as_float(last_bounce ? -2 : -1));
+  out.w[2] = make_float4(envDir.x, envDir.y, envDir.z, __int_as_float(shadow ? 1 : 0));
   // accumulatedReflectance *= bsdfThroughput (:508) is a pure product of two values known here: storing it now gives
   // the same f32 bits as multiplying in the next pass and keeps the record at six words = three 32-byte sectors
   const v3 next_reflectance = mul(reflectance, bsdfThroughput);
-  st_path(A.ps.thr(slot), make_float4(next_reflectance.x, next_reflectance.y, next_reflectance.z, weights.y));
-  st_path(A.ps.pend(slot), make_float4(pend.x, pend.y, pend.z, __int_as_float(((i + 0x100) & 0xffff) | (refractions << 16))));
-  st_path(A.ps.col(slot), make_float4(color.x, color.y, color.z, 0.0f));
+  out.w[3] = make_float4(next_reflectance.x, next_reflectance.y, next_reflectance.z, weights.y);
+  out.w[4] = make_float4(pend.x, pend.y, pend.z, __int_as_float(((i + 0x100) & 0xffff) | (refractions << 16)));
+  out.w[5] = make_float4(color.x, color.y, color.z, __int_as_float(slot));  // the path's identity travels with it
   return true;
 }
 
@@ -473,9 +489,11 @@ __device__ __forceinline__ bool shade_hit(const ShadeArgs& A, int slot, bool& sh
 #ifndef SHADE_MIN_BLOCKS
 #define SHADE_MIN_BLOCKS 6
 #endif
-// Iterates the SAME list the traversal kernel consumed (identity for primary rays), so slots stay in roughly
-// ascending order from bounce to bounce and path records are streamed rather than gathered; the traversal kernel
-// only leaves a hit/miss byte per list position.  The reference's per-fragment `if (result.index < 0)` branches
+// Path state is STREAM-COMPACTED every bounce: this kernel reads the dense record array the traversal just worked on
+// (position i = i-th surviving path, in roughly ascending pixel order) and writes the records of the paths that
+// continue to the next free positions of a second array, so record traffic is sequential in both kernels and no
+// index lists exist except for shadow rays.  The traversal kernel leaves one hit/miss byte per position.
+// The reference's per-fragment `if (result.index < 0)` branches
 // (tracer.fs:442,509) are resolved per block: every 128-item tile pushes its hits and its misses into two block-local
 // queues and work starts only on full groups of one kind, so hit shading and miss shading never share a warp.
 __global__ void __launch_bounds__(SHADE_THREADS, SHADE_MIN_BLOCKS) k_shade(const ShadeArgs A) {
@@ -493,8 +511,8 @@ __global__ void __launch_bounds__(SHADE_THREADS, SHADE_MIN_BLOCKS) k_shade(const
     if (!last) {
       const int it = tile * SHADE_THREADS + threadIdx.x;
       const bool live = it < n;
-      const int slot = live ? (A.list_in ? ld_list(A.list_in + it) : it) : 0;
-      const bool hit = live && A.hit_flag[it] != 0;  // written by k_trace per list position: a coalesced read
+      const int slot = it;  // records are dense: position == list position
+      const bool hit = live && A.hit_flag[it] != 0;  // written by k_trace per position: a coalesced read
       const unsigned mh = __ballot_sync(0xffffffffu, hit), mm = __ballot_sync(0xffffffffu, live && !hit);
       if (lane == 0) { s_hits[warp] = __popc(mh); s_miss[warp] = __popc(mm); }
       __syncthreads();
@@ -513,13 +531,16 @@ __global__ void __launch_bounds__(SHADE_THREADS, SHADE_MIN_BLOCKS) k_shade(const
     while (nh >= SHADE_THREADS || (last && nh > 0)) {
       const int take = nh < SHADE_THREADS ? nh : SHADE_THREADS;
       bool cont = false, shadow = false;
-      int my = 0;
-      if ((int)threadIdx.x < take) {
-        my = q_hit[nh - take + threadIdx.x];
-        cont = shade_hit(A, my, shadow);
+      PathRecord rec;
+      if ((int)threadIdx.x < take) cont = shade_hit(A, q_hit[nh - take + threadIdx.x], shadow, rec);
+      // stream compaction of the surviving paths: the new record goes to the next free position of ps_out
+      const int pos_out = append_pos(cont, A.counts_out + 0);
+      if (cont) {
+        float4* dst = A.ps_out.rec + FSPT_PATH_WORDS * (size_t)pos_out;
+#pragma unroll
+        for (int w = 0; w < 6; ++w) st_path(dst[w], rec.w[w]);
       }
-      append(cont, my, A.list_cont_out, A.counts_out + 0);
-      append(shadow, my, A.list_shadow_out, A.counts_out + 1);
+      append(shadow, pos_out, A.list_shadow_out, A.counts_out + 1);
       nh -= take;
       __syncthreads();
     }

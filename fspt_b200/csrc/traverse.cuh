@@ -29,8 +29,7 @@ struct TraceArgs {
   cudaTextureObject_t tris_tex;
   int root_ref;
   PathState ps;           // rays in, hits out (words 0..2 of the path record)
-  const int* list_cont;   // path slots of continuation rays; NULL = identity
-  const int* list_shadow; // path slots of shadow rays
+  const int* list_shadow; // record positions of the paths that cast a shadow ray (continuation rays: every record)
   const int* counts;      // counts[0] = #continuation, counts[1] = #shadow
   int* next;              // work-fetch cursor (zeroed before launch)
   unsigned long long* stats;  // [0] rays, [1] node visits, [2] leaf visits
@@ -176,7 +175,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(const TraceArgs A) {
               dx = d.x; dy = d.y; dz = d.z;
             } else {
               kind = my >= n_cont;
-              slot = kind ? ld_list(A.list_shadow + (my - n_cont)) : (A.list_cont ? ld_list(A.list_cont + my) : my);
+              slot = kind ? ld_list(A.list_shadow + (my - n_cont)) : my;
               const float4 o4 = ld_path(A.ps.ro(slot));
               const float4 d4 = ld_path(kind ? A.ps.sd(slot) : A.ps.rd(slot));
               ox = o4.x; oy = o4.y; oz = o4.z;
