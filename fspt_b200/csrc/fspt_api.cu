@@ -50,6 +50,8 @@ struct Ctx {
   int atlas_R = 0, atlas_L = 0, env_W = 0, env_H = 0;       // dims of the resident arrays (reused across uploads)
   size_t cap_nodes = 0, cap_tris = 0, cap_shade = 0, cap_bins = 0, cap_layer_info = 0;
   uint8_t* h_stage = nullptr;                               // pinned staging for the atlas (one slot per layer)
+  uint8_t* h_geo = nullptr;                                 // pinned staging for geometry records, bins, env
+  size_t geo_stage_bytes = 0;
   size_t stage_bytes = 0;
   size_t scene_bytes = 0;
 
@@ -125,6 +127,8 @@ void free_scene(Ctx* c) {
   c->cap_nodes = c->cap_tris = c->cap_shade = c->cap_bins = c->cap_layer_info = 0;
   if (c->h_stage) cudaFreeHost(c->h_stage);
   c->h_stage = nullptr; c->stage_bytes = 0;
+  if (c->h_geo) cudaFreeHost(c->h_geo);
+  c->h_geo = nullptr; c->geo_stage_bytes = 0;
   c->sc = DeviceScene{};
   c->has_scene = false;
 }
@@ -387,7 +391,21 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
   c->has_scene = false;  // device buffers, arrays and texture objects of the previous scene are reused when they fit
   lap("sync");
   const int N = s->n_nodes, T = s->n_triangles;
-  // ---- BVH repack: reference node i = [left,right,triIndex | min | max] -> Node64 per interior node ----
+  const int R = s->atlas_res, L = s->atlas_layers;
+  const size_t layer_texels = (size_t)R * R, layer_bytes = layer_texels * 4;
+  const int hw = (int)std::max(4u, std::min(32u, std::thread::hardware_concurrency()));
+  auto parallel = [&](int n_items, int max_workers, const std::function<void(int)>& fn) {
+    std::atomic<int> next_item(0);
+    const int n_workers = std::max(1, std::min(n_items, max_workers));
+    std::vector<std::thread> workers;
+    for (int w = 0; w < n_workers; ++w)
+      workers.emplace_back([&]() {
+        cudaSetDevice(c->device);
+        for (;;) { const int i = next_item.fetch_add(1); if (i >= n_items) break; fn(i); }
+      });
+    for (auto& t : workers) t.join();
+  };
+  // ---- serial pre-pass over the nodes: reference node i = [left,right,triIndex | min | max] -> child references
   std::vector<int32_t> ref((size_t)N);   // child reference of node i
   std::vector<int32_t> interior_of;      // reference node index of interior record k
   auto ibits = [&](int node, int k) { int32_t v; memcpy(&v, s->bvh + (size_t)node * 9 + k, 4); return v; };
@@ -402,55 +420,11 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
     }
   }
   const size_t NI = interior_of.size();
-  std::vector<float> nodes(std::max<size_t>(NI, 1) * 16, 0.0f);
-  for (size_t k = 0; k < NI; ++k) {
-    const int i = interior_of[k];
-    const int32_t l = ibits(i, 0), r = ibits(i, 1);
-    if (l < 0 || l >= N || r < 0 || r >= N || l == i || r == i)
-      return fail(c, FSPT_E_INVALID, "node %d: child index out of range (%d, %d)", i, l, r);
-    const float* lb = s->bvh + (size_t)l * 9 + 3;
-    const float* rb = s->bvh + (size_t)r * 9 + 3;
-    float* o = nodes.data() + k * 16;
-    // (left, right) pairs per component, the operand layout of the packed f32x2 slab test (traverse.cuh)
-    for (int k = 0; k < 6; ++k) { o[2 * k] = lb[k]; o[2 * k + 1] = rb[k]; }
-    const int32_t lr = ref[l], rr = ref[r];
-    memcpy(o + 12, &lr, 4); memcpy(o + 13, &rr, 4);
-  }
-  // depth / stack bound check (the reference has int stack[64], tracer.fs:368): iterative DFS
-  {
-    std::vector<std::pair<int, int>> st;
-    st.push_back({0, 1});
-    int max_depth = 0;
-    size_t visited = 0;
-    while (!st.empty()) {
-      auto [n, d] = st.back(); st.pop_back();
-      if (++visited > (size_t)N) return fail(c, FSPT_E_INVALID, "BVH is not a tree (cycle or shared node)");
-      max_depth = std::max(max_depth, d);
-      if (ibits(n, 2) > -1) continue;
-      st.push_back({ibits(n, 0), d + 1});
-      st.push_back({ibits(n, 1), d + 1});
-    }
-    if (max_depth + 1 > FSPT_STACK)
-      return fail(c, FSPT_E_LIMIT, "BVH depth %d exceeds the traversal stack (%d, as in tracer.fs:368)", max_depth, FSPT_STACK);
-  }
-  lap("bvh repack + depth check");
-  // ---- triangles: v1, e1, e2 (tracer.fs:301-302) + LEAF_SIZE-1 padBuffer-style (-1,-1,-1) tail records ----
-  std::vector<float> tris((size_t)(T + 3) * 12, 0.0f);
-  for (int t = 0; t < T + 3; ++t) {
-    float v[9];
-    if (t < T) memcpy(v, s->triangles + (size_t)t * 9, sizeof v);
-    else for (float& x : v) x = -1.0f;
-    float* o = tris.data() + (size_t)t * 12;
-    o[0] = v[0]; o[1] = v[1]; o[2] = v[2];
-    volatile float e;  // keep these as single f32 subtractions
-    e = v[3] - v[0]; o[3] = e; e = v[4] - v[1]; o[4] = e; e = v[5] - v[2]; o[5] = e;
-    e = v[6] - v[0]; o[6] = e; e = v[7] - v[1]; o[7] = e; e = v[8] - v[2]; o[8] = e;
-  }
-  // ---- shading records ------------------------------------------------------------------------------------
-  std::vector<float> shade((size_t)T * 48, 0.0f);
-  bool dielectric = false;
-  // materials = distinct quadruples of atlas layers (diffuse, emission, metallic-roughness, normal), tracer.fs:453-456
+  // ---- serial pre-pass over the triangles: materials = distinct quadruples of atlas layers (diffuse, emission,
+  // metallic-roughness, normal), tracer.fs:453-456
+  std::vector<int32_t> mat_id((size_t)T);
   std::vector<std::array<int, 4>> mats;
+  bool dielectric = false;
   {
     std::map<std::array<int, 4>, int> ids;
     std::array<int, 4> last = {-1, -1, -1, -1};
@@ -462,31 +436,128 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
       return (int)(q < 0 ? 0 : (q >= s->atlas_layers ? s->atlas_layers - 1 : q));
     };
     for (int t = 0; t < T; ++t) {
-      float* o = shade.data() + (size_t)t * 48;
-      memcpy(o, s->materials + (size_t)t * 12, 48);
-      memcpy(o + 12, s->uvs + (size_t)t * 6, 24);
-      memcpy(o + 20, s->normals + (size_t)t * 27, 108);
+      const float* o = s->materials + (size_t)t * 12;
       if (o[10] >= 0.0f) dielectric = true;
+      if (t > 0 && memcmp(o, o - 12, 16) == 0) { mat_id[t] = last_id; continue; }  // same four layer floats as the previous triangle
       const std::array<int, 4> key = {layer_of(o[0]), layer_of(o[1]), layer_of(o[3]), layer_of(o[2])};
       if (key != last) {
         auto it = ids.find(key);
         if (it == ids.end()) { it = ids.emplace(key, (int)mats.size()).first; mats.push_back(key); }
         last = key; last_id = it->second;
       }
-      memcpy(o + 18, &last_id, 4);  // material id in the record's padding
+      mat_id[t] = last_id;
     }
   }
-  std::vector<float> bins((size_t)s->env_bins * 4);
-  for (size_t i = 0; i < bins.size(); ++i) bins[i] = (float)s->radiance_bins[i];  // vec4(radianceBins[idx]), tracer.fs:424
-
-  lap("tri + shade records");
+  lap("node + material pre-pass");
+  // ---- host staging block (pinned, kept between uploads): every copy below is a true async DMA and the user's
+  // buffers are no longer referenced when this function returns.  Very large scenes stage in pageable memory.
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t o_nodes = 0, o_tris = o_nodes + al(std::max<size_t>(NI, 1) * 64), o_shade = o_tris + al((size_t)(T + 3) * 48),
+               o_bins = o_shade + al((size_t)T * 192), o_layer = o_bins + al((size_t)s->env_bins * 16),
+               o_mat = o_layer + al((size_t)L * 8), o_env = o_mat + al(std::max<size_t>(32, mats.size() * 32)),
+               geo_bytes = o_env + al((size_t)s->env_width * s->env_height * 4);
+  std::vector<uint8_t> pageable_geo;
+  uint8_t* hg;
+  if (geo_bytes <= ((size_t)1 << 30)) {
+    if (c->geo_stage_bytes < geo_bytes) {
+      if (c->h_geo) cudaFreeHost(c->h_geo);
+      c->h_geo = nullptr; c->geo_stage_bytes = 0;
+      CK(cudaMallocHost(&c->h_geo, geo_bytes));
+      c->geo_stage_bytes = geo_bytes;
+    }
+    hg = c->h_geo;
+  } else {
+    pageable_geo.resize(geo_bytes);
+    hg = pageable_geo.data();
+  }
+  float* nodes = reinterpret_cast<float*>(hg + o_nodes);
+  float* tris = reinterpret_cast<float*>(hg + o_tris);
+  float* shade = reinterpret_cast<float*>(hg + o_shade);
+  float* bins = reinterpret_cast<float*>(hg + o_bins);
+  uint32_t* layer_info = reinterpret_cast<uint32_t*>(hg + o_layer);
+  int32_t* mat_info = reinterpret_cast<int32_t*>(hg + o_mat);
+  const size_t n_mat_info = std::max<size_t>(8, mats.size() * 8);
+  // ---- geometry records: built by a background thread (which fans out) while this thread stages the atlas ------
+  struct GeoStatus { int code = FSPT_OK; char msg[192] = {0}; } geo;
+  std::mutex geo_mu;
+  auto geo_fail = [&](int code, const char* fmt, int a0, int a1, int a2) {
+    std::lock_guard<std::mutex> g(geo_mu);
+    if (geo.code == FSPT_OK) { geo.code = code; snprintf(geo.msg, sizeof geo.msg, fmt, a0, a1, a2); }
+  };
+  const int geo_workers = std::max(2, hw / 4);
+  std::thread geo_thread([&]() {
+    // Node64 per interior node: (left, right) pairs per component, the operand layout of the packed f32x2 slab test
+    if (NI == 0) memset(nodes, 0, 64);
+    const int node_chunks = (int)((NI + 16383) / 16384);
+    parallel(node_chunks, geo_workers, [&](int ch) {
+      const size_t k1 = std::min(NI, (size_t)(ch + 1) * 16384);
+      for (size_t k = (size_t)ch * 16384; k < k1; ++k) {
+        const int i = interior_of[k];
+        const int32_t l = ibits(i, 0), r = ibits(i, 1);
+        float* o = nodes + k * 16;
+        if (l < 0 || l >= N || r < 0 || r >= N || l == i || r == i) {
+          geo_fail(FSPT_E_INVALID, "node %d: child index out of range (%d, %d)", i, l, r);
+          memset(o, 0, 64);
+          continue;
+        }
+        const float* lb = s->bvh + (size_t)l * 9 + 3;
+        const float* rb = s->bvh + (size_t)r * 9 + 3;
+        for (int q = 0; q < 6; ++q) { o[2 * q] = lb[q]; o[2 * q + 1] = rb[q]; }
+        const int32_t lr = ref[l], rr = ref[r];
+        memcpy(o + 12, &lr, 4); memcpy(o + 13, &rr, 4);
+        o[14] = o[15] = 0.0f;
+      }
+    });
+    // triangles: v1, e1, e2 (tracer.fs:301-302) + LEAF_SIZE-1 padBuffer-style (-1,-1,-1) tail records; shading
+    // records: material (12) | uvs (6) | material id | pad | normals (27) | pad
+    const int tri_chunks = (T + 3 + 16383) / 16384;
+    parallel(tri_chunks, geo_workers, [&](int ch) {
+      const int t1 = std::min(T + 3, (ch + 1) * 16384);
+      for (int t = ch * 16384; t < t1; ++t) {
+        float v[9];
+        if (t < T) memcpy(v, s->triangles + (size_t)t * 9, sizeof v);
+        else for (float& x : v) x = -1.0f;
+        float* o = tris + (size_t)t * 12;
+        o[0] = v[0]; o[1] = v[1]; o[2] = v[2];
+        volatile float e;  // keep these as single f32 subtractions
+        e = v[3] - v[0]; o[3] = e; e = v[4] - v[1]; o[4] = e; e = v[5] - v[2]; o[5] = e;
+        e = v[6] - v[0]; o[6] = e; e = v[7] - v[1]; o[7] = e; e = v[8] - v[2]; o[8] = e;
+        o[9] = o[10] = o[11] = 0.0f;
+        if (t >= T) continue;
+        float* h = shade + (size_t)t * 48;
+        memcpy(h, s->materials + (size_t)t * 12, 48);
+        memcpy(h + 12, s->uvs + (size_t)t * 6, 24);
+        memcpy(h + 18, &mat_id[t], 4);  // material id in the record's padding
+        h[19] = 0.0f;
+        memcpy(h + 20, s->normals + (size_t)t * 27, 108);
+        h[47] = 0.0f;
+      }
+    });
+    for (size_t i = 0; i < (size_t)s->env_bins * 4; ++i) bins[i] = (float)s->radiance_bins[i];  // vec4(radianceBins[idx]), tracer.fs:424
+    memcpy(hg + o_env, s->env, (size_t)s->env_width * s->env_height * 4);
+    // depth / stack bound check (the reference has int stack[64], tracer.fs:368): iterative DFS
+    if (geo.code == FSPT_OK) {
+      std::vector<std::pair<int, int>> st;
+      st.push_back({0, 1});
+      int max_depth = 0;
+      size_t visited = 0;
+      while (!st.empty()) {
+        auto [n, d] = st.back(); st.pop_back();
+        if (++visited > (size_t)N) { geo_fail(FSPT_E_INVALID, "BVH is not a tree (cycle or shared node)", 0, 0, 0); break; }
+        max_depth = std::max(max_depth, d);
+        if (ibits(n, 2) > -1) continue;
+        st.push_back({ibits(n, 0), d + 1});
+        st.push_back({ibits(n, 1), d + 1});
+      }
+      if (geo.code == FSPT_OK && max_depth + 1 > FSPT_STACK)
+        geo_fail(FSPT_E_LIMIT, "BVH depth %d exceeds the traversal stack (%d, as in tracer.fs:368)", max_depth, FSPT_STACK, 0);
+    }
+  });
+  struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } geo_join{geo_thread};
   // ---- atlas (main.js:548-560).  Constant-colour layers are detected (exact: every texel compared), then the atlas
   // is re-interleaved per material into 16-byte texels (device_common.cuh "MatTexel") in pinned memory by a few host
   // threads and DMA'd layer by layer as the layers land; a scene with so many layer combinations that this would not
   // fit falls back to the plain RGBA8 layered array.
-  const int R = s->atlas_res, L = s->atlas_layers;
-  const size_t layer_texels = (size_t)R * R, layer_bytes = layer_texels * 4;
-  std::vector<uint32_t> layer_info((size_t)L * 2);
   cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
   cudaResourceDesc rd = {};
   rd.resType = cudaResourceTypeArray;
@@ -495,28 +566,30 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
   td.filterMode = cudaFilterModePoint;
   td.readMode = cudaReadModeElementType;
   td.normalizedCoords = 0;
-  auto parallel = [&](int n_items, const std::function<void(int)>& fn) {
-    std::atomic<int> next_item(0);
-    const int n_workers = std::max(1, std::min(n_items, 8));
-    std::vector<std::thread> workers;
-    for (int w = 0; w < n_workers; ++w)
-      workers.emplace_back([&]() {
-        cudaSetDevice(c->device);
-        for (;;) { const int i = next_item.fetch_add(1); if (i >= n_items) break; fn(i); }
-      });
-    for (auto& t : workers) t.join();
-  };
-  parallel(L, [&](int l) {
-    const uint32_t* px = reinterpret_cast<const uint32_t*>(s->atlas) + (size_t)l * layer_texels;
-    uint32_t first;
-    memcpy(&first, px, 4);
-    bool same = true;
-    for (size_t i = 1; i < layer_texels && same; ++i) same = (px[i] == first);
-    layer_info[2 * l] = same ? 1u : 0u;
-    layer_info[2 * l + 1] = first;
-  });
+  const int atlas_workers = std::max(2, hw - hw / 4);
+  {
+    // constant <=> every texel equals its successor; work item = (layer, band), abandoned once the layer is known varied
+    const int bands = 8;
+    std::vector<std::atomic<int>> varied((size_t)L);
+    for (auto& v : varied) v.store(0);
+    parallel(L * bands, atlas_workers, [&](int item) {
+      const int l = item / bands, band = item % bands;
+      if (varied[l].load(std::memory_order_relaxed)) return;
+      const uint32_t* px = reinterpret_cast<const uint32_t*>(s->atlas) + (size_t)l * layer_texels;
+      const size_t i0 = layer_texels * band / bands, i1 = std::min(layer_texels - 1, layer_texels * (band + 1) / bands);
+      for (size_t i = i0; i < i1;) {
+        const size_t n = std::min<size_t>(i1 - i, 16384);
+        if (memcmp(px + i, px + i + 1, n * 4) != 0) { varied[l].store(1, std::memory_order_relaxed); return; }
+        i += n;
+      }
+    });
+    for (int l = 0; l < L; ++l) {
+      layer_info[2 * l] = varied[l].load() ? 0u : 1u;
+      memcpy(&layer_info[2 * l + 1], s->atlas + (size_t)l * layer_bytes, 4);
+    }
+  }
   lap("constant-layer scan");
-  std::vector<int32_t> mat_info(mats.size() * 8, 0);
+  memset(mat_info, 0, n_mat_info * 4);
   int n_tex_mats = 0;
   for (size_t m = 0; m < mats.size(); ++m) {
     bool all_const = true;
@@ -550,10 +623,10 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
       c->stage_bytes = need;
     }
     // work item = (textured material, band of rows): interleave the four source layers, DMA the band
-    const int bands = std::max(1, std::min(R, 8));
+    const int bands = std::max(1, std::min(R, 16));
     std::vector<int> tex_mat_ids;
     for (size_t m = 0; m < mats.size(); ++m) if (mat_info[8 * m] >= 0) tex_mat_ids.push_back((int)m);
-    parallel((int)tex_mat_ids.size() * bands, [&](int item) {
+    parallel((int)tex_mat_ids.size() * bands, atlas_workers, [&](int item) {
       const int m = tex_mat_ids[item / bands], band = item % bands;
       const int tl = mat_info[8 * m];
       const int y0 = (int)((long long)R * band / bands), y1 = (int)((long long)R * (band + 1) / bands);
@@ -594,7 +667,7 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
       CK(cudaMallocHost(&c->h_stage, layer_bytes * L));
       c->stage_bytes = layer_bytes * L;
     }
-    parallel(L, [&](int l) {
+    parallel(L, atlas_workers, [&](int l) {
       uint8_t* dst = c->h_stage + (size_t)l * layer_bytes;
       memcpy(dst, s->atlas + (size_t)l * layer_bytes, layer_bytes);
       cudaMemcpy3DParms cp = {};
@@ -610,19 +683,24 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
   }
   if (cuda_err.load()) return fail(c, FSPT_E_CUDA, "atlas upload failed: %s", cudaGetErrorString((cudaError_t)cuda_err.load()));
   lap("atlas stage + scan + enqueue");
+  geo_thread.join();
+  if (geo.code != FSPT_OK) return fail(c, geo.code, "%s", geo.msg);
+  lap("join geometry thread");
   int rc_;
-  if ((rc_ = ensure(c, c->d_layer_info, c->cap_layer_info, layer_info.size() * 4))) return rc_;
-  if ((rc_ = ensure(c, c->d_mat_info, c->cap_mat_info, std::max<size_t>(32, mat_info.size() * 4)))) return rc_;
-  if ((rc_ = ensure(c, c->d_nodes, c->cap_nodes, nodes.size() * 4))) return rc_;
-  if ((rc_ = ensure(c, c->d_tris, c->cap_tris, tris.size() * 4))) return rc_;
-  if ((rc_ = ensure(c, c->d_shade, c->cap_shade, shade.size() * 4))) return rc_;
-  if ((rc_ = ensure(c, c->d_bins, c->cap_bins, bins.size() * 4))) return rc_;
-  CK(cudaMemcpyAsync(c->d_layer_info, layer_info.data(), layer_info.size() * 4, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->d_mat_info, mat_info.data(), mat_info.size() * 4, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->d_nodes, nodes.data(), nodes.size() * 4, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->d_tris, tris.data(), tris.size() * 4, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->d_shade, shade.data(), shade.size() * 4, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->d_bins, bins.data(), bins.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  const size_t nodes_bytes = std::max<size_t>(NI, 1) * 64, tris_bytes = (size_t)(T + 3) * 48, shade_bytes = (size_t)T * 192,
+               bins_bytes = (size_t)s->env_bins * 16;
+  if ((rc_ = ensure(c, c->d_layer_info, c->cap_layer_info, (size_t)L * 8))) return rc_;
+  if ((rc_ = ensure(c, c->d_mat_info, c->cap_mat_info, n_mat_info * 4))) return rc_;
+  if ((rc_ = ensure(c, c->d_nodes, c->cap_nodes, nodes_bytes))) return rc_;
+  if ((rc_ = ensure(c, c->d_tris, c->cap_tris, tris_bytes))) return rc_;
+  if ((rc_ = ensure(c, c->d_shade, c->cap_shade, shade_bytes))) return rc_;
+  if ((rc_ = ensure(c, c->d_bins, c->cap_bins, bins_bytes))) return rc_;
+  CK(cudaMemcpyAsync(c->d_layer_info, layer_info, (size_t)L * 8, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_mat_info, mat_info, n_mat_info * 4, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_nodes, nodes, nodes_bytes, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_tris, tris, tris_bytes, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_shade, shade, shade_bytes, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_bins, bins, bins_bytes, cudaMemcpyHostToDevice, c->stream));
   lap("malloc + enqueue geometry");
   // ---- environment: 2D array, RGBA8 RGBE (main.js:170-180) ----------------------------------------------------
   if (!c->env_arr || c->env_W != s->env_width || c->env_H != s->env_height) {
@@ -635,27 +713,29 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
     CK(cudaCreateTextureObject(&c->sc.env, &rd, &td, nullptr));
     c->env_W = s->env_width; c->env_H = s->env_height;
   }
-  CK(cudaMemcpy2DToArrayAsync(c->env_arr, 0, 0, s->env, (size_t)s->env_width * 4, (size_t)s->env_width * 4,
+  CK(cudaMemcpy2DToArrayAsync(c->env_arr, 0, 0, hg + o_env, (size_t)s->env_width * 4, (size_t)s->env_width * 4,
                               s->env_height, cudaMemcpyHostToDevice, c->stream));
   {
     cudaResourceDesc nr = {};
     nr.resType = cudaResourceTypeLinear;
     nr.res.linear.devPtr = c->d_nodes;
     nr.res.linear.desc = cudaCreateChannelDesc<float4>();
-    nr.res.linear.sizeInBytes = nodes.size() * 4;
+    nr.res.linear.sizeInBytes = nodes_bytes;
     cudaTextureDesc nt = {};
     nt.readMode = cudaReadModeElementType;
     if (c->nodes_tex) cudaDestroyTextureObject(c->nodes_tex);
     if (c->tris_tex) cudaDestroyTextureObject(c->tris_tex);
     c->nodes_tex = c->tris_tex = 0;
     const size_t max_texels = (size_t)1 << 27;  // linear-texture limit; beyond it the kernels use plain loads
-    if (nodes.size() / 4 <= max_texels) CK(cudaCreateTextureObject(&c->nodes_tex, &nr, &nt, nullptr));
+    if (nodes_bytes / 16 <= max_texels) CK(cudaCreateTextureObject(&c->nodes_tex, &nr, &nt, nullptr));
     nr.res.linear.devPtr = c->d_tris;
-    nr.res.linear.sizeInBytes = tris.size() * 4;
-    if (tris.size() / 4 <= max_texels) CK(cudaCreateTextureObject(&c->tris_tex, &nr, &nt, nullptr));
+    nr.res.linear.sizeInBytes = tris_bytes;
+    if (tris_bytes / 16 <= max_texels) CK(cudaCreateTextureObject(&c->tris_tex, &nr, &nt, nullptr));
   }
-  CK(cudaStreamSynchronize(c->stream));
-  lap("env + textures + sync");
+  // no synchronisation: everything the DMA engine still reads lives in the context's pinned staging blocks, which the
+  // next upload (and destroy) only touch after synchronising the stream; work enqueued by fspt_render waits in order
+  if (!pageable_geo.empty() || timing) CK(cudaStreamSynchronize(c->stream));
+  lap("env + textures (+ sync when timing)");
   c->sc.nodes = reinterpret_cast<const float4*>(c->d_nodes);
   c->sc.tris = reinterpret_cast<const float4*>(c->d_tris);
   c->sc.shade = reinterpret_cast<const float4*>(c->d_shade);
