@@ -145,7 +145,7 @@ int ensure(Ctx* c, void*& p, size_t& cap, size_t bytes) {
 
 int alloc_wave(Ctx* c) {
   // samples in flight: traversal launches amortise their ramp/tail over tens of millions of rays (measured:
-  // 4 -> 16 -> 32 samples per wave at 1280x720 = +14 % -> +3 %); 32 M paths x (128 B record + lists) = ~5 GB of 180 GB
+  // 4 -> 16 -> 32 samples per wave at 1280x720 = +14 % -> +3 %); 32 M paths x (2 x 96 B records + lists) = ~7 GB of 180 GB
   const size_t target_paths = (size_t)32 << 20;
   int S = (int)std::max<size_t>(1, target_paths / (size_t)c->n_pixels);
   S = std::min(S, 32);
