@@ -47,7 +47,7 @@ def workload_config(args, sa, n_gpus):
         "anyhit": "shadow rays and last-bounce continuation rays stop at their first intersection (identical image; "
                   "roofline bytes count the node/leaf visits actually executed)",
         "parallelism": "sample-set sharding x%d + NCCL reduce(sum)" % n_gpus,
-        "l2": "L2 flushed (512 MB write) between timed steps; per-wave path state (32 samples x 0.92 M paths x 96 B = 2.8 GB) "
+        "l2": "L2 flushed (512 MB write) between timed steps; per-wave path state (64 samples x 0.92 M paths x 2 x 96 B = 11.3 GB) "
               "and the 184 MB atlas exceed the 126 MB L2; BVH+triangles (~7 MB) stay L2-resident inside a step by design",
     }
 

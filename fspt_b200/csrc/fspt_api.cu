@@ -144,11 +144,12 @@ int ensure(Ctx* c, void*& p, size_t& cap, size_t bytes) {
 }
 
 int alloc_wave(Ctx* c) {
-  // samples in flight: traversal launches amortise their ramp/tail over tens of millions of rays (measured:
-  // 4 -> 16 -> 32 samples per wave at 1280x720 = +14 % -> +3 %); 32 M paths x (2 x 96 B records + lists) = ~7 GB of 180 GB
-  const size_t target_paths = (size_t)32 << 20;
+  // samples in flight: traversal launches amortise their ramp/tail over tens of millions of rays (measured at
+  // 1280x720: 4 -> 16 -> 32 -> 64 samples per wave = +14 % -> +3 % -> +2.7 %); 64 M paths x (2 x 96 B records + lists)
+  // = ~14 GB of 180 GB
+  const size_t target_paths = (size_t)64 << 20;
   int S = (int)std::max<size_t>(1, target_paths / (size_t)c->n_pixels);
-  S = std::min(S, 32);
+  S = std::min(S, 64);
   if (const char* e = getenv("FSPT_WAVE_SAMPLES")) S = std::max(1, std::min(64, atoi(e)));  // tuning knob
   c->wave_samples = S;
   c->wave_paths = (size_t)S * c->n_pixels;
