@@ -51,7 +51,7 @@ EXPORTS = [
     "fspt_abi_version", "fspt_create", "fspt_destroy", "fspt_last_error", "fspt_scene_upload", "fspt_clear",
     "fspt_render", "fspt_resolve", "fspt_read_accum", "fspt_write_accum", "fspt_set_accum_mode",
     "fspt_accum_device_ptr", "fspt_set_accum_samples", "fspt_debug_primary", "fspt_debug_trace",
-    "fspt_debug_last_color", "fspt_debug_math", "fspt_get_stats", "fspt_synchronize", "fspt_bvh_build", "fspt_bvh_build2",
+    "fspt_debug_last_color", "fspt_debug_math", "fspt_debug_read_bandwidth", "fspt_get_stats", "fspt_synchronize", "fspt_bvh_build", "fspt_bvh_build2",
     "fspt_env_bins", "fspt_pack_layer", "fspt_set_param",
 ]
 PARAM_ANYHIT, PARAM_MAX_REFRACTIONS, PARAM_SANITIZE_NAN = 1, 2, 3
@@ -271,6 +271,12 @@ class Context:
         out = np.empty((self.height, self.width, 4), np.float32)
         self._ck(self.lib.fspt_debug_last_color(self.h, ptr(out)))
         return out
+
+    def debug_read_bandwidth(self, nbytes, iters=20):
+        """GB/s of a streaming read over an nbytes buffer (L2 ceiling when it fits L2, HBM ceiling when it does not)."""
+        out = C.c_double(0.0)
+        self._ck(self.lib.fspt_debug_read_bandwidth(self.h, C.c_uint64(int(nbytes)), C.c_int32(int(iters)), C.byref(out)))
+        return out.value
 
     def debug_math(self, fn, x, y=None):
         names = {"sin": 0, "cos": 1, "atan2": 2, "asin": 3, "exp2": 4, "pow": 5, "sincos_s": 6, "sincos_c": 7}

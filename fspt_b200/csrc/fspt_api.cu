@@ -974,6 +974,46 @@ int fspt_debug_math(fspt_ctx* ctx, int32_t fn, const float* x, const float* y, f
   return FSPT_OK;
 }
 
+__global__ void __launch_bounds__(256) k_read_bw(const uint4* __restrict__ buf, size_t n16, int iters, unsigned* sink) {
+  unsigned acc = 0;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (int it = 0; it < iters; ++it) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n16; i += 4 * stride) {  // four independent loads in flight per thread
+      const uint4 a = __ldcg(buf + i), b = __ldcg(buf + i + stride), c2 = __ldcg(buf + i + 2 * stride), d = __ldcg(buf + i + 3 * stride);
+      acc ^= a.x ^ a.y ^ a.z ^ a.w ^ b.x ^ b.y ^ b.z ^ b.w ^ c2.x ^ c2.y ^ c2.z ^ c2.w ^ d.x ^ d.y ^ d.z ^ d.w;
+    }
+    for (; i < n16; i += stride) { const uint4 a = __ldcg(buf + i); acc ^= a.x ^ a.y ^ a.z ^ a.w; }
+  }
+  if (acc == 0x9e3779b9u) *sink = acc;  // keeps the loads alive
+}
+
+int fspt_debug_read_bandwidth(fspt_ctx* ctx, uint64_t bytes, int32_t iters, double* gb_per_s_out) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  if (!c || !gb_per_s_out || bytes < 4096 || iters < 1) return FSPT_E_INVALID;
+  CK(cudaSetDevice(c->device));
+  uint4* buf = nullptr;
+  unsigned* sink = nullptr;
+  const size_t n16 = (size_t)bytes / 16;
+  CK(cudaMalloc(&buf, n16 * 16));
+  CK(cudaMalloc(&sink, 4));
+  CK(cudaMemsetAsync(buf, 1, n16 * 16, c->stream));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  const int blocks = c->sm_count * 8;
+  k_read_bw<<<blocks, 256, 0, c->stream>>>(buf, n16, 1, sink);  // warm-up: brings the buffer into L2 when it fits
+  CK(cudaEventRecord(e0, c->stream));
+  k_read_bw<<<blocks, 256, 0, c->stream>>>(buf, n16, iters, sink);
+  CK(cudaEventRecord(e1, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  float ms = 0.0f;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(buf); cudaFree(sink);
+  *gb_per_s_out = (double)n16 * 16.0 * iters / (ms * 1e-3) / 1e9;
+  return FSPT_OK;
+}
+
 int fspt_set_param(fspt_ctx* ctx, int32_t key, int32_t value) {
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
   if (!c) return FSPT_E_INVALID;

@@ -41,7 +41,9 @@ struct TraceArgs {
   int anyhit;             // 1: hit-or-miss rays (shadow rays, marked last-bounce rays) stop at their first intersection
 };
 
+#ifndef TRACE_THREADS
 #define TRACE_THREADS 128
+#endif
 #ifndef TRACE_NODE_TEX
 #define TRACE_NODE_TEX 15  /* bit k: word k of the node record comes through the texture pipe */
 #endif

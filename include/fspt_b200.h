@@ -149,6 +149,12 @@ int fspt_debug_last_color(fspt_ctx* ctx, float* rgba32f_out);
  * 5 pow(x,y)); parity aid for the platform built-ins the shaders rely on (tracer.fs:181,412,417). */
 int fspt_debug_math(fspt_ctx* ctx, int32_t fn, const float* x, const float* y, float* out, int32_t n);
 
+/* Streaming-read microbenchmark on the context's device: `iters` passes over a `bytes`-sized buffer with L1-bypassing
+ * 16-byte loads from a persistent grid; GB/s out.  With bytes well below the L2 size this is the L2->SM read
+ * ceiling that bounds the traversal kernel (SURVEY 8d asks for this denominator); with bytes >> L2 it is the HBM
+ * read ceiling.  Measurement aid, no reference counterpart. */
+int fspt_debug_read_bandwidth(fspt_ctx* ctx, uint64_t bytes, int32_t iters, double* gb_per_s_out);
+
 /* Tuning / behaviour switches (none changes an image).  Unknown keys return FSPT_E_INVALID. */
 enum {
   FSPT_PARAM_ANYHIT = 1,          /* 1 (default): rays whose outcome is only tested for hit-or-miss -- every shadow ray
