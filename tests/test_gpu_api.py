@@ -124,3 +124,52 @@ def test_sum_mode_single_gpu(small_bunny, oracle_mod):
         assert ptr and n == W * H * 4 and s == N
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("wave,n", [("3", 10), (None, 70)])
+def test_renders_longer_than_one_wave_bit_exact(small_bunny, oracle_mod, monkeypatch, wave, n):
+    """A render call with more samples than fit in flight is cut into waves (3+3+3+1 samples here, 64+6 with the
+    default sizing); the running mean must continue across the cuts exactly as tracer.fs:517 does per pass."""
+    sa, cam = small_bunny
+    W, H = 40, 24
+    if wave:
+        monkeypatch.setenv("FSPT_WAVE_SAMPLES", wave)
+    O = oracle_mod.Oracle(sa)
+    rc, rt = scenes.rand_bases(n, 9)
+    ctx = capi.Context(W, H)
+    try:
+        ctx.scene_upload(sa)
+        ctx.render(_frame(ctx, cam), 0, rc, rt)
+        fb, rays = None, 0
+        for k in range(n):
+            pos, d = oracle_mod.camera(W, H, cam["eye"], cam["dir"], cam["fov_scale"], scenes.lens_features(cam), rc[k])
+            fb, _, st = O.trace(pos, d, W, H, k, rt[k], cam["env_theta"], fb_prev=fb, want_color=True)
+            rays += st["rays"]
+        assert np.array_equal(ctx.read_accum()[..., :3].view(np.uint32), fb[..., :3].view(np.uint32))
+        assert ctx.stats()["last_rays"] == rays
+    finally:
+        ctx.close()
+
+
+def test_two_triangle_scene_root_is_a_leaf(oracle_mod):
+    """<= 4 triangles: the BVH root is a leaf (bvh.js:22) and the traversal starts on a leaf reference."""
+    sa, cam = scenes.quad_scene()
+    W, H = 48, 32
+    O = oracle_mod.Oracle(sa)
+    rc, rt = scenes.rand_bases(3, 2)
+    ctx = capi.Context(W, H)
+    try:
+        ctx.scene_upload(sa)
+        fr = _frame(ctx, cam)
+        idx, t, cnt, pos, d = ctx.debug_primary(fr, rc[0])
+        oidx, ot, ocnt, _ = O.bvh_test(pos, d)
+        assert np.array_equal(idx, oidx) and np.array_equal(t.view(np.uint32), ot.view(np.uint32)) and np.array_equal(cnt, ocnt)
+        assert int(cnt.max()) == 1
+        ctx.render(fr, 0, rc, rt)
+        fb = None
+        for k in range(3):
+            pos, d = oracle_mod.camera(W, H, cam["eye"], cam["dir"], cam["fov_scale"], scenes.lens_features(cam), rc[k])
+            fb, _ = O.trace(pos, d, W, H, k, rt[k], cam["env_theta"], fb_prev=fb)
+        assert np.array_equal(ctx.read_accum()[..., :3].view(np.uint32), fb[..., :3].view(np.uint32))
+    finally:
+        ctx.close()
