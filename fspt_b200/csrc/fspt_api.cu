@@ -7,6 +7,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <algorithm>
 #include <array>
 #include <atomic>
@@ -50,6 +53,8 @@ struct Ctx {
   int atlas_R = 0, atlas_L = 0, env_W = 0, env_H = 0;       // dims of the resident arrays (reused across uploads)
   size_t cap_nodes = 0, cap_tris = 0, cap_shade = 0, cap_bins = 0, cap_layer_info = 0;
   uint8_t* h_stage = nullptr;                               // pinned staging for the atlas (one slot per layer)
+  cudaStream_t copy_stream = nullptr;                       // atlas DMA, overlaps the primary traversal
+  cudaEvent_t ev_atlas = nullptr;
   uint8_t* h_geo = nullptr;                                 // pinned staging for geometry records, bins, env
   size_t geo_stage_bytes = 0;
   size_t stage_bytes = 0;
@@ -249,6 +254,7 @@ int render_wave(Ctx* c, const FrameParams& fp, uint32_t first_tick, int S, const
   A.max_refractions = c->max_refractions;
   A.anyhit = c->anyhit;
   const int hard_cap = FSPT_NUM_BOUNCES + 1 + (c->has_dielectric ? c->max_refractions + 2 : 0);
+  CK(cudaStreamWaitEvent(c->stream, c->ev_atlas, 0));  // atlas DMA of the last upload (no-op once it has completed)
   int cur = 0;
   for (int b = 0; b < hard_cap; ++b) {
     const int nxt = cur ^ 1;
@@ -321,6 +327,8 @@ int fspt_create(fspt_ctx** out, int32_t width, int32_t height, int32_t device) {
 #define CKC(call) if ((err = (call)) != cudaSuccess) { g_create_error = std::string(#call) + ": " + cudaGetErrorString(err); delete ctx; return FSPT_E_CUDA; }
   CKC(cudaSetDevice(device));
   CKC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CKC(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  CKC(cudaEventCreateWithFlags(&c->ev_atlas, cudaEventDisableTiming));
   CKC(cudaEventCreate(&c->ev_begin));
   CKC(cudaEventCreate(&c->ev_end));
   CKC(cudaMalloc(&c->d_fb, (size_t)c->n_pixels * 16));
@@ -357,6 +365,7 @@ void fspt_destroy(fspt_ctx* ctx) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
   free_scene(c);
   dfree(c->d_fb); dfree(c->d_last_color); dfree(c->d_sample_color); dfree(c->d_cam_pos); dfree(c->d_cam_dir); dfree(c->d_rgba8);
   dfree(c->ps2[0].rec); dfree(c->ps2[1].rec);
@@ -366,6 +375,8 @@ void fspt_destroy(fspt_ctx* ctx) {
   for (auto e : c->ev_trace) cudaEventDestroy(e);
   if (c->ev_begin) cudaEventDestroy(c->ev_begin);
   if (c->ev_end) cudaEventDestroy(c->ev_end);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->ev_atlas) cudaEventDestroy(c->ev_atlas);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -389,6 +400,7 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
   if (s->leaf_size != 4) return fail(c, FSPT_E_INVALID, "scene_upload: LEAF_SIZE must be 4 (main.js:45), got %d", s->leaf_size);
   CK(cudaSetDevice(c->device));
   CK(cudaStreamSynchronize(c->stream));
+  CK(cudaStreamSynchronize(c->copy_stream));
   c->has_scene = false;  // device buffers, arrays and texture objects of the previous scene are reused when they fit
   lap("sync");
   const int N = s->n_nodes, T = s->n_triangles;
@@ -406,21 +418,46 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
       });
     for (auto& t : workers) t.join();
   };
-  // ---- serial pre-pass over the nodes: reference node i = [left,right,triIndex | min | max] -> child references
+  struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } };
+  // ---- constant-colour layers (exact: every texel compared), scanned in the background while the pre-passes run.
+  // constant <=> every texel equals its successor; work item = (layer, band), abandoned once the layer is known varied
+  const int atlas_workers = std::max(2, hw - hw / 4);
+  std::vector<std::atomic<int>> varied((size_t)L);
+  for (auto& v : varied) v.store(0);
+  std::thread scan_thread([&]() {
+    const int bands = 8;
+    parallel(L * bands, atlas_workers, [&](int item) {
+      const int l = item / bands, band = item % bands;
+      if (varied[l].load(std::memory_order_relaxed)) return;
+      const uint32_t* px = reinterpret_cast<const uint32_t*>(s->atlas) + (size_t)l * layer_texels;
+      const size_t i0 = layer_texels * band / bands, i1 = std::min(layer_texels - 1, layer_texels * (band + 1) / bands);
+      for (size_t i = i0; i < i1;) {
+        const size_t n = std::min<size_t>(i1 - i, 16384);
+        if (memcmp(px + i, px + i + 1, n * 4) != 0) { varied[l].store(1, std::memory_order_relaxed); return; }
+        i += n;
+      }
+    });
+  });
+  Joiner scan_join{scan_thread};
+  // ---- serial pre-pass over the nodes (own thread): reference node i = [left,right,triIndex | min | max] -> child references
   std::vector<int32_t> ref((size_t)N);   // child reference of node i
   std::vector<int32_t> interior_of;      // reference node index of interior record k
   auto ibits = [&](int node, int k) { int32_t v; memcpy(&v, s->bvh + (size_t)node * 9 + k, 4); return v; };
-  for (int i = 0; i < N; ++i) {
-    const int32_t tri = ibits(i, 2);
-    if (tri > -1) {  // `current.triangles > -1`, tracer.fs:379
-      if (tri >= T) return fail(c, FSPT_E_INVALID, "node %d: triangle index %d out of range", i, tri);
-      ref[i] = ~tri;
-    } else {
-      ref[i] = (int32_t)interior_of.size();
-      interior_of.push_back(i);
+  int bad_node = -1, bad_tri = 0;
+  std::thread node_thread([&]() {
+    interior_of.reserve((size_t)N / 2 + 1);
+    for (int i = 0; i < N; ++i) {
+      const int32_t tri = ibits(i, 2);
+      if (tri > -1) {  // `current.triangles > -1`, tracer.fs:379
+        if (tri >= T) { bad_node = i; bad_tri = tri; return; }
+        ref[i] = ~tri;
+      } else {
+        ref[i] = (int32_t)interior_of.size();
+        interior_of.push_back(i);
+      }
     }
-  }
-  const size_t NI = interior_of.size();
+  });
+  Joiner node_join{node_thread};
   // ---- serial pre-pass over the triangles: materials = distinct quadruples of atlas layers (diffuse, emission,
   // metallic-roughness, normal), tracer.fs:453-456
   std::vector<int32_t> mat_id((size_t)T);
@@ -449,6 +486,9 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
       mat_id[t] = last_id;
     }
   }
+  node_thread.join();
+  if (bad_node >= 0) return fail(c, FSPT_E_INVALID, "node %d: triangle index %d out of range", bad_node, bad_tri);
+  const size_t NI = interior_of.size();
   lap("node + material pre-pass");
   // ---- host staging block (pinned, kept between uploads): every copy below is a true async DMA and the user's
   // buffers are no longer referenced when this function returns.  Very large scenes stage in pageable memory.
@@ -487,6 +527,31 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
   };
   const int geo_workers = std::max(2, hw / 4);
   std::thread geo_thread([&]() {
+    std::thread env_thread([&]() {
+      for (size_t i = 0; i < (size_t)s->env_bins * 4; ++i) bins[i] = (float)s->radiance_bins[i];  // vec4(radianceBins[idx]), tracer.fs:424
+      memcpy(hg + o_env, s->env, (size_t)s->env_width * s->env_height * 4);
+    });
+    // depth / stack bound check (the reference has int stack[64], tracer.fs:368): iterative DFS; child indices out
+    // of range end it silently, the node loop below reports them
+    std::thread dfs_thread([&]() {
+      std::vector<std::pair<int, int>> st;
+      st.reserve(256);
+      st.push_back({0, 1});
+      int max_depth = 0;
+      size_t visited = 0;
+      while (!st.empty()) {
+        auto [n, d] = st.back(); st.pop_back();
+        if (++visited > (size_t)N) { geo_fail(FSPT_E_INVALID, "BVH is not a tree (cycle or shared node)", 0, 0, 0); return; }
+        max_depth = std::max(max_depth, d);
+        if (ibits(n, 2) > -1) continue;
+        const int32_t l = ibits(n, 0), r = ibits(n, 1);
+        if (l < 0 || l >= N || r < 0 || r >= N) return;
+        st.push_back({l, d + 1});
+        st.push_back({r, d + 1});
+      }
+      if (max_depth + 1 > FSPT_STACK)
+        geo_fail(FSPT_E_LIMIT, "BVH depth %d exceeds the traversal stack (%d, as in tracer.fs:368)", max_depth, FSPT_STACK, 0);
+    });
     // Node64 per interior node: (left, right) pairs per component, the operand layout of the packed f32x2 slab test
     if (NI == 0) memset(nodes, 0, 64);
     const int node_chunks = (int)((NI + 16383) / 16384);
@@ -534,27 +599,10 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
         h[47] = 0.0f;
       }
     });
-    for (size_t i = 0; i < (size_t)s->env_bins * 4; ++i) bins[i] = (float)s->radiance_bins[i];  // vec4(radianceBins[idx]), tracer.fs:424
-    memcpy(hg + o_env, s->env, (size_t)s->env_width * s->env_height * 4);
-    // depth / stack bound check (the reference has int stack[64], tracer.fs:368): iterative DFS
-    if (geo.code == FSPT_OK) {
-      std::vector<std::pair<int, int>> st;
-      st.push_back({0, 1});
-      int max_depth = 0;
-      size_t visited = 0;
-      while (!st.empty()) {
-        auto [n, d] = st.back(); st.pop_back();
-        if (++visited > (size_t)N) { geo_fail(FSPT_E_INVALID, "BVH is not a tree (cycle or shared node)", 0, 0, 0); break; }
-        max_depth = std::max(max_depth, d);
-        if (ibits(n, 2) > -1) continue;
-        st.push_back({ibits(n, 0), d + 1});
-        st.push_back({ibits(n, 1), d + 1});
-      }
-      if (geo.code == FSPT_OK && max_depth + 1 > FSPT_STACK)
-        geo_fail(FSPT_E_LIMIT, "BVH depth %d exceeds the traversal stack (%d, as in tracer.fs:368)", max_depth, FSPT_STACK, 0);
-    }
+    env_thread.join();
+    dfs_thread.join();
   });
-  struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } geo_join{geo_thread};
+  Joiner geo_join{geo_thread};
   // ---- atlas (main.js:548-560).  Constant-colour layers are detected (exact: every texel compared), then the atlas
   // is re-interleaved per material into 16-byte texels (device_common.cuh "MatTexel") in pinned memory by a few host
   // threads and DMA'd layer by layer as the layers land; a scene with so many layer combinations that this would not
@@ -567,27 +615,10 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
   td.filterMode = cudaFilterModePoint;
   td.readMode = cudaReadModeElementType;
   td.normalizedCoords = 0;
-  const int atlas_workers = std::max(2, hw - hw / 4);
-  {
-    // constant <=> every texel equals its successor; work item = (layer, band), abandoned once the layer is known varied
-    const int bands = 8;
-    std::vector<std::atomic<int>> varied((size_t)L);
-    for (auto& v : varied) v.store(0);
-    parallel(L * bands, atlas_workers, [&](int item) {
-      const int l = item / bands, band = item % bands;
-      if (varied[l].load(std::memory_order_relaxed)) return;
-      const uint32_t* px = reinterpret_cast<const uint32_t*>(s->atlas) + (size_t)l * layer_texels;
-      const size_t i0 = layer_texels * band / bands, i1 = std::min(layer_texels - 1, layer_texels * (band + 1) / bands);
-      for (size_t i = i0; i < i1;) {
-        const size_t n = std::min<size_t>(i1 - i, 16384);
-        if (memcmp(px + i, px + i + 1, n * 4) != 0) { varied[l].store(1, std::memory_order_relaxed); return; }
-        i += n;
-      }
-    });
-    for (int l = 0; l < L; ++l) {
-      layer_info[2 * l] = varied[l].load() ? 0u : 1u;
-      memcpy(&layer_info[2 * l + 1], s->atlas + (size_t)l * layer_bytes, 4);
-    }
+  scan_thread.join();
+  for (int l = 0; l < L; ++l) {
+    layer_info[2 * l] = varied[l].load() ? 0u : 1u;
+    memcpy(&layer_info[2 * l + 1], s->atlas + (size_t)l * layer_bytes, 4);
   }
   lap("constant-layer scan");
   memset(mat_info, 0, n_mat_info * 4);
@@ -635,7 +666,26 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
       for (int k = 0; k < 4; ++k) src[k] = reinterpret_cast<const uint32_t*>(s->atlas) + (size_t)mats[m][k] * layer_texels;
       uint32_t* dst = reinterpret_cast<uint32_t*>(c->h_stage) + ((size_t)tl * layer_texels + (size_t)y0 * R) * 4;
       const size_t i0 = (size_t)y0 * R, n = (size_t)(y1 - y0) * R;
-      for (size_t i = 0; i < n; ++i) {
+      size_t i = 0;
+#if defined(__SSE2__)
+      // 4x4 transpose of 32-bit texels, written with non-temporal stores: the staging block is only read by the DMA
+      // engine, so it should neither be fetched for ownership nor displace the source layers from the CPU caches
+      for (; i + 4 <= n; i += 4) {
+        const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src[0] + i0 + i));
+        const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src[1] + i0 + i));
+        const __m128i c2 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src[2] + i0 + i));
+        const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src[3] + i0 + i));
+        const __m128i ab_lo = _mm_unpacklo_epi32(a, b), ab_hi = _mm_unpackhi_epi32(a, b);
+        const __m128i cd_lo = _mm_unpacklo_epi32(c2, d), cd_hi = _mm_unpackhi_epi32(c2, d);
+        __m128i* o = reinterpret_cast<__m128i*>(dst + 4 * i);  // 16-byte aligned: pinned block + multiples of 16
+        _mm_stream_si128(o + 0, _mm_unpacklo_epi64(ab_lo, cd_lo));
+        _mm_stream_si128(o + 1, _mm_unpackhi_epi64(ab_lo, cd_lo));
+        _mm_stream_si128(o + 2, _mm_unpacklo_epi64(ab_hi, cd_hi));
+        _mm_stream_si128(o + 3, _mm_unpackhi_epi64(ab_hi, cd_hi));
+      }
+      _mm_sfence();
+#endif
+      for (; i < n; ++i) {
         dst[4 * i + 0] = src[0][i0 + i]; dst[4 * i + 1] = src[1][i0 + i];
         dst[4 * i + 2] = src[2][i0 + i]; dst[4 * i + 3] = src[3][i0 + i];
       }
@@ -646,7 +696,7 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
       cp.extent = make_cudaExtent(R, y1 - y0, 1);
       cp.kind = cudaMemcpyHostToDevice;
       std::lock_guard<std::mutex> g(mu);
-      cudaError_t e = cudaMemcpy3DAsync(&cp, c->stream);
+      cudaError_t e = cudaMemcpy3DAsync(&cp, c->copy_stream);
       if (e != cudaSuccess) cuda_err.store((int)e);
     });
   } else {
@@ -678,11 +728,14 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
       cp.extent = make_cudaExtent(R, R, 1);
       cp.kind = cudaMemcpyHostToDevice;
       std::lock_guard<std::mutex> g(mu);
-      cudaError_t e = cudaMemcpy3DAsync(&cp, c->stream);
+      cudaError_t e = cudaMemcpy3DAsync(&cp, c->copy_stream);
       if (e != cudaSuccess) cuda_err.store((int)e);
     });
   }
   if (cuda_err.load()) return fail(c, FSPT_E_CUDA, "atlas upload failed: %s", cudaGetErrorString((cudaError_t)cuda_err.load()));
+  // the atlas travels on its own stream: only k_shade needs it, so the camera + primary traversal launch of the next
+  // render overlaps the tail of this DMA (render_wave waits on the event before its first k_shade)
+  CK(cudaEventRecord(c->ev_atlas, c->copy_stream));
   lap("atlas stage + scan + enqueue");
   geo_thread.join();
   if (geo.code != FSPT_OK) return fail(c, geo.code, "%s", geo.msg);
@@ -735,7 +788,7 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
   }
   // no synchronisation: everything the DMA engine still reads lives in the context's pinned staging blocks, which the
   // next upload (and destroy) only touch after synchronising the stream; work enqueued by fspt_render waits in order
-  if (!pageable_geo.empty() || timing) CK(cudaStreamSynchronize(c->stream));
+  if (!pageable_geo.empty() || timing) { CK(cudaStreamSynchronize(c->stream)); CK(cudaStreamSynchronize(c->copy_stream)); }
   lap("env + textures (+ sync when timing)");
   c->sc.nodes = reinterpret_cast<const float4*>(c->d_nodes);
   c->sc.tris = reinterpret_cast<const float4*>(c->d_tris);
@@ -812,6 +865,7 @@ int fspt_synchronize(fspt_ctx* ctx) {
   if (!c) return FSPT_E_INVALID;
   CK(cudaSetDevice(c->device));
   CK(cudaStreamSynchronize(c->stream));
+  CK(cudaStreamSynchronize(c->copy_stream));
   return FSPT_OK;
 }
 
