@@ -484,17 +484,18 @@ __device__ __forceinline__ bool shade_hit(const ShadeArgs& A, int pos, bool& sha
 }
 
 #ifndef SHADE_THREADS
-#define SHADE_THREADS 128
+#define SHADE_THREADS 256
 #endif
 #ifndef SHADE_MIN_BLOCKS
-#define SHADE_MIN_BLOCKS 7  // 72 registers: 28 warps/SM; measured 5: +8 %, 6: 0, 7: -7 %, 8: -5.5 % shading time
+#define SHADE_MIN_BLOCKS 4  // 64 registers, 32 warps/SM.  Measured shading time vs 128 threads x 6 blocks (80 regs):
+                            // 128x5 +8 %, 128x7 -7 %, 128x8 -5.5 %, 224x4 -8 %, 256x4 -9 %, 448x2 -3 %, 64x14 -5.5 %
 #endif
 // Path state is STREAM-COMPACTED every bounce: this kernel reads the dense record array the traversal just worked on
 // (position i = i-th surviving path, in roughly ascending pixel order) and writes the records of the paths that
 // continue to the next free positions of a second array, so record traffic is sequential in both kernels and no
 // index lists exist except for shadow rays.  The traversal kernel leaves one hit/miss byte per position.
 // The reference's per-fragment `if (result.index < 0)` branches
-// (tracer.fs:442,509) are resolved per block: every 128-item tile pushes its hits and its misses into two block-local
+// (tracer.fs:442,509) are resolved per block: every 256-item tile pushes its hits and its misses into two block-local
 // queues and work starts only on full groups of one kind, so hit shading and miss shading never share a warp.
 __global__ void __launch_bounds__(SHADE_THREADS, SHADE_MIN_BLOCKS) k_shade(const ShadeArgs A) {
   init_unorm8_lut();
