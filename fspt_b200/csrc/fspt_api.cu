@@ -82,7 +82,7 @@ struct Ctx {
   int* d_list = nullptr;      // shadow list: record positions
   int* d_counts = nullptr;    // set k at [2k, 2k+1] = (#continuation, #shadow), [4] fetch cursor, [5..7] pad
   int* d_count_out = nullptr; // per-slot visit count (debug)
-  unsigned char* d_hit_flag = nullptr;  // per list position (ordered mode)
+  unsigned char* d_hit_flag = nullptr;  // hit / miss per record position
   unsigned long long* d_stats = nullptr;  // rays, nodes, leaves, capped
   float* d_rb = nullptr;      // rand bases of one render call: [0,cap) camera, [cap,2cap) tracer
   float* h_rb = nullptr;      // pinned staging

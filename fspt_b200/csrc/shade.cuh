@@ -512,7 +512,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, SHADE_MIN_BLOCKS) k_shade(const
     if (!last) {
       const int it = tile * SHADE_THREADS + threadIdx.x;
       const bool live = it < n;
-      const int slot = it;  // records are dense: position == list position
+      const int slot = it;  // record position
       const bool hit = live && A.hit_flag[it] != 0;  // written by k_trace per position: a coalesced read
       const unsigned mh = __ballot_sync(0xffffffffu, hit), mm = __ballot_sync(0xffffffffu, live && !hit);
       if (lane == 0) { s_hits[warp] = __popc(mh); s_miss[warp] = __popc(mm); }

@@ -17,7 +17,7 @@
 // then the idle lanes are refilled from a global queue with one atomicAdd per warp (__ballot_sync +
 // popc prefix = the compaction), so short rays do not wait for the longest ray of their warp.  Inside the
 // loop the warp votes each iteration whether to run an interior step or a leaf step (majority of lanes).
-// Results go back into the path record plus one hit/miss byte per list position for the shading kernel.
+// Results go back into the path record plus one hit/miss byte per record position for the shading kernel.
 #pragma once
 #include "camera.cuh"
 #include "device_common.cuh"
@@ -34,7 +34,7 @@ struct TraceArgs {
   int* next;              // work-fetch cursor (zeroed before launch)
   unsigned long long* stats;  // [0] rays, [1] node visits, [2] leaf visits
   int* count_out;         // per-slot visit count (debug / bvh_test mode) or NULL
-  unsigned char* hit_flag;  // per continuation-list position: 1 = hit (read coalesced by k_shade) or NULL
+  unsigned char* hit_flag;  // per record position: 1 = hit (read coalesced by k_shade) or NULL
   FrameParams f;          // CAMERA mode: primary rays are generated in the fetch instead of being read
   const float* rb_cam;
   int n_samples;
@@ -116,7 +116,7 @@ __device__ __forceinline__ float tri_test(const float4 q0, const float4 q1, cons
 }
 
 // CAMERA = the primary launch of a render wave: the ray of slot `my` is generated on the fly (camera.fs) and the whole
-// ray + hit record is written at retirement, so the camera pass, its 32 B/path of writes and this launch's 128-byte
+// ray + hit record is written at retirement, so the camera pass, its 32 B/path of writes and this launch's
 // record reads disappear.
 template <bool WRITE_COUNT, bool CAMERA>
 __global__ void __launch_bounds__(TRACE_THREADS) k_trace(const TraceArgs A) {
