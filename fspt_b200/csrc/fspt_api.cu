@@ -209,9 +209,15 @@ int launch_trace(Ctx* c, int which, bool hit_flags, bool write_count, const Fram
   A.count_out = write_count ? c->d_count_out : nullptr;
   A.hit_flag = hit_flags ? c->d_hit_flag : nullptr;
   record_trace_begin(c);
-  if (cam) k_trace<false, true><<<c->trace_blocks_cam, TRACE_THREADS, 0, c->stream>>>(A);
-  else if (write_count) k_trace<true, false><<<c->trace_blocks_cnt, TRACE_THREADS, 0, c->stream>>>(A);
-  else k_trace<false, false><<<c->trace_blocks, TRACE_THREADS, 0, c->stream>>>(A);
+  if (A.nodes_tex) {
+    if (cam) k_trace<false, true, true><<<c->trace_blocks_cam, TRACE_THREADS, 0, c->stream>>>(A);
+    else if (write_count) k_trace<true, false, true><<<c->trace_blocks_cnt, TRACE_THREADS, 0, c->stream>>>(A);
+    else k_trace<false, false, true><<<c->trace_blocks, TRACE_THREADS, 0, c->stream>>>(A);
+  } else {  // node array beyond the linear-texture limit
+    if (cam) k_trace<false, true, false><<<c->trace_blocks_cam, TRACE_THREADS, 0, c->stream>>>(A);
+    else if (write_count) k_trace<true, false, false><<<c->trace_blocks_cnt, TRACE_THREADS, 0, c->stream>>>(A);
+    else k_trace<false, false, false><<<c->trace_blocks, TRACE_THREADS, 0, c->stream>>>(A);
+  }
   record_trace_end(c);
   c->stats.kernel_launches++;
   CK(cudaGetLastError());
@@ -342,17 +348,20 @@ int fspt_create(fspt_ctx** out, int32_t width, int32_t height, int32_t device) {
   if (rc) { g_create_error = c->error; fspt_destroy(reinterpret_cast<fspt_ctx*>(c)); return rc; }
   // traversal uses no shared memory: give the whole unified array to L1 (BVH nodes + triangles live there)
   if (!getenv("FSPT_NO_CARVEOUT")) {
-    cudaFuncSetAttribute(k_trace<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-    cudaFuncSetAttribute(k_trace<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-    cudaFuncSetAttribute(k_trace<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(k_trace<false, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(k_trace<true, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(k_trace<false, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(k_trace<false, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(k_trace<true, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    cudaFuncSetAttribute(k_trace<false, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
   }
   // persistent grids: resident CTAs per SM x SM count
   int per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<false, false>, TRACE_THREADS, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<false, false, true>, TRACE_THREADS, 0);
   c->trace_blocks = std::max(1, per_sm) * c->sm_count;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<true, false>, TRACE_THREADS, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<true, false, true>, TRACE_THREADS, 0);
   c->trace_blocks_cnt = std::max(1, per_sm) * c->sm_count;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<false, true>, TRACE_THREADS, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<false, true, true>, TRACE_THREADS, 0);
   c->trace_blocks_cam = std::max(1, per_sm) * c->sm_count;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shade, SHADE_THREADS, 1024);
   c->shade_blocks = std::max(1, per_sm) * c->sm_count;

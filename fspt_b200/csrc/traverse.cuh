@@ -118,7 +118,8 @@ __device__ __forceinline__ float tri_test(const float4 q0, const float4 q1, cons
 // CAMERA = the primary launch of a render wave: the ray of slot `my` is generated on the fly (camera.fs) and the whole
 // ray + hit record is written at retirement, so the camera pass, its 32 B/path of writes and this launch's
 // record reads disappear.
-template <bool WRITE_COUNT, bool CAMERA>
+// NODE_TEX = false: the node array is too large for a linear texture (2^27 texels), everything goes through the LSU.
+template <bool WRITE_COUNT, bool CAMERA, bool NODE_TEX>
 __global__ void __launch_bounds__(TRACE_THREADS) k_trace(const TraceArgs A) {
   const unsigned lane = threadIdx.x & 31u;
   const unsigned FULL = 0xffffffffu;
@@ -214,11 +215,10 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(const TraceArgs A) {
           // The record's four words are split between the two L1 data pipes (texture fetch / LSU load): the
           // kernel is bound by L1 wavefronts (ncu: l1tex data-pipe ~60 % busy), not by issue slots.
           const float4* np = A.nodes + 4 * (size_t)cur;
-          const bool tex_ok = A.nodes_tex != 0;  // 0: array too large for a linear texture (2^27 texels)
-          const float4 a = ((TRACE_NODE_TEX & 1) && tex_ok) ? tex1Dfetch<float4>(A.nodes_tex, 4 * cur) : __ldg(np);
-          const float4 b = ((TRACE_NODE_TEX & 2) && tex_ok) ? tex1Dfetch<float4>(A.nodes_tex, 4 * cur + 1) : __ldg(np + 1);
-          const float4 c = ((TRACE_NODE_TEX & 4) && tex_ok) ? tex1Dfetch<float4>(A.nodes_tex, 4 * cur + 2) : __ldg(np + 2);
-          const float4 df = ((TRACE_NODE_TEX & 8) && tex_ok) ? tex1Dfetch<float4>(A.nodes_tex, 4 * cur + 3) : __ldg(np + 3);
+          const float4 a = ((TRACE_NODE_TEX & 1) && NODE_TEX) ? tex1Dfetch<float4>(A.nodes_tex, 4 * cur) : __ldg(np);
+          const float4 b = ((TRACE_NODE_TEX & 2) && NODE_TEX) ? tex1Dfetch<float4>(A.nodes_tex, 4 * cur + 1) : __ldg(np + 1);
+          const float4 c = ((TRACE_NODE_TEX & 4) && NODE_TEX) ? tex1Dfetch<float4>(A.nodes_tex, 4 * cur + 2) : __ldg(np + 2);
+          const float4 df = ((TRACE_NODE_TEX & 8) && NODE_TEX) ? tex1Dfetch<float4>(A.nodes_tex, 4 * cur + 3) : __ldg(np + 3);
           int4 d = make_int4(__float_as_int(df.x), __float_as_int(df.y), 0, 0);
 #if TRACE_DUP_LOADS  /* sensitivity experiment: issue the record's loads a second time through the LSU pipe */
           {
