@@ -271,7 +271,8 @@ int render_wave(Ctx* c, const FrameParams& fp, uint32_t first_tick, int S, const
     A.counts_in = c->d_counts + 2 * cur;
     A.counts_out = c->d_counts + 2 * nxt;
     record_trace_begin(c, 1);
-    k_shade<<<c->shade_blocks, SHADE_THREADS, 1024, c->stream>>>(A);
+    if (c->sc.mat_tex) k_shade<true><<<c->shade_blocks, SHADE_THREADS, 1024, c->stream>>>(A);
+    else k_shade<false><<<c->shade_blocks, SHADE_THREADS, 1024, c->stream>>>(A);
     record_trace_end(c);
     c->stats.kernel_launches++;
     CK(cudaGetLastError());
@@ -363,7 +364,7 @@ int fspt_create(fspt_ctx** out, int32_t width, int32_t height, int32_t device) {
   c->trace_blocks_cnt = std::max(1, per_sm) * c->sm_count;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<false, true, true>, TRACE_THREADS, 0);
   c->trace_blocks_cam = std::max(1, per_sm) * c->sm_count;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shade, SHADE_THREADS, 1024);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shade<true>, SHADE_THREADS, 1024);
   c->shade_blocks = std::max(1, per_sm) * c->sm_count;
   *out = reinterpret_cast<fspt_ctx*>(c);
   return FSPT_OK;

@@ -296,6 +296,7 @@ __device__ __forceinline__ void shade_miss(const ShadeArgs& A, int pos) {
 // One loop iteration of tracer.fs main (:446-513) for a path whose ray HIT, split at the intersectScene calls.
 // Returns true when the path continues; `out` then holds its new 6-word record (continuation ray, shadow ray, state).
 struct PathRecord { float4 w[6]; };
+template <bool MAT_TEX>
 __device__ __forceinline__ bool shade_hit(const ShadeArgs& A, int pos, bool& shadow, PathRecord& out) {
   const DeviceScene& sc = A.sc;
   int slot = pos;  // path identity; equals the record position only in the first pass
@@ -348,7 +349,7 @@ __device__ __forceinline__ bool shade_hit(const ShadeArgs& A, int pos, bool& sha
   const float tcy = bu * u0.y + bv * u0.w + bw_ * u1.y;
   const float layers[4] = {mapDiffuse, mapSpecular, mapRoughness, mapNormal};
   float4 tex[4];
-  if (sc.mat_tex) texture_material(sc, tcx, tcy, __float_as_int(u1.z), tex);  // :453-456
+  if (MAT_TEX) texture_material(sc, tcx, tcy, __float_as_int(u1.z), tex);  // :453-456
   else texture_atlas4(sc, tcx, tcy, layers, tex);
   const float4 tD = tex[0], tE = tex[1], tMR = tex[2], tN = tex[3];
   const v3 texDiffuse = mk3(tD.x, tD.y, tD.z), texEmmissive = mk3(tE.x, tE.y, tE.z);
@@ -497,6 +498,9 @@ __device__ __forceinline__ bool shade_hit(const ShadeArgs& A, int pos, bool& sha
 // The reference's per-fragment `if (result.index < 0)` branches
 // (tracer.fs:442,509) are resolved per block: every 256-item tile pushes its hits and its misses into two block-local
 // queues and work starts only on full groups of one kind, so hit shading and miss shading never share a warp.
+// MAT_TEX: the atlas is the material-interleaved one (false = plain RGBA8 layers, the fallback of fspt_scene_upload);
+// a template parameter so that only one of the two sampling routines is in the kernel's instruction footprint.
+template <bool MAT_TEX>
 __global__ void __launch_bounds__(SHADE_THREADS, SHADE_MIN_BLOCKS) k_shade(const ShadeArgs A) {
   init_unorm8_lut();
   // block-local queues: every tile pushes its hits and misses, and work is only started on FULL groups of
@@ -533,7 +537,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, SHADE_MIN_BLOCKS) k_shade(const
       const int take = nh < SHADE_THREADS ? nh : SHADE_THREADS;
       bool cont = false, shadow = false;
       PathRecord rec;
-      if ((int)threadIdx.x < take) cont = shade_hit(A, q_hit[nh - take + threadIdx.x], shadow, rec);
+      if ((int)threadIdx.x < take) cont = shade_hit<MAT_TEX>(A, q_hit[nh - take + threadIdx.x], shadow, rec);
       // stream compaction of the surviving paths: the new record goes to the next free position of ps_out
       const int pos_out = append_pos(cont, A.counts_out + 0);
       if (cont) {
