@@ -173,3 +173,24 @@ def test_two_triangle_scene_root_is_a_leaf(oracle_mod):
         assert np.array_equal(ctx.read_accum()[..., :3].view(np.uint32), fb[..., :3].view(np.uint32))
     finally:
         ctx.close()
+
+
+def test_plain_atlas_fallback_is_bit_identical(monkeypatch):
+    """fspt_scene_upload falls back to the plain RGBA8 layered atlas when the material-interleaved one would not fit;
+    both sampling routines must produce the same bits (FSPT_PLAIN_ATLAS forces the fallback)."""
+    sa, cam = scenes.pbr_scene(atlas_res=64, subdiv=2, env_size=(128, 64))
+    W, H = 96, 64
+    rc, rt = scenes.rand_bases(4, 13)
+    out = []
+    for plain in (False, True):
+        if plain:
+            monkeypatch.setenv("FSPT_PLAIN_ATLAS", "1")
+        ctx = capi.Context(W, H)
+        try:
+            ctx.scene_upload(sa)
+            ctx.render(_frame(ctx, cam), 0, rc, rt)
+            out.append(ctx.read_accum().copy())
+        finally:
+            ctx.close()
+    assert np.array_equal(out[0].view(np.uint32), out[1].view(np.uint32))
+    assert float(out[0][..., :3].max()) > 0.0
