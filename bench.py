@@ -195,6 +195,7 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        fdist.share_host_threads()
 
     sa, cam = build_scene(args)
     W, H, spp = args.width, args.height, args.spp

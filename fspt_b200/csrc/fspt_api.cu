@@ -416,7 +416,10 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
   const int N = s->n_nodes, T = s->n_triangles;
   const int R = s->atlas_res, L = s->atlas_layers;
   const size_t layer_texels = (size_t)R * R, layer_bytes = layer_texels * 4;
-  const int hw = (int)std::max(4u, std::min(32u, std::thread::hardware_concurrency()));
+  // host threads for staging: all cores of a single-process host; one process per GPU shares them
+  // (dist.share_host_threads sets FSPT_UPLOAD_THREADS = cores / processes on this node)
+  int hw = (int)std::max(4u, std::min(32u, std::thread::hardware_concurrency()));
+  if (const char* e = getenv("FSPT_UPLOAD_THREADS")) hw = std::max(4, std::min(64, atoi(e)));
   auto parallel = [&](int n_items, int max_workers, const std::function<void(int)>& fn) {
     std::atomic<int> next_item(0);
     const int n_workers = std::max(1, std::min(n_items, max_workers));

@@ -17,6 +17,16 @@ def accum_tensor(ctx, device_index):
     return torch.as_tensor(_DevBuf(ptr, n), device=torch.device("cuda", device_index))
 
 
+def share_host_threads(local_world=None):
+    """One process per GPU: divide the node's cores between the processes' scene-upload staging threads."""
+    import os
+    if local_world is None:
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
+    n = max(4, (os.cpu_count() or 4) // max(1, local_world))
+    os.environ.setdefault("FSPT_UPLOAD_THREADS", str(n))
+    return n
+
+
 def shard_ticks(n_total, rank, world):
     """Sample-set sharding: the tick indices rank `rank` renders."""
     return np.arange(rank, n_total, world)

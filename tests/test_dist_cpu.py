@@ -58,3 +58,15 @@ def test_sample_set_sharding_reduce_matches_single_process(tmp_path, oracle_mod)
     for k in range(N):
         mean = cols[k][..., :3] if mean is None else (cols[k][..., :3] + mean * np.float32(k)) / np.float32(k + 1)
     assert np.allclose(got[..., :3] / N, mean, rtol=2e-6, atol=1e-7)
+
+
+def test_share_host_threads(monkeypatch):
+    import os
+    from fspt_b200 import dist as fdist
+    monkeypatch.delenv("FSPT_UPLOAD_THREADS", raising=False)
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "8")
+    n = fdist.share_host_threads()
+    assert n == max(4, (os.cpu_count() or 4) // 8) and os.environ["FSPT_UPLOAD_THREADS"] == str(n)
+    monkeypatch.setenv("FSPT_UPLOAD_THREADS", "5")  # an explicit setting wins
+    fdist.share_host_threads()
+    assert os.environ["FSPT_UPLOAD_THREADS"] == "5"
