@@ -187,7 +187,7 @@ __device__ __forceinline__ float gtr2_pdf(v3 incident, v3 normal, v2 mr, v3 bsdf
   return pdfgtr2 / (4.0f * fabsf(dot(bsdfDir, halfVec)));
 }
 __device__ __forceinline__ float schlick(v3 incident, v3 normal, v2 ns) {
-  float r0 = (ns.x - ns.y) / (ns.x + ns.y);
+  float r0 = div_z(ns.x - ns.y, ns.x + ns.y);  // ior 1 gives 0 / 2
   r0 *= r0;
   float cosTheta = dot(normal, incident);
   if (ns.x > ns.y) {
@@ -425,9 +425,9 @@ __device__ __forceinline__ bool shade_hit(const ShadeArgs& A, int pos, bool& sha
   if (specular) {
     rayDir = reflect(neg(incident), microNormal);  // :477
     bsdfPdf = gtr2_pdf(incident, macroNormal, texMR, rayDir);
-    bsdfThroughput = div(mul(eval_specular(incident, macroNormal, texDiffuse, texMR, rayDir),
+    bsdfThroughput = div_z(mul(eval_specular(incident, macroNormal, texDiffuse, texMR, rayDir),
                              clampf(dot(macroNormal, rayDir), 0.0f, 1.0f)), bsdfPdf);
-    envThroughput = div(mul(eval_specular(incident, macroNormal, texDiffuse, texMR, envDir),
+    envThroughput = div_z(mul(eval_specular(incident, macroNormal, texDiffuse, texMR, envDir),
                             clampf(cosEnv, 0.0f, 1.0f)), envPdf);
   } else if (matDielectric >= 0.0f) {  // :481-488
     bsdfPdf = 1.0f;
@@ -457,8 +457,8 @@ __device__ __forceinline__ bool shade_hit(const ShadeArgs& A, int pos, bool& sha
     }
     bsdfPdf = fabsf(dot(rayDir, macroNormal)) * FSPT_INV_PI;  // lambertPdf, :235-237
     const v3 lam = mul(texDiffuse, FSPT_INV_PI);               // evalLambert, :296-298
-    bsdfThroughput = div(mul(lam, clampf(dot(macroNormal, rayDir), 0.0f, 1.0f)), bsdfPdf);
-    envThroughput = div(mul(lam, clampf(cosEnv, 0.0f, 1.0f)), envPdf);
+    bsdfThroughput = div_z(mul(lam, clampf(dot(macroNormal, rayDir), 0.0f, 1.0f)), bsdfPdf);
+    envThroughput = div_z(mul(lam, clampf(cosEnv, 0.0f, 1.0f)), envPdf);
   }
   if (inside) {  // Beer's-law override, :497
     const v3 om_ = sub(mk3(1.0f, 1.0f, 1.0f), texDiffuse);
