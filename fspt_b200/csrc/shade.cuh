@@ -214,7 +214,8 @@ __device__ __forceinline__ v3 eval_specular(v3 incident, v3 normal, v3 diffuseCo
 }
 __device__ __forceinline__ void tangent_frame(v3 normal, v3& tangent, v3& bitangent) {  // tracer.fs:259-261
   const v3 up = fabsf(normal.z) < 0.999f ? mk3(0.0f, 0.0f, 1.0f) : mk3(1.0f, 0.0f, 0.0f);
-  tangent = normalize(cross(up, normal));
+  const v3 t = cross(up, normal);  // one component is exactly 0 (up is an axis): keep it out of the divide sequence
+  tangent = div_z(t, length(t));
   bitangent = cross(normal, tangent);
 }
 
