@@ -23,9 +23,8 @@ __device__ __forceinline__ void camera_ray(const FrameParams& f, const float* __
   const float uvx = (fx / resx) * 2.0f - 1.0f, uvy = (fy / resy) * 2.0f - 1.0f;  // `uv` varying (camera.vs)
   float seed = rb_cam[s] + fx * resy + fy;  // :38
   const v3 P = mk3(f.eye[0], f.eye[1], f.eye[2]), I = mk3(f.dir[0], f.dir[1], f.dir[2]);
-  const v3 bx = cross(I, mk3(0.0f, 1.0f, 0.0f));  // y component exactly 0: kept out of the divide sequence (div_z)
-  const v3 basisX = div_z(bx, length(bx));        // :39
-  const v3 basisY = normalize(cross(basisX, I));                 // :40
+  const v3 basisX = mk3(f.basis_x[0], f.basis_x[1], f.basis_x[2]);  // :39, normalize(cross(I, vec3(0, 1, 0)))
+  const v3 basisY = mk3(f.basis_y[0], f.basis_y[1], f.basis_y[2]);  // :40, normalize(cross(basisX, I))
   const float inCamX = uvx * (resx / resy), inCamY = uvy * 1.0f;  // getScreen, :21-24
   const v3 screen = add(add(add(mul(mul(inCamX, basisX), f.fov_scale), mul(mul(inCamY, basisY), f.fov_scale)), I), P);
   const float theta = rnd(seed) * 3.14159265f * 2.0f;  // getAA, :26-30

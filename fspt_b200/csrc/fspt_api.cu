@@ -235,6 +235,13 @@ FrameParams make_frame(const Ctx* c, const fspt_frame_params* f) {
   for (int k = 0; k < 3; ++k) { p.eye[k] = f->eye[k]; p.dir[k] = f->dir[k]; }
   p.fov_scale = f->fov_scale; p.lens0 = f->lens_features[0]; p.lens1 = f->lens_features[1];
   p.env_theta = f->env_theta;
+  {
+    const v3 I = mk3(p.dir[0], p.dir[1], p.dir[2]);
+    const v3 bx = normalize(cross(I, mk3(0.0f, 1.0f, 0.0f)));  // camera.fs:39
+    const v3 by = normalize(cross(bx, I));                     // camera.fs:40
+    p.basis_x[0] = bx.x; p.basis_x[1] = bx.y; p.basis_x[2] = bx.z;
+    p.basis_y[0] = by.x; p.basis_y[1] = by.y; p.basis_y[2] = by.z;
+  }
   p.width = c->width; p.height = c->height;
   p.tiled = (c->width % 8 == 0 && c->height % 4 == 0) ? 1 : 0;
   return p;
