@@ -47,6 +47,11 @@ struct Ctx {
   void *d_nodes = nullptr, *d_tris = nullptr, *d_shade = nullptr, *d_bins = nullptr, *d_layer_info = nullptr;
   cudaArray_t atlas_arr = nullptr, env_arr = nullptr, mat_arr = nullptr;
   int mat_R = 0, mat_L = 0;
+  bool mat_surface = false;           // mat_arr was created with cudaArraySurfaceLoadStore (GPU-side interleave)
+  cudaSurfaceObject_t mat_surf = 0;   // write view of mat_arr for k_interleave_atlas
+  void* d_raw = nullptr;              // distinct varying atlas layers as uploaded (RGBA8), source of the GPU interleave
+  void* d_mat_src = nullptr;          // MatSrc per textured material
+  size_t cap_raw = 0, cap_mat_src = 0;
   void* d_mat_info = nullptr;
   size_t cap_mat_info = 0;
   cudaTextureObject_t nodes_tex = 0, tris_tex = 0;
@@ -121,6 +126,9 @@ void free_scene(Ctx* c) {
   if (c->tris_tex) cudaDestroyTextureObject(c->tris_tex);
   c->nodes_tex = c->tris_tex = 0;
   if (c->sc.mat_tex) cudaDestroyTextureObject(c->sc.mat_tex);
+  if (c->mat_surf) cudaDestroySurfaceObject(c->mat_surf);
+  c->mat_surf = 0; c->mat_surface = false;
+  dfree(c->d_raw); dfree(c->d_mat_src); c->cap_raw = c->cap_mat_src = 0;
   if (c->atlas_arr) cudaFreeArray(c->atlas_arr);
   if (c->env_arr) cudaFreeArray(c->env_arr);
   if (c->mat_arr) cudaFreeArray(c->mat_arr);
@@ -186,6 +194,23 @@ void record_trace_begin(Ctx* c, int tag = 0) {
 void record_trace_end(Ctx* c) {
   cudaEventRecord(c->ev_trace[c->ev_trace_used + 1], c->stream);
   c->ev_trace_used += 2;
+}
+
+// One texel of a material layer = the RGBA8 texels of its four maps (device_common.cuh "MatTexel"), each taken from an
+// uploaded raw layer or, for a colour layer, from its constant.
+struct MatSrc { int raw[4]; unsigned cst[4]; };
+__global__ void __launch_bounds__(256) k_interleave_atlas(cudaSurfaceObject_t surf, const uint32_t* __restrict__ raw,
+                                                          const MatSrc* __restrict__ src, int R, size_t layer_texels) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= R || y >= R) return;
+  const MatSrc m = src[blockIdx.z];
+  const size_t i = (size_t)y * R + x;
+  uint4 v;
+  v.x = m.raw[0] >= 0 ? raw[(size_t)m.raw[0] * layer_texels + i] : m.cst[0];
+  v.y = m.raw[1] >= 0 ? raw[(size_t)m.raw[1] * layer_texels + i] : m.cst[1];
+  v.z = m.raw[2] >= 0 ? raw[(size_t)m.raw[2] * layer_texels + i] : m.cst[2];
+  v.w = m.raw[3] >= 0 ? raw[(size_t)m.raw[3] * layer_texels + i] : m.cst[3];
+  surf2DLayeredwrite(v, surf, x * 16, y, blockIdx.z);
 }
 
 __global__ void k_set_counts(int* counts, int n_cont, int n_shadow) {
@@ -515,7 +540,8 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
   const size_t o_nodes = 0, o_tris = o_nodes + al(std::max<size_t>(NI, 1) * 64), o_shade = o_tris + al((size_t)(T + 3) * 48),
                o_bins = o_shade + al((size_t)T * 192), o_layer = o_bins + al((size_t)s->env_bins * 16),
-               o_mat = o_layer + al((size_t)L * 8), o_env = o_mat + al(std::max<size_t>(32, mats.size() * 32)),
+               o_mat = o_layer + al((size_t)L * 8), o_matsrc = o_mat + al(std::max<size_t>(32, mats.size() * 32)),
+               o_env = o_matsrc + al(std::max<size_t>(32, mats.size() * sizeof(MatSrc))),
                geo_bytes = o_env + al((size_t)s->env_width * s->env_height * 4);
   std::vector<uint8_t> pageable_geo;
   uint8_t* hg;
@@ -656,71 +682,119 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
     if (c->sc.atlas) { cudaDestroyTextureObject(c->sc.atlas); c->sc.atlas = 0; }
     if (c->atlas_arr) { cudaFreeArray(c->atlas_arr); c->atlas_arr = nullptr; c->atlas_R = c->atlas_L = 0; }
     const int ML = std::max(1, n_tex_mats);
-    if (!c->mat_arr || c->mat_R != R || c->mat_L != ML) {
+    // Where the interleave runs.  On the host (default): the 16-byte texels are built in pinned memory and DMA'd.  On the
+    // GPU: only the DISTINCT varying layers cross PCIe as raw RGBA8 and k_interleave_atlas builds the texels through a
+    // surface -- a material with one image map and three colours then costs 1 layer of staging and DMA instead of 4.
+    // Measured break-even (bench scene, 7 varying layers behind 2 materials: GPU path 20 % slower): chosen when the raw
+    // layers are at most half of the interleaved bytes.  FSPT_ATLAS_INTERLEAVE=gpu|cpu overrides.
+    std::vector<int> raw_of((size_t)L, -1), raw_layers;
+    MatSrc* mat_src = reinterpret_cast<MatSrc*>(hg + o_matsrc);
+    for (size_t m = 0; m < mats.size(); ++m) {
+      const int tl = mat_info[8 * m];
+      if (tl < 0) continue;
+      for (int k = 0; k < 4; ++k) {
+        const int l = mats[m][k];
+        if (!layer_info[2 * l] && raw_of[l] < 0) { raw_of[l] = (int)raw_layers.size(); raw_layers.push_back(l); }
+        mat_src[tl].raw[k] = layer_info[2 * l] ? -1 : raw_of[l];
+        mat_src[tl].cst[k] = layer_info[2 * l + 1];
+      }
+    }
+    bool gpu_interleave = n_tex_mats > 0 && raw_layers.size() * 2 <= (size_t)n_tex_mats * 4;
+    if (const char* e = getenv("FSPT_ATLAS_INTERLEAVE")) gpu_interleave = n_tex_mats > 0 && !strcmp(e, "gpu");
+    if (!c->mat_arr || c->mat_R != R || c->mat_L != ML || c->mat_surface != gpu_interleave) {
       if (c->sc.mat_tex) cudaDestroyTextureObject(c->sc.mat_tex);
       c->sc.mat_tex = 0;
+      if (c->mat_surf) cudaDestroySurfaceObject(c->mat_surf);
+      c->mat_surf = 0;
       if (c->mat_arr) cudaFreeArray(c->mat_arr);
       c->mat_arr = nullptr;
       cudaChannelFormatDesc fmt4 = cudaCreateChannelDesc<uint4>();
-      CK(cudaMalloc3DArray(&c->mat_arr, &fmt4, make_cudaExtent(R, R, ML), cudaArrayLayered));
+      CK(cudaMalloc3DArray(&c->mat_arr, &fmt4, make_cudaExtent(R, R, ML),
+                           cudaArrayLayered | (gpu_interleave ? cudaArraySurfaceLoadStore : 0)));
       rd.res.array.array = c->mat_arr;
       CK(cudaCreateTextureObject(&c->sc.mat_tex, &rd, &td, nullptr));
-      c->mat_R = R; c->mat_L = ML;
+      if (gpu_interleave) CK(cudaCreateSurfaceObject(&c->mat_surf, &rd));
+      c->mat_R = R; c->mat_L = ML; c->mat_surface = gpu_interleave;
     }
-    const size_t need = layer_texels * 16 * (size_t)ML;
+    const size_t need = gpu_interleave ? layer_bytes * raw_layers.size() : layer_texels * 16 * (size_t)ML;
     if (c->stage_bytes < need) {
       if (c->h_stage) cudaFreeHost(c->h_stage);
       c->h_stage = nullptr; c->stage_bytes = 0;
       CK(cudaMallocHost(&c->h_stage, need));
       c->stage_bytes = need;
     }
-    // work item = (textured material, band of rows): interleave the four source layers, DMA the band
-    const int bands = std::max(1, std::min(R, 16));
-    std::vector<int> tex_mat_ids;
-    for (size_t m = 0; m < mats.size(); ++m) if (mat_info[8 * m] >= 0) tex_mat_ids.push_back((int)m);
-    parallel((int)tex_mat_ids.size() * bands, atlas_workers, [&](int item) {
-      const int m = tex_mat_ids[item / bands], band = item % bands;
-      const int tl = mat_info[8 * m];
-      const int y0 = (int)((long long)R * band / bands), y1 = (int)((long long)R * (band + 1) / bands);
-      const uint32_t* src[4];
-      for (int k = 0; k < 4; ++k) src[k] = reinterpret_cast<const uint32_t*>(s->atlas) + (size_t)mats[m][k] * layer_texels;
-      uint32_t* dst = reinterpret_cast<uint32_t*>(c->h_stage) + ((size_t)tl * layer_texels + (size_t)y0 * R) * 4;
-      const size_t i0 = (size_t)y0 * R, n = (size_t)(y1 - y0) * R;
-      size_t i = 0;
+    if (gpu_interleave) {
+      int rc2;
+      if ((rc2 = ensure(c, c->d_raw, c->cap_raw, need))) return rc2;
+      if ((rc2 = ensure(c, c->d_mat_src, c->cap_mat_src, sizeof(MatSrc) * (size_t)ML))) return rc2;
+      // work item = (raw layer, band of rows): copy into the pinned block, DMA the band
+      const int bands = std::max(1, std::min(R, 16));
+      parallel((int)raw_layers.size() * bands, atlas_workers, [&](int item) {
+        const int ri = item / bands, band = item % bands;
+        const size_t y0 = (size_t)R * band / bands, y1 = (size_t)R * (band + 1) / bands;
+        const size_t off = (size_t)ri * layer_bytes + y0 * R * 4, bytes = (y1 - y0) * R * 4;
+        memcpy(c->h_stage + off, s->atlas + (size_t)raw_layers[ri] * layer_bytes + y0 * R * 4, bytes);
+        std::lock_guard<std::mutex> g(mu);
+        cudaError_t e = cudaMemcpyAsync(reinterpret_cast<uint8_t*>(c->d_raw) + off, c->h_stage + off, bytes, cudaMemcpyHostToDevice, c->copy_stream);
+        if (e != cudaSuccess) cuda_err.store((int)e);
+      });
+      CK(cudaMemcpyAsync(c->d_mat_src, mat_src, sizeof(MatSrc) * (size_t)n_tex_mats, cudaMemcpyHostToDevice, c->copy_stream));
+      const dim3 blk(32, 8), grd((R + 31) / 32, (R + 7) / 8, n_tex_mats);
+      k_interleave_atlas<<<grd, blk, 0, c->copy_stream>>>(c->mat_surf, reinterpret_cast<const uint32_t*>(c->d_raw),
+                                                          reinterpret_cast<const MatSrc*>(c->d_mat_src), R, layer_texels);
+      c->stats.kernel_launches++;
+      CK(cudaGetLastError());
+    } else {
+      // work item = (textured material, band of rows): interleave the four source layers, DMA the band
+      const int bands = std::max(1, std::min(R, 16));
+      std::vector<int> tex_mat_ids;
+      for (size_t m = 0; m < mats.size(); ++m) if (mat_info[8 * m] >= 0) tex_mat_ids.push_back((int)m);
+      parallel((int)tex_mat_ids.size() * bands, atlas_workers, [&](int item) {
+        const int m = tex_mat_ids[item / bands], band = item % bands;
+        const int tl = mat_info[8 * m];
+        const int y0 = (int)((long long)R * band / bands), y1 = (int)((long long)R * (band + 1) / bands);
+        const uint32_t* src[4];
+        for (int k = 0; k < 4; ++k) src[k] = reinterpret_cast<const uint32_t*>(s->atlas) + (size_t)mats[m][k] * layer_texels;
+        uint32_t* dst = reinterpret_cast<uint32_t*>(c->h_stage) + ((size_t)tl * layer_texels + (size_t)y0 * R) * 4;
+        const size_t i0 = (size_t)y0 * R, n = (size_t)(y1 - y0) * R;
+        size_t i = 0;
 #if defined(__SSE2__)
-      // 4x4 transpose of 32-bit texels, written with non-temporal stores: the staging block is only read by the DMA
-      // engine, so it should neither be fetched for ownership nor displace the source layers from the CPU caches
-      for (; i + 4 <= n; i += 4) {
-        const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src[0] + i0 + i));
-        const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src[1] + i0 + i));
-        const __m128i c2 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src[2] + i0 + i));
-        const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src[3] + i0 + i));
-        const __m128i ab_lo = _mm_unpacklo_epi32(a, b), ab_hi = _mm_unpackhi_epi32(a, b);
-        const __m128i cd_lo = _mm_unpacklo_epi32(c2, d), cd_hi = _mm_unpackhi_epi32(c2, d);
-        __m128i* o = reinterpret_cast<__m128i*>(dst + 4 * i);  // 16-byte aligned: pinned block + multiples of 16
-        _mm_stream_si128(o + 0, _mm_unpacklo_epi64(ab_lo, cd_lo));
-        _mm_stream_si128(o + 1, _mm_unpackhi_epi64(ab_lo, cd_lo));
-        _mm_stream_si128(o + 2, _mm_unpacklo_epi64(ab_hi, cd_hi));
-        _mm_stream_si128(o + 3, _mm_unpackhi_epi64(ab_hi, cd_hi));
-      }
-      _mm_sfence();
+        // 4x4 transpose of 32-bit texels, written with non-temporal stores: the staging block is only read by the DMA
+        // engine, so it should neither be fetched for ownership nor displace the source layers from the CPU caches
+        for (; i + 4 <= n; i += 4) {
+          const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src[0] + i0 + i));
+          const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src[1] + i0 + i));
+          const __m128i c2 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src[2] + i0 + i));
+          const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src[3] + i0 + i));
+          const __m128i ab_lo = _mm_unpacklo_epi32(a, b), ab_hi = _mm_unpackhi_epi32(a, b);
+          const __m128i cd_lo = _mm_unpacklo_epi32(c2, d), cd_hi = _mm_unpackhi_epi32(c2, d);
+          __m128i* o = reinterpret_cast<__m128i*>(dst + 4 * i);  // 16-byte aligned: pinned block + multiples of 16
+          _mm_stream_si128(o + 0, _mm_unpacklo_epi64(ab_lo, cd_lo));
+          _mm_stream_si128(o + 1, _mm_unpackhi_epi64(ab_lo, cd_lo));
+          _mm_stream_si128(o + 2, _mm_unpacklo_epi64(ab_hi, cd_hi));
+          _mm_stream_si128(o + 3, _mm_unpackhi_epi64(ab_hi, cd_hi));
+        }
+        _mm_sfence();
 #endif
-      for (; i < n; ++i) {
-        dst[4 * i + 0] = src[0][i0 + i]; dst[4 * i + 1] = src[1][i0 + i];
-        dst[4 * i + 2] = src[2][i0 + i]; dst[4 * i + 3] = src[3][i0 + i];
-      }
-      cudaMemcpy3DParms cp = {};
-      cp.srcPtr = make_cudaPitchedPtr(dst, (size_t)R * 16, R, y1 - y0);
-      cp.dstArray = c->mat_arr;
-      cp.dstPos = make_cudaPos(0, y0, tl);
-      cp.extent = make_cudaExtent(R, y1 - y0, 1);
-      cp.kind = cudaMemcpyHostToDevice;
-      std::lock_guard<std::mutex> g(mu);
-      cudaError_t e = cudaMemcpy3DAsync(&cp, c->copy_stream);
-      if (e != cudaSuccess) cuda_err.store((int)e);
-    });
+        for (; i < n; ++i) {
+          dst[4 * i + 0] = src[0][i0 + i]; dst[4 * i + 1] = src[1][i0 + i];
+          dst[4 * i + 2] = src[2][i0 + i]; dst[4 * i + 3] = src[3][i0 + i];
+        }
+        cudaMemcpy3DParms cp = {};
+        cp.srcPtr = make_cudaPitchedPtr(dst, (size_t)R * 16, R, y1 - y0);
+        cp.dstArray = c->mat_arr;
+        cp.dstPos = make_cudaPos(0, y0, tl);
+        cp.extent = make_cudaExtent(R, y1 - y0, 1);
+        cp.kind = cudaMemcpyHostToDevice;
+        std::lock_guard<std::mutex> g(mu);
+        cudaError_t e = cudaMemcpy3DAsync(&cp, c->copy_stream);
+        if (e != cudaSuccess) cuda_err.store((int)e);
+      });
+    }
   } else {
     if (c->sc.mat_tex) { cudaDestroyTextureObject(c->sc.mat_tex); c->sc.mat_tex = 0; }
+    if (c->mat_surf) { cudaDestroySurfaceObject(c->mat_surf); c->mat_surf = 0; }
+    c->mat_surface = false;
     if (c->mat_arr) { cudaFreeArray(c->mat_arr); c->mat_arr = nullptr; c->mat_R = c->mat_L = 0; }
     if (!c->atlas_arr || c->atlas_R != R || c->atlas_L != L) {
       if (c->sc.atlas) cudaDestroyTextureObject(c->sc.atlas);

@@ -194,3 +194,24 @@ def test_plain_atlas_fallback_is_bit_identical(monkeypatch):
             ctx.close()
     assert np.array_equal(out[0].view(np.uint32), out[1].view(np.uint32))
     assert float(out[0][..., :3].max()) > 0.0
+
+
+def test_gpu_and_host_atlas_interleave_are_bit_identical(monkeypatch):
+    """The material-interleaved atlas is built on the host (default for scenes whose materials use most of their four
+    maps) or by k_interleave_atlas from the raw layers (chosen when few maps vary); FSPT_ATLAS_INTERLEAVE forces one."""
+    sa, cam = scenes.pbr_scene(atlas_res=64, subdiv=2, env_size=(128, 64))
+    W, H = 96, 64
+    rc, rt = scenes.rand_bases(4, 21)
+    out = []
+    for mode in ("cpu", "gpu", "cpu"):  # the third upload re-creates the array without the surface flag
+        monkeypatch.setenv("FSPT_ATLAS_INTERLEAVE", mode)
+        if not out:
+            ctx = capi.Context(W, H)
+        ctx.scene_upload(sa)
+        ctx.clear()
+        ctx.render(_frame(ctx, cam), 0, rc, rt)
+        out.append(ctx.read_accum().copy())
+    ctx.close()
+    assert np.array_equal(out[0].view(np.uint32), out[1].view(np.uint32))
+    assert np.array_equal(out[0].view(np.uint32), out[2].view(np.uint32))
+    assert float(out[0][..., :3].max()) > 0.0
