@@ -14,7 +14,11 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <stdio.h>
+#include <stdlib.h>
+
 #include <algorithm>
+#include <chrono>
 #include <atomic>
 #include <future>
 #include <thread>
@@ -45,8 +49,8 @@ struct Ctx {
   const Aabb* tb;             // per-triangle boxes seen by the presorts and the SAH sweeps (Triangle.boundingBox)
   const Aabb* nb;             // per-triangle boxes of the current vertices (node boxes, BoundingBox.addNode)
   int32_t* idx[3];            // centroid-sorted triangle ids, partitioned in place
-  int32_t* tmp;               // partition scratch, indexed by position
-  double* sback;              // suffix surface areas, indexed by position
+  int32_t* tmp[2];            // partition scratch (one per concurrently partitioned axis), indexed by position
+  double* sback[3];           // suffix surface areas per axis, indexed by position
   uint8_t* side;              // per-triangle "goes left" flag
   std::vector<BuildNode> nodes;
   std::atomic<int32_t> n_nodes{0};
@@ -56,6 +60,88 @@ struct Ctx {
   int max_tris;
 };
 
+template <class F>
+void run_parallel(int n_threads, int n_items, F fn) {
+  const int helpers = std::max(0, std::min(n_threads, n_items) - 1);
+  std::atomic<int> next(0);
+  auto work = [&]() { for (;;) { const int k = next.fetch_add(1); if (k >= n_items) break; fn(k); } };
+  std::vector<std::thread> th;
+  for (int i = 0; i < helpers; ++i) th.emplace_back(work);
+  work();
+  for (auto& t : th) t.join();
+}
+
+// Intra-node parallelism for the few huge nodes at the top of the tree (below them, sibling subtrees are the
+// parallelism): up to `want` helper threads are borrowed from the same budget the subtree tasks use.
+int grab(Ctx& c, int want) {
+  int avail = c.tasks_free.load();
+  for (;;) {
+    const int take = std::min(avail, want);
+    if (take <= 0) return 0;
+    if (c.tasks_free.compare_exchange_weak(avail, avail - take)) return take;
+  }
+}
+template <class F>
+void par_items(Ctx& c, int n_items, F fn) {
+  const int helpers = n_items > 1 ? grab(c, n_items - 1) : 0;
+  if (helpers == 0) { for (int k = 0; k < n_items; ++k) fn(k); return; }
+  std::atomic<int> next(0);
+  auto work = [&]() { for (;;) { const int k = next.fetch_add(1); if (k >= n_items) break; fn(k); } };
+  std::vector<std::thread> th;
+  for (int i = 0; i < helpers; ++i) th.emplace_back(work);
+  work();
+  for (auto& t : th) t.join();
+  c.tasks_free.fetch_add(helpers);
+}
+constexpr int32_t kParNode = 1 << 17;   // nodes at least this large are processed in chunks by several threads
+constexpr int32_t kChunk = 1 << 15;
+
+// Node.setSplit (bvh.js:168-197) for a huge node: min/max are exact and associative (incl. the signed-zero rule), so the
+// front/back boxes of every position can be produced chunk by chunk from the unions of the chunks before/after it --
+// the same doubles as the sequential sweep, hence the same costs and, merging in (axis, position) order with strict <,
+// the same first minimum.
+void split_parallel(Ctx& c, int32_t lo, int32_t hi, double parent, double& best, int& best_axis, int32_t& best_i) {
+  const int32_t n = hi - lo;
+  const int K = (int)std::min<int64_t>(64, ((int64_t)n + kChunk - 1) / kChunk);
+  auto c0 = [&](int k) { return lo + (int32_t)((int64_t)n * k / K); };
+  std::vector<Aabb> cbox((size_t)3 * K), pre((size_t)3 * K), suf((size_t)3 * K);
+  par_items(c, 3 * K, [&](int item) {
+    const int axis = item / K, k = item % K;
+    const int32_t* ix = c.idx[axis];
+    Aabb bb; bb.reset();
+    for (int32_t i = c0(k); i < c0(k + 1); ++i) bb.grow(c.tb[ix[i]]);
+    cbox[item] = bb;
+  });
+  for (int axis = 0; axis < 3; ++axis) {
+    Aabb bb; bb.reset();
+    for (int k = 0; k < K; ++k) { pre[axis * K + k] = bb; bb.grow(cbox[axis * K + k]); }
+    bb.reset();
+    for (int k = K - 1; k >= 0; --k) { suf[axis * K + k] = bb; bb.grow(cbox[axis * K + k]); }
+  }
+  std::vector<double> cbest((size_t)3 * K, INFINITY);
+  std::vector<int32_t> cbest_i((size_t)3 * K, -1);
+  par_items(c, 3 * K, [&](int item) {
+    const int axis = item / K, k = item % K;
+    const int32_t* ix = c.idx[axis];
+    double* sback = c.sback[axis];
+    const int32_t a = c0(k), b = c0(k + 1);
+    Aabb bb = suf[item];
+    for (int32_t i = b - 1; i >= a; --i) { bb.grow(c.tb[ix[i]]); sback[i] = bb.area(); }
+    bb = pre[item];
+    double bst = INFINITY; int32_t bi = -1;
+    for (int32_t i = a; i < b; ++i) {
+      bb.grow(c.tb[ix[i]]);
+      const double sAf = bb.area(), sAb = sback[i];
+      const int32_t kk = i - lo;
+      const double cost = 1 + (sAf / parent) * 1 * (double)(kk + 1) + (sAb / parent) * 1 * (double)(n - 1 - kk);
+      if (cost < bst) { bst = cost; bi = kk + 1; }
+    }
+    cbest[item] = bst; cbest_i[item] = bi;
+  });
+  for (int item = 0; item < 3 * K; ++item)
+    if (cbest[item] < best) { best = cbest[item]; best_i = cbest_i[item]; best_axis = item / K; }
+}
+
 int32_t build(Ctx& c, int32_t lo, int32_t hi, int d) {
   int32_t self = c.n_nodes.fetch_add(1);
   BuildNode nd;
@@ -64,20 +150,35 @@ int32_t build(Ctx& c, int32_t lo, int32_t hi, int d) {
   while (d > prev && !c.depth.compare_exchange_weak(prev, d)) {}
   const int32_t n = hi - lo;
   nd.box.reset();
-  for (int32_t i = lo; i < hi; ++i) nd.box.grow(c.nb[c.idx[0][i]]);  // BoundingBox.addNode, bvh.js:122-128
+  const bool big = n >= kParNode && c.tasks_free.load() > 0;  // helpers available (otherwise the plain sweep is cheaper)
+  if (!big) {
+    for (int32_t i = lo; i < hi; ++i) nd.box.grow(c.nb[c.idx[0][i]]);  // BoundingBox.addNode, bvh.js:122-128
+  } else {
+    const int K = (int)std::min<int64_t>(64, ((int64_t)n + kChunk - 1) / kChunk);
+    std::vector<Aabb> part((size_t)K);
+    par_items(c, K, [&](int k) {
+      Aabb bb; bb.reset();
+      const int32_t a = lo + (int32_t)((int64_t)n * k / K), b = lo + (int32_t)((int64_t)n * (k + 1) / K);
+      for (int32_t i = a; i < b; ++i) bb.grow(c.nb[c.idx[0][i]]);
+      part[k] = bb;
+    });
+    for (int k = 0; k < K; ++k) nd.box.grow(part[k]);
+  }
   if (n <= c.max_tris) { c.nodes[self] = nd; return self; }          // bvh.js:22 (split of a leaf is unused)
   // Node.setSplit, bvh.js:168-197
   double best = INFINITY;
   int best_axis = -1; int32_t best_i = -1;
   const double parent = nd.box.area();
-  for (int axis = 0; axis < 3; ++axis) {
+  if (big) split_parallel(c, lo, hi, parent, best, best_axis, best_i);
+  else for (int axis = 0; axis < 3; ++axis) {
     const int32_t* ix = c.idx[axis];
+    double* sback = c.sback[0];
     Aabb bb; bb.reset();
-    for (int32_t i = hi - 1; i >= lo; --i) { bb.grow(c.tb[ix[i]]); c.sback[i] = bb.area(); }
+    for (int32_t i = hi - 1; i >= lo; --i) { bb.grow(c.tb[ix[i]]); sback[i] = bb.area(); }
     bb.reset();
     for (int32_t i = lo; i < hi; ++i) {
       bb.grow(c.tb[ix[i]]);
-      const double sAf = bb.area(), sAb = c.sback[i];
+      const double sAf = bb.area(), sAb = sback[i];
       const int32_t k = i - lo;
       const double cost = 1 + (sAf / parent) * 1 * (double)(k + 1) + (sAb / parent) * 1 * (double)(n - 1 - k);
       if (cost < best) { best = cost; best_i = k + 1; best_axis = axis; }
@@ -91,13 +192,16 @@ int32_t build(Ctx& c, int32_t lo, int32_t hi, int d) {
   // _constructCachedIndexList, bvh.js:52-76: stable partition of the other two axes
   const int32_t mid = lo + best_i;
   for (int32_t i = lo; i < hi; ++i) c.side[c.idx[best_axis][i]] = (i < mid);
-  for (int axis = 0; axis < 3; ++axis) {
-    if (axis == best_axis) continue;
+  auto partition_axis = [&](int which) {  // which = 0, 1: the two axes other than best_axis, each with its own scratch
+    const int axis = (best_axis + 1 + which) % 3;
     int32_t* ix = c.idx[axis];
+    int32_t* tmp = c.tmp[which];
     int32_t l = lo, r = 0;
-    for (int32_t i = lo; i < hi; ++i) { int32_t t = ix[i]; if (c.side[t]) ix[l++] = t; else c.tmp[lo + r++] = t; }
-    memcpy(ix + l, c.tmp + lo, sizeof(int32_t) * (size_t)r);
-  }
+    for (int32_t i = lo; i < hi; ++i) { int32_t t = ix[i]; if (c.side[t]) ix[l++] = t; else tmp[lo + r++] = t; }
+    memcpy(ix + l, tmp + lo, sizeof(int32_t) * (size_t)r);
+  };
+  if (big) par_items(c, 2, partition_axis);
+  else { partition_axis(0); partition_axis(1); }
   int32_t L, R;
   bool spawn = false;
   if (n > 32768) {  // sibling subtrees touch disjoint ranges / triangles: build them concurrently
@@ -160,60 +264,96 @@ extern "C" int fspt_bvh_build2(const double* verts, const double* box_verts, int
                                float* nodes_out, int32_t* order_out, int32_t* n_nodes_out, int32_t* depth_out,
                                int32_t n_threads) {
   if (!verts || !nodes_out || !order_out || n_tris <= 0 || max_tris <= 0) return FSPT_E_INVALID;
+  const bool timing = getenv("FSPT_TIMING") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[fspt bvh] %-24s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+    t_prev = now;
+  };
   const double* bv = box_verts ? box_verts : verts;
   std::vector<Aabb> tb((size_t)n_tris), nb;
   if (box_verts) nb.resize((size_t)n_tris);
   std::vector<double> cen[3];
   for (int a = 0; a < 3; ++a) cen[a].resize((size_t)n_tris);
-  for (int32_t i = 0; i < n_tris; ++i) {  // Triangle.boundingBox, bvh.js:208
-    Aabb& b = tb[i]; b.reset();
-    for (int v = 0; v < 3; ++v)
-      for (int k = 0; k < 3; ++k) {
-        double x = bv[(size_t)i * 9 + v * 3 + k];
-        if (!(x == x) || isinf(x)) return FSPT_E_INVALID;
-        b.mn[k] = Aabb::lo(x, b.mn[k]);
-        b.mx[k] = Aabb::hi(x, b.mx[k]);
-      }
-    for (int k = 0; k < 3; ++k) cen[k][i] = (b.mn[k] + b.mx[k]) * 0.5;  // centroid, bvh.js:130-135
-    if (box_verts) {
-      Aabb& n = nb[i]; n.reset();
+  if (n_threads <= 0) n_threads = (int)std::thread::hardware_concurrency();
+  n_threads = std::max(1, n_threads);
+  std::atomic<int> bad(0);
+  const int box_chunks = (int)std::min<int64_t>(256, ((int64_t)n_tris + 65535) / 65536);
+  run_parallel(n_threads, box_chunks, [&](int ch) {
+    const int32_t i0 = (int32_t)((int64_t)n_tris * ch / box_chunks), i1 = (int32_t)((int64_t)n_tris * (ch + 1) / box_chunks);
+    for (int32_t i = i0; i < i1; ++i) {  // Triangle.boundingBox, bvh.js:208
+      Aabb& b = tb[i]; b.reset();
       for (int v = 0; v < 3; ++v)
         for (int k = 0; k < 3; ++k) {
-          double x = verts[(size_t)i * 9 + v * 3 + k];
-          if (!(x == x) || isinf(x)) return FSPT_E_INVALID;
-          n.mn[k] = Aabb::lo(x, n.mn[k]);
-          n.mx[k] = Aabb::hi(x, n.mx[k]);
+          double x = bv[(size_t)i * 9 + v * 3 + k];
+          if (!(x == x) || isinf(x)) { bad.store(1); return; }
+          b.mn[k] = Aabb::lo(x, b.mn[k]);
+          b.mx[k] = Aabb::hi(x, b.mx[k]);
         }
+      for (int k = 0; k < 3; ++k) cen[k][i] = (b.mn[k] + b.mx[k]) * 0.5;  // centroid, bvh.js:130-135
+      if (box_verts) {
+        Aabb& n = nb[i]; n.reset();
+        for (int v = 0; v < 3; ++v)
+          for (int k = 0; k < 3; ++k) {
+            double x = verts[(size_t)i * 9 + v * 3 + k];
+            if (!(x == x) || isinf(x)) { bad.store(1); return; }
+            n.mn[k] = Aabb::lo(x, n.mn[k]);
+            n.mx[k] = Aabb::hi(x, n.mx[k]);
+          }
+      }
     }
-  }
-  std::vector<int32_t> ix[3], tmp((size_t)n_tris);
-  std::vector<double> sback((size_t)n_tris);
+  });
+  if (bad.load()) return FSPT_E_INVALID;
+  lap("boxes + centroids");
+  std::vector<int32_t> ix[3], tmp[2];
+  for (auto& t : tmp) t.resize((size_t)n_tris);
+  std::vector<double> sback[3];
+  sback[0].resize((size_t)n_tris);
+  if (n_tris >= kParNode) { sback[1].resize((size_t)n_tris); sback[2].resize((size_t)n_tris); }
   std::vector<uint8_t> side((size_t)n_tris);
   {
-    std::vector<std::thread> th;  // _sortIndices x3 (bvh.js:78-90): stable, by centroid
-    for (int a = 0; a < 3; ++a) {
-      ix[a].resize((size_t)n_tris);
-      th.emplace_back([&, a]() {
-        for (int32_t i = 0; i < n_tris; ++i) ix[a][i] = i;
+    // _sortIndices x3 (bvh.js:78-90): stable, by centroid.  Large inputs: every axis is cut into runs that are
+    // stable-sorted concurrently and then merged pairwise (a stable merge of adjacent runs yields the one stable order).
+    const int P = n_tris >= kParNode ? 8 : 1;
+    auto run0 = [&](int r) { return (int32_t)((int64_t)n_tris * r / P); };
+    for (int a = 0; a < 3; ++a) ix[a].resize((size_t)n_tris);
+    run_parallel(n_threads, 3 * P, [&](int item) {
+      const int a = item / P, r = item % P;
+      const double* cc = cen[a].data();
+      int32_t* v = ix[a].data();
+      for (int32_t i = run0(r); i < run0(r + 1); ++i) v[i] = i;
+      std::stable_sort(v + run0(r), v + run0(r + 1), [cc](int32_t p, int32_t q) { return cc[p] < cc[q]; });
+    });
+    for (int width = 1; width < P; width *= 2) {
+      const int pairs = P / (2 * width);
+      run_parallel(n_threads, 3 * pairs, [&](int item) {
+        const int a = item / pairs, j = item % pairs;
         const double* cc = cen[a].data();
-        std::stable_sort(ix[a].begin(), ix[a].end(), [cc](int32_t p, int32_t q) { return cc[p] < cc[q]; });
+        int32_t* v = ix[a].data();
+        std::inplace_merge(v + run0(2 * j * width), v + run0((2 * j + 1) * width), v + run0((2 * j + 2) * width),
+                           [cc](int32_t p, int32_t q) { return cc[p] < cc[q]; });
       });
     }
-    for (auto& t : th) t.join();
   }
+  lap("presort x3");
   Ctx c;
   c.tb = tb.data();
   c.nb = box_verts ? nb.data() : tb.data();
   for (int a = 0; a < 3; ++a) c.idx[a] = ix[a].data();
-  c.tmp = tmp.data(); c.sback = sback.data(); c.side = side.data();
+  c.tmp[0] = tmp[0].data(); c.tmp[1] = tmp[1].data();
+  for (int a = 0; a < 3; ++a) c.sback[a] = sback[a].empty() ? sback[0].data() : sback[a].data();
+  c.side = side.data();
   c.nodes.resize((size_t)2 * n_tris + 1);
   c.max_tris = max_tris;
-  if (n_threads <= 0) n_threads = (int)std::thread::hardware_concurrency();
   c.tasks_free.store(n_threads > 1 ? n_threads - 1 : 0);
   int32_t root = build(c, 0, n_tris, 0);
+  lap("build");
   if (c.failed.load()) return FSPT_E_LIMIT;
   int32_t n = 0;
   flatten(c, root, nodes_out, order_out, &n);
+  lap("flatten");
   if (n_nodes_out) *n_nodes_out = n;
   if (depth_out) *depth_out = c.depth.load();
   return FSPT_OK;

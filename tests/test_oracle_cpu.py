@@ -428,3 +428,20 @@ def test_native_pack_layer_matches_blit_restatement(oracle_mod):
     assert np.array_equal(out[::-1, :, :3], sq[..., :3])
     with pytest.raises(capi.FsptError):
         capi.pack_layer(img, 8, False, [0, 1, 2, 7])
+
+
+def test_native_builder_parallel_paths_match_oracle_on_large_tie_heavy_input(oracle_mod):
+    """>= 2^17 triangles take the chunked sweeps / run-merged presorts of csrc/bvh_builder.cpp; coordinates snapped to a
+    1/32 grid and pairs of identical triangles make equal centroids and equal SAH costs common, so the first-minimum and
+    stable-order rules (bvh.js:78-90,190) are what decides the tree."""
+    from fspt_b200 import capi
+    rng = np.random.default_rng(5)
+    c = np.round(rng.uniform(-1, 1, (140000, 1, 3)) * 32) / 32
+    v = (c + np.round(rng.uniform(-0.1, 0.1, (140000, 3, 3)) * 32) / 32).reshape(-1, 9)
+    v[1::5] = v[0::5][:v[1::5].shape[0]]
+    par = capi.bvh_build(v, 4, n_threads=8)
+    seq = capi.bvh_build(v, 4, n_threads=1)
+    ref = oracle_mod.bvh_build(v, 4)
+    for other in (seq, ref):
+        assert np.array_equal(par[0].view(np.uint32), other[0].view(np.uint32))
+        assert np.array_equal(par[1], other[1]) and par[2] == other[2]
