@@ -3,19 +3,28 @@
 scene at 1280x720, 64 spp, bokeh DoF + HDRi importance sampling, on 1/2/4/8 B200.
 
   python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
-  python bench.py --impl reference ...                     (the CPU restatement of the reference shaders)
+  python bench.py --impl reference ...                     (the reference's algorithm on the host CPU)
+  python bench.py --config {1..5}                          (the other BASELINE.json configs; default 2 = the metric's)
+  python bench.py --gpus N --scaling strong                (ONE fixed frame split over N GPUs by tiles x sample sets)
 
-A "step" = one 64-spp frame of the workload (58.98 M path samples at 1280x720).
+A "step" = one frame of the workload (config 2: 64 spp of 1280x720 = 58.98 M path samples).
   value : device-resident throughput -- scene already in HBM, CUDA events on the library's launch stream around
           camera + traversal + shading + accumulation (+ the NCCL reduce for N>1), max over ranks.
-  e2e   : the same frame through the public host API with HOST buffers: scene upload (H2D) + render + post-pass
-          + RGBA8 read-back (D2H) inside the timed region, wall clock bracketed by synchronize.
-Multi-GPU = sample-set sharding (every rank renders its own 64 spp of the same frame with its own rand-base
-stream, weak scaling), f32 sum buffers combined with one NCCL reduce per frame, root runs the post-pass.
+  e2e   : the same frame through the public host API with HOST buffers: scene upload (H2D; N>1: rank 0 uploads,
+          the other ranks receive it with fspt_scene_broadcast over NVLink) + render + reduce + post-pass + RGBA8
+          read-back (D2H) inside the timed region, wall clock bracketed by synchronize + barrier.
+  parity: a small frame rendered through the SAME multi-rank path (sharding, collectives behind the C ABI) compared
+          bit for bit with the CPU oracle, outside the timed region.
+Multi-GPU: every collective runs inside the library (fspt_comm_init / fspt_reduce_accum / fspt_scene_broadcast);
+torch.distributed only launches the ranks and carries the NCCL unique id.
+  weak   (default, what the driver's scaling run measures): every rank renders its own --spp samples of the frame
+         (sample-set sharding), one ncclReduce(sum) per frame.
+  strong : the frame's --spp samples are fixed; ranks split it by tiles x sample sets (fspt_b200.dist.partition).
 """
 import argparse
 import json
 import os
+import shutil
 import subprocess
 import sys
 import threading
@@ -26,29 +35,53 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-WIDTH, HEIGHT, SPP = 1280, 720, 64
 METRIC = "Mpath-samples/s"
 
+# BASELINE.json configs; "spp" is what one bench step renders (config 5: a 64-sample slice of its 1024 spp)
+CONFIGS = {
+    1: dict(name="configs[0]: bunny-class scene, 800x800, 1 spp (the reference's own CPU-runnable case)",
+            scene="bunny", res=(800, 800), spp=1),
+    2: dict(name="configs[1]: bunny-class scene, 1280x720, 64 spp, aperture 0.02 DoF, env NEE+MIS", scene="bunny",
+            res=(1280, 720), spp=64),
+    3: dict(name="configs[2]: 327680-triangle icosphere + 672320-triangle soup (1.0 M), 1280x720, primary + 4 bounces, "
+                 "Lambert 0.8", scene="soup", res=(1280, 720), spp=16),
+    4: dict(name="configs[3]: textured PBR scene (all four atlas maps, refractive prop ior 1.4), 1920x1080, 256 spp",
+            scene="pbr", res=(1920, 1080), spp=256),
+    5: dict(name="configs[4]: 10 M-triangle scene (subdiv-8 icosphere + 8.69 M soup, seed 4321), 3840x2160, one "
+                 "64-sample slice of the 1024 spp per step", scene="soup10m", res=(3840, 2160), spp=64),
+}
 
-def build_scene(args):
+
+def build_scene(args, host=None):
     from fspt_b200 import scenes
-    sa, cam = scenes.bunny_class(subdiv=args.subdiv, atlas_res=args.atlas_res, env_size=(2048, 1024))
-    return sa, cam
+    kind = CONFIGS[args.config]["scene"]
+    if kind == "bunny":
+        return scenes.bunny_class(subdiv=args.subdiv, atlas_res=args.atlas_res, env_size=(2048, 1024), host=host)
+    if kind == "soup":
+        return scenes.sphere_soup()
+    if kind == "pbr":
+        return scenes.pbr_scene(atlas_res=args.atlas_res)
+    if kind == "soup10m":
+        return scenes.sphere_soup(subdiv=8, n_soup=10000000 - 1310720, seed=4321)
+    raise ValueError(kind)
 
 
-def workload_config(args, sa, n_gpus):
+def workload_config(args, sa, n_gpus, parallelism):
+    cfg = CONFIGS[args.config]
+    l2 = ("L2 flushed (512 MB write) between timed steps; per-wave path state (2 x 96 B per path, up to 64 Mi paths) "
+          "and the atlas exceed the 126 MB L2; BVH nodes + triangles (%.0f MB) %s" %
+          ((sa.bvh.shape[0] * 0.5 * 64 + sa.n_tris * 48) / 1e6,
+           "stay L2-resident inside a step by design" if args.config != 5 else "exceed the L2: HBM-bound traversal"))
     return {
-        "workload": "BASELINE configs[1]: bunny-class scene (lumpy icosphere %d tris + 2 textured quads of scene/bunny.json, "
-                    "procedural 2048x1024 RGBE env with sun, %d-layer %dx%d atlas), %dx%d, %d spp/GPU, aperture 0.02 DoF, "
-                    "env NEE+MIS" % (sa.n_tris - 4, sa.atlas.shape[0], sa.atlas.shape[1], sa.atlas.shape[1], args.width,
-                                     args.height, args.spp),
-        "resolution": [args.width, args.height], "spp_per_gpu": args.spp, "triangles": int(sa.n_tris),
+        "workload": "BASELINE %s; %d triangles, %d BVH nodes, procedural 2048x1024 RGBE env with sun, %d-layer %dx%d atlas"
+                    % (cfg["name"], sa.n_tris, sa.bvh.shape[0], sa.atlas.shape[0], sa.atlas.shape[1], sa.atlas.shape[1]),
+        "baseline_config": args.config,
+        "resolution": [args.width, args.height], "spp_per_step": args.spp, "triangles": int(sa.n_tris),
         "bvh_nodes": int(sa.bvh.shape[0]),
         "anyhit": "shadow rays and last-bounce continuation rays stop at their first intersection (identical image; "
                   "roofline bytes count the node/leaf visits actually executed)",
-        "parallelism": "sample-set sharding x%d + NCCL reduce(sum)" % n_gpus,
-        "l2": "L2 flushed (512 MB write) between timed steps; per-wave path state (64 samples x 0.92 M paths x 2 x 96 B = 11.3 GB) "
-              "and the 184 MB atlas exceed the 126 MB L2; BVH+triangles (~7 MB) stay L2-resident inside a step by design",
+        "parallelism": parallelism,
+        "l2": l2,
     }
 
 
@@ -95,7 +128,7 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def measured_peak():
+def measured_hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         try:
@@ -105,12 +138,17 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic():
-    """dram bytes per k_trace launch from the committed ncu --set full capture, if one was recorded."""
+def ncu_traffic(config):
+    """dram bytes per k_trace launch from the committed ncu --set full capture of this config, if one was recorded."""
     p = os.path.join(ROOT, "profiles", "trace_kernel_ncu.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get("dram_bytes_per_launch")
+            d = json.load(open(p))
+            per = d.get("per_config", {}).get(str(config))
+            if per:
+                return per.get("dram_bytes_per_launch")
+            if config == 2:
+                return d.get("dram_bytes_per_launch")
         except Exception:
             pass
     return None
@@ -121,19 +159,51 @@ def algorithmic_bytes(st):
     return 60 * st["node_visits"] + 144 * st["leaf_visits"] + 32 * st["rays"]
 
 
+def find_browser():
+    """the preferred CPU baseline is the unmodified reference in headless Chromium on SwiftShader.
+    Probed at run time; this image has none (and no network to fetch one)."""
+    for name in ("chromium", "chromium-browser", "google-chrome", "google-chrome-stable", "chrome", "headless_shell"):
+        p = shutil.which(name)
+        if p:
+            return p
+    return os.environ.get("FSPT_BROWSER") or None
+
+
 def run_reference(args, rank):
-    """--impl reference: the reference's own algorithm on the host CPU.  The reference is GLSL+browser JS and cannot
-    execute in this image (no browser, Node or GLSL compiler), so this arm times the repo's C++ restatement of its
-    shaders (oracle/, kind "port") with every host thread, one 1-spp pass of the same frame per step."""
+    """--impl reference: the reference's own algorithm on the host CPU, all host threads, one 1-spp pass per step.
+    Preferred: the unmodified shaders in headless Chromium on SwiftShader (oracle/swiftshader/run_harness.py), used when
+    a browser AND a copy of the reference are present at run time.  Neither exists on the GPU box (probed below), so the
+    arm that actually runs is the repo's C++ restatement of the shaders (oracle/, kind "port"), with the scene compiled
+    by the oracle's own host code -- the product library is not loaded in this arm."""
     if rank != 0:
         return
     import oracle
     from fspt_b200 import scenes
-    oracle.build()
-    sa, cam = build_scene(args)
-    O = oracle.Oracle(sa)
     W, H = args.width, args.height
     cores = os.cpu_count() or 1
+    browser, ref_root = find_browser(), os.environ.get("FSPT_REFERENCE_ROOT", "/root/reference")
+    if browser and os.path.isdir(ref_root) and CONFIGS[args.config]["scene"] == "bunny":
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "oracle", "swiftshader"))
+            import run_harness
+            r = run_harness.time_reference(browser, ref_root, W, H, args.steps, args.warmup)
+            val = args.steps * W * H / r["seconds"] / 1e6
+            print(json.dumps({
+                "impl": "reference", "metric": METRIC, "value": val, "unit": "Mpath-samples/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["seconds"] / args.steps * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "unmodified reference shaders, headless Chromium + SwiftShader, scene/bunny.json "
+                                       "with the missing blobs substituted, %dx%d" % (W, H)},
+                "cpu_baseline": {"value": val, "unit": "Mpath-samples/s", "cores": cores, "kind": "reference",
+                                 "sample": "%d x (drawCamera + drawTracer) passes, gl.finish-bracketed" % args.steps},
+                "e2e": {"value": val, "unit": "Mpath-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            }))
+            return
+        except Exception as e:  # fall through to the port, say why
+            sys.stderr.write("SwiftShader harness failed (%s); timing the C++ port instead\n" % e)
+    oracle.build()
+    sa, cam = build_scene(args, host=oracle if CONFIGS[args.config]["scene"] == "bunny" else None)
+    O = oracle.Oracle(sa)
     rc, rt = scenes.rand_bases(args.steps + args.warmup, 1)
     lens = scenes.lens_features(cam)
 
@@ -155,10 +225,65 @@ def run_reference(args, rank):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "mrays_per_s": rays / dt / 1e6,
-        "config": workload_config(args, sa, 1),
-        "cpu_baseline": {"value": val, "unit": "Mpath-samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": workload_config(args, sa, 1, "host CPU, %d threads" % cores),
+        "cpu_baseline": {"value": val, "unit": "Mpath-samples/s", "cores": cores, "kind": "port", "sample": sample,
+                         "browser_probe": browser or "none found (chromium / google-chrome / chrome / headless_shell)"},
         "e2e": {"value": val, "unit": "Mpath-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def verify_parity(rank, world, local_rank, comm_ok):
+    """A 96x64 frame, 8 samples, through the same path as the benchmark (rank 0 uploads, fspt_scene_broadcast,
+    tiles x sample sets, fspt_reduce_accum) against the CPU oracle, bit for bit.  Returns (ok, what) on rank 0."""
+    from fspt_b200 import capi, scenes, dist as fdist
+    W, H, N = 96, 64, 8
+    sa, cam = scenes.bunny_class(subdiv=3, atlas_res=32, env_size=(128, 64))
+    ctx = capi.Context(W, H, local_rank)
+    try:
+        if world > 1:
+            fdist.init_comm(ctx, rank, world)
+            if rank == 0:
+                ctx.scene_upload(sa)
+            ctx.scene_broadcast(0)
+        else:
+            ctx.scene_upload(sa)
+        ctx.set_accum_mode(1)
+        rc, rt = scenes.rand_bases(N, 21)
+        fr = ctx.frame(cam["eye"], cam["dir"], cam["fov_scale"], scenes.lens_features(cam), cam["env_theta"])
+        n_tiles = max(1, world // 2) if world % 2 == 0 else 1  # two sample sets per tile: a two-term f32 sum is order-free
+        rect, ticks = fdist.partition(rank, world, W, H, N, n_tiles=n_tiles)
+        ctx.set_tile(*rect)
+        ctx.clear()
+        ctx.render(fr, 0, rc[ticks], rt[ticks])
+        if world > 1:
+            ctx.reduce_accum(0)
+        got = ctx.read_accum()
+    finally:
+        ctx.close()
+    if rank != 0:
+        return None, None
+    import oracle
+    oracle.build()
+    O = oracle.Oracle(sa)
+    cols = []
+    for k in range(N):
+        pos, d = oracle.camera(W, H, cam["eye"], cam["dir"], cam["fov_scale"], scenes.lens_features(cam), rc[k])
+        _, col, _ = O.trace(pos, d, W, H, 0, rt[k], cam["env_theta"], want_color=True)
+        cols.append(col[..., :3])
+    # the association the partition implies: per tile, sum over its sample sets of (sequential sum of that set's ticks)
+    n_sets = world // n_tiles
+    ref = np.zeros((H, W, 3), np.float32)
+    for t in range(n_tiles):
+        (x0, y0, w, h), _ = fdist.partition(t * n_sets, world, W, H, N, n_tiles=n_tiles)
+        tile = None
+        for s in range(n_sets):
+            part = np.zeros((h, w, 3), np.float32)
+            for k in fdist.shard_ticks(N, s, n_sets):
+                part = part + cols[k][y0:y0 + h, x0:x0 + w]
+            tile = part if tile is None else tile + part
+        ref[y0:y0 + h, x0:x0 + w] = tile
+    ok = bool(np.array_equal(got[..., :3].view(np.uint32), ref.view(np.uint32)) and np.all(got[..., 3] == N))
+    return ok, "96x64, 8 samples, %d tile(s) x %d sample set(s), accumulation sum bit-exact vs CPU oracle" % (n_tiles, n_sets)
 
 
 def main():
@@ -167,14 +292,22 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--width", type=int, default=WIDTH)
-    ap.add_argument("--height", type=int, default=HEIGHT)
-    ap.add_argument("--spp", type=int, default=SPP)
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--tiles", type=int, default=None, help="strong scaling: number of image tiles (default: automatic)")
+    ap.add_argument("--width", type=int, default=None)
+    ap.add_argument("--height", type=int, default=None)
+    ap.add_argument("--spp", type=int, default=None)
     ap.add_argument("--subdiv", type=int, default=6)
     ap.add_argument("--atlas-res", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-verify", action="store_true")
     args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    args.width = args.width or cfg["res"][0]
+    args.height = args.height or cfg["res"][1]
+    args.spp = args.spp or cfg["spp"]
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -197,55 +330,69 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         fdist.share_host_threads()
 
+    parity = None
+    if not args.no_verify:
+        parity = verify_parity(rank, world, local_rank, True)
+
     sa, cam = build_scene(args)
     W, H, spp = args.width, args.height, args.spp
     pt = PathTracer(sa, (W, H), cam, device=local_rank)
+    ctx = pt.ctx
     if world > 1:
-        pt.ctx.set_accum_mode(1)  # f32 sum + count, reduced over NVLink
-    # rank r renders ticks r, r+G, ... of a (G*spp)-sample frame: its own rand-base entries
-    rc_all, rt_all = scenes.rand_bases(world * spp, 1)
-    rc, rt = rc_all[rank::world].copy(), rt_all[rank::world].copy()
+        fdist.init_comm(ctx, rank, world)   # NCCL communicator inside the library (C ABI)
+        ctx.set_accum_mode(1)               # f32 sum + per-pixel sample count, reduced over NVLink
+    if args.scaling == "strong":
+        # ONE frame of `spp` samples split over the ranks: tiles x sample sets
+        rect, ticks = fdist.partition(rank, world, W, H, spp, n_tiles=args.tiles)
+        n_tiles, n_sets = fdist.tile_grid(world, W, H, args.tiles)
+        rc_all, rt_all = scenes.rand_bases(spp, 1)
+        parallelism = "strong scaling: %d tile(s) x %d sample set(s), ncclReduce(sum) behind the C ABI" % (n_tiles, n_sets)
+        samples_per_step = float(W) * H * spp
+    else:
+        # rank r renders ticks r, r+G, ... of a (G*spp)-sample frame: its own rand-base entries
+        rect, ticks = (0, 0, W, H), fdist.shard_ticks(world * spp, rank, world)
+        rc_all, rt_all = scenes.rand_bases(world * spp, 1)
+        parallelism = "weak scaling: sample-set sharding x%d (%d spp per GPU), ncclReduce(sum) behind the C ABI" % (world, spp)
+        samples_per_step = float(W) * H * spp * world
+    ctx.set_tile(*rect)
+    rc, rt = rc_all[ticks].copy(), rt_all[ticks].copy()
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
     out8 = np.empty((H, W, 4), np.uint8)
 
     def barrier():
-        pt.ctx.synchronize()
+        ctx.synchronize()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
 
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-
-    def step(timed):
-        """clear + 64 spp (+ reduce).  Returns (device ms of this step, stats of the render)."""
+    def step():
+        """clear + this rank's samples (+ reduce), all enqueued on the library's stream.  Returns (device ms, stats)."""
         pt.clear()
-        pt.tick(spp, rc, rt)
-        st = pt.stats()  # synchronises the library stream; render_ms/trace_ms are CUDA-event times on it
-        ms = st["render_ms"]
+        if len(rc):
+            ctx.render(pt._frame(), 0, rc, rt)
         if world > 1:
-            ev0.record()
-            fdist.reduce_accum(pt.ctx, dst=0, n_local_samples=spp, world=world)
-            ev1.record()
-            torch.cuda.synchronize()
-            ms += ev0.elapsed_time(ev1)
+            ctx.reduce_accum(0)
+        st = pt.stats()  # synchronises the library stream; render_ms / trace_ms / reduce_ms are CUDA-event times on it
+        ms = (st["render_ms"] if len(rc) else 0.0) + (st["reduce_ms"] if world > 1 else 0.0)
         return ms, st
 
     for _ in range(args.warmup):
-        step(False)
+        step()
         if rank == 0:
             pt.drawQuad(out8)
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = pt.stats()["kernel_launches"]
-    dev_ms, trace_ms, alg_bytes, rays, trace_launches = 0.0, 0.0, 0, 0, 0
+    dev_ms, trace_ms, shade_ms, alg_bytes, rays = 0.0, 0.0, 0.0, 0, 0
     t_wall0 = time.perf_counter()
     for _ in range(args.steps):
         flush.fill_(1)  # L2 flush between timed iterations (outside the event-timed region)
         torch.cuda.synchronize()
-        ms, st = step(True)
+        ms, st = step()
         dev_ms += ms
         trace_ms += st["trace_ms"]
+        shade_ms += st["shade_ms"]
         rays += st["last_rays"]
         alg_bytes += algorithmic_bytes({"node_visits": st["last_node_visits"], "leaf_visits": st["last_leaf_visits"],
                                         "rays": st["last_rays"]})
@@ -262,8 +409,7 @@ def main():
         dev_ms_max, rays_total = float(tmax[0]), float(tsum[1])
     else:
         dev_ms_max, rays_total = dev_ms, float(rays)
-    samples_total = float(args.steps) * W * H * spp * world
-    value = samples_total / (dev_ms_max * 1e-3) / 1e6
+    value = samples_per_step * args.steps / (dev_ms_max * 1e-3) / 1e6
 
     # ---- end-to-end through the host API with host buffers ---------------------------------------------------
     e2e = None
@@ -273,48 +419,59 @@ def main():
         t0 = time.perf_counter()
         h2d = 0
         for _ in range(n_e2e):
-            h2d = pt.ctx.scene_upload(sa) + 2 * 4 * spp
-            step(True)
+            if rank == 0:
+                h2d = ctx.scene_upload(sa) + 2 * 4 * len(rc)   # host buffers -> HBM, once per box
+            if world > 1:
+                ctx.scene_broadcast(0)                         # device -> device over NVLink
+            step()
             if rank == 0:
                 pt.drawQuad(out8)  # post-pass + D2H of the RGBA8 frame
         barrier()
         e2e_s = time.perf_counter() - t0
-        e2e = {"value": n_e2e * W * H * spp * world / e2e_s / 1e6, "unit": "Mpath-samples/s",
+        e2e = {"value": n_e2e * samples_per_step / e2e_s / 1e6, "unit": "Mpath-samples/s",
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(W * H * 4), "steps": n_e2e,
                "ms_per_step": e2e_s / n_e2e * 1e3,
-               "includes": "fspt_scene_upload (all scene buffers from host) + clear + 64 spp render + NCCL reduce + "
-                           "post-pass + RGBA8 read-back"}
+               "includes": "fspt_scene_upload on rank 0 (all scene buffers from host)%s + clear + render + "
+                           "ncclReduce + post-pass + RGBA8 read-back" % (" + fspt_scene_broadcast to the other ranks" if world > 1 else "")}
 
     if rank == 0:
-        peak, peak_src = measured_peak()
+        hbm_peak, hbm_src = measured_hbm_peak()
         achieved = alg_bytes / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else 0.0
-        # the ceiling that actually applies to an L2-resident BVH: streaming reads over a 32 MB buffer, measured live
+        # the ceiling that applies to an L2-resident BVH: streaming reads over a 32 MB buffer, measured live
         try:
-            l2_gbs = max(pt.ctx.debug_read_bandwidth(32 << 20, 200) for _ in range(3))
-            hbm_read_gbs = pt.ctx.debug_read_bandwidth(4 << 30, 4)
+            l2_gbs = max(ctx.debug_read_bandwidth(32 << 20, 200) for _ in range(3))
+            hbm_read_gbs = ctx.debug_read_bandwidth(4 << 30, 4)
         except Exception:
             l2_gbs = hbm_read_gbs = None
-        n_trace_launches = None
+        l2_resident = args.config != 5 and l2_gbs
+        if l2_resident:
+            bound, peak, peak_src = "l2", l2_gbs, ("measured live: fspt_debug_read_bandwidth over 32 MB (L1-bypassing 16-byte "
+                                                   "loads, persistent grid) = the L2->SM read ceiling SURVEY 8d names for an "
+                                                   "L2-resident BVH")
+        else:
+            bound, peak, peak_src = "hbm", hbm_peak, hbm_src
         line = {
             "metric": METRIC, "value": value, "unit": "Mpath-samples/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "mrays_per_s": rays_total / (dev_ms_max * 1e-3) / 1e6,
             "wall_ms_per_step": wall_ms / args.steps,
-            "config": workload_config(args, sa, world),
+            "config": workload_config(args, sa, world, parallelism),
             "clocks": clocks, "gpu_launches": int(launches),
             "roofline": {
-                "bound": "hbm", "kernel": "k_trace (BVH traversal + ray-triangle)", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
+                "bound": bound, "kernel": "k_trace (BVH traversal + ray-triangle)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": ncu_traffic(args.config),
+                "peak_source": peak_src,
                 "algorithmic_bytes": "sum over rays of 60*V + 144*L + 32 (reference-layout bytes, SURVEY 8d), V/L counted on device",
                 "kernel_ms_per_step": trace_ms / args.steps, "share_of_step": trace_ms / dev_ms if dev_ms else None,
-                "l2_read_peak": l2_gbs, "frac_of_l2_read_peak": (achieved / l2_gbs) if l2_gbs else None,
-                "hbm_read_measured_here": hbm_read_gbs,
-                "note": "BVH+triangles are L2-resident, so algorithmic bytes can exceed the HBM copy peak (the contract's "
-                        "denominator); l2_read_peak = fspt_debug_read_bandwidth over 32 MB (L1-bypassing 16-byte loads, "
-                        "persistent grid), the ceiling SURVEY 8d names for this kernel",
+                "shade_ms_per_step": shade_ms / args.steps,
+                "hbm_copy_peak": hbm_peak, "frac_of_hbm_copy_peak": achieved / hbm_peak,
+                "l2_read_peak": l2_gbs, "hbm_read_measured_here": hbm_read_gbs,
             },
         }
+        if parity is not None and parity[0] is not None:
+            line["parity"] = parity[0]
+            line["parity_check"] = parity[1]
         if e2e:
             line["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline:

@@ -41,7 +41,7 @@ class Stats(C.Structure):
     _fields_ = [("samples", C.c_uint64), ("rays", C.c_uint64), ("node_visits", C.c_uint64), ("leaf_visits", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("trace_ms", C.c_double), ("render_ms", C.c_double),
                 ("last_rays", C.c_uint64), ("last_node_visits", C.c_uint64), ("last_leaf_visits", C.c_uint64),
-                ("capped_paths", C.c_uint64), ("shade_ms", C.c_double)]
+                ("capped_paths", C.c_uint64), ("shade_ms", C.c_double), ("reduce_ms", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -52,7 +52,8 @@ EXPORTS = [
     "fspt_render", "fspt_resolve", "fspt_read_accum", "fspt_write_accum", "fspt_set_accum_mode",
     "fspt_accum_device_ptr", "fspt_set_accum_samples", "fspt_debug_primary", "fspt_debug_trace",
     "fspt_debug_last_color", "fspt_debug_math", "fspt_debug_read_bandwidth", "fspt_get_stats", "fspt_synchronize", "fspt_bvh_build", "fspt_bvh_build2",
-    "fspt_env_bins", "fspt_pack_layer", "fspt_set_param",
+    "fspt_env_bins", "fspt_pack_layer", "fspt_set_param", "fspt_set_tile", "fspt_comm_unique_id", "fspt_comm_init",
+    "fspt_comm_destroy", "fspt_reduce_accum", "fspt_scene_broadcast",
 ]
 PARAM_ANYHIT, PARAM_MAX_REFRACTIONS, PARAM_SANITIZE_NAN = 1, 2, 3
 
@@ -79,9 +80,23 @@ def load(build_if_needed=True):
     lib.fspt_destroy.restype = None
     lib.fspt_destroy.argtypes = [C.c_void_p]
     for name in EXPORTS:
-        getattr(lib, name)  # AttributeError here = header and library disagree
+        try:
+            getattr(lib, name)  # AttributeError here = header and library disagree
+        except AttributeError:
+            if not os.environ.get("FSPT_LIB"):  # an explicitly chosen A/B variant may predate an entry point
+                raise
     _lib = lib
     return lib
+
+
+def comm_unique_id():
+    """fspt_comm_unique_id: 128 bytes from ncclGetUniqueId (rank 0 calls it, the host ships it to the other ranks)."""
+    lib = load()
+    buf = (C.c_uint8 * 128)()
+    rc = lib.fspt_comm_unique_id(buf)
+    if rc != FSPT_OK:
+        raise FsptError(rc, (lib.fspt_last_error(None) or b"").decode())
+    return bytes(buf)
 
 
 def ptr(a):
@@ -243,6 +258,23 @@ class Context:
         s = C.c_uint64(0)
         self._ck(self.lib.fspt_accum_device_ptr(self.h, C.byref(p), C.byref(n), C.byref(s)))
         return p.value, int(n.value), int(s.value)
+
+    def set_tile(self, x0, y0, w, h):
+        """The pixel rectangle of the frame this context renders (GL row order); default = whole frame."""
+        self._ck(self.lib.fspt_set_tile(self.h, C.c_int32(x0), C.c_int32(y0), C.c_int32(w), C.c_int32(h)))
+
+    def comm_init(self, unique_id, rank, world):
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
+        self._ck(self.lib.fspt_comm_init(self.h, buf, C.c_int32(rank), C.c_int32(world)))
+
+    def comm_destroy(self):
+        self._ck(self.lib.fspt_comm_destroy(self.h))
+
+    def reduce_accum(self, root=0):
+        self._ck(self.lib.fspt_reduce_accum(self.h, C.c_int32(root)))
+
+    def scene_broadcast(self, root=0):
+        self._ck(self.lib.fspt_scene_broadcast(self.h, C.c_int32(root)))
 
     def set_accum_samples(self, n):
         self._ck(self.lib.fspt_set_accum_samples(self.h, C.c_uint64(n)))

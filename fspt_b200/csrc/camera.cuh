@@ -17,9 +17,9 @@ __device__ __forceinline__ float rnd(float& seed) {
 __device__ __forceinline__ void camera_ray(const FrameParams& f, const float* __restrict__ rb_cam, int n_samples, int p,
                                            v3& o, v3& d, int& x, int& y) {
   const int j = p / n_samples, s = p - j * n_samples;
-  path_to_pixel(f, j, x, y);
+  path_to_pixel(f, j, x, y);  // inside the context's rectangle; gl_FragCoord is the frame pixel
   const float resx = (float)f.width, resy = (float)f.height;
-  const float fx = (float)x + 0.5f, fy = (float)y + 0.5f;  // gl_FragCoord
+  const float fx = (float)(x + f.rx0) + 0.5f, fy = (float)(y + f.ry0) + 0.5f;  // gl_FragCoord
   const float uvx = (fx / resx) * 2.0f - 1.0f, uvy = (fy / resy) * 2.0f - 1.0f;  // `uv` varying (camera.vs)
   float seed = rb_cam[s] + fx * resy + fy;  // :38
   const v3 P = mk3(f.eye[0], f.eye[1], f.eye[2]), I = mk3(f.dir[0], f.dir[1], f.dir[2]);

@@ -2,6 +2,8 @@
 // libfspt_b200.so (include/fspt_b200.h).  Host side of what main.js does between initBVH() and tick():
 // texImage uploads (main.js:408-437,548-560,170-180), drawCamera/drawTracer/drawQuad (main.js:741-824).
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types only: the library is resolved with dlopen at fspt_comm_init, there is no link-time dependency
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -33,6 +35,7 @@ thread_local std::string g_create_error;
 struct Ctx {
   int device = 0, sm_count = 0;
   int width = 0, height = 0, n_pixels = 0;
+  int rx0 = 0, ry0 = 0, rw = 0, rh = 0;  // the pixel rectangle this context renders (fspt_set_tile); default = frame
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
   std::vector<cudaEvent_t> ev_trace;  // pairs around traversal (tag 0) / shading (tag 1) launches of the last render
@@ -45,6 +48,9 @@ struct Ctx {
   bool has_scene = false, has_dielectric = false;
   DeviceScene sc{};
   void *d_nodes = nullptr, *d_tris = nullptr, *d_shade = nullptr, *d_bins = nullptr, *d_layer_info = nullptr;
+  void* d_leaves = nullptr;
+  size_t cap_leaves = 0;
+  int n_leaves = 0;
   cudaArray_t atlas_arr = nullptr, env_arr = nullptr, mat_arr = nullptr;
   int mat_R = 0, mat_L = 0;
   bool mat_surface = false;           // mat_arr was created with cudaArraySurfaceLoadStore (GPU-side interleave)
@@ -54,7 +60,7 @@ struct Ctx {
   size_t cap_raw = 0, cap_mat_src = 0;
   void* d_mat_info = nullptr;
   size_t cap_mat_info = 0;
-  cudaTextureObject_t nodes_tex = 0, tris_tex = 0;
+  cudaTextureObject_t nodes_tex = 0;
   int atlas_R = 0, atlas_L = 0, env_W = 0, env_H = 0;       // dims of the resident arrays (reused across uploads)
   size_t cap_nodes = 0, cap_tris = 0, cap_shade = 0, cap_bins = 0, cap_layer_info = 0;
   uint8_t* h_stage = nullptr;                               // pinned staging for the atlas (one slot per layer)
@@ -80,22 +86,45 @@ struct Ctx {
   int anyhit = 1;
 
   // wavefront state
-  int wave_samples = 0;       // samples in flight per wave
+  int wave_samples = 0;       // samples in flight per wave (whole frame)
+  int wave_cap = 64;
   size_t wave_paths = 0;
   PathState ps{};             // = ps2[0] (debug entry points)
   PathState ps2[2]{};         // dense path-record arrays, ping-pong: shade reads one, compacts survivors into the other
   int* d_list = nullptr;      // shadow list: record positions
-  int* d_counts = nullptr;    // set k at [2k, 2k+1] = (#continuation, #shadow), [4] fetch cursor, [5..7] pad
+  int* d_counts = nullptr;    // set k at [2k, 2k+1] = (#continuation, #shadow), [32] fetch cursor (own cache line)
   int* d_count_out = nullptr; // per-slot visit count (debug)
   unsigned char* d_hit_flag = nullptr;  // hit / miss per record position
   unsigned long long* d_stats = nullptr;  // rays, nodes, leaves, capped
   float* d_rb = nullptr;      // rand bases of one render call: [0,cap) camera, [cap,2cap) tracer
-  float* h_rb = nullptr;      // pinned staging
+  // pinned staging, a ring of RB_SLOTS blocks of 2*rb_cap floats: a slot is rewritten only after the copy that last
+  // read it has completed (its event), so fspt_render never waits for the GPU to drain
+  static constexpr int RB_SLOTS = 8;
+  float* h_rb = nullptr;
+  cudaEvent_t ev_rb[RB_SLOTS] = {};
+  int rb_slot = 0;
   int rb_cap = 0;
+  // refraction bounces beyond NUM_BOUNCES (tracer.fs:488): path counts polled two iterations behind the enqueue
+  static constexpr int POLL_SLOTS = 8;
+  int* h_poll = nullptr;      // pinned
+  cudaEvent_t ev_poll[POLL_SLOTS] = {};
+  // collectives (fspt_comm_init): NCCL communicator over NVLink / NVSwitch
+  ncclComm_t comm = nullptr;
+  int comm_rank = 0, comm_world = 1;
+  cudaEvent_t ev_red0 = nullptr, ev_red1 = nullptr;  // around the last fspt_reduce_accum
+  bool reduce_timed = false;
+  void* d_lin = nullptr;      // linear staging of the environment + atlas arrays for fspt_scene_broadcast
+  size_t cap_lin = 0;
+  void* d_hdr = nullptr;      // broadcast header
+  size_t bytes_nodes = 0, bytes_tris = 0, bytes_shade = 0, bytes_leaves = 0, bytes_bins = 0, bytes_layer_info = 0,
+         bytes_mat_info = 0;
   int trace_blocks = 0, trace_blocks_cnt = 0, trace_blocks_cam = 0, shade_blocks = 0;
+  int trace_blocks_nt = 0, trace_blocks_cnt_nt = 0, trace_blocks_cam_nt = 0;  // NODE_TEX = false instantiations
 
   fspt_stats stats{};
 };
+
+void comm_free(Ctx* c);
 
 int fail(Ctx* c, int code, const char* fmt, ...) {
   char buf[512];
@@ -123,8 +152,7 @@ void free_scene(Ctx* c) {
   if (c->sc.atlas) cudaDestroyTextureObject(c->sc.atlas);
   if (c->sc.env) cudaDestroyTextureObject(c->sc.env);
   if (c->nodes_tex) cudaDestroyTextureObject(c->nodes_tex);
-  if (c->tris_tex) cudaDestroyTextureObject(c->tris_tex);
-  c->nodes_tex = c->tris_tex = 0;
+  c->nodes_tex = 0;
   if (c->sc.mat_tex) cudaDestroyTextureObject(c->sc.mat_tex);
   if (c->mat_surf) cudaDestroySurfaceObject(c->mat_surf);
   c->mat_surf = 0; c->mat_surface = false;
@@ -136,8 +164,8 @@ void free_scene(Ctx* c) {
   c->mat_R = c->mat_L = 0;
   dfree(c->d_mat_info); c->cap_mat_info = 0;
   c->atlas_R = c->atlas_L = c->env_W = c->env_H = 0;
-  dfree(c->d_nodes); dfree(c->d_tris); dfree(c->d_shade); dfree(c->d_bins); dfree(c->d_layer_info);
-  c->cap_nodes = c->cap_tris = c->cap_shade = c->cap_bins = c->cap_layer_info = 0;
+  dfree(c->d_nodes); dfree(c->d_tris); dfree(c->d_shade); dfree(c->d_bins); dfree(c->d_layer_info); dfree(c->d_leaves);
+  c->cap_nodes = c->cap_tris = c->cap_shade = c->cap_bins = c->cap_layer_info = c->cap_leaves = 0;
   if (c->h_stage) cudaFreeHost(c->h_stage);
   c->h_stage = nullptr; c->stage_bytes = 0;
   if (c->h_geo) cudaFreeHost(c->h_geo);
@@ -163,14 +191,17 @@ int alloc_wave(Ctx* c) {
   const size_t target_paths = (size_t)64 << 20;
   int S = (int)std::max<size_t>(1, target_paths / (size_t)c->n_pixels);
   S = std::min(S, 64);
-  if (const char* e = getenv("FSPT_WAVE_SAMPLES")) S = std::max(1, std::min(64, atoi(e)));  // tuning knob
+  c->wave_cap = 64;
+  if (const char* e = getenv("FSPT_WAVE_SAMPLES")) c->wave_cap = S = std::max(1, std::min(64, atoi(e)));  // tuning knob
   c->wave_samples = S;
   c->wave_paths = (size_t)S * c->n_pixels;
   const size_t W = c->wave_paths;
   for (int k = 0; k < 2; ++k) CK(cudaMalloc(&c->ps2[k].rec, W * 16 * FSPT_PATH_WORDS));
   c->ps = c->ps2[0];
   CK(cudaMalloc(&c->d_list, W * sizeof(int)));
-  CK(cudaMalloc(&c->d_counts, 8 * sizeof(int)));
+  CK(cudaMalloc(&c->d_counts, 64 * sizeof(int)));  // [0..3] the two count pairs; [32] the fetch cursor, on its own 128-byte
+                                                   // line: every warp's atomicAdd hits it, nothing else should
+  CK(cudaMemset(c->d_counts, 0, 64 * sizeof(int)));
   CK(cudaMalloc(&c->d_count_out, W * sizeof(int)));
   CK(cudaMalloc(&c->d_hit_flag, W));
   CK(cudaMalloc(&c->d_stats, 8 * sizeof(unsigned long long)));  // [0..3] live, [4..7] snapshot at render start
@@ -178,7 +209,10 @@ int alloc_wave(Ctx* c) {
   CK(cudaMalloc(&c->d_sample_color, W * 16));
   c->rb_cap = 64;
   CK(cudaMalloc(&c->d_rb, 2 * (size_t)c->rb_cap * sizeof(float)));
-  CK(cudaMallocHost(&c->h_rb, 2 * (size_t)c->rb_cap * sizeof(float)));
+  CK(cudaMallocHost(&c->h_rb, Ctx::RB_SLOTS * 2 * (size_t)c->rb_cap * sizeof(float)));
+  for (auto& e : c->ev_rb) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  CK(cudaMallocHost(&c->h_poll, Ctx::POLL_SLOTS * sizeof(int)));
+  for (auto& e : c->ev_poll) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   return FSPT_OK;
 }
 
@@ -214,7 +248,7 @@ __global__ void __launch_bounds__(256) k_interleave_atlas(cudaSurfaceObject_t su
 }
 
 __global__ void k_set_counts(int* counts, int n_cont, int n_shadow) {
-  counts[0] = n_cont; counts[1] = n_shadow; counts[2] = 0; counts[3] = 0; counts[4] = 0;
+  counts[0] = n_cont; counts[1] = n_shadow; counts[2] = 0; counts[3] = 0; counts[32] = 0;
 }
 
 // Traverses the continuation ray of every record of array `which` (d_counts[2*which] of them) + d_counts[2*which+1]
@@ -225,11 +259,11 @@ int launch_trace(Ctx* c, int which, bool hit_flags, bool write_count, const Fram
   if (cam) A.f = *cam; else memset(&A.f, 0, sizeof A.f);
   A.rb_cam = rb_cam; A.n_samples = n_samples;
   A.anyhit = c->anyhit;
-  A.nodes = c->sc.nodes; A.tris = c->sc.tris; A.root_ref = c->sc.root_ref; A.nodes_tex = c->nodes_tex; A.tris_tex = c->tris_tex;
+  A.nodes = c->sc.nodes; A.tris = c->sc.tris; A.leaves = c->sc.leaves; A.root_ref = c->sc.root_ref; A.nodes_tex = c->nodes_tex;
   A.ps = c->ps2[which];
   A.list_shadow = c->d_list;
   A.counts = c->d_counts + 2 * which;
-  A.next = c->d_counts + 4;
+  A.next = c->d_counts + 32;
   A.stats = c->d_stats;
   A.count_out = write_count ? c->d_count_out : nullptr;
   A.hit_flag = hit_flags ? c->d_hit_flag : nullptr;
@@ -239,9 +273,9 @@ int launch_trace(Ctx* c, int which, bool hit_flags, bool write_count, const Fram
     else if (write_count) k_trace<true, false, true><<<c->trace_blocks_cnt, TRACE_THREADS, 0, c->stream>>>(A);
     else k_trace<false, false, true><<<c->trace_blocks, TRACE_THREADS, 0, c->stream>>>(A);
   } else {  // node array beyond the linear-texture limit
-    if (cam) k_trace<false, true, false><<<c->trace_blocks_cam, TRACE_THREADS, 0, c->stream>>>(A);
-    else if (write_count) k_trace<true, false, false><<<c->trace_blocks_cnt, TRACE_THREADS, 0, c->stream>>>(A);
-    else k_trace<false, false, false><<<c->trace_blocks, TRACE_THREADS, 0, c->stream>>>(A);
+    if (cam) k_trace<false, true, false><<<c->trace_blocks_cam_nt, TRACE_THREADS, 0, c->stream>>>(A);
+    else if (write_count) k_trace<true, false, false><<<c->trace_blocks_cnt_nt, TRACE_THREADS, 0, c->stream>>>(A);
+    else k_trace<false, false, false><<<c->trace_blocks_nt, TRACE_THREADS, 0, c->stream>>>(A);
   }
   record_trace_end(c);
   c->stats.kernel_launches++;
@@ -255,7 +289,7 @@ int set_counts(Ctx* c, int n_cont, int n_shadow) {  // also zeroes #hit, #miss a
   return FSPT_OK;
 }
 
-FrameParams make_frame(const Ctx* c, const fspt_frame_params* f) {
+FrameParams make_frame(const Ctx* c, const fspt_frame_params* f, bool whole_frame = false) {
   FrameParams p;
   for (int k = 0; k < 3; ++k) { p.eye[k] = f->eye[k]; p.dir[k] = f->dir[k]; }
   p.fov_scale = f->fov_scale; p.lens0 = f->lens_features[0]; p.lens1 = f->lens_features[1];
@@ -268,14 +302,40 @@ FrameParams make_frame(const Ctx* c, const fspt_frame_params* f) {
     p.basis_y[0] = by.x; p.basis_y[1] = by.y; p.basis_y[2] = by.z;
   }
   p.width = c->width; p.height = c->height;
-  p.tiled = (c->width % 8 == 0 && c->height % 4 == 0) ? 1 : 0;
+  p.rx0 = whole_frame ? 0 : c->rx0; p.ry0 = whole_frame ? 0 : c->ry0;
+  p.rw = whole_frame ? c->width : c->rw; p.rh = whole_frame ? c->height : c->rh;
+  p.tiled = (p.rw % 8 == 0 && p.rh % 4 == 0) ? 1 : 0;
   return p;
 }
 
+// Rand bases of one call -> device: [0,cap) camera, [cap,2cap) tracer.  The pinned staging is a ring; a slot is reused
+// only after the DMA that read it has finished, so there is no stream synchronisation on the render path.
+int stage_rand_bases(Ctx* c, const float* cam, const float* trace, int n) {
+  if (n > c->rb_cap) {  // grow (rare): everything in flight must finish first
+    CK(cudaStreamSynchronize(c->stream));
+    dfree(c->d_rb);
+    if (c->h_rb) cudaFreeHost(c->h_rb);
+    c->h_rb = nullptr;
+    c->rb_cap = std::max(n, 2 * c->rb_cap);
+    CK(cudaMalloc(&c->d_rb, 2 * (size_t)c->rb_cap * sizeof(float)));
+    CK(cudaMallocHost(&c->h_rb, Ctx::RB_SLOTS * 2 * (size_t)c->rb_cap * sizeof(float)));
+  }
+  if (n <= 0) return FSPT_OK;
+  const int slot = c->rb_slot;
+  c->rb_slot = (slot + 1) % Ctx::RB_SLOTS;
+  CK(cudaEventSynchronize(c->ev_rb[slot]));  // returns at once unless RB_SLOTS calls are still queued
+  float* h = c->h_rb + (size_t)slot * 2 * c->rb_cap;
+  memcpy(h, cam, (size_t)n * sizeof(float));
+  if (trace) memcpy(h + c->rb_cap, trace, (size_t)n * sizeof(float));
+  CK(cudaMemcpyAsync(c->d_rb, h, 2 * (size_t)c->rb_cap * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaEventRecord(c->ev_rb[slot], c->stream));
+  return FSPT_OK;
+}
+
 // One wave.  Path records are dense arrays that ping-pong: set k = (array ps2[k], counts d_counts[2k .. 2k+1] =
-// #records, #shadow rays); the shadow list holds record positions; fetch cursor at d_counts[4].
+// #records, #shadow rays); the shadow list holds record positions; fetch cursor at d_counts[32].
 int render_wave(Ctx* c, const FrameParams& fp, uint32_t first_tick, int S, const float* rb_cam, const float* rb_trace) {
-  const int P = c->n_pixels;
+  const int P = fp.rw * fp.rh;
   const int n_paths = S * P;
   int rc = set_counts(c, n_paths, 0);
   if (rc) return rc;
@@ -311,21 +371,90 @@ int render_wave(Ctx* c, const FrameParams& fp, uint32_t first_tick, int S, const
     cur = nxt;
     if (b >= FSPT_NUM_BOUNCES) {
       if (!c->has_dielectric) break;  // every surviving path had i == NUM_BOUNCES: nothing was appended
-      int h[2];
-      CK(cudaMemcpyAsync(h, c->d_counts + 2 * cur, sizeof h, cudaMemcpyDeviceToHost, c->stream));
-      CK(cudaStreamSynchronize(c->stream));
-      if (h[0] == 0) break;
+      // Refractions do not count as bounces (`i--`, tracer.fs:488), so paths may survive.  The number of live paths is
+      // copied out after every extra iteration, but the host reads the value of TWO iterations ago: the GPU always has
+      // work queued and never waits for the host; at most two empty iterations (kernels that find zero items) are wasted.
+      const int k = b % Ctx::POLL_SLOTS;
+      CK(cudaMemcpyAsync(c->h_poll + k, c->d_counts + 2 * cur, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaEventRecord(c->ev_poll[k], c->stream));
+      if (b >= FSPT_NUM_BOUNCES + 2) {
+        const int k2 = (b - 2) % Ctx::POLL_SLOTS;
+        CK(cudaEventSynchronize(c->ev_poll[k2]));
+        if (c->h_poll[k2] == 0) break;
+      }
     }
-    CK(cudaMemsetAsync(c->d_counts + 4, 0, sizeof(int), c->stream));  // fetch cursor
+    CK(cudaMemsetAsync(c->d_counts + 32, 0, sizeof(int), c->stream));  // fetch cursor
     rc = launch_trace(c, cur, true, false);  // tracer.fs:501,507
     if (rc) return rc;
   }
-  k_accumulate<<<(P + 255) / 256, 256, 0, c->stream>>>(c->d_sample_color, c->d_fb, c->d_last_color, P, S, first_tick,
-                                                       c->accum_mode, c->sanitize);
+  k_accumulate<<<(P + 255) / 256, 256, 0, c->stream>>>(c->d_sample_color, c->d_fb, c->d_last_color, fp.rx0, fp.ry0, fp.rw,
+                                                       fp.rh, fp.width, S, first_tick, c->accum_mode, c->sanitize);
   c->stats.kernel_launches++;
   CK(cudaGetLastError());
   return FSPT_OK;
 }
+
+// ---- NCCL, resolved at run time ----------------------------------------------------------------------------------
+// The library has no link-time dependency on NCCL: a single-GPU host never loads it.  dlopen("libnccl.so.2") returns
+// the copy already mapped into the process when there is one (e.g. the one a PyTorch host brought along), else the
+// system library.
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Reduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  std::string error;
+};
+NcclApi* nccl_api() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, []() {
+    const char* names[] = {getenv("FSPT_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      if (!n || !*n) continue;
+      api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (api.handle) break;
+    }
+    if (!api.handle) { api.error = std::string("dlopen(libnccl.so.2) failed: ") + dlerror(); return; }
+    auto sym = [&](const char* name) {
+      void* p = dlsym(api.handle, name);
+      if (!p && api.error.empty()) api.error = std::string("NCCL symbol missing: ") + name;
+      return p;
+    };
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+    api.Reduce = reinterpret_cast<decltype(api.Reduce)>(sym("ncclReduce"));
+    api.Broadcast = reinterpret_cast<decltype(api.Broadcast)>(sym("ncclBroadcast"));
+    api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
+    api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+  });
+  return &api;
+}
+#define NK(call)                                                                                               \
+  do {                                                                                                         \
+    ncclResult_t r_ = (call);                                                                                  \
+    if (r_ != ncclSuccess) return fail(c, FSPT_E_NCCL, "%s failed: %s", #call, nccl_api()->GetErrorString(r_)); \
+  } while (0)
+
+void comm_free(Ctx* c) {
+  if (c->comm) nccl_api()->CommDestroy(c->comm);
+  c->comm = nullptr;
+  c->comm_rank = 0; c->comm_world = 1;
+}
+
+// what a receiving rank has to know before the buffers of fspt_scene_broadcast arrive
+struct SceneHeader {
+  uint64_t bytes_nodes, bytes_tris, bytes_shade, bytes_leaves, bytes_bins, bytes_layer_info, bytes_mat_info, scene_bytes;
+  int32_t root_ref, n_tris, n_interior, n_leaves, atlas_res, atlas_layers, env_w, env_h, n_bins;
+  int32_t mat_R, mat_L, use_mat_tex, has_dielectric, magic;
+};
 
 int pull_stats(Ctx* c) {
   unsigned long long h[8];
@@ -362,6 +491,7 @@ int fspt_create(fspt_ctx** out, int32_t width, int32_t height, int32_t device) {
   c = ctx;
   c->device = device; c->sm_count = prop.multiProcessorCount;
   c->width = width; c->height = height; c->n_pixels = width * height;
+  c->rx0 = c->ry0 = 0; c->rw = width; c->rh = height;
   cudaError_t err;
 #define CKC(call) if ((err = (call)) != cudaSuccess) { g_create_error = std::string(#call) + ": " + cudaGetErrorString(err); delete ctx; return FSPT_E_CUDA; }
   CKC(cudaSetDevice(device));
@@ -379,23 +509,33 @@ int fspt_create(fspt_ctx** out, int32_t width, int32_t height, int32_t device) {
 #undef CKC
   int rc = alloc_wave(c);
   if (rc) { g_create_error = c->error; fspt_destroy(reinterpret_cast<fspt_ctx*>(c)); return rc; }
-  // traversal uses no shared memory: give the whole unified array to L1 (BVH nodes + triangles live there)
-  if (!getenv("FSPT_NO_CARVEOUT")) {
-    cudaFuncSetAttribute(k_trace<false, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-    cudaFuncSetAttribute(k_trace<true, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-    cudaFuncSetAttribute(k_trace<false, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-    cudaFuncSetAttribute(k_trace<false, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-    cudaFuncSetAttribute(k_trace<true, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-    cudaFuncSetAttribute(k_trace<false, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-  }
-  // persistent grids: resident CTAs per SM x SM count
+  // persistent grids: resident CTAs per SM x SM count.  The traversal kernel keeps its short stacks and a few per-ray
+  // values in shared memory; everything else of the unified array should stay L1 (BVH nodes and leaf blocks live
+  // there), so the carveout is set to what the resident CTAs need and no more.
+  int max_smem_sm = 0;
+  cudaDeviceGetAttribute(&max_smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
+  auto persistent = [&](auto kernel) {
+    int per_sm = 0;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TRACE_THREADS, 0);
+    per_sm = std::max(1, per_sm);
+    cudaFuncAttributes fa{};
+    cudaFuncGetAttributes(&fa, kernel);
+    if (!getenv("FSPT_NO_CARVEOUT") && max_smem_sm > 0) {
+      const size_t need = (size_t)per_sm * (fa.sharedSizeBytes + 1024);  // + the per-CTA reservation
+      int pct = (int)std::min<size_t>(100, (need * 100 + (size_t)max_smem_sm - 1) / (size_t)max_smem_sm);
+      if (const char* e = getenv("FSPT_CARVEOUT_PCT")) pct = std::max(0, std::min(100, atoi(e)));  // measurement knob
+      cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    }
+    return per_sm * c->sm_count;
+  };
+  c->trace_blocks = persistent(k_trace<false, false, true>);
+  c->trace_blocks_cnt = persistent(k_trace<true, false, true>);
+  c->trace_blocks_cam = persistent(k_trace<false, true, true>);
+  c->trace_blocks_nt = persistent(k_trace<false, false, false>);
+  c->trace_blocks_cnt_nt = persistent(k_trace<true, false, false>);
+  c->trace_blocks_cam_nt = persistent(k_trace<false, true, false>);
   int per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<false, false, true>, TRACE_THREADS, 0);
-  c->trace_blocks = std::max(1, per_sm) * c->sm_count;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<true, false, true>, TRACE_THREADS, 0);
-  c->trace_blocks_cnt = std::max(1, per_sm) * c->sm_count;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<false, true, true>, TRACE_THREADS, 0);
-  c->trace_blocks_cam = std::max(1, per_sm) * c->sm_count;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shade<true>, SHADE_THREADS, 1024);
   c->shade_blocks = std::max(1, per_sm) * c->sm_count;
   *out = reinterpret_cast<fspt_ctx*>(c);
@@ -414,6 +554,13 @@ void fspt_destroy(fspt_ctx* ctx) {
   dfree(c->d_list);
   dfree(c->d_counts); dfree(c->d_count_out); dfree(c->d_hit_flag); dfree(c->d_stats); dfree(c->d_rb);
   if (c->h_rb) cudaFreeHost(c->h_rb);
+  if (c->h_poll) cudaFreeHost(c->h_poll);
+  for (auto e : c->ev_rb) if (e) cudaEventDestroy(e);
+  for (auto e : c->ev_poll) if (e) cudaEventDestroy(e);
+  comm_free(c);
+  if (c->ev_red0) cudaEventDestroy(c->ev_red0);
+  if (c->ev_red1) cudaEventDestroy(c->ev_red1);
+  dfree(c->d_lin); dfree(c->d_hdr);
   for (auto e : c->ev_trace) cudaEventDestroy(e);
   if (c->ev_begin) cudaEventDestroy(c->ev_begin);
   if (c->ev_end) cudaEventDestroy(c->ev_end);
@@ -487,15 +634,22 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
   // ---- serial pre-pass over the nodes (own thread): reference node i = [left,right,triIndex | min | max] -> child references
   std::vector<int32_t> ref((size_t)N);   // child reference of node i
   std::vector<int32_t> interior_of;      // reference node index of interior record k
+  std::vector<int32_t> leaf_first;       // first triangle of leaf k (leaves in node order = pre-order)
   auto ibits = [&](int node, int k) { int32_t v; memcpy(&v, s->bvh + (size_t)node * 9 + k, 4); return v; };
   int bad_node = -1, bad_tri = 0;
   std::thread node_thread([&]() {
     interior_of.reserve((size_t)N / 2 + 1);
+    leaf_first.reserve((size_t)N / 2 + 1);
     for (int i = 0; i < N; ++i) {
       const int32_t tri = ibits(i, 2);
       if (tri > -1) {  // `current.triangles > -1`, tracer.fs:379
         if (tri >= T) { bad_node = i; bad_tri = tri; return; }
+#if TRACE_LEAF_BLOCKS
+        ref[i] = ~(int32_t)leaf_first.size();
+        leaf_first.push_back(tri);
+#else
         ref[i] = ~tri;
+#endif
       } else {
         ref[i] = (int32_t)interior_of.size();
         interior_of.push_back(i);
@@ -534,12 +688,13 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
   node_thread.join();
   if (bad_node >= 0) return fail(c, FSPT_E_INVALID, "node %d: triangle index %d out of range", bad_node, bad_tri);
   const size_t NI = interior_of.size();
+  const size_t NL = std::max<size_t>(1, leaf_first.size());
   lap("node + material pre-pass");
   // ---- host staging block (pinned, kept between uploads): every copy below is a true async DMA and the user's
   // buffers are no longer referenced when this function returns.  Very large scenes stage in pageable memory.
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
   const size_t o_nodes = 0, o_tris = o_nodes + al(std::max<size_t>(NI, 1) * 64), o_shade = o_tris + al((size_t)(T + 3) * 48),
-               o_bins = o_shade + al((size_t)T * 192), o_layer = o_bins + al((size_t)s->env_bins * 16),
+               o_leaves = o_shade + al((size_t)T * 192), o_bins = o_leaves + al(NL * 160), o_layer = o_bins + al((size_t)s->env_bins * 16),
                o_mat = o_layer + al((size_t)L * 8), o_matsrc = o_mat + al(std::max<size_t>(32, mats.size() * 32)),
                o_env = o_matsrc + al(std::max<size_t>(32, mats.size() * sizeof(MatSrc))),
                geo_bytes = o_env + al((size_t)s->env_width * s->env_height * 4);
@@ -560,6 +715,7 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
   float* nodes = reinterpret_cast<float*>(hg + o_nodes);
   float* tris = reinterpret_cast<float*>(hg + o_tris);
   float* shade = reinterpret_cast<float*>(hg + o_shade);
+  float* leaves = reinterpret_cast<float*>(hg + o_leaves);
   float* bins = reinterpret_cast<float*>(hg + o_bins);
   uint32_t* layer_info = reinterpret_cast<uint32_t*>(hg + o_layer);
   int32_t* mat_info = reinterpret_cast<int32_t*>(hg + o_mat);
@@ -622,18 +778,38 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
     });
     // triangles: v1, e1, e2 (tracer.fs:301-302) + LEAF_SIZE-1 padBuffer-style (-1,-1,-1) tail records; shading
     // records: material (12) | uvs (6) | material id | pad | normals (27) | pad
+    auto tri9 = [&](int t, float* o) {  // v1 | e1 | e2 of triangle t (t >= T: padBuffer's -1 fill, main.js:143-154)
+      float v[9];
+      if (t < T) memcpy(v, s->triangles + (size_t)t * 9, sizeof v);
+      else for (float& x : v) x = -1.0f;
+      o[0] = v[0]; o[1] = v[1]; o[2] = v[2];
+      volatile float e;  // keep these as single f32 subtractions
+      e = v[3] - v[0]; o[3] = e; e = v[4] - v[1]; o[4] = e; e = v[5] - v[2]; o[5] = e;
+      e = v[6] - v[0]; o[6] = e; e = v[7] - v[1]; o[7] = e; e = v[8] - v[2]; o[8] = e;
+    };
+    // LeafBlock160 per leaf: the four triangles a leaf visit tests as two component-major pairs (device_common.cuh)
+    if (leaf_first.empty()) memset(leaves, 0, 160);
+    const int leaf_chunks = (int)((leaf_first.size() + 16383) / 16384);
+    parallel(leaf_chunks, geo_workers, [&](int ch) {
+      const size_t k1 = std::min(leaf_first.size(), (size_t)(ch + 1) * 16384);
+      for (size_t k = (size_t)ch * 16384; k < k1; ++k) {
+        const int first = leaf_first[k];
+        float* o = leaves + k * 40;
+        for (int j = 0; j < 4; ++j) {
+          float t9[9];
+          tri9(first + j, t9);
+          for (int comp = 0; comp < 9; ++comp) o[(j < 2 ? 4 : 22) + 2 * comp + (j & 1)] = t9[comp];
+        }
+        memcpy(o, &first, 4);
+        o[1] = o[2] = o[3] = 0.0f;
+      }
+    });
     const int tri_chunks = (T + 3 + 16383) / 16384;
     parallel(tri_chunks, geo_workers, [&](int ch) {
       const int t1 = std::min(T + 3, (ch + 1) * 16384);
       for (int t = ch * 16384; t < t1; ++t) {
-        float v[9];
-        if (t < T) memcpy(v, s->triangles + (size_t)t * 9, sizeof v);
-        else for (float& x : v) x = -1.0f;
         float* o = tris + (size_t)t * 12;
-        o[0] = v[0]; o[1] = v[1]; o[2] = v[2];
-        volatile float e;  // keep these as single f32 subtractions
-        e = v[3] - v[0]; o[3] = e; e = v[4] - v[1]; o[4] = e; e = v[5] - v[2]; o[5] = e;
-        e = v[6] - v[0]; o[6] = e; e = v[7] - v[1]; o[7] = e; e = v[8] - v[2]; o[8] = e;
+        tri9(t, o);
         o[9] = o[10] = o[11] = 0.0f;
         if (t >= T) continue;
         float* h = shade + (size_t)t * 48;
@@ -836,18 +1012,20 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
   lap("join geometry thread");
   int rc_;
   const size_t nodes_bytes = std::max<size_t>(NI, 1) * 64, tris_bytes = (size_t)(T + 3) * 48, shade_bytes = (size_t)T * 192,
-               bins_bytes = (size_t)s->env_bins * 16;
+               bins_bytes = (size_t)s->env_bins * 16, leaves_bytes = NL * 160;
   if ((rc_ = ensure(c, c->d_layer_info, c->cap_layer_info, (size_t)L * 8))) return rc_;
   if ((rc_ = ensure(c, c->d_mat_info, c->cap_mat_info, n_mat_info * 4))) return rc_;
   if ((rc_ = ensure(c, c->d_nodes, c->cap_nodes, nodes_bytes))) return rc_;
   if ((rc_ = ensure(c, c->d_tris, c->cap_tris, tris_bytes))) return rc_;
   if ((rc_ = ensure(c, c->d_shade, c->cap_shade, shade_bytes))) return rc_;
+  if ((rc_ = ensure(c, c->d_leaves, c->cap_leaves, leaves_bytes))) return rc_;
   if ((rc_ = ensure(c, c->d_bins, c->cap_bins, bins_bytes))) return rc_;
   CK(cudaMemcpyAsync(c->d_layer_info, layer_info, (size_t)L * 8, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->d_mat_info, mat_info, n_mat_info * 4, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->d_nodes, nodes, nodes_bytes, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->d_tris, tris, tris_bytes, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->d_shade, shade, shade_bytes, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_leaves, leaves, leaves_bytes, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->d_bins, bins, bins_bytes, cudaMemcpyHostToDevice, c->stream));
   lap("malloc + enqueue geometry");
   // ---- environment: 2D array, RGBA8 RGBE (main.js:170-180) ----------------------------------------------------
@@ -872,13 +1050,10 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
     cudaTextureDesc nt = {};
     nt.readMode = cudaReadModeElementType;
     if (c->nodes_tex) cudaDestroyTextureObject(c->nodes_tex);
-    if (c->tris_tex) cudaDestroyTextureObject(c->tris_tex);
-    c->nodes_tex = c->tris_tex = 0;
+    c->nodes_tex = 0;
     const size_t max_texels = (size_t)1 << 27;  // linear-texture limit; beyond it the kernels use plain loads
-    if (nodes_bytes / 16 <= max_texels) CK(cudaCreateTextureObject(&c->nodes_tex, &nr, &nt, nullptr));
-    nr.res.linear.devPtr = c->d_tris;
-    nr.res.linear.sizeInBytes = tris_bytes;
-    if (tris_bytes / 16 <= max_texels) CK(cudaCreateTextureObject(&c->tris_tex, &nr, &nt, nullptr));
+    if (nodes_bytes / 16 <= max_texels && !getenv("FSPT_NO_NODE_TEX"))  // env: test knob for the LSU-only instantiation
+      CK(cudaCreateTextureObject(&c->nodes_tex, &nr, &nt, nullptr));
   }
   // no synchronisation: everything the DMA engine still reads lives in the context's pinned staging blocks, which the
   // next upload (and destroy) only touch after synchronising the stream; work enqueued by fspt_render waits in order
@@ -887,9 +1062,13 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
   c->sc.nodes = reinterpret_cast<const float4*>(c->d_nodes);
   c->sc.tris = reinterpret_cast<const float4*>(c->d_tris);
   c->sc.shade = reinterpret_cast<const float4*>(c->d_shade);
+  c->sc.leaves = reinterpret_cast<const float4*>(c->d_leaves);
+  c->n_leaves = (int)leaf_first.size();
   c->sc.bins = reinterpret_cast<const float4*>(c->d_bins);
   c->sc.layer_info = reinterpret_cast<const uint2*>(c->d_layer_info);
   c->sc.mat_info = reinterpret_cast<const int4*>(c->d_mat_info);
+  c->bytes_nodes = nodes_bytes; c->bytes_tris = tris_bytes; c->bytes_shade = shade_bytes; c->bytes_leaves = leaves_bytes;
+  c->bytes_bins = bins_bytes; c->bytes_layer_info = (size_t)L * 8; c->bytes_mat_info = n_mat_info * 4;
   c->sc.root_ref = ref[0];
   c->sc.n_tris = T; c->sc.n_interior = (int)NI;
   c->sc.atlas_res = s->atlas_res; c->sc.atlas_layers = s->atlas_layers; c->sc.env_w = s->env_width; c->sc.env_h = s->env_height;
@@ -924,24 +1103,16 @@ int fspt_render(fspt_ctx* ctx, const fspt_frame_params* frame, uint32_t first_ti
   c->ev_trace_used = 0;
   CK(cudaMemcpyAsync(c->d_stats + 4, c->d_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, c->stream));
   // all rand bases of this call go up in one copy: [0,cap) camera, [cap,2cap) tracer
-  if (n_samples > c->rb_cap) {
-    CK(cudaStreamSynchronize(c->stream));
-    dfree(c->d_rb);
-    if (c->h_rb) cudaFreeHost(c->h_rb);
-    c->h_rb = nullptr;
-    c->rb_cap = std::max(n_samples, 2 * c->rb_cap);
-    CK(cudaMalloc(&c->d_rb, 2 * (size_t)c->rb_cap * sizeof(float)));
-    CK(cudaMallocHost(&c->h_rb, 2 * (size_t)c->rb_cap * sizeof(float)));
-  }
-  if (n_samples > 0) {
-    CK(cudaStreamSynchronize(c->stream));  // previous call may still read the staging buffer
-    memcpy(c->h_rb, rand_base_camera, (size_t)n_samples * sizeof(float));
-    memcpy(c->h_rb + c->rb_cap, rand_base_tracer, (size_t)n_samples * sizeof(float));
-    CK(cudaMemcpyAsync(c->d_rb, c->h_rb, 2 * (size_t)c->rb_cap * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  {
+    int rc0 = stage_rand_bases(c, rand_base_camera, rand_base_tracer, n_samples);
+    if (rc0) return rc0;
   }
   CK(cudaEventRecord(c->ev_begin, c->stream));
+  // samples in flight per wave: the path-state arrays hold wave_paths records; a tile of the frame keeps more samples
+  // in flight than the whole frame would (3840x2160 whole: 8, one of 8 tiles: 64)
+  const int wave_S = (int)std::max<size_t>(1, std::min<size_t>((size_t)c->wave_cap, c->wave_paths / ((size_t)fp.rw * fp.rh)));
   for (int done = 0; done < n_samples;) {
-    const int S = std::min(c->wave_samples, n_samples - done);
+    const int S = std::min(wave_S, n_samples - done);
     int rc = render_wave(c, fp, first_tick + (uint32_t)done, S, c->d_rb + done, c->d_rb + c->rb_cap + done);
     if (rc) return rc;
     done += S;
@@ -950,7 +1121,7 @@ int fspt_render(fspt_ctx* ctx, const fspt_frame_params* frame, uint32_t first_ti
   c->render_timed = true;
   c->next_tick = first_tick + (uint32_t)n_samples;
   c->accum_samples += (uint64_t)n_samples;
-  c->stats.samples += (uint64_t)n_samples * (uint64_t)c->n_pixels;
+  c->stats.samples += (uint64_t)n_samples * (uint64_t)fp.rw * (uint64_t)fp.rh;
   return FSPT_OK;
 }
 
@@ -969,10 +1140,9 @@ int fspt_resolve(fspt_ctx* ctx, const fspt_post_params* post, uint8_t* rgba8_out
   if (!post || !rgba8_out) return fail(c, FSPT_E_INVALID, "fspt_resolve: NULL argument");
   CK(cudaSetDevice(c->device));
   dim3 blk(32, 8), grd((c->width + 31) / 32, (c->height + 7) / 8);
-  const int use_div = c->accum_mode == 1;
-  const float count = (float)std::max<uint64_t>(1, c->accum_samples);
+  const int use_div = c->accum_mode == 1;  // sum mode: every pixel is divided by its own sample count (alpha channel)
   k_post<<<grd, blk, 0, c->stream>>>(c->d_fb, c->d_rgba8, c->width, c->height, post->exposure, post->saturation,
-                                     post->denoise ? 1 : 0, post->max_sigma, post->scale, count, use_div);
+                                     post->denoise ? 1 : 0, post->max_sigma, post->scale, use_div);
   c->stats.kernel_launches++;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(rgba8_out, c->d_rgba8, (size_t)c->n_pixels * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -1031,10 +1201,12 @@ int fspt_debug_primary(fspt_ctx* ctx, const fspt_frame_params* frame, float rand
   if (!c || !frame) return FSPT_E_INVALID;
   if (!c->has_scene) return fail(c, FSPT_E_STATE, "fspt_debug_primary before fspt_scene_upload");
   CK(cudaSetDevice(c->device));
-  const FrameParams fp = make_frame(c, frame);
+  const FrameParams fp = make_frame(c, frame, true);  // always the whole frame
   const int P = c->n_pixels;
-  c->h_rb[0] = rand_base_camera;
-  CK(cudaMemcpyAsync(c->d_rb, c->h_rb, sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  {
+    int rc0 = stage_rand_bases(c, &rand_base_camera, nullptr, 1);
+    if (rc0) return rc0;
+  }
   k_camera<<<(P + 255) / 256, 256, 0, c->stream>>>(fp, c->d_rb, P, 1, c->ps, c->d_cam_pos, c->d_cam_dir);
   c->stats.kernel_launches++;
   int rc = set_counts(c, P, 0);
@@ -1111,14 +1283,16 @@ int fspt_debug_math(fspt_ctx* ctx, int32_t fn, const float* x, const float* y, f
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
   if (!c || !x || !out || n < 0) return FSPT_E_INVALID;
   CK(cudaSetDevice(c->device));
-  float *dx = nullptr, *dy = nullptr, *dout = nullptr;
-  CK(cudaMalloc(&dx, (size_t)n * 4 + 4)); CK(cudaMalloc(&dy, (size_t)n * 4 + 4)); CK(cudaMalloc(&dout, (size_t)n * 4 + 4));
+  float* buf = nullptr;  // one allocation (x | y | out), released on every path
+  const size_t stride = (size_t)n + 1;
+  CK(cudaMalloc(&buf, 3 * stride * 4));
+  struct Free { float* p; ~Free() { cudaFree(p); } } guard{buf};
+  float *dx = buf, *dy = buf + stride, *dout = buf + 2 * stride;
   CK(cudaMemcpy(dx, x, (size_t)n * 4, cudaMemcpyHostToDevice));
   if (y) CK(cudaMemcpy(dy, y, (size_t)n * 4, cudaMemcpyHostToDevice)); else CK(cudaMemset(dy, 0, (size_t)n * 4));
   if (n) k_debug_math<<<(n + 255) / 256, 256, 0, c->stream>>>(fn, dx, dy, dout, n);
   CK(cudaStreamSynchronize(c->stream));
   CK(cudaMemcpy(out, dout, (size_t)n * 4, cudaMemcpyDeviceToHost));
-  cudaFree(dx); cudaFree(dy); cudaFree(dout);
   return FSPT_OK;
 }
 
@@ -1162,6 +1336,233 @@ int fspt_debug_read_bandwidth(fspt_ctx* ctx, uint64_t bytes, int32_t iters, doub
   return FSPT_OK;
 }
 
+int fspt_set_tile(fspt_ctx* ctx, int32_t x0, int32_t y0, int32_t w, int32_t h) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  if (!c) return FSPT_E_INVALID;
+  if (w <= 0 || h <= 0 || x0 < 0 || y0 < 0 || (int64_t)x0 + w > c->width || (int64_t)y0 + h > c->height)
+    return fail(c, FSPT_E_INVALID, "fspt_set_tile: rectangle %d,%d %dx%d is not inside the %dx%d frame", x0, y0, w, h, c->width, c->height);
+  c->rx0 = x0; c->ry0 = y0; c->rw = w; c->rh = h;
+  return FSPT_OK;
+}
+
+int fspt_comm_unique_id(uint8_t* id_out) {
+  Ctx* c = nullptr;
+  if (!id_out) return FSPT_E_INVALID;
+  NcclApi* N = nccl_api();
+  if (!N->error.empty()) return fail(c, FSPT_E_NCCL, "%s", N->error.c_str());
+  ncclUniqueId id;
+  NK(N->GetUniqueId(&id));
+  static_assert(sizeof(id) == FSPT_COMM_ID_BYTES, "ncclUniqueId size");
+  memcpy(id_out, &id, sizeof id);
+  return FSPT_OK;
+}
+
+int fspt_comm_init(fspt_ctx* ctx, const uint8_t* id_bytes, int32_t rank, int32_t world) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  if (!c || !id_bytes || world < 1 || rank < 0 || rank >= world) return FSPT_E_INVALID;
+  NcclApi* N = nccl_api();
+  if (!N->error.empty()) return fail(c, FSPT_E_NCCL, "%s", N->error.c_str());
+  CK(cudaSetDevice(c->device));
+  comm_free(c);
+  ncclUniqueId id;
+  memcpy(&id, id_bytes, sizeof id);
+  NK(N->CommInitRank(&c->comm, world, id, rank));
+  c->comm_rank = rank; c->comm_world = world;
+  if (!c->d_hdr) CK(cudaMalloc(&c->d_hdr, 256));
+  return FSPT_OK;
+}
+
+int fspt_comm_destroy(fspt_ctx* ctx) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  if (!c) return FSPT_E_INVALID;
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  comm_free(c);
+  return FSPT_OK;
+}
+
+// sum of the accumulation targets of every rank -> root's target, in place, on the context's stream (ordered after the
+// render kernels already enqueued, no host synchronisation).  In sum mode the alpha channel carries every pixel's sample
+// count, so tiles, sample sets and unequal shards all resolve correctly on the root.
+int fspt_reduce_accum(fspt_ctx* ctx, int32_t root) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  if (!c) return FSPT_E_INVALID;
+  if (!c->comm) return fail(c, FSPT_E_STATE, "fspt_reduce_accum before fspt_comm_init");
+  if (root < 0 || root >= c->comm_world) return fail(c, FSPT_E_INVALID, "fspt_reduce_accum: root %d of %d ranks", root, c->comm_world);
+  if (c->accum_mode != 1) return fail(c, FSPT_E_STATE, "fspt_reduce_accum needs the sum accumulation mode (fspt_set_accum_mode(ctx, 1))");
+  CK(cudaSetDevice(c->device));
+  NcclApi* N = nccl_api();
+  if (!c->ev_red0) { CK(cudaEventCreate(&c->ev_red0)); CK(cudaEventCreate(&c->ev_red1)); }
+  CK(cudaEventRecord(c->ev_red0, c->stream));
+  NK(N->Reduce(c->d_fb, c->d_fb, (size_t)c->n_pixels * 4, ncclFloat32, ncclSum, root, c->comm, c->stream));
+  CK(cudaEventRecord(c->ev_red1, c->stream));
+  c->reduce_timed = true;
+  c->stats.kernel_launches++;
+  return FSPT_OK;
+}
+
+// The scene resident on `root` -> every other rank, device to device over NVLink: the records fspt_scene_upload built
+// (Node64, Tri48, LeafBlock160, ShadeRec, bins, layer / material tables) and linear copies of the environment and atlas
+// arrays.  One host stages and uploads a scene once instead of every rank repeating the same 200 MB of host work.
+int fspt_scene_broadcast(fspt_ctx* ctx, int32_t root) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  if (!c) return FSPT_E_INVALID;
+  if (!c->comm) return fail(c, FSPT_E_STATE, "fspt_scene_broadcast before fspt_comm_init");
+  if (root < 0 || root >= c->comm_world) return fail(c, FSPT_E_INVALID, "fspt_scene_broadcast: root %d of %d ranks", root, c->comm_world);
+  const bool is_root = c->comm_rank == root;
+  if (is_root && !c->has_scene) return fail(c, FSPT_E_STATE, "fspt_scene_broadcast: the root has no scene (fspt_scene_upload first)");
+  CK(cudaSetDevice(c->device));
+  NcclApi* N = nccl_api();
+  SceneHeader h;
+  memset(&h, 0, sizeof h);
+  static_assert(sizeof(SceneHeader) <= 256, "header buffer");
+  if (is_root) {
+    h.bytes_nodes = c->bytes_nodes; h.bytes_tris = c->bytes_tris; h.bytes_shade = c->bytes_shade; h.bytes_leaves = c->bytes_leaves;
+    h.bytes_bins = c->bytes_bins; h.bytes_layer_info = c->bytes_layer_info; h.bytes_mat_info = c->bytes_mat_info;
+    h.scene_bytes = c->scene_bytes;
+    h.root_ref = c->sc.root_ref; h.n_tris = c->sc.n_tris; h.n_interior = c->sc.n_interior; h.n_leaves = c->n_leaves;
+    h.atlas_res = c->sc.atlas_res; h.atlas_layers = c->sc.atlas_layers; h.env_w = c->sc.env_w; h.env_h = c->sc.env_h;
+    h.n_bins = c->sc.n_bins;
+    h.use_mat_tex = c->sc.mat_tex ? 1 : 0;
+    h.mat_R = h.use_mat_tex ? c->mat_R : c->atlas_R;
+    h.mat_L = h.use_mat_tex ? c->mat_L : c->atlas_L;
+    h.has_dielectric = c->has_dielectric ? 1 : 0;
+    h.magic = 0x46535054;
+    CK(cudaMemcpyAsync(c->d_hdr, &h, sizeof h, cudaMemcpyHostToDevice, c->stream));
+  } else {
+    CK(cudaStreamSynchronize(c->stream));  // buffers of the previous scene may be in use
+    CK(cudaStreamSynchronize(c->copy_stream));
+    c->has_scene = false;
+  }
+  NK(N->Broadcast(c->d_hdr, c->d_hdr, sizeof h, ncclUint8, root, c->comm, c->stream));
+  if (!is_root) {
+    CK(cudaMemcpyAsync(&h, c->d_hdr, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (h.magic != 0x46535054) return fail(c, FSPT_E_NCCL, "fspt_scene_broadcast: bad header from rank %d", root);
+  }
+  const size_t texel = h.use_mat_tex ? 16 : 4;
+  const size_t env_bytes = (size_t)h.env_w * h.env_h * 4, atlas_bytes = (size_t)h.mat_R * h.mat_R * texel * (size_t)h.mat_L;
+  int rc;
+  if ((rc = ensure(c, c->d_lin, c->cap_lin, env_bytes + atlas_bytes))) return rc;
+  uint8_t* lin = reinterpret_cast<uint8_t*>(c->d_lin);
+  cudaMemcpy3DParms cp = {};
+  cp.extent = make_cudaExtent(h.mat_R, h.mat_R, h.mat_L);
+  cp.kind = cudaMemcpyDeviceToDevice;
+  if (is_root) {
+    CK(cudaStreamWaitEvent(c->stream, c->ev_atlas, 0));  // the atlas DMA of the upload runs on its own stream
+    CK(cudaMemcpy2DFromArrayAsync(lin, (size_t)h.env_w * 4, c->env_arr, 0, 0, (size_t)h.env_w * 4, h.env_h,
+                                  cudaMemcpyDeviceToDevice, c->stream));
+    cp.srcArray = h.use_mat_tex ? c->mat_arr : c->atlas_arr;
+    cp.dstPtr = make_cudaPitchedPtr(lin + env_bytes, (size_t)h.mat_R * texel, h.mat_R, h.mat_R);
+    CK(cudaMemcpy3DAsync(&cp, c->stream));
+  } else {
+    // storage on the receiving side: same reuse rules as fspt_scene_upload
+    if ((rc = ensure(c, c->d_nodes, c->cap_nodes, h.bytes_nodes))) return rc;
+    if ((rc = ensure(c, c->d_tris, c->cap_tris, h.bytes_tris))) return rc;
+    if ((rc = ensure(c, c->d_shade, c->cap_shade, h.bytes_shade))) return rc;
+    if ((rc = ensure(c, c->d_leaves, c->cap_leaves, h.bytes_leaves))) return rc;
+    if ((rc = ensure(c, c->d_bins, c->cap_bins, h.bytes_bins))) return rc;
+    if ((rc = ensure(c, c->d_layer_info, c->cap_layer_info, h.bytes_layer_info))) return rc;
+    if ((rc = ensure(c, c->d_mat_info, c->cap_mat_info, h.bytes_mat_info))) return rc;
+    cudaResourceDesc rd = {};
+    rd.resType = cudaResourceTypeArray;
+    cudaTextureDesc td = {};
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+    td.filterMode = cudaFilterModePoint;
+    td.readMode = cudaReadModeElementType;
+    cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
+    if (!c->env_arr || c->env_W != h.env_w || c->env_H != h.env_h) {
+      if (c->sc.env) cudaDestroyTextureObject(c->sc.env);
+      c->sc.env = 0;
+      if (c->env_arr) cudaFreeArray(c->env_arr);
+      c->env_arr = nullptr;
+      CK(cudaMallocArray(&c->env_arr, &fmt, h.env_w, h.env_h));
+      rd.res.array.array = c->env_arr;
+      CK(cudaCreateTextureObject(&c->sc.env, &rd, &td, nullptr));
+      c->env_W = h.env_w; c->env_H = h.env_h;
+    }
+    if (h.use_mat_tex) {
+      if (c->sc.atlas) { cudaDestroyTextureObject(c->sc.atlas); c->sc.atlas = 0; }
+      if (c->atlas_arr) { cudaFreeArray(c->atlas_arr); c->atlas_arr = nullptr; c->atlas_R = c->atlas_L = 0; }
+      if (!c->mat_arr || c->mat_R != h.mat_R || c->mat_L != h.mat_L) {
+        if (c->sc.mat_tex) cudaDestroyTextureObject(c->sc.mat_tex);
+        c->sc.mat_tex = 0;
+        if (c->mat_surf) cudaDestroySurfaceObject(c->mat_surf);
+        c->mat_surf = 0; c->mat_surface = false;
+        if (c->mat_arr) cudaFreeArray(c->mat_arr);
+        c->mat_arr = nullptr;
+        cudaChannelFormatDesc fmt4 = cudaCreateChannelDesc<uint4>();
+        CK(cudaMalloc3DArray(&c->mat_arr, &fmt4, make_cudaExtent(h.mat_R, h.mat_R, h.mat_L), cudaArrayLayered));
+        rd.res.array.array = c->mat_arr;
+        CK(cudaCreateTextureObject(&c->sc.mat_tex, &rd, &td, nullptr));
+        c->mat_R = h.mat_R; c->mat_L = h.mat_L;
+      }
+    } else {
+      if (c->sc.mat_tex) { cudaDestroyTextureObject(c->sc.mat_tex); c->sc.mat_tex = 0; }
+      if (c->mat_surf) { cudaDestroySurfaceObject(c->mat_surf); c->mat_surf = 0; }
+      c->mat_surface = false;
+      if (c->mat_arr) { cudaFreeArray(c->mat_arr); c->mat_arr = nullptr; c->mat_R = c->mat_L = 0; }
+      if (!c->atlas_arr || c->atlas_R != h.mat_R || c->atlas_L != h.mat_L) {
+        if (c->sc.atlas) cudaDestroyTextureObject(c->sc.atlas);
+        c->sc.atlas = 0;
+        if (c->atlas_arr) cudaFreeArray(c->atlas_arr);
+        c->atlas_arr = nullptr;
+        CK(cudaMalloc3DArray(&c->atlas_arr, &fmt, make_cudaExtent(h.mat_R, h.mat_R, h.mat_L), cudaArrayLayered));
+        rd.res.array.array = c->atlas_arr;
+        CK(cudaCreateTextureObject(&c->sc.atlas, &rd, &td, nullptr));
+        c->atlas_R = h.mat_R; c->atlas_L = h.mat_L;
+      }
+    }
+  }
+  NK(N->GroupStart());
+  NK(N->Broadcast(c->d_nodes, c->d_nodes, h.bytes_nodes, ncclUint8, root, c->comm, c->stream));
+  NK(N->Broadcast(c->d_tris, c->d_tris, h.bytes_tris, ncclUint8, root, c->comm, c->stream));
+  NK(N->Broadcast(c->d_shade, c->d_shade, h.bytes_shade, ncclUint8, root, c->comm, c->stream));
+  NK(N->Broadcast(c->d_leaves, c->d_leaves, h.bytes_leaves, ncclUint8, root, c->comm, c->stream));
+  NK(N->Broadcast(c->d_bins, c->d_bins, h.bytes_bins, ncclUint8, root, c->comm, c->stream));
+  NK(N->Broadcast(c->d_layer_info, c->d_layer_info, h.bytes_layer_info, ncclUint8, root, c->comm, c->stream));
+  NK(N->Broadcast(c->d_mat_info, c->d_mat_info, h.bytes_mat_info, ncclUint8, root, c->comm, c->stream));
+  NK(N->Broadcast(lin, lin, env_bytes + atlas_bytes, ncclUint8, root, c->comm, c->stream));
+  NK(N->GroupEnd());
+  c->stats.kernel_launches += 8;
+  if (!is_root) {
+    CK(cudaMemcpy2DToArrayAsync(c->env_arr, 0, 0, lin, (size_t)h.env_w * 4, (size_t)h.env_w * 4, h.env_h,
+                                cudaMemcpyDeviceToDevice, c->stream));
+    cp.srcPtr = make_cudaPitchedPtr(lin + env_bytes, (size_t)h.mat_R * texel, h.mat_R, h.mat_R);
+    cp.dstArray = h.use_mat_tex ? c->mat_arr : c->atlas_arr;
+    CK(cudaMemcpy3DAsync(&cp, c->stream));
+    CK(cudaEventRecord(c->ev_atlas, c->stream));
+    if (c->nodes_tex) cudaDestroyTextureObject(c->nodes_tex);
+    c->nodes_tex = 0;
+    if (h.bytes_nodes / 16 <= ((size_t)1 << 27)) {
+      cudaResourceDesc nr = {};
+      nr.resType = cudaResourceTypeLinear;
+      nr.res.linear.devPtr = c->d_nodes;
+      nr.res.linear.desc = cudaCreateChannelDesc<float4>();
+      nr.res.linear.sizeInBytes = h.bytes_nodes;
+      cudaTextureDesc nt = {};
+      nt.readMode = cudaReadModeElementType;
+      CK(cudaCreateTextureObject(&c->nodes_tex, &nr, &nt, nullptr));
+    }
+    c->bytes_nodes = h.bytes_nodes; c->bytes_tris = h.bytes_tris; c->bytes_shade = h.bytes_shade; c->bytes_leaves = h.bytes_leaves;
+    c->bytes_bins = h.bytes_bins; c->bytes_layer_info = h.bytes_layer_info; c->bytes_mat_info = h.bytes_mat_info;
+    c->sc.nodes = reinterpret_cast<const float4*>(c->d_nodes);
+    c->sc.tris = reinterpret_cast<const float4*>(c->d_tris);
+    c->sc.shade = reinterpret_cast<const float4*>(c->d_shade);
+    c->sc.leaves = reinterpret_cast<const float4*>(c->d_leaves);
+    c->sc.bins = reinterpret_cast<const float4*>(c->d_bins);
+    c->sc.layer_info = reinterpret_cast<const uint2*>(c->d_layer_info);
+    c->sc.mat_info = reinterpret_cast<const int4*>(c->d_mat_info);
+    c->sc.root_ref = h.root_ref; c->sc.n_tris = h.n_tris; c->sc.n_interior = h.n_interior; c->n_leaves = h.n_leaves;
+    c->sc.atlas_res = h.atlas_res; c->sc.atlas_layers = h.atlas_layers; c->sc.env_w = h.env_w; c->sc.env_h = h.env_h;
+    c->sc.n_bins = h.n_bins;
+    c->has_dielectric = h.has_dielectric != 0;
+    c->scene_bytes = h.scene_bytes;
+    c->has_scene = true;
+  }
+  return FSPT_OK;
+}
+
 int fspt_set_param(fspt_ctx* ctx, int32_t key, int32_t value) {
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
   if (!c) return FSPT_E_INVALID;
@@ -1190,6 +1591,8 @@ int fspt_get_stats(fspt_ctx* ctx, fspt_stats* out) {
     if (cudaEventElapsedTime(&t, c->ev_trace[i], c->ev_trace[i + 1]) == cudaSuccess) (c->ev_tag[i / 2] ? sh : tr) += t;
   }
   c->stats.shade_ms = sh;
+  c->stats.reduce_ms = 0.0;
+  if (c->reduce_timed && cudaEventElapsedTime(&ms, c->ev_red0, c->ev_red1) == cudaSuccess) c->stats.reduce_ms = ms;
   (void)cudaGetLastError();  // event queries must not leave a sticky status for the next launch check
   c->stats.trace_ms = tr;
   *out = c->stats;

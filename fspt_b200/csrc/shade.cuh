@@ -25,9 +25,10 @@ __global__ void __launch_bounds__(256) k_camera(const FrameParams f, const float
   camera_ray(f, rb_cam, n_samples, p, o, d, x, y);
   st_path(ps.ro(p), make_float4(o.x, o.y, o.z, FSPT_MAX_T));
   st_path(ps.rd(p), make_float4(d.x, d.y, d.z, __int_as_float(-1)));
-  if (cam_pos_out) {
-    cam_pos_out[(size_t)y * f.width + x] = make_float4(o.x, o.y, o.z, 1.0f);
-    cam_dir_out[(size_t)y * f.width + x] = make_float4(d.x, d.y, d.z, 1.0f);
+  if (cam_pos_out) {  // frame-sized targets
+    const size_t px = (size_t)(y + f.ry0) * f.width + (size_t)(x + f.rx0);
+    cam_pos_out[px] = make_float4(o.x, o.y, o.z, 1.0f);
+    cam_dir_out[px] = make_float4(d.x, d.y, d.z, 1.0f);
   }
 }
 
@@ -266,7 +267,7 @@ __device__ __forceinline__ void write_sample(const ShadeArgs& A, int slot, v3 co
   int x, y;
   path_to_pixel(A.f, j, x, y);
   // [pixel][sample]: the samples of a pixel finish in adjacent lanes and land in adjacent 16-byte entries
-  A.sample_color[((size_t)y * A.f.width + x) * A.n_samples + s] = make_float4(color.x, color.y, color.z, 1.0f);
+  A.sample_color[((size_t)y * A.f.rw + x) * A.n_samples + s] = make_float4(color.x, color.y, color.z, 1.0f);
 }
 
 // The tail of the previous loop iteration for a path whose ray MISSED: tracer.fs:442-443 (primary) or
@@ -563,14 +564,17 @@ __global__ void __launch_bounds__(SHADE_THREADS, SHADE_MIN_BLOCKS) k_shade(const
 // ---------------------------------------------------------------------------------------------------------
 // tracer.fs:515-517: clamp, then running mean over ticks (mode 0) or plain sum (mode 1), per pixel in tick
 // order so that the f32 result equals the reference's sequence of passes.
+// sample_color is indexed by the pixel inside the context's rectangle (rw x rh at rx0, ry0), fb by the frame pixel.
 __global__ void __launch_bounds__(256) k_accumulate(const float4* __restrict__ sample_color, float4* fb, float4* last_color,
-                                                    int n_pixels, int n_samples, unsigned first_tick, int mode, int sanitize) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n_pixels) return;
+                                                    int rx0, int ry0, int rw, int rh, int width, int n_samples,
+                                                    unsigned first_tick, int mode, int sanitize) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= rw * rh) return;
+  const size_t p = (size_t)(ry0 + q / rw) * width + (size_t)(rx0 + q % rw);
   float4 acc = fb[p];
   v3 c = mk3(0.0f, 0.0f, 0.0f);
   for (int s = 0; s < n_samples; ++s) {
-    const float4 c4 = sample_color[(size_t)p * n_samples + s];
+    const float4 c4 = sample_color[(size_t)q * n_samples + s];
     c = mk3(c4.x, c4.y, c4.z);
     if (sanitize) {  // deviation from the reference, which lets NaN stick
       if (c.x != c.x) c.x = 0.0f;
@@ -584,7 +588,7 @@ __global__ void __launch_bounds__(256) k_accumulate(const float4* __restrict__ s
       const v3 o = div(add(c, mul(t, ft)), ft + 1.0f);  // :517
       acc = make_float4(o.x, o.y, o.z, 1.0f);
     } else {
-      acc = make_float4(acc.x + c.x, acc.y + c.y, acc.z + c.z, 1.0f);
+      acc = make_float4(acc.x + c.x, acc.y + c.y, acc.z + c.z, acc.w + 1.0f);  // alpha = this pixel's sample count
     }
   }
   fb[p] = acc;
@@ -593,11 +597,12 @@ __global__ void __launch_bounds__(256) k_accumulate(const float4* __restrict__ s
 
 // ---------------------------------------------------------------------------------------------------------
 // draw.fs main (:82-93) with filterFireflies (:50-80) and ACESFitted (:39-48), fused: one pass RGBA32F -> RGBA8.
-// In sum mode (multi-GPU) the buffer is divided by the sample count on the fly.
-__device__ __forceinline__ v3 fb_fetch(const float4* fb, int W, int H, long long cx, long long cy, float inv_count, int use_div) {
+// In sum mode (multi-GPU: sample sets and / or tiles reduced with NCCL) every pixel is divided on the fly by its own
+// sample count, which the accumulation kernel keeps in the alpha channel (exact in f32 below 2^24 samples).
+__device__ __forceinline__ v3 fb_fetch(const float4* fb, int W, int H, long long cx, long long cy, int use_div) {
   if (cx < 0 || cy < 0 || cx >= W || cy >= H) return mk3(0.0f, 0.0f, 0.0f);  // robust texelFetch
   const float4 v = fb[(size_t)cy * W + (size_t)cx];
-  if (use_div) return mk3(v.x / inv_count, v.y / inv_count, v.z / inv_count);
+  if (use_div) return v.w > 0.0f ? mk3(v.x / v.w, v.y / v.w, v.z / v.w) : mk3(0.0f, 0.0f, 0.0f);
   return mk3(v.x, v.y, v.z);
 }
 __device__ __forceinline__ float rrt_odt_fit(float v) {  // draw.fs:32-37
@@ -611,8 +616,7 @@ __device__ __forceinline__ unsigned char quant8(float v) {
   return (unsigned char)(int)floorf(v * 255.0f + 0.5f);
 }
 __global__ void __launch_bounds__(256) k_post(const float4* __restrict__ fb, uchar4* out, int W, int H, float exposure,
-                                              float saturation, int denoise, float maxSigma, float scale,
-                                              float count, int use_div) {
+                                              float saturation, int denoise, float maxSigma, float scale, int use_div) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= W || y >= H) return;
   const v3 lumaCoefs = mk3(0.2126f, 0.7152f, 0.0722f);
@@ -627,7 +631,7 @@ __global__ void __launch_bounds__(256) k_post(const float4* __restrict__ fb, uch
     for (int i = 0; i < 5; i++)
       for (int j = 0; j < 5; j++) {
         const int osx = i - 2, osy = j - 2;
-        const v3 color = fb_fetch(fb, W, H, bx + osx, by + osy, count, use_div);
+        const v3 color = fb_fetch(fb, W, H, bx + osx, by + osy, use_div);
         const float luma = dot(color, lumaCoefs);
         if (osx == 0 && osy == 0) { middle = color; middleLuma = luma; continue; }
         sum += luma;
@@ -639,7 +643,7 @@ __global__ void __launch_bounds__(256) k_post(const float4* __restrict__ fb, uch
     if (fabsf(middleLuma - mean) > maxSigma * sigma) middle = mul(middle, mean / middleLuma);
     texColor = mul(middle, exposure);
   } else {
-    texColor = mul(fb_fetch(fb, W, H, bx, by, count, use_div), exposure);
+    texColor = mul(fb_fetch(fb, W, H, bx, by, use_div), exposure);
   }
   const v3 c = texColor;
   v3 a = mk3(c.x * 0.59719f + c.y * 0.35458f + c.z * 0.04823f, c.x * 0.07600f + c.y * 0.90834f + c.z * 0.01566f,

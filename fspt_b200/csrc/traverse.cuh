@@ -14,10 +14,25 @@
 // have no observable effect and are skipped.
 //
 // Execution model: one ray per lane, a warp keeps running until fewer than REFILL lanes still have a ray,
-// then the idle lanes are refilled from a global queue with one atomicAdd per warp (__ballot_sync +
-// popc prefix = the compaction), so short rays do not wait for the longest ray of their warp.  Inside the
-// loop the warp votes each iteration whether to run an interior step or a leaf step (majority of lanes).
-// Results go back into the path record plus one hit/miss byte per record position for the shading kernel.
+// then the idle lanes are refilled from a global queue (__ballot_sync + popc prefix = the compaction), so
+// short rays do not wait for the longest ray of their warp.  Inside the loop the warp votes each iteration
+// whether to run an interior step or a leaf step (majority of lanes).
+//
+// Round-2 changes, each from the ncu source page of the round-1 build (profiles/r01_final_k_trace_ncu.txt):
+//   - SHORT STACK IN SHARED MEMORY: the reference's `int stack[64]` lived in local memory, whose L1 hit rate
+//     was 71-78 % (it competes with nodes and triangles), so every fourth pop waited for L2 before the dependent
+//     node fetch could issue.  The first TRACE_SMEM_STACK entries now sit in shared memory, laid out
+//     [depth][thread] (bank = lane for every per-lane depth: conflict-free), deeper entries spill to local memory.
+//   - LEAF BLOCKS: a leaf visit used to run four serialised load -> Moller-Trumbore rounds (4 dependent memory
+//     round trips, 294 warp instructions).  The upload now writes one 160-byte block per leaf (five whole
+//     sectors) holding its four test triangles component-major -- word c = component c of triangles 0..3 -- so
+//     the visit reads 160 contiguous bytes and evaluates the four tests as two packed f32x2 streams (FADD2/FMUL2:
+//     two independent IEEE f32 operations per instruction, bit-identical per lane), triangles (0,1) then (2,3).
+//   - BROADCAST OPERANDS: ray origin / direction / inverse direction are kept as scalars and packed at the use
+//     site; ptxas folds `mov.b64 {x, x}` into the `.F32` scalar-broadcast operand of FADD2/FMUL2, which frees the
+//     nine registers the materialised (x, x) pairs occupied.
+//   - WORK POOLS: a warp reserves TRACE_POOL consecutive queue items with one atomicAdd and hands them to its
+//     idle lanes at later refills (no atomic round trip on most refills; a warp's rays are consecutive records).
 #pragma once
 #include "camera.cuh"
 #include "device_common.cuh"
@@ -25,8 +40,8 @@
 struct TraceArgs {
   const float4* nodes;
   const float4* tris;
-  cudaTextureObject_t nodes_tex;  // the node / triangle arrays again as linear textures (second L1 data pipe)
-  cudaTextureObject_t tris_tex;
+  const float4* leaves;   // LeafBlock160: 10 x float4 per leaf (device_common.cuh)
+  cudaTextureObject_t nodes_tex;  // the node array again as a linear texture (second L1 data pipe)
   int root_ref;
   PathState ps;           // rays in, hits out (words 0..2 of the path record)
   const int* list_shadow; // record positions of the paths that cast a shadow ray (continuation rays: every record)
@@ -47,18 +62,35 @@ struct TraceArgs {
 #ifndef TRACE_NODE_TEX
 #define TRACE_NODE_TEX 15  /* bit k: word k of the node record comes through the texture pipe */
 #endif
-#ifndef TRACE_TRI_TEX
-#define TRACE_TRI_TEX 0    /* bit k: word k of a triangle record comes through the texture pipe */
-#endif
-#ifndef TRACE_DUP_LOADS
-#define TRACE_DUP_LOADS 0
-#endif
 #ifndef TRACE_REFILL
 #define TRACE_REFILL 12
 #endif
 #ifndef TRACE_INT_WEIGHT
 #define TRACE_INT_WEIGHT 1
 #define TRACE_LEAF_WEIGHT 1
+#endif
+#ifndef TRACE_SMEM_STACK
+#define TRACE_SMEM_STACK 12  /* stack entries per thread held in shared memory (0 = all in local memory) */
+#endif
+#ifndef TRACE_LEAF_BLOCKS
+#define TRACE_LEAF_BLOCKS 1  /* 1: leaf refs are ~leaf ordinal and index LeafBlock160; 0: ~first triangle, Tri48 */
+#endif
+#ifndef TRACE_LEAF_ROUNDS
+#define TRACE_LEAF_ROUNDS 2  /* 1: all ten loads of a leaf block up front (36 live data registers); 2: one pair per round */
+#endif
+#ifndef TRACE_BCAST
+#define TRACE_BCAST 1        /* 1: ray origin / inverse direction are scalars, packed at the use site (ptxas folds the (x, x)
+                                pair into the `.F32` broadcast operand of FADD2 / FMUL2); 0: materialised (x, x) register pairs */
+#endif
+#ifndef TRACE_SMEM_RAY
+#define TRACE_SMEM_RAY 1     /* 1: per-ray values used by one phase only (1/d: interior steps, d: leaf steps, slot: retirement)
+                                live in shared memory [value][thread] instead of registers */
+#endif
+#ifndef TRACE_POOL
+#define TRACE_POOL 0         /* queue items a warp reserves per atomicAdd (0 = one atomicAdd per refill) */
+#endif
+#ifndef TRACE_MIN_BLOCKS
+#define TRACE_MIN_BLOCKS 8   /* resident CTAs per SM the register allocation is held to (8 x 128 threads = 64 registers) */
 #endif
 
 __device__ __forceinline__ float slab(float bminx, float bminy, float bminz, float bmaxx, float bmaxy, float bmaxz,
@@ -71,14 +103,18 @@ __device__ __forceinline__ float slab(float bminx, float bminy, float bminz, flo
   return (tMax >= tMin && tMax > 0.0f) ? tMin : FSPT_MAX_T;
 }
 
-// Both child boxes at once with Blackwell's packed f32x2 pipe: FADD2 / FMUL2 perform two independent IEEE
-// round-to-nearest f32 operations per instruction (lane 0 = left child, lane 1 = right child), so the 24
-// subtract/multiply operations of the two slab tests issue as 12 instructions.  Bitwise identical to slab().
+// Blackwell's packed f32x2 pipe: FADD2 / FMUL2 perform two independent IEEE round-to-nearest f32 operations per
+// instruction.  pack2(x, x) of a scalar costs nothing: ptxas folds it into the instruction's `.F32` broadcast operand.
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ f32x2 bc2(float v) { return pack2(v, v); }
 __device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
 __device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
+// Both child boxes at once (lane 0 of a pair = left child, lane 1 = right child): the 24 subtract/multiply
+// operations of the two slab tests issue as 12 instructions.  Bitwise identical to slab().
 __device__ __forceinline__ void slab_pair(const float4 w0, const float4 w1, const float4 w2, f32x2 ox2, f32x2 oy2, f32x2 oz2,
                                           f32x2 ix2, f32x2 iy2, f32x2 iz2, float& lh, float& rh) {
   // record words: w0 = (lmin.x rmin.x lmin.y rmin.y)  w1 = (lmin.z rmin.z lmax.x rmax.x)  w2 = (lmax.y rmax.y lmax.z rmax.z)
@@ -115,61 +151,187 @@ __device__ __forceinline__ float tri_test(const float4 q0, const float4 q1, cons
   return dist > FSPT_EPSILON ? dist : FSPT_MAX_T;
 }
 
+// The same test for two triangles at once: every f32 operation of tri_test, in the same order, once per half of the
+// pair.  PRODUCTS run on the packed pipe (FMUL2: two IEEE multiplications per instruction); SUMS and DIFFERENCES of
+// products stay scalar FADDs on purpose: ptxas 12.9 contracts `mul.rn.f32x2` + `add.rn.f32x2` into FFMA2 even with
+// -fmad=false and explicit .rn (measured: the hit distances moved by an ulp), and it does not fuse across the
+// packed / scalar boundary.  The early returns become one predicate per triangle: a rejected test yields MAX_T
+// whatever the later (then meaningless) values are, so evaluating all of them changes nothing (tracer.fs:300-315).
+struct f2 { float a, b; };
+__device__ __forceinline__ f2 prod2(f32x2 x, f32x2 y) { f2 r; unpack2(mul2(x, y), r.a, r.b); return r; }
+__device__ __forceinline__ f32x2 pk(f2 v) { return pack2(v.a, v.b); }
+__device__ __forceinline__ f2 dif(f2 x, f2 y) { f2 r; r.a = x.a - y.a; r.b = x.b - y.b; return r; }
+__device__ __forceinline__ f2 sum3(f2 x, f2 y, f2 z) { f2 r; r.a = x.a + y.a + z.a; r.b = x.b + y.b + z.b; return r; }
+__device__ __forceinline__ void tri_test2(f32x2 v1x, f32x2 v1y, f32x2 v1z, f32x2 e1x, f32x2 e1y, f32x2 e1z, f32x2 e2x,
+                                          f32x2 e2y, f32x2 e2z, float ox, float oy, float oz, float dx, float dy, float dz,
+                                          float& r0, float& r1) {
+  const f32x2 DX = bc2(dx), DY = bc2(dy), DZ = bc2(dz);
+  // cross(dir, e2)
+  const f2 px = dif(prod2(DY, e2z), prod2(e2y, DZ)), py = dif(prod2(DZ, e2x), prod2(e2z, DX)), pz = dif(prod2(DX, e2y), prod2(e2x, DY));
+  const f32x2 PX = pk(px), PY = pk(py), PZ = pk(pz);
+  const f2 det = sum3(prod2(e1x, PX), prod2(e1y, PY), prod2(e1z, PZ));
+  const f32x2 inv = pack2(1.0f / det.a, 1.0f / det.b);
+  f2 t;  // t = origin - v1 (a difference of non-products: nothing to contract)
+  unpack2(sub2(bc2(ox), v1x), t.a, t.b); const f32x2 TX = pk(t);
+  unpack2(sub2(bc2(oy), v1y), t.a, t.b); const f32x2 TY = pk(t);
+  unpack2(sub2(bc2(oz), v1z), t.a, t.b); const f32x2 TZ = pk(t);
+  const f2 u = prod2(pk(sum3(prod2(TX, PX), prod2(TY, PY), prod2(TZ, PZ))), inv);
+  // cross(t, e1)
+  const f2 qx = dif(prod2(TY, e1z), prod2(e1y, TZ)), qy = dif(prod2(TZ, e1x), prod2(e1z, TX)), qz = dif(prod2(TX, e1y), prod2(e1x, TY));
+  const f32x2 QX = pk(qx), QY = pk(qy), QZ = pk(qz);
+  const f2 v = prod2(pk(sum3(prod2(DX, QX), prod2(DY, QY), prod2(DZ, QZ))), inv);
+  const f2 dist = prod2(pk(sum3(prod2(e2x, QX), prod2(e2y, QY), prod2(e2z, QZ))), inv);
+  const float uv0 = u.a + v.a, uv1 = u.b + v.b;
+  const bool rej0 = (fabsf(det.a) < FSPT_EPSILON) || (u.a < 0.0f || u.a > 1.0f) || (v.a < 0.0f || uv0 > 1.0f);
+  const bool rej1 = (fabsf(det.b) < FSPT_EPSILON) || (u.b < 0.0f || u.b > 1.0f) || (v.b < 0.0f || uv1 > 1.0f);
+  r0 = (!rej0 && dist.a > FSPT_EPSILON) ? dist.a : FSPT_MAX_T;
+  r1 = (!rej1 && dist.b > FSPT_EPSILON) ? dist.b : FSPT_MAX_T;
+}
+
 // CAMERA = the primary launch of a render wave: the ray of slot `my` is generated on the fly (camera.fs) and the whole
 // ray + hit record is written at retirement, so the camera pass, its 32 B/path of writes and this launch's
 // record reads disappear.
 // NODE_TEX = false: the node array is too large for a linear texture (2^27 texels), everything goes through the LSU.
 template <bool WRITE_COUNT, bool CAMERA, bool NODE_TEX>
-__global__ void __launch_bounds__(TRACE_THREADS) k_trace(const TraceArgs A) {
+__global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const TraceArgs A) {
   const unsigned lane = threadIdx.x & 31u;
   const unsigned FULL = 0xffffffffu;
-  const int n_cont = A.counts[0];
-  const int total = n_cont + A.counts[1];
+  // queue sizes: read once per CTA into shared memory.  (Re-reading them from global memory at every refill was a
+  // measured 26 % regression: they share a sector with nothing hot any more, but any per-refill global load sits on
+  // the critical path of the fetch.)
+  __shared__ int s_counts[2];
+  if (threadIdx.x == 0) { s_counts[0] = A.counts[0]; s_counts[1] = A.counts[1]; }
+  __syncthreads();
 
+#if TRACE_SMEM_STACK
+  // [depth][thread]: bank = lane whatever the per-lane depth.  `sp` is the BYTE offset of the thread's next free entry
+  // (depth * 4 * TRACE_THREADS + 4 * thread), so one register is both the depth and the address.
+  __shared__ int s_stack[TRACE_SMEM_STACK * TRACE_THREADS];
+  int spill[FSPT_STACK - TRACE_SMEM_STACK];
+  constexpr unsigned ROW = 4u * TRACE_THREADS, SMEM_END = ROW * TRACE_SMEM_STACK;
+  const unsigned sp0 = 4u * threadIdx.x;
+#define STACK_AT(off) (*reinterpret_cast<int*>(reinterpret_cast<char*>(s_stack) + (off)))
+#define STACK_PUSH(v)                                                              \
+  do {                                                                             \
+    if (sp < SMEM_END) STACK_AT(sp) = (v);                                         \
+    else spill[(sp - SMEM_END) / ROW] = (v);                                       \
+    sp += ROW;                                                                     \
+  } while (0)
+#define STACK_POP(dst)                                                             \
+  do {                                                                             \
+    sp -= ROW;                                                                     \
+    if (sp < SMEM_END) dst = STACK_AT(sp);                                         \
+    else dst = spill[(sp - SMEM_END) / ROW];                                       \
+  } while (0)
+#else
   int stack[FSPT_STACK];
-  int cur = FSPT_SENTINEL, sp = 0;
-  int slot = -1, kind = 0, cnt = 0, item = 0;
-  float ox = 0, oy = 0, oz = 0, dx = 0, dy = 0, dz = 0;
-  f32x2 ox2 = 0, oy2 = 0, oz2 = 0, ix2 = 0, iy2 = 0, iz2 = 0;  // (v, v) pairs for the packed slab test
+  const unsigned sp0 = 0;
+#define STACK_PUSH(v) do { stack[sp++] = (v); } while (0)
+#define STACK_POP(dst) do { dst = stack[--sp]; } while (0)
+#endif
+  int cur = FSPT_SENTINEL;
+  unsigned sp = sp0;
+  unsigned cnt = 0;  // visits of the current ray: low 16 bits all nodes, high 16 bits leaves (statistics; the bvh_test
+                     // count of the WRITE_COUNT variant is kept separately and exact)
+  int cnt_exact = 0;
+  bool kind = false, have = false;
+#if TRACE_SMEM_RAY
+  // ray values that only one phase reads stay out of the register file: 1/d (interior steps), d (leaf steps), slot
+  // (retirement).  [value][thread]: conflict-free.  The loads overlap the node / leaf-block fetch of the same step.
+  __shared__ float s_ray[7 * TRACE_THREADS];
+  float* const my_ray = s_ray + threadIdx.x;
+#define RAY_DX my_ray[0 * TRACE_THREADS]
+#define RAY_DY my_ray[1 * TRACE_THREADS]
+#define RAY_DZ my_ray[2 * TRACE_THREADS]
+#define RAY_IX my_ray[3 * TRACE_THREADS]
+#define RAY_IY my_ray[4 * TRACE_THREADS]
+#define RAY_IZ my_ray[5 * TRACE_THREADS]
+#define RAY_SLOT (reinterpret_cast<int*>(my_ray)[6 * TRACE_THREADS])
+#else
+  float r_dx = 0, r_dy = 0, r_dz = 0, r_ix = 0, r_iy = 0, r_iz = 0;
+  int r_slot = -1;
+#define RAY_DX r_dx
+#define RAY_DY r_dy
+#define RAY_DZ r_dz
+#define RAY_IX r_ix
+#define RAY_IY r_iy
+#define RAY_IZ r_iz
+#define RAY_SLOT r_slot
+#endif
+  float ox = 0, oy = 0, oz = 0;
+#if !TRACE_BCAST
+  f32x2 ox2 = 0, oy2 = 0, oz2 = 0, ix2 = 0, iy2 = 0, iz2 = 0;
+#endif
   float tbest = FSPT_MAX_T;
   int ibest = -1;
-  unsigned long long n_rays = 0, n_nodes = 0, n_leaves = 0;
+  unsigned n_nodes = 0, n_leaves = 0;  // per thread and launch: far below 2^32 (touched at retirement only)
   bool drained = false;
   bool boolean_ray = false;  // only hit-or-miss is consumed (tracer.fs:502, :509 at the last bounce)
+#if TRACE_POOL
+  int pool_next = 0, pool_end = 0;  // warp-uniform: queue items reserved by this warp and not handed out yet
+  bool exhausted = false;           // the global queue has no item beyond this warp's run
+#endif
 
   for (;;) {
     const bool need = (cur == FSPT_SENTINEL);
-    const bool retire = need && slot >= 0;
+    const bool retire = need && have;
     if (retire) {  // retire the finished ray
+      const int slot = RAY_SLOT;
       if (CAMERA) {
         st_path(A.ps.ro(slot), make_float4(ox, oy, oz, tbest));
-        st_path(A.ps.rd(slot), make_float4(dx, dy, dz, __int_as_float(ibest)));
-      } else if (kind == 0) {
+        st_path(A.ps.rd(slot), make_float4(RAY_DX, RAY_DY, RAY_DZ, __int_as_float(ibest)));
+      } else if (!kind) {
         st_path_w(A.ps.ro(slot), tbest);
         st_path_w(A.ps.rd(slot), __int_as_float(ibest));
       } else {
         st_path_w(A.ps.sd(slot), __int_as_float((ibest == -1) ? 2 : 3));
       }
-      if (WRITE_COUNT) A.count_out[slot] = cnt;
-      if (A.hit_flag && kind == 0) A.hit_flag[item] = (ibest != -1);
-      n_nodes += (unsigned long long)cnt;
+      if (WRITE_COUNT) A.count_out[slot] = cnt_exact;
+      if (A.hit_flag && !kind) A.hit_flag[slot] = (ibest != -1);  // continuation rays: slot = queue position
+      n_nodes += cnt & 0xffffu;
+      n_leaves += cnt >> 16;
+      have = false;
     }
-    if (retire) slot = -1;
     if (!drained) {
       const unsigned m = __ballot_sync(FULL, need);
       if (m) {
-        const int leader = __ffs(m) - 1;
+        const int n_cont = s_counts[0], total = n_cont + s_counts[1];  // shared memory: two fewer live registers
         const int want = __popc(m);
+        const int rank = __popc(m & ((1u << lane) - 1u));
+        int my;
+#if TRACE_POOL
+        const int left = pool_end - pool_next;
+        if (left < want && !exhausted) {
+          // not enough reserved items for every idle lane: the lowest-ranked lanes take what is left of the old run
+          // (no item is skipped), the others start a new run reserved with one atomicAdd
+          int base = 0;
+          if (lane == 0) base = atomicAdd(A.next, TRACE_POOL);
+          base = __shfl_sync(FULL, base, 0);
+          my = rank < left ? pool_next + rank : base + (rank - left);
+          exhausted = base + TRACE_POOL >= total;  // every later reservation starts beyond the queue
+          pool_end = exhausted ? total : base + TRACE_POOL;
+          pool_next = base + (want - left);
+          if (pool_next > pool_end) pool_next = pool_end;
+          if (base >= total) pool_next = pool_end = 0;
+        } else {
+          my = rank < left ? pool_next + rank : total;
+          pool_next += want < left ? want : left;
+        }
+        if (exhausted && pool_next >= pool_end) drained = true;
+#else
+        const int leader = __ffs(m) - 1;
         int base = 0;
         if ((int)lane == leader) base = atomicAdd(A.next, want);
         base = __shfl_sync(FULL, base, leader);
         if (base + want >= total) drained = true;
+        my = base + rank;
+#endif
         if (need) {
-          const int my = base + __popc(m & ((1u << lane) - 1u));
           if (my < total) {
-            item = my;
+            float dx, dy, dz;
+            int slot;
             if (CAMERA) {
-              kind = 0;
+              kind = false;
               slot = my;
               v3 o, d;
               int px, py;
@@ -184,15 +346,22 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(const TraceArgs A) {
               ox = o4.x; oy = o4.y; oz = o4.z;
               dx = d4.x; dy = d4.y; dz = d4.z;
               // shadow rays always; continuation rays when k_shade marked the path's last bounce (index word = -2)
-              boolean_ray = A.anyhit && (kind == 1 || __float_as_int(d4.w) == -2);
+              boolean_ray = A.anyhit && (kind || __float_as_int(d4.w) == -2);
             }
+            RAY_SLOT = slot;
+            RAY_DX = dx; RAY_DY = dy; RAY_DZ = dz;
             const float ix = 1.0f / dx, iy = 1.0f / dy, iz = 1.0f / dz;  // `vec3 inverse = 1.0 / ray.dir`, tracer.fs:318
+#if TRACE_BCAST
+            RAY_IX = ix; RAY_IY = iy; RAY_IZ = iz;
+#else
             ox2 = pack2(ox, ox); oy2 = pack2(oy, oy); oz2 = pack2(oz, oz);
             ix2 = pack2(ix, ix); iy2 = pack2(iy, iy); iz2 = pack2(iz, iz);
-            tbest = FSPT_MAX_T; ibest = -1; cnt = 0;
-            stack[0] = FSPT_SENTINEL; sp = 1;
+#endif
+            have = true;
+            tbest = FSPT_MAX_T; ibest = -1; cnt = 0; cnt_exact = 0;
+            sp = sp0;
+            STACK_PUSH(FSPT_SENTINEL);
             cur = A.root_ref;
-            n_rays++;
           }
         }
       }
@@ -211,6 +380,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(const TraceArgs A) {
       if (ni * TRACE_INT_WEIGHT >= nl * TRACE_LEAF_WEIGHT) {
         // ---- interior node: both child boxes from one 64-byte record --------------------------------
         if (is_int) {
+          if (WRITE_COUNT) cnt_exact++;
           cnt++;
           // The record's four words are split between the two L1 data pipes (texture fetch / LSU load): the
           // kernel is bound by L1 wavefronts (ncu: l1tex data-pipe ~60 % busy), not by issue slots.
@@ -219,61 +389,101 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(const TraceArgs A) {
           const float4 b = ((TRACE_NODE_TEX & 2) && NODE_TEX) ? tex1Dfetch<float4>(A.nodes_tex, 4 * cur + 1) : __ldg(np + 1);
           const float4 c = ((TRACE_NODE_TEX & 4) && NODE_TEX) ? tex1Dfetch<float4>(A.nodes_tex, 4 * cur + 2) : __ldg(np + 2);
           const float4 df = ((TRACE_NODE_TEX & 8) && NODE_TEX) ? tex1Dfetch<float4>(A.nodes_tex, 4 * cur + 3) : __ldg(np + 3);
-          int4 d = make_int4(__float_as_int(df.x), __float_as_int(df.y), 0, 0);
-#if TRACE_DUP_LOADS  /* sensitivity experiment: issue the record's loads a second time through the LSU pipe */
-          {
-            float4 e0, e1, e2, e3;
-            asm volatile("ld.global.ca.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(e0.x), "=f"(e0.y), "=f"(e0.z), "=f"(e0.w) : "l"(np));
-            asm volatile("ld.global.ca.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(e1.x), "=f"(e1.y), "=f"(e1.z), "=f"(e1.w) : "l"(np + 1));
-            asm volatile("ld.global.ca.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(e2.x), "=f"(e2.y), "=f"(e2.z), "=f"(e2.w) : "l"(np + 2));
-            asm volatile("ld.global.ca.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(e3.x), "=f"(e3.y), "=f"(e3.z), "=f"(e3.w) : "l"(np + 3));
-            if (e0.x + e1.x + e2.x + e3.x == 12345.678f) d.x = 0;  // keep the loads alive
-          }
-#endif
+          const int cl = __float_as_int(df.x), cr = __float_as_int(df.y);
           float lh, rh;
+#if TRACE_BCAST
+          slab_pair(a, b, c, bc2(ox), bc2(oy), bc2(oz), bc2(RAY_IX), bc2(RAY_IY), bc2(RAY_IZ), lh, rh);
+#else
           slab_pair(a, b, c, ox2, oy2, oz2, ix2, iy2, iz2, lh, rh);
+#endif
           const bool tl = lh < tbest, tr = rh < tbest;
           const bool right_first = lh > rh;                   // tracer.fs:384 (ties go left)
           if (tl && tr) {
-            stack[sp++] = right_first ? d.x : d.y;            // deferred child, tracer.fs:391
-            cur = right_first ? d.y : d.x;
+            STACK_PUSH(right_first ? cl : cr);                // deferred child, tracer.fs:391
+            cur = right_first ? cr : cl;
           } else if (tl || tr) {
-            cur = tl ? d.x : d.y;
+            cur = tl ? cl : cr;
           } else {
-            cur = stack[--sp];
+            STACK_POP(cur);
           }
         }
       } else {
         // ---- leaf: 4 consecutive triangles ----------------------------------------------------------
         if (is_leaf) {
-          cnt++;
-          n_leaves++;
+          if (WRITE_COUNT) cnt_exact++;
+          cnt += 0x10001u;
+          const float dx = RAY_DX, dy = RAY_DY, dz = RAY_DZ;
+#if TRACE_LEAF_BLOCKS
+          // block words: w0 = {first, -, -, -}; pair A (triangles 0,1) = w1..w4 + w5.xy; pair B (2,3) = w5.zw + w6..w9;
+          // each pair component-major: (c.t0, c.t1) for c = v1.xyz, e1.xyz, e2.xyz
+          const float4* lp = A.leaves + 10 * (size_t)(~cur);
+          const int first = __float_as_int(__ldg(&lp[0].x));
+          const float4 w1 = __ldg(lp + 1), w2 = __ldg(lp + 2), w3 = __ldg(lp + 3), w4 = __ldg(lp + 4), w5 = __ldg(lp + 5);
+#if TRACE_LEAF_ROUNDS == 2
+          // second pair in a second round trip (18 fewer live registers); its two remaining sectors are requested now.
+          // Measured: the CCTL.PF1 prefetches cost +25 % traversal time -- kept as a documented dead end.
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(lp + 6));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(lp + 8));
+#endif
+#if TRACE_LEAF_ROUNDS == 3
+          // one word of each of the second pair's two remaining sectors is loaded now (8 registers instead of 18): the
+          // second round's other two loads then hit L1
+          const float4 w6 = __ldg(lp + 6), w8 = __ldg(lp + 8);
+#endif
+          float r0, r1, r2, r3;
+          tri_test2(pack2(w1.x, w1.y), pack2(w1.z, w1.w), pack2(w2.x, w2.y), pack2(w2.z, w2.w), pack2(w3.x, w3.y),
+                    pack2(w3.z, w3.w), pack2(w4.x, w4.y), pack2(w4.z, w4.w), pack2(w5.x, w5.y), ox, oy, oz, dx, dy, dz, r0, r1);
+#if TRACE_LEAF_ROUNDS == 2
+          asm volatile("" ::: "memory");
+#endif
+#if TRACE_LEAF_ROUNDS == 3
+          asm volatile("" ::: "memory");
+          const float4 w7 = __ldg(lp + 7), w9 = __ldg(lp + 9);
+#else
+          const float4 w6 = __ldg(lp + 6), w7 = __ldg(lp + 7), w8 = __ldg(lp + 8), w9 = __ldg(lp + 9);
+#endif
+          tri_test2(pack2(w5.z, w5.w), pack2(w6.x, w6.y), pack2(w6.z, w6.w), pack2(w7.x, w7.y), pack2(w7.z, w7.w),
+                    pack2(w8.x, w8.y), pack2(w8.z, w8.w), pack2(w9.x, w9.y), pack2(w9.z, w9.w), ox, oy, oz, dx, dy, dz, r2, r3);
+          if (r0 < tbest) { ibest = first; tbest = r0; }      // in triangle order, strict `<`: tracer.fs:357-362
+          if (r1 < tbest) { ibest = first + 1; tbest = r1; }
+          if (r2 < tbest) { ibest = first + 2; tbest = r2; }
+          if (r3 < tbest) { ibest = first + 3; tbest = r3; }
+#else
           const int first = ~cur;
           const float4* tp = A.tris + 3 * (size_t)first;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const float4 q0 = (TRACE_TRI_TEX & 1) ? tex1Dfetch<float4>(A.tris_tex, 3 * (first + k)) : __ldg(tp + 3 * k);
-            const float4 q1 = (TRACE_TRI_TEX & 2) ? tex1Dfetch<float4>(A.tris_tex, 3 * (first + k) + 1) : __ldg(tp + 3 * k + 1);
-            const float4 q2 = (TRACE_TRI_TEX & 4) ? tex1Dfetch<float4>(A.tris_tex, 3 * (first + k) + 2) : __ldg(tp + 3 * k + 2);
+            const float4 q0 = __ldg(tp + 3 * k), q1 = __ldg(tp + 3 * k + 1), q2 = __ldg(tp + 3 * k + 2);
             const float res = tri_test(q0, q1, q2, ox, oy, oz, dx, dy, dz);
             if (res < tbest) { ibest = first + k; tbest = res; }
           }
-          cur = stack[--sp];
+#endif
+          STACK_POP(cur);
           if (!CAMERA && boolean_ray && ibest != -1) cur = FSPT_SENTINEL;  // any hit settles it
         }
       }
     }
   }
   // per-warp statistics -> 3 atomics per warp
+  unsigned long long s_nodes = n_nodes, s_leaves = n_leaves;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    n_rays += __shfl_xor_sync(FULL, n_rays, o);
-    n_nodes += __shfl_xor_sync(FULL, n_nodes, o);
-    n_leaves += __shfl_xor_sync(FULL, n_leaves, o);
+    s_nodes += __shfl_xor_sync(FULL, s_nodes, o);
+    s_leaves += __shfl_xor_sync(FULL, s_leaves, o);
   }
   if (lane == 0) {
-    atomicAdd(A.stats + 0, n_rays);
-    atomicAdd(A.stats + 1, n_nodes);
-    atomicAdd(A.stats + 2, n_leaves);
+    atomicAdd(A.stats + 1, s_nodes);
+    atomicAdd(A.stats + 2, s_leaves);
   }
+  // every queue item is one ray and every item is traced exactly once
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(A.stats + 0, (unsigned long long)(A.counts[0] + A.counts[1]));
+#undef STACK_PUSH
+#undef STACK_POP
+#undef RAY_DX
+#undef RAY_DY
+#undef RAY_DZ
+#undef RAY_IX
+#undef RAY_IY
+#undef RAY_IZ
+#undef RAY_SLOT
 }

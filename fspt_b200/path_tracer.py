@@ -35,7 +35,9 @@ class PathTracer:
         pt = cls(sa, resolution, cam, device=device, seed=seed, exposure=cam.get("exposure", 1.0),
                  max_samples=cam.get("samples", 2000), **kw)
         if autofocus:
-            dist = scene_json.autofocus_distance(sa.tris.astype(np.float64), pt.eye, pt.dir)
+            # the reference shoots the ray through its f64 Triangle.verts, not through the f32 upload (main.js:447-546)
+            v64 = sa.verts64 if sa.verts64 is not None else sa.tris.astype(np.float64)
+            dist = scene_json.autofocus_distance(v64, pt.eye, pt.dir)
             pt.lensFeatures[0] = 1.0 - 1.0 / dist   # main.js:543-544
         return pt
 

@@ -26,6 +26,7 @@ class SceneArrays:
     leaf_size: int = 4
     depth: int = 0
     order: np.ndarray = None         # source triangle of each triTex slot
+    verts64: np.ndarray = None       # (T,9) f64 Triangle.verts in leaf order: what shootAutoFocusRay walks (main.js:447-546)
 
     @property
     def n_tris(self):
@@ -39,9 +40,14 @@ def get_material(prop, group_material, packer, assets, base_path=""):
     """getMaterial (main.js:206-270).  `assets` maps url -> image dict.  Returns the material record."""
     gm = group_material or {}
 
-    def tex(url, corrected=False, swizzle=None):
-        img = dict(assets[url])
-        if swizzle is not None:
+    _keep = object()
+
+    def tex(url, corrected=False, swizzle=_keep):
+        # one mutable record per url, like the reference's Image elements: `img.swizzle = ...` is assigned on the
+        # shared object for metallic-roughness maps only (main.js:228-229,235-236, `undefined` included) and is read
+        # when the atlas is packed, so the LAST assignment wins for every layer made from that image
+        img = assets[url]
+        if swizzle is not _keep:
             img["swizzle"] = swizzle
         return packer.addTexture(img, corrected)
 
@@ -57,11 +63,11 @@ def get_material(prop, group_material, packer, assets, base_path=""):
         diffuse = packer.addColor([0.5, 0.5, 0.5])
 
     if gm.get("map_pmr"):
-        rough = tex(base_path + "/" + gm["map_pmr"], False, gm.get("pmr_swizzle"))
+        rough = tex(base_path + "/" + gm["map_pmr"], None, gm.get("pmr_swizzle"))  # addTexture(img): corrected = undefined
     elif gm.get("pmr"):
         rough = packer.addColor(gm["pmr"])
     elif isinstance(prop.get("metallicRoughness"), str):
-        rough = tex(prop["metallicRoughness"], False, prop.get("mrSwizzle"))
+        rough = tex(prop["metallicRoughness"], None, prop.get("mrSwizzle"))
     elif isinstance(prop.get("metallicRoughness"), (list, tuple)):
         rough = packer.addColor(prop["metallicRoughness"])
     else:
@@ -139,4 +145,4 @@ def flatten(triangle_sets, atlas, env, bins, normalize=None, n_threads=0, builde
         atlas=atlas, env=env, bins=bins,
         lights=np.concatenate(lights, axis=0).astype(np.float32) if lights else None,
         light_ranges=np.asarray(ranges, np.float32) if ranges else None,
-        depth=depth, order=order)
+        depth=depth, order=order, verts64=verts[order].reshape(-1, 9))

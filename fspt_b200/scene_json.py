@@ -79,6 +79,13 @@ def parse_obj(obj_text, read_text, base_path, skips=()):
             if group not in groups:
                 groups.append(group)
             idx = [[_js_parse_float(x) for x in s.split("/")] for s in vals]
+            # relative (negative / zero) indices resolve against the vertices and normals read SO FAR
+            # (parseTriangle, obj_loader.js:107-113: `vertices.length + idx + 1` at the time of the face line)
+            for c in idx:
+                if c[0] < 1:
+                    c[0] = len(vertices) + c[0] + 1
+                if len(c) > 2 and c[2] == c[2] and c[2] < 1:
+                    c[2] = len(mesh_normals) + c[2] + 1
             for i in range(len(idx) - 2):  # parseFace
                 faces.append((group, [list(idx[0]), list(idx[i + 1]), list(idx[i + 2])]))
         elif arr[0] == "vt":
@@ -98,20 +105,15 @@ def obj_to_triangle_sets(parsed, prop, world_transforms):
     """parseTriangle + smooth normals + calcTangents for every group of one OBJ (obj_loader.js:103-212).
     Smooth normals are averaged over ALL faces of the OBJ that share a vertex index, in file order."""
     V = parsed["vertices"]
-    nV, nN = V.shape[0], len(parsed["mesh_normals"])
     vi, ti, ni, gid = [], [], [], []
     gindex = {g: k for k, g in enumerate(parsed["groups"])}
     for g, tri in parsed["faces"]:
         row_v, row_t, row_n = [], [], []
         for c in tri:
-            v = c[0]
-            v = nV + v + 1 if v < 1 else v            # negative / relative indices (obj_loader.js:107-108)
-            row_v.append(int(v) - 1)
+            row_v.append(int(c[0]) - 1)                 # relative indices were resolved while parsing the face line
             t = c[1] if len(c) > 1 else float("nan")
             row_t.append(int(t) - 1 if t == t else -1)  # vt indices are used as given (obj_loader.js:109-110)
             n = c[2] if len(c) > 2 else float("nan")
-            if n == n:
-                n = nN + n + 1 if n < 1 else n
             row_n.append(int(n) - 1 if n == n else -1)
         vi.append(row_v); ti.append(row_t); ni.append(row_n); gid.append(gindex[g])
     vi, ti, ni, gid = np.asarray(vi, np.int64), np.asarray(ti, np.int64), np.asarray(ni, np.int64), np.asarray(gid)

@@ -12,15 +12,17 @@ BUNNY_CAMERA = dict(eye=[-0.751, 0.665, 1.820], dir=[0.304, -0.489, -0.818], fov
                     aperture=0.02, focal_depth=2.0)
 
 
-def _env(env_size, kind="sun"):
+def _env(env_size, kind="sun", host=None):
     w, h = env_size
     env = pr.environment(w, h) if kind == "sun" else pr.constant_environment(w, h, kind)
-    return env, capi.env_bins(env)
+    return env, (host or capi).env_bins(env)
 
 
-def bunny_class(subdiv=6, atlas_res=2048, env_size=(2048, 1024), textured=True):
+def bunny_class(subdiv=6, atlas_res=2048, env_size=(2048, 1024), textured=True, host=None):
     """scene/bunny.json with the missing bunny replaced by a lumpy icosphere (20*4^subdiv triangles) and the
-    dungeon maps by procedural PBR maps.  Props, transforms and material constants follow scene/bunny.json:6-41."""
+    dungeon maps by procedural PBR maps.  Props, transforms and material constants follow scene/bunny.json:6-41.
+    host: the module that supplies the host-side scene compilers bvh_build / env_bins / pack_layer -- default the
+    product's native ones (capi); the reference arm of bench.py passes the oracle so that it never loads the product."""
     v, f = pr.icosphere(subdiv)
     props = [
         dict(mesh=(pr.lumpy(v), f, None), scale=0.35, rotate=[{"angle": 0, "axis": [0, 0, 1]}], translate=[0.1, -0.4, 0],
@@ -41,11 +43,13 @@ def bunny_class(subdiv=6, atlas_res=2048, env_size=(2048, 1024), textured=True):
         for p in props[1:]:
             for k in ("diffuse", "metallicRoughness", "normal", "emission"):
                 p.pop(k, None)
-    return compile_props(props, assets, atlas_res, _env(env_size)), dict(BUNNY_CAMERA)
+    return compile_props(props, assets, atlas_res, _env(env_size, host=host), host=host), dict(BUNNY_CAMERA)
 
 
-def compile_props(props, assets, atlas_res, env_and_bins, n_threads=0, builder=None):
-    packer = TexturePacker(atlas_res)
+def compile_props(props, assets, atlas_res, env_and_bins, n_threads=0, builder=None, host=None):
+    packer = TexturePacker(atlas_res, pack_layer=host.pack_layer if host else None)
+    if host is not None and builder is None:
+        builder = host.bvh_build
     sets = []
     for p in props:
         vtx, faces, face_uvs = p["mesh"]

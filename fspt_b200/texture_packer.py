@@ -8,8 +8,9 @@ import numpy as np
 
 
 class TexturePacker:
-    def __init__(self, atlas_res):
+    def __init__(self, atlas_res, pack_layer=None):
         self.res = atlas_res          # texture_packer.js:7
+        self._pack_layer = pack_layer  # the blit; default = the native fspt_pack_layer
         self.imageSet = []
         self.imageKeys = {}
         self.maxRes = 1
@@ -19,7 +20,9 @@ class TexturePacker:
         if self.imageKeys.get(key):   # `if (this.imageKeys[key])`: index 0 is never deduplicated (:14)
             return self.imageKeys[key]
         self.maxRes = max(self.maxRes, image["pixels"].shape[0])
-        image = dict(image)
+        # the reference stores the Image OBJECT and sets `image.corrected` on it (:18-19): every layer that refers to
+        # the same object is blitted with the object's final `corrected` / `swizzle` (read in getPixels), so the
+        # record is shared and mutated here, not copied
         image["corrected"] = corrected
         self.imageSet.append(image)
         self.imageKeys[key] = len(self.imageSet) - 1
@@ -49,8 +52,11 @@ class TexturePacker:
                 out[i, :, :, :3] = np.floor(c * np.float32(255.0) + np.float32(0.5)).astype(np.uint8)
                 out[i, :, :, 3] = 255
             else:
-                from . import capi  # the blit itself is native (csrc/atlas_packer.cpp)
-                out[i] = capi.pack_layer(img["pixels"], res, bool(img.get("corrected")), img.get("swizzle"))
+                blit = self._pack_layer
+                if blit is None:
+                    from . import capi  # the blit itself is native (csrc/atlas_packer.cpp)
+                    blit = capi.pack_layer
+                out[i] = blit(img["pixels"], res, bool(img.get("corrected")), img.get("swizzle"))
         return out
 
 

@@ -26,14 +26,15 @@
 extern "C" {
 #endif
 
-#define FSPT_ABI_VERSION 1
+#define FSPT_ABI_VERSION 2
 
 enum {
   FSPT_OK = 0,
   FSPT_E_INVALID = -1, /* bad argument / malformed scene buffers */
   FSPT_E_CUDA = -2,    /* CUDA runtime error, or no usable device */
   FSPT_E_STATE = -3,   /* call out of order (e.g. render before scene upload) */
-  FSPT_E_LIMIT = -4    /* scene exceeds a documented limit (BVH deeper than the traversal stack) */
+  FSPT_E_LIMIT = -4,   /* scene exceeds a documented limit (BVH deeper than the traversal stack) */
+  FSPT_E_NCCL = -5     /* NCCL could not be loaded, or a collective failed */
 };
 
 typedef struct fspt_ctx fspt_ctx;
@@ -91,6 +92,7 @@ typedef struct fspt_stats {
   uint64_t last_rays, last_node_visits, last_leaf_visits; /* of the last fspt_render only            */
   uint64_t capped_paths;  /* paths stopped by the refraction safety cap                              */
   double shade_ms;        /* CUDA-event time spent in shading kernels during the last fspt_render    */
+  double reduce_ms;       /* CUDA-event time of the last fspt_reduce_accum (NCCL reduce on the context's stream) */
 } fspt_stats;
 
 int fspt_abi_version(void);
@@ -124,12 +126,38 @@ int fspt_read_accum(fspt_ctx* ctx, float* rgba32f_out);
 int fspt_write_accum(fspt_ctx* ctx, const float* rgba32f_in, uint32_t next_tick);
 
 /* Accumulation mode: 0 = the reference's running mean (tracer.fs:517), bit-faithful, default;
- * 1 = plain f32 sum + sample count (what sample-set sharding across GPUs reduces with NCCL). */
+ * 1 = plain f32 sum, with every pixel's sample count in the alpha channel (what tile / sample-set sharding across
+ * GPUs reduces with NCCL); fspt_resolve then divides each pixel by its own count. */
 int fspt_set_accum_mode(fspt_ctx* ctx, int32_t mode);
 /* Device pointer + element count (floats) of the accumulation buffer and the number of samples summed
  * into it, for torch.distributed / NCCL reduction by the host.  The pointer stays valid until destroy. */
 int fspt_accum_device_ptr(fspt_ctx* ctx, void** dptr, uint64_t* n_floats, uint64_t* n_samples);
 int fspt_set_accum_samples(fspt_ctx* ctx, uint64_t n_samples);
+
+/* ---- multi-GPU: one context per GPU (one process per GPU, or several contexts in one process) ------------------
+ * The reference renders one image on one GPU, one sample per requestAnimationFrame (main.js:838-857); every (pixel,
+ * sample) of tracer.fs main() (:436-518) is independent, so the frame shards by image TILES and by SAMPLE SETS
+ * (README.md:26-28 lists "Tiled rendering" as a TODO).  Collectives run inside the library on the context's stream
+ * over NCCL (NVLink / NVSwitch); NCCL is dlopen'ed at fspt_comm_init, single-GPU hosts never load it. */
+
+/* The pixel rectangle of the frame this context renders (gl.scissor-style, GL row order); default = whole frame.
+ * camera.fs / tracer.fs see the same gl_FragCoord and resolution as in a whole-frame render, so a pixel's samples
+ * are bit-identical whichever rectangle contains it.  The accumulation target stays frame-sized. */
+int fspt_set_tile(fspt_ctx* ctx, int32_t x0, int32_t y0, int32_t width, int32_t height);
+
+#define FSPT_COMM_ID_BYTES 128
+/* ncclGetUniqueId: called once (by rank 0); the host ships the 128 bytes to the other ranks by any means. */
+int fspt_comm_unique_id(uint8_t* id_out);
+/* ncclCommInitRank on the context's device; collective over all `world` contexts. */
+int fspt_comm_init(fspt_ctx* ctx, const uint8_t* id, int32_t rank, int32_t world);
+int fspt_comm_destroy(fspt_ctx* ctx);
+/* Sum of every rank's accumulation target -> root's, in place (ncclReduce, f32, 16 bytes/pixel), enqueued on the
+ * context's stream after the renders already queued; sum mode only.  Collective. */
+int fspt_reduce_accum(fspt_ctx* ctx, int32_t root);
+/* The scene uploaded on `root` (fspt_scene_upload) -> every other rank, device to device (ncclBroadcast of the
+ * records the upload built + the environment and atlas texels): replaces the per-GPU repetition of the texImage
+ * uploads of initBVH() (main.js:408-437,548-560).  Collective. */
+int fspt_scene_broadcast(fspt_ctx* ctx, int32_t root);
 
 /* mode=test (main.js:882-884, bvh_test.fs:224-232): one drawCamera() + primary intersectScene with the
  * visit counter.  Exports what bvh_test.fs computes but does not write out: result.index, result.t, count.

@@ -215,3 +215,81 @@ def test_gpu_and_host_atlas_interleave_are_bit_identical(monkeypatch):
     assert np.array_equal(out[0].view(np.uint32), out[1].view(np.uint32))
     assert np.array_equal(out[0].view(np.uint32), out[2].view(np.uint32))
     assert float(out[0][..., :3].max()) > 0.0
+
+
+def test_tiles_rendered_one_after_the_other_equal_the_whole_frame(small_bunny, oracle_mod):
+    """fspt_set_tile: a pixel's samples do not depend on which rectangle contains it (same gl_FragCoord, same
+    resolution, same rand bases), so rendering the frame as bands -- even unaligned ones that use the row-major path
+    ordering -- reproduces the whole-frame accumulation bit for bit, in both accumulation modes."""
+    sa, cam = small_bunny
+    W, H, N = 64, 48, 3
+    rc, rt = scenes.rand_bases(N, 12)
+    ctx = capi.Context(W, H)
+    try:
+        ctx.scene_upload(sa)
+        fr = _frame(ctx, cam)
+        for mode in (0, 1):
+            ctx.set_accum_mode(mode)
+            ctx.set_tile(0, 0, W, H)
+            ctx.clear()
+            ctx.render(fr, 0, rc, rt)
+            whole = ctx.read_accum()
+            ctx.clear()
+            for rect in [(0, 0, W, 16), (0, 16, 24, 32), (24, 16, 40, 13), (24, 29, 40, 19)]:
+                ctx.set_tile(*rect)
+                ctx.render(fr, 0, rc, rt)
+            tiled = ctx.read_accum()
+            assert np.array_equal(whole.view(np.uint32), tiled.view(np.uint32)), mode
+        with pytest.raises(capi.FsptError):
+            ctx.set_tile(0, 0, W + 1, H)
+        # the oracle agrees with the tiled result as well (running mean)
+        ctx.set_accum_mode(0)
+        ctx.set_tile(0, 0, W, H)
+        O = oracle_mod.Oracle(sa)
+        fb = None
+        for k in range(N):
+            pos, d = oracle_mod.camera(W, H, cam["eye"], cam["dir"], cam["fov_scale"], scenes.lens_features(cam), rc[k])
+            fb, _ = O.trace(pos, d, W, H, k, rt[k], cam["env_theta"], fb_prev=fb)
+        ctx.clear()
+        for rect in [(0, 0, W, 20), (0, 20, W, 28)]:
+            ctx.set_tile(*rect)
+            ctx.render(fr, 0, rc, rt)
+        assert np.array_equal(ctx.read_accum()[..., :3].view(np.uint32), fb[..., :3].view(np.uint32))
+    finally:
+        ctx.close()
+
+
+def test_back_to_back_renders_do_not_wait_and_stay_exact(small_bunny, oracle_mod):
+    """fspt_render is asynchronous across calls (rand bases are staged through a ring of pinned slots): twenty
+    single-sample calls enqueued without any synchronisation equal one twenty-sample call bit for bit, and a
+    fspt_debug_primary right behind a render does not disturb the render's rand bases."""
+    sa, cam = small_bunny
+    W, H, N = 48, 32, 20
+    rc, rt = scenes.rand_bases(N, 14)
+    ctx = capi.Context(W, H)
+    try:
+        ctx.scene_upload(sa)
+        fr = _frame(ctx, cam)
+        ctx.render(fr, 0, rc, rt)
+        one = ctx.read_accum()
+        ctx.clear()
+        for k in range(N):
+            ctx.render(fr, k, rc[k:k + 1], rt[k:k + 1])
+        ctx.debug_primary(fr, 123.0)
+        many = ctx.read_accum()
+        assert np.array_equal(one.view(np.uint32), many.view(np.uint32))
+    finally:
+        ctx.close()
+
+
+def test_collectives_need_a_communicator(small_bunny):
+    sa, _ = small_bunny
+    ctx = capi.Context(32, 16)
+    try:
+        ctx.scene_upload(sa)
+        for call in (ctx.reduce_accum, ctx.scene_broadcast):
+            with pytest.raises(capi.FsptError) as e:
+                call(0)
+            assert e.value.code == -3  # FSPT_E_STATE
+    finally:
+        ctx.close()

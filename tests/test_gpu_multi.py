@@ -1,6 +1,9 @@
 """Multi-GPU parity (needs >= 2 B200s on one box: `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`;
-skipped on a single-GPU box).  Sample-set sharding + NCCL reduce(sum) over NVLink must equal the sum of the
-oracle's per-sample colours, and its mean must match the reference running mean within f32 summation-order error."""
+skipped on a single-GPU box; `bench.py --gpus N` repeats the same check as its "parity" key so that the driver's scaling
+run records it).  Everything collective goes through the C ABI (fspt_comm_init / fspt_scene_broadcast /
+fspt_reduce_accum): sample-set sharding + ncclReduce(sum) over NVLink must equal the sum of the oracle's per-sample
+colours, its mean must match the reference running mean within f32 summation-order error, a scene received by
+ncclBroadcast must render the same bits as one uploaded from the host, and tile sharding must assemble the frame."""
 import os
 import sys
 
@@ -23,18 +26,37 @@ def _worker(rank, world, port, out_dir):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     sa, cam = scenes.bunny_class(subdiv=3, atlas_res=32, env_size=(128, 64))
     ctx = capi.Context(W, H, rank)
-    ctx.scene_upload(sa)
+    fdist.init_comm(ctx, rank, world)       # NCCL communicator inside the library
+    if rank == 0:
+        ctx.scene_upload(sa)                # only rank 0 touches the host buffers ...
+    ctx.scene_broadcast(0)                  # ... the other rank receives the device-resident records over NVLink
     ctx.set_accum_mode(1)
     rc, rt = scenes.rand_bases(N, 21)
-    ticks = fdist.shard_ticks(N, rank, world)
     fr = ctx.frame(cam["eye"], cam["dir"], cam["fov_scale"], scenes.lens_features(cam), cam["env_theta"])
+    # (1) sample-set sharding
+    ticks = fdist.shard_ticks(N, rank, world)
     ctx.clear()
     ctx.render(fr, 0, rc[ticks], rt[ticks])
-    fdist.reduce_accum(ctx, dst=0, n_local_samples=len(ticks), world=world, device_index=rank)
-    torch.cuda.synchronize()
+    ctx.reduce_accum(0)                     # enqueued on the library's stream; read_accum synchronises
     if rank == 0:
         np.save(os.path.join(out_dir, "sum.npy"), ctx.read_accum())
         np.save(os.path.join(out_dir, "rgba.npy"), ctx.resolve())
+    # (2) tile sharding: rank r renders every tick of its own band
+    rect, tks = fdist.partition(rank, world, W, H, N, n_tiles=world)
+    ctx.set_tile(*rect)
+    ctx.clear()
+    ctx.render(fr, 0, rc[tks], rt[tks])
+    ctx.reduce_accum(0)
+    if rank == 0:
+        np.save(os.path.join(out_dir, "tiles.npy"), ctx.read_accum())
+    # (3) unequal sample sets (5 ticks over 2 ranks): per-pixel counts in the alpha channel keep the mean exact
+    ctx.set_tile(0, 0, W, H)
+    ticks5 = fdist.shard_ticks(5, rank, world)
+    ctx.clear()
+    ctx.render(fr, 0, rc[ticks5], rt[ticks5])
+    ctx.reduce_accum(0)
+    if rank == 0:
+        np.save(os.path.join(out_dir, "sum5.npy"), ctx.read_accum())
     ctx.close()
     dist.destroy_process_group()
 
@@ -60,7 +82,18 @@ def test_two_gpu_sample_sharding_matches_oracle(tmp_path, oracle_mod):
     got = np.load(tmp_path / "sum.npy")[..., :3]
     assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
     assert np.allclose(got / N, mean, rtol=3e-6, atol=1e-7)
+    assert np.all(np.load(tmp_path / "sum.npy")[..., 3] == N)   # per-pixel sample counts
     rgba = np.load(tmp_path / "rgba.npy")
     full = np.zeros((H, W, 4), np.float32)
     full[..., :3] = got / np.float32(N)
     assert np.abs(rgba.astype(int) - oracle_mod.draw(full).astype(int)).max() <= 1
+    # tile sharding: every pixel received all N samples in tick order from ONE rank -> plain sequential sum
+    seq = z.copy()
+    for k in range(N):
+        seq = seq + cols[k]
+    tiles = np.load(tmp_path / "tiles.npy")
+    assert np.array_equal(tiles[..., :3].view(np.uint32), seq.view(np.uint32)) and np.all(tiles[..., 3] == N)
+    # unequal shards: ticks {0,2,4} + {1,3}
+    ref5 = (((z + cols[0]) + cols[2]) + cols[4]) + ((z + cols[1]) + cols[3])
+    sum5 = np.load(tmp_path / "sum5.npy")
+    assert np.array_equal(sum5[..., :3].view(np.uint32), ref5.view(np.uint32)) and np.all(sum5[..., 3] == 5)

@@ -179,8 +179,10 @@ def _full_frame_check(oracle_mod, sa, cam, W, H, n, seed):
 
 
 def test_full_size_bunny_frame_bit_exact(oracle_mod):
-    """BASELINE configs[1] geometry and resolution (1280x720, 81,920-triangle bunny-class mesh + textured quads)."""
-    sa, cam = scenes.bunny_class(subdiv=6, atlas_res=512)
+    """BASELINE configs[1] exactly as bench.py renders it: 1280x720, 81,920-triangle bunny-class mesh + the two textured
+    quads, 2048x2048 atlas (11 layers), 2048x1024 environment."""
+    sa, cam = scenes.bunny_class(subdiv=6, atlas_res=2048)
+    assert sa.atlas.shape[1] == 2048
     _full_frame_check(oracle_mod, sa, cam, 1280, 720, 2, 3)
 
 
@@ -196,3 +198,29 @@ def test_refractive_pbr_scene_bit_exact(oracle_mod):
     sa, cam = scenes.pbr_scene(atlas_res=256, subdiv=4)
     _full_frame_check(oracle_mod, sa, cam, 480, 270, 3, 9)
     assert (sa.mats[:, 10] >= 0).any()
+
+
+def test_refractive_pbr_scene_full_size_bit_exact(oracle_mod):
+    """BASELINE configs[3] at its own size: 1920x1080, atlasRes 2048, refraction (paths beyond NUM_BOUNCES go through the
+    pipelined live-path poll of render_wave)."""
+    sa, cam = scenes.pbr_scene(atlas_res=2048)
+    assert sa.atlas.shape[1] == 2048 and (sa.mats[:, 10] >= 0).any()
+    _full_frame_check(oracle_mod, sa, cam, 1920, 1080, 2, 13)
+
+
+def test_ten_million_triangles_at_4k_bit_exact(oracle_mod):
+    """BASELINE configs[4] geometry and resolution: 10 M triangles (subdiv-8 icosphere + 8.69 M soup, seed 4321) at
+    3840x2160, 1 sample: camera rays (gl_FragCoord seeds beyond 2^22, where `seed += 0.2113` stalls in f32,
+    camera.fs:19,38), primary (index, t, count), the accumulator with and without any-hit, and the device V / L counters
+    against the CPU oracle.  The BVH (0.7 GB of nodes + leaf blocks + triangles) no longer fits the L2."""
+    sa, cam = scenes.sphere_soup(subdiv=8, n_soup=10000000 - 1310720, seed=4321)
+    assert sa.n_tris == 10000000 and sa.depth <= 64
+    _full_frame_check(oracle_mod, sa, cam, 3840, 2160, 1, 17)
+
+
+def test_node_records_through_the_lsu_path_bit_exact(oracle_mod, monkeypatch, small_bunny):
+    """k_trace<.., NODE_TEX = false>: the instantiation used when the node array exceeds the 2^27-texel limit of a linear
+    texture (> 33 M interior nodes) -- forced here on a small scene."""
+    monkeypatch.setenv("FSPT_NO_NODE_TEX", "1")
+    sa, cam = small_bunny
+    _full_frame_check(oracle_mod, sa, cam, 160, 96, 2, 19)

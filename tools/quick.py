@@ -30,8 +30,10 @@ for r in range(a.reps + 1):
     pt.tick(a.spp, rc, rt)
     st = pt.stats()
     if r:
+        import zlib
+        crc = zlib.crc32(pt.accumulation().tobytes())
         n = W * H * a.spp
-        print("render %.2f ms  trace %.2f  shade %.2f  other %.2f | %.1f Mpaths/s %.1f Mrays/s | V/ray %.1f L/ray %.2f" % (
+        print("render %.2f ms  trace %.2f  shade %.2f  other %.2f | %.1f Mpaths/s %.1f Mrays/s | V/ray %.1f L/ray %.2f | crc %08x" % (
             st["render_ms"], st["trace_ms"], st["shade_ms"], st["render_ms"] - st["trace_ms"] - st["shade_ms"],
             n / st["render_ms"] / 1e3, st["last_rays"] / st["render_ms"] / 1e3,
-            st["last_node_visits"] / st["last_rays"], st["last_leaf_visits"] / st["last_rays"]))
+            st["last_node_visits"] / st["last_rays"], st["last_leaf_visits"] / st["last_rays"], crc))
