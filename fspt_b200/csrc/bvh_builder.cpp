@@ -359,9 +359,9 @@ extern "C" int fspt_bvh_build2(const double* verts, const double* box_verts, int
   return FSPT_OK;
 }
 
-// ProcessEnvRadiance (env_sampler.js:1-74).  Same boxes as the JavaScript, but region sums come from a
-// summed-area table over exactly-representable per-texel terms when that is provably exact, otherwise from
-// the reference's own x-major double accumulation order.
+// ProcessEnvRadiance (env_sampler.js:1-74).  Same boxes as the JavaScript: region sums are accumulated in the
+// reference's own order (x-major double additions over the first half of every box, env_sampler.js:36-41), because the
+// split decisions compare those rounded sums -- a summed-area table would change them in the last place.
 extern "C" int fspt_env_bins(const uint8_t* data, int32_t width, int32_t height, uint16_t* bins_out,
                              int32_t capacity, int32_t* n_u16_out) {
   if (!data || !bins_out || width <= 0 || height <= 0 || capacity < 4) return FSPT_E_INVALID;

@@ -94,7 +94,7 @@ struct Ctx {
   int* d_list = nullptr;      // shadow list: record positions
   int* d_counts = nullptr;    // set k at [2k, 2k+1] = (#continuation, #shadow), [32] fetch cursor (own cache line)
   int* d_count_out = nullptr; // per-slot visit count (debug)
-  unsigned char* d_hit_flag = nullptr;  // hit / miss per record position
+  int* d_hit_index = nullptr;  // per record position: triangle hit by the continuation ray, -1 = miss
   unsigned long long* d_stats = nullptr;  // rays, nodes, leaves, capped
   float* d_rb = nullptr;      // rand bases of one render call: [0,cap) camera, [cap,2cap) tracer
   // pinned staging, a ring of RB_SLOTS blocks of 2*rb_cap floats: a slot is rewritten only after the copy that last
@@ -203,7 +203,7 @@ int alloc_wave(Ctx* c) {
                                                    // line: every warp's atomicAdd hits it, nothing else should
   CK(cudaMemset(c->d_counts, 0, 64 * sizeof(int)));
   CK(cudaMalloc(&c->d_count_out, W * sizeof(int)));
-  CK(cudaMalloc(&c->d_hit_flag, W));
+  CK(cudaMalloc(&c->d_hit_index, W * sizeof(int)));
   CK(cudaMalloc(&c->d_stats, 8 * sizeof(unsigned long long)));  // [0..3] live, [4..7] snapshot at render start
   CK(cudaMemset(c->d_stats, 0, 8 * sizeof(unsigned long long)));
   CK(cudaMalloc(&c->d_sample_color, W * 16));
@@ -266,7 +266,7 @@ int launch_trace(Ctx* c, int which, bool hit_flags, bool write_count, const Fram
   A.next = c->d_counts + 32;
   A.stats = c->d_stats;
   A.count_out = write_count ? c->d_count_out : nullptr;
-  A.hit_flag = hit_flags ? c->d_hit_flag : nullptr;
+  A.hit_index = hit_flags ? c->d_hit_index : nullptr;
   record_trace_begin(c);
   if (A.nodes_tex) {
     if (cam) k_trace<false, true, true><<<c->trace_blocks_cam, TRACE_THREADS, 0, c->stream>>>(A);
@@ -344,7 +344,7 @@ int render_wave(Ctx* c, const FrameParams& fp, uint32_t first_tick, int S, const
   ShadeArgs A;
   A.sc = c->sc; A.f = fp;
   A.rb_trace = rb_trace;
-  A.hit_flag = c->d_hit_flag;
+  A.hit_index = c->d_hit_index;
   A.list_shadow_out = c->d_list;
   A.sample_color = c->d_sample_color;
   A.capped = c->d_stats + 3;
@@ -552,7 +552,7 @@ void fspt_destroy(fspt_ctx* ctx) {
   dfree(c->d_fb); dfree(c->d_last_color); dfree(c->d_sample_color); dfree(c->d_cam_pos); dfree(c->d_cam_dir); dfree(c->d_rgba8);
   dfree(c->ps2[0].rec); dfree(c->ps2[1].rec);
   dfree(c->d_list);
-  dfree(c->d_counts); dfree(c->d_count_out); dfree(c->d_hit_flag); dfree(c->d_stats); dfree(c->d_rb);
+  dfree(c->d_counts); dfree(c->d_count_out); dfree(c->d_hit_index); dfree(c->d_stats); dfree(c->d_rb);
   if (c->h_rb) cudaFreeHost(c->h_rb);
   if (c->h_poll) cudaFreeHost(c->h_poll);
   for (auto e : c->ev_rb) if (e) cudaEventDestroy(e);
@@ -688,7 +688,7 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
   node_thread.join();
   if (bad_node >= 0) return fail(c, FSPT_E_INVALID, "node %d: triangle index %d out of range", bad_node, bad_tri);
   const size_t NI = interior_of.size();
-  const size_t NL = std::max<size_t>(1, leaf_first.size());
+  const size_t NL = std::max<size_t>(1, leaf_first.size());  // (no leaf blocks in this build: one dummy block)
   lap("node + material pre-pass");
   // ---- host staging block (pinned, kept between uploads): every copy below is a true async DMA and the user's
   // buffers are no longer referenced when this function returns.  Very large scenes stage in pageable memory.
@@ -788,7 +788,7 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
       e = v[6] - v[0]; o[6] = e; e = v[7] - v[1]; o[7] = e; e = v[8] - v[2]; o[8] = e;
     };
     // LeafBlock160 per leaf: the four triangles a leaf visit tests as two component-major pairs (device_common.cuh)
-    if (leaf_first.empty()) memset(leaves, 0, 160);
+    if (leaf_first.empty()) memset(leaves, 0, 160);  // TRACE_LEAF_BLOCKS == 0: leaf_first stays empty, nothing is built
     const int leaf_chunks = (int)((leaf_first.size() + 16383) / 16384);
     parallel(leaf_chunks, geo_workers, [&](int ch) {
       const size_t k1 = std::min(leaf_first.size(), (size_t)(ch + 1) * 16384);
@@ -851,9 +851,22 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
     mat_info[8 * m] = all_const ? -1 : n_tex_mats++;
     for (int k = 0; k < 4; ++k) mat_info[8 * m + 1 + k] = (int32_t)layer_info[2 * mats[m][k] + 1];
   }
-  const bool use_mat_tex = (size_t)n_tex_mats * layer_texels * 16 <= ((size_t)48 << 30) && !getenv("FSPT_PLAIN_ATLAS");
+  // The interleaved atlas costs res^2 * 16 bytes per TEXTURED MATERIAL (distinct layer quadruple) and the same again in
+  // pinned staging; quadruples can outnumber layers, so it is bounded against the plain atlas (4 x its bytes, at least
+  // 256 MB) and against the free device memory, and any allocation failure falls back to the plain RGBA8 array.
+  bool use_mat_tex = !getenv("FSPT_PLAIN_ATLAS");
+  {
+    const size_t inter = (size_t)n_tex_mats * layer_texels * 16, plain = (size_t)L * layer_bytes;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { (void)cudaGetLastError(); free_b = (size_t)48 << 30; }
+    const size_t resident = c->mat_arr ? (size_t)c->mat_R * c->mat_R * 16 * (size_t)c->mat_L : 0;  // reused when it fits
+    if (inter > std::max<size_t>(4 * plain, (size_t)256 << 20) || inter > ((size_t)48 << 30) || inter > (free_b + resident) / 2)
+      use_mat_tex = false;
+    if (getenv("FSPT_FORCE_MAT_TEX")) use_mat_tex = true;  // test knob: exercise the allocation-failure fallback
+  }
   std::atomic<int> cuda_err(0);
   std::mutex mu;
+  bool plain_atlas = !use_mat_tex;
   if (use_mat_tex) {
     if (c->sc.atlas) { cudaDestroyTextureObject(c->sc.atlas); c->sc.atlas = 0; }
     if (c->atlas_arr) { cudaFreeArray(c->atlas_arr); c->atlas_arr = nullptr; c->atlas_R = c->atlas_L = 0; }
@@ -885,21 +898,36 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
       if (c->mat_arr) cudaFreeArray(c->mat_arr);
       c->mat_arr = nullptr;
       cudaChannelFormatDesc fmt4 = cudaCreateChannelDesc<uint4>();
-      CK(cudaMalloc3DArray(&c->mat_arr, &fmt4, make_cudaExtent(R, R, ML),
-                           cudaArrayLayered | (gpu_interleave ? cudaArraySurfaceLoadStore : 0)));
-      rd.res.array.array = c->mat_arr;
-      CK(cudaCreateTextureObject(&c->sc.mat_tex, &rd, &td, nullptr));
-      if (gpu_interleave) CK(cudaCreateSurfaceObject(&c->mat_surf, &rd));
-      c->mat_R = R; c->mat_L = ML; c->mat_surface = gpu_interleave;
+      c->mat_R = c->mat_L = 0;
+      const size_t max_ml = getenv("FSPT_FORCE_MAT_TEX") ? (size_t)atoi(getenv("FSPT_FORCE_MAT_TEX")) : (size_t)1 << 30;
+      if ((size_t)ML > max_ml ||  // (test knob: pretend the device cannot hold more than that many material layers)
+          cudaMalloc3DArray(&c->mat_arr, &fmt4, make_cudaExtent(R, R, ML),
+                            cudaArrayLayered | (gpu_interleave ? cudaArraySurfaceLoadStore : 0)) != cudaSuccess) {
+        (void)cudaGetLastError();
+        c->mat_arr = nullptr;
+        plain_atlas = true;
+      } else {
+        rd.res.array.array = c->mat_arr;
+        CK(cudaCreateTextureObject(&c->sc.mat_tex, &rd, &td, nullptr));
+        if (gpu_interleave) CK(cudaCreateSurfaceObject(&c->mat_surf, &rd));
+        c->mat_R = R; c->mat_L = ML; c->mat_surface = gpu_interleave;
+      }
     }
     const size_t need = gpu_interleave ? layer_bytes * raw_layers.size() : layer_texels * 16 * (size_t)ML;
-    if (c->stage_bytes < need) {
+    if (!plain_atlas && c->stage_bytes < need) {
       if (c->h_stage) cudaFreeHost(c->h_stage);
       c->h_stage = nullptr; c->stage_bytes = 0;
-      CK(cudaMallocHost(&c->h_stage, need));
-      c->stage_bytes = need;
+      if (cudaMallocHost(&c->h_stage, need) != cudaSuccess) {
+        (void)cudaGetLastError();
+        c->h_stage = nullptr;
+        plain_atlas = true;
+      } else {
+        c->stage_bytes = need;
+      }
     }
-    if (gpu_interleave) {
+    if (plain_atlas) {
+      // could not hold the interleaved atlas: every material becomes "plain" (mat_info is rebuilt below)
+    } else if (gpu_interleave) {
       int rc2;
       if ((rc2 = ensure(c, c->d_raw, c->cap_raw, need))) return rc2;
       if ((rc2 = ensure(c, c->d_mat_src, c->cap_mat_src, sizeof(MatSrc) * (size_t)ML))) return rc2;
@@ -967,7 +995,8 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
         if (e != cudaSuccess) cuda_err.store((int)e);
       });
     }
-  } else {
+  }
+  if (plain_atlas) {
     if (c->sc.mat_tex) { cudaDestroyTextureObject(c->sc.mat_tex); c->sc.mat_tex = 0; }
     if (c->mat_surf) { cudaDestroySurfaceObject(c->mat_surf); c->mat_surf = 0; }
     c->mat_surface = false;

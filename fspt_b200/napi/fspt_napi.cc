@@ -9,6 +9,8 @@
 //                          env: Uint8Array, radianceBins: Uint16Array, atlasRes, atlasLayers, envWidth, envHeight});
 //   fspt.render(ctx, {eye, dir, fovScale, lensFeatures, envTheta}, firstTick, randBaseCamera, randBaseTracer);
 //   const rgba8 = fspt.resolve(ctx, {exposure, saturation, maxSigma, scale, denoise});
+// Multi-GPU (one process per GPU, see main_multi.mjs): fspt.commUniqueId() / commInit(ctx, id, rank, world) /
+//   sceneBroadcast(ctx, root) / setTile(ctx, x0, y0, w, h) / setAccumMode(ctx, 1) / reduceAccum(ctx, root).
 #include <node_api.h>
 
 #include <cstring>
@@ -232,10 +234,81 @@ napi_value BvhBuild(napi_env env, napi_callback_info info) {  // new BVH(triangl
   return res;
 }
 
+// ---- multi-GPU: one Node process (or worker) per GPU; the collectives run inside libfspt_b200.so over NCCL ---------
+int32_t Int32Arg(napi_env env, napi_value v) { int32_t x = 0; napi_get_value_int32(env, v, &x); return x; }
+
+napi_value SetTile(napi_env env, napi_callback_info info) {  // setTile(ctx, x0, y0, w, h)
+  size_t argc = 5;
+  napi_value argv[5];
+  NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+  fspt_ctx* ctx = Unwrap(env, argv[0]);
+  int r = fspt_set_tile(ctx, Int32Arg(env, argv[1]), Int32Arg(env, argv[2]), Int32Arg(env, argv[3]), Int32Arg(env, argv[4]));
+  if (r) return Throw(env, ctx, r);
+  return nullptr;
+}
+
+napi_value SetAccumMode(napi_env env, napi_callback_info info) {  // setAccumMode(ctx, 0 | 1)
+  size_t argc = 2;
+  napi_value argv[2];
+  NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+  fspt_ctx* ctx = Unwrap(env, argv[0]);
+  int r = fspt_set_accum_mode(ctx, Int32Arg(env, argv[1]));
+  if (r) return Throw(env, ctx, r);
+  return nullptr;
+}
+
+napi_value CommUniqueId(napi_env env, napi_callback_info) {  // -> Uint8Array(128); rank 0 calls it and ships it
+  void* data = nullptr;
+  napi_value ab, out;
+  NAPI_OK(napi_create_arraybuffer(env, FSPT_COMM_ID_BYTES, &data, &ab));
+  int r = fspt_comm_unique_id(static_cast<uint8_t*>(data));
+  if (r) return Throw(env, nullptr, r);
+  NAPI_OK(napi_create_typedarray(env, napi_uint8_array, FSPT_COMM_ID_BYTES, ab, 0, &out));
+  return out;
+}
+
+napi_value CommInit(napi_env env, napi_callback_info info) {  // commInit(ctx, idUint8Array, rank, world)
+  size_t argc = 4;
+  napi_value argv[4];
+  NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+  fspt_ctx* ctx = Unwrap(env, argv[0]);
+  napi_typedarray_type t;
+  size_t n = 0, off;
+  void* id = nullptr;
+  napi_value ab;
+  NAPI_OK(napi_get_typedarray_info(env, argv[1], &t, &n, &id, &ab, &off));
+  if (n < FSPT_COMM_ID_BYTES) { napi_throw_error(env, nullptr, "commInit: the id must hold 128 bytes"); return nullptr; }
+  int r = fspt_comm_init(ctx, static_cast<uint8_t*>(id), Int32Arg(env, argv[2]), Int32Arg(env, argv[3]));
+  if (r) return Throw(env, ctx, r);
+  return nullptr;
+}
+
+napi_value ReduceAccum(napi_env env, napi_callback_info info) {  // reduceAccum(ctx, root)
+  size_t argc = 2;
+  napi_value argv[2];
+  NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+  fspt_ctx* ctx = Unwrap(env, argv[0]);
+  int r = fspt_reduce_accum(ctx, Int32Arg(env, argv[1]));
+  if (r) return Throw(env, ctx, r);
+  return nullptr;
+}
+
+napi_value SceneBroadcast(napi_env env, napi_callback_info info) {  // sceneBroadcast(ctx, root)
+  size_t argc = 2;
+  napi_value argv[2];
+  NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+  fspt_ctx* ctx = Unwrap(env, argv[0]);
+  int r = fspt_scene_broadcast(ctx, Int32Arg(env, argv[1]));
+  if (r) return Throw(env, ctx, r);
+  return nullptr;
+}
+
 napi_value Init(napi_env env, napi_value exports) {
   const struct { const char* name; napi_callback fn; } fns[] = {
       {"create", Create}, {"sceneUpload", SceneUpload}, {"render", Render}, {"clear", Clear},
-      {"resolve", Resolve}, {"readAccum", ReadAccum}, {"bvhBuild", BvhBuild}};
+      {"resolve", Resolve}, {"readAccum", ReadAccum}, {"bvhBuild", BvhBuild},
+      {"setTile", SetTile}, {"setAccumMode", SetAccumMode}, {"commUniqueId", CommUniqueId}, {"commInit", CommInit},
+      {"reduceAccum", ReduceAccum}, {"sceneBroadcast", SceneBroadcast}};
   for (auto& f : fns) {
     napi_value fn;
     napi_create_function(env, f.name, NAPI_AUTO_LENGTH, f.fn, nullptr, &fn);

@@ -70,3 +70,72 @@ def test_share_host_threads(monkeypatch):
     monkeypatch.setenv("FSPT_UPLOAD_THREADS", "5")  # an explicit setting wins
     fdist.share_host_threads()
     assert os.environ["FSPT_UPLOAD_THREADS"] == "5"
+
+
+def test_partition_covers_every_pixel_sample_exactly_once():
+    """tiles x sample sets (fspt_b200.dist.partition): whatever the world size, every (pixel, tick) belongs to exactly
+    one rank; tile heights are multiples of 4 rows (the 8x4 path ordering of k_trace) except possibly the last."""
+    from fspt_b200 import dist as fdist
+    for world, W, H, N, tiles in [(1, 64, 48, 5, None), (2, 64, 48, 5, 2), (4, 96, 50, 7, 2), (8, 384, 216, 24, 8),
+                                  (8, 128, 72, 64, None), (8, 128, 70, 3, 8), (6, 64, 36, 10, 3)]:
+        cover = np.zeros((H, W, N), np.int32)
+        n_tiles, n_sets = fdist.tile_grid(world, W, H, tiles)
+        assert n_tiles * n_sets == world
+        for r in range(world):
+            (x0, y0, w, h), ticks = fdist.partition(r, world, W, H, N, n_tiles=tiles)
+            assert w == W and x0 == 0 and h > 0 and (y0 % 4 == 0)
+            assert h % 4 == 0 or y0 + h == H
+            cover[y0:y0 + h, x0:x0 + w][:, :, ticks] += 1
+        assert np.all(cover == 1), (world, W, H, N)
+    # 4K with 8 GPUs: the automatic grid picks tiles, so that a wave holds 64 samples again (8 when untiled)
+    assert fdist.tile_grid(8, 3840, 2160)[0] == 8 and fdist.tile_grid(8, 1280, 720) == (1, 8)
+    rows = np.zeros(2160, np.int32)
+    for r in range(8):
+        (x0, y0, w, h), ticks = fdist.partition(r, 8, 3840, 2160, 1024)
+        rows[y0:y0 + h] += 1
+        assert (x0, w) == (0, 3840) and len(ticks) == 1024 and h % 4 == 0
+    assert np.all(rows == 1)
+
+
+def _tile_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    import oracle
+    from fspt_b200 import dist as fdist, scenes
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sa, cam = scenes.bunny_class(subdiv=2, atlas_res=16, env_size=(64, 32))
+    O = oracle.Oracle(sa)
+    W, H, N = 32, 24, 5
+    rc, rt = scenes.rand_bases(N, 9)
+    (x0, y0, w, h), ticks = fdist.partition(rank, world, W, H, N, n_tiles=2)
+    local = np.zeros((H, W, 4), np.float32)     # what the library's sum mode holds: rgb sum + sample count in alpha
+    for k in ticks:
+        pos, d = oracle.camera(W, H, cam["eye"], cam["dir"], cam["fov_scale"], scenes.lens_features(cam), rc[k], nthreads=1)
+        _, col, _ = O.trace(pos, d, W, H, 0, rt[k], cam["env_theta"], want_color=True, nthreads=1)
+        local[y0:y0 + h, x0:x0 + w, :3] += col[y0:y0 + h, x0:x0 + w, :3]
+        local[y0:y0 + h, x0:x0 + w, 3] += 1.0
+    total = fdist.reduce_arrays_cpu(local, dst=0)
+    if rank == 0:
+        np.save(os.path.join(out_dir, "tiles.npy"), total)
+    dist.destroy_process_group()
+
+
+def test_tile_sharding_reduce_carries_per_pixel_counts(tmp_path, oracle_mod):
+    """world 2 = 2 tiles x 1 sample set: the reduced buffer is the frame, every pixel with its own sample count (the
+    divisor fspt_resolve uses), equal to the single-process sum."""
+    world, port = 2, 29100 + (os.getpid() % 500)
+    mp.spawn(_tile_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    from fspt_b200 import scenes
+    sa, cam = scenes.bunny_class(subdiv=2, atlas_res=16, env_size=(64, 32))
+    O = oracle_mod.Oracle(sa)
+    W, H, N = 32, 24, 5
+    rc, rt = scenes.rand_bases(N, 9)
+    ref = np.zeros((H, W, 3), np.float32)
+    for k in range(N):
+        pos, d = oracle_mod.camera(W, H, cam["eye"], cam["dir"], cam["fov_scale"], scenes.lens_features(cam), rc[k])
+        _, col, _ = O.trace(pos, d, W, H, 0, rt[k], cam["env_theta"], want_color=True)
+        ref = ref + col[..., :3]
+    got = np.load(tmp_path / "tiles.npy")
+    assert np.array_equal(got[..., :3], ref) and np.all(got[..., 3] == N)

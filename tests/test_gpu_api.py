@@ -196,6 +196,32 @@ def test_plain_atlas_fallback_is_bit_identical(monkeypatch):
     assert float(out[0][..., :3].max()) > 0.0
 
 
+def test_interleaved_atlas_allocation_failure_falls_back_to_the_plain_atlas(monkeypatch):
+    """When the material-interleaved array (or its pinned staging) cannot be allocated the upload must not fail: it takes
+    the plain-atlas branch on the SAME context, after an interleaved scene was resident (FSPT_FORCE_MAT_TEX=0 makes every
+    interleaved allocation 'fail')."""
+    sa, cam = scenes.pbr_scene(atlas_res=64, subdiv=2, env_size=(128, 64))
+    sb, _ = scenes.pbr_scene(atlas_res=32, subdiv=2, env_size=(128, 64))   # another atlas size: forces a re-allocation
+    W, H = 96, 64
+    rc, rt = scenes.rand_bases(3, 15)
+    ctx = capi.Context(W, H)
+    try:
+        ctx.scene_upload(sb)
+        ctx.render(_frame(ctx, cam), 0, rc, rt)
+        ctx.scene_upload(sa)
+        ctx.clear()
+        ctx.render(_frame(ctx, cam), 0, rc, rt)
+        ref = ctx.read_accum().copy()
+        ctx.scene_upload(sb)
+        monkeypatch.setenv("FSPT_FORCE_MAT_TEX", "0")
+        ctx.scene_upload(sa)            # interleaved array "cannot be allocated" -> plain RGBA8 layers
+        ctx.clear()
+        ctx.render(_frame(ctx, cam), 0, rc, rt)
+        assert np.array_equal(ref.view(np.uint32), ctx.read_accum().view(np.uint32))
+    finally:
+        ctx.close()
+
+
 def test_gpu_and_host_atlas_interleave_are_bit_identical(monkeypatch):
     """The material-interleaved atlas is built on the host (default for scenes whose materials use most of their four
     maps) or by k_interleave_atlas from the raw layers (chosen when few maps vary); FSPT_ATLAS_INTERLEAVE forces one."""
