@@ -94,7 +94,7 @@ struct Ctx {
   int* d_list = nullptr;      // shadow list: record positions
   int* d_counts = nullptr;    // set k at [2k, 2k+1] = (#continuation, #shadow), [32] fetch cursor (own cache line)
   int* d_count_out = nullptr; // per-slot visit count (debug)
-  int* d_hit_index = nullptr;  // per record position: triangle hit by the continuation ray, -1 = miss
+  unsigned char* d_hit_flag = nullptr;  // hit / miss per record position
   unsigned long long* d_stats = nullptr;  // rays, nodes, leaves, capped
   float* d_rb = nullptr;      // rand bases of one render call: [0,cap) camera, [cap,2cap) tracer
   // pinned staging, a ring of RB_SLOTS blocks of 2*rb_cap floats: a slot is rewritten only after the copy that last
@@ -203,7 +203,7 @@ int alloc_wave(Ctx* c) {
                                                    // line: every warp's atomicAdd hits it, nothing else should
   CK(cudaMemset(c->d_counts, 0, 64 * sizeof(int)));
   CK(cudaMalloc(&c->d_count_out, W * sizeof(int)));
-  CK(cudaMalloc(&c->d_hit_index, W * sizeof(int)));
+  CK(cudaMalloc(&c->d_hit_flag, W));
   CK(cudaMalloc(&c->d_stats, 8 * sizeof(unsigned long long)));  // [0..3] live, [4..7] snapshot at render start
   CK(cudaMemset(c->d_stats, 0, 8 * sizeof(unsigned long long)));
   CK(cudaMalloc(&c->d_sample_color, W * 16));
@@ -266,7 +266,7 @@ int launch_trace(Ctx* c, int which, bool hit_flags, bool write_count, const Fram
   A.next = c->d_counts + 32;
   A.stats = c->d_stats;
   A.count_out = write_count ? c->d_count_out : nullptr;
-  A.hit_index = hit_flags ? c->d_hit_index : nullptr;
+  A.hit_flag = hit_flags ? c->d_hit_flag : nullptr;
   record_trace_begin(c);
   if (A.nodes_tex) {
     if (cam) k_trace<false, true, true><<<c->trace_blocks_cam, TRACE_THREADS, 0, c->stream>>>(A);
@@ -344,7 +344,7 @@ int render_wave(Ctx* c, const FrameParams& fp, uint32_t first_tick, int S, const
   ShadeArgs A;
   A.sc = c->sc; A.f = fp;
   A.rb_trace = rb_trace;
-  A.hit_index = c->d_hit_index;
+  A.hit_flag = c->d_hit_flag;
   A.list_shadow_out = c->d_list;
   A.sample_color = c->d_sample_color;
   A.capped = c->d_stats + 3;
@@ -552,7 +552,7 @@ void fspt_destroy(fspt_ctx* ctx) {
   dfree(c->d_fb); dfree(c->d_last_color); dfree(c->d_sample_color); dfree(c->d_cam_pos); dfree(c->d_cam_dir); dfree(c->d_rgba8);
   dfree(c->ps2[0].rec); dfree(c->ps2[1].rec);
   dfree(c->d_list);
-  dfree(c->d_counts); dfree(c->d_count_out); dfree(c->d_hit_index); dfree(c->d_stats); dfree(c->d_rb);
+  dfree(c->d_counts); dfree(c->d_count_out); dfree(c->d_hit_flag); dfree(c->d_stats); dfree(c->d_rb);
   if (c->h_rb) cudaFreeHost(c->h_rb);
   if (c->h_poll) cudaFreeHost(c->h_poll);
   for (auto e : c->ev_rb) if (e) cudaEventDestroy(e);

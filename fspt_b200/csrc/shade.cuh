@@ -235,9 +235,10 @@ struct ShadeArgs {
   int first;                  // 1: slots hold fresh primary rays (tracer.fs:440-445)
   int max_refractions;
   int anyhit;
-  const int* hit_index;       // per record position, written by k_trace: index of the triangle the continuation ray hit,
-                              // -1 = miss.  Read coalesced when a tile is classified, so the shading records of a hit can
-                              // be requested together with its path record (two dependent round trips instead of three)
+  const unsigned char* hit_flag;  // hit / miss per record position, written by k_trace.  (Measured and dropped: a 4-byte hit
+                                  // INDEX per position carried through the queues, so that the shading records are requested
+                                  // together with the path record -- shade +2.4 %: wider reads and queues cost more than
+                                  // the shorter dependent chain saves at 32 warps/SM.)
 };
 
 // Warp-aggregated append: one atomicAdd per warp per list (ballot + popc prefix); call with all 32 lanes
@@ -301,12 +302,13 @@ __device__ __forceinline__ void shade_miss(const ShadeArgs& A, int pos) {
 // Returns true when the path continues; `out` then holds its new 6-word record (continuation ray, shadow ray, state).
 struct PathRecord { float4 w[6]; };
 template <bool MAT_TEX>
-__device__ __forceinline__ bool shade_hit(const ShadeArgs& A, int pos, int hit_index, bool& shadow, PathRecord& out) {
+__device__ __forceinline__ bool shade_hit(const ShadeArgs& A, int pos, bool& shadow, PathRecord& out) {
   const DeviceScene& sc = A.sc;
   int slot = pos;  // path identity; equals the record position only in the first pass
   const float4 o4 = ld_path(A.ps.ro(pos)), d4 = ld_path(A.ps.rd(pos));
   v3 rayOrigin = mk3(o4.x, o4.y, o4.z), rayDir = mk3(d4.x, d4.y, d4.z);
-  const float hit_t = o4.w;  // (hit_index == the index word of d4: it arrives through the queue, ahead of the record)
+  const float hit_t = o4.w;
+  const int hit_index = __float_as_int(d4.w);
   const float envTheta = A.f.env_theta;
   v3 color, reflectance;
   int i = 0, refractions = 0;
@@ -491,7 +493,8 @@ __device__ __forceinline__ bool shade_hit(const ShadeArgs& A, int pos, int hit_i
 #define SHADE_THREADS 256
 #endif
 #ifndef SHADE_BLOCK_APPEND
-#define SHADE_BLOCK_APPEND 0
+#define SHADE_BLOCK_APPEND 0  /* 1: one atomicAdd per block and list instead of one per warp -- measured shade +2 % (the two
+                                 extra block barriers cost more than the 8x fewer same-address atomics save) */
 #endif
 #ifndef SHADE_MIN_BLOCKS
 #define SHADE_MIN_BLOCKS 4  // 64 registers, 32 warps/SM.  Measured shading time vs 128 threads x 6 blocks (80 regs):
@@ -511,7 +514,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, SHADE_MIN_BLOCKS) k_shade(const
   init_unorm8_lut();
   // block-local queues: every tile pushes its hits and misses, and work is only started on FULL groups of
   // SHADE_THREADS items of one kind, so hit shading and miss shading never share a warp (or a block)
-  __shared__ int q_hit[2 * SHADE_THREADS], q_hit_tri[2 * SHADE_THREADS], q_miss[2 * SHADE_THREADS];
+  __shared__ int q_hit[2 * SHADE_THREADS], q_miss[2 * SHADE_THREADS];
   __shared__ int s_hits[SHADE_THREADS / 32], s_miss[SHADE_THREADS / 32];
 #if SHADE_BLOCK_APPEND
   __shared__ int s_wc[SHADE_THREADS / 32], s_ws[SHADE_THREADS / 32], s_base[2];
@@ -526,8 +529,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, SHADE_MIN_BLOCKS) k_shade(const
       const int it = tile * SHADE_THREADS + threadIdx.x;
       const bool live = it < n;
       const int slot = it;  // record position
-      const int tri = live ? A.hit_index[it] : -1;  // written by k_trace per position: a coalesced read
-      const bool hit = tri != -1;
+      const bool hit = live && A.hit_flag[it] != 0;  // written by k_trace per position: a coalesced read
       const unsigned mh = __ballot_sync(0xffffffffu, hit), mm = __ballot_sync(0xffffffffu, live && !hit);
       if (lane == 0) { s_hits[warp] = __popc(mh); s_miss[warp] = __popc(mm); }
       __syncthreads();
@@ -538,7 +540,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, SHADE_MIN_BLOCKS) k_shade(const
         t_hit += s_hits[w]; t_miss += s_miss[w];
       }
       const unsigned lt = (1u << lane) - 1u;
-      if (hit) { const int q = nh + hits_before + __popc(mh & lt); q_hit[q] = slot; q_hit_tri[q] = tri; }
+      if (hit) q_hit[nh + hits_before + __popc(mh & lt)] = slot;
       else if (live) q_miss[nm + miss_before + __popc(mm & lt)] = slot;
       nh += t_hit; nm += t_miss;
       __syncthreads();
@@ -547,8 +549,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, SHADE_MIN_BLOCKS) k_shade(const
       const int take = nh < SHADE_THREADS ? nh : SHADE_THREADS;
       bool cont = false, shadow = false;
       PathRecord rec;
-      if ((int)threadIdx.x < take)
-        cont = shade_hit<MAT_TEX>(A, q_hit[nh - take + threadIdx.x], q_hit_tri[nh - take + threadIdx.x], shadow, rec);
+      if ((int)threadIdx.x < take) cont = shade_hit<MAT_TEX>(A, q_hit[nh - take + threadIdx.x], shadow, rec);
       // stream compaction of the surviving paths: the new record goes to the next free position of ps_out
 #if SHADE_BLOCK_APPEND
       // one atomicAdd per BLOCK and list instead of one per warp: the per-warp counts are prefix-summed in shared memory

@@ -49,8 +49,7 @@ struct TraceArgs {
   int* next;              // work-fetch cursor (zeroed before launch)
   unsigned long long* stats;  // [0] rays, [1] node visits, [2] leaf visits
   int* count_out;         // per-slot visit count (debug / bvh_test mode) or NULL
-  int* hit_index;         // per record position: triangle hit by the continuation ray, -1 = miss (read coalesced by
-                          // k_shade) or NULL
+  unsigned char* hit_flag;  // per record position: 1 = hit (read coalesced by k_shade) or NULL
   FrameParams f;          // CAMERA mode: primary rays are generated in the fetch instead of being read
   const float* rb_cam;
   int n_samples;
@@ -61,7 +60,9 @@ struct TraceArgs {
 #define TRACE_THREADS 128
 #endif
 #ifndef TRACE_NODE_TEX
-#define TRACE_NODE_TEX 15  /* bit k: word k of the node record comes through the texture pipe */
+#define TRACE_NODE_TEX 3   /* bit k: word k of the node record comes through the texture pipe, the others through the LSU
+                               (measured with 36 warps/SM: words 0,1 via TLD + words 2,3 via LDG is 0.5 % / 2.5 % faster than all
+                               four via TLD on the 82 k / 1 M-triangle scenes; all via LDG is 2 % / 11 % slower) */
 #endif
 #ifndef TRACE_REFILL
 #define TRACE_REFILL 16      /* a warp fetches new rays when fewer lanes than this still hold one (with 36 warps/SM:
@@ -87,6 +88,9 @@ struct TraceArgs {
 #ifndef TRACE_SMEM_RAY
 #define TRACE_SMEM_RAY 1     /* 1: per-ray values used by one phase only (1/d: interior steps, d: leaf steps, slot: retirement)
                                 live in shared memory [value][thread] instead of registers */
+#endif
+#ifndef TRACE_TRI_BRANCHLESS
+#define TRACE_TRI_BRANCHLESS 0
 #endif
 #ifndef TRACE_POOL
 #define TRACE_POOL 0         /* queue items a warp reserves per atomicAdd (0 = one atomicAdd per refill) */
@@ -151,6 +155,25 @@ __device__ __forceinline__ float tri_test(const float4 q0, const float4 q1, cons
   if (v < 0.0f || u + v > 1.0f) return FSPT_MAX_T;
   const float dist = (e2x * qx + e2y * qy + e2z * qz) * invDet;
   return dist > FSPT_EPSILON ? dist : FSPT_MAX_T;
+}
+
+// Branch-free form of tri_test: the reference's early returns (tracer.fs:305,309,312) become one predicate.  A rejected
+// test yields MAX_T whatever the later (then meaningless, possibly NaN / inf) values are, so evaluating all of them is
+// the same function; in a divergent warp some lane nearly always needs the full test anyway, and the four
+// branch + reconvergence pairs per triangle disappear.
+__device__ __forceinline__ float tri_test_nb(const float4 q0, const float4 q1, const float4 q2, float ox, float oy,
+                                             float oz, float dx, float dy, float dz) {
+  const float e1x = q0.w, e1y = q1.x, e1z = q1.y, e2x = q1.z, e2y = q1.w, e2z = q2.x;
+  const float px = dy * e2z - e2y * dz, py = dz * e2x - e2z * dx, pz = dx * e2y - e2x * dy;  // cross(dir,e2)
+  const float det = e1x * px + e1y * py + e1z * pz;
+  const float invDet = 1.0f / det;
+  const float tx = ox - q0.x, ty = oy - q0.y, tz = oz - q0.z;
+  const float u = (tx * px + ty * py + tz * pz) * invDet;
+  const float qx = ty * e1z - e1y * tz, qy = tz * e1x - e1z * tx, qz = tx * e1y - e1x * ty;  // cross(t,e1)
+  const float v = (dx * qx + dy * qy + dz * qz) * invDet;
+  const float dist = (e2x * qx + e2y * qy + e2z * qz) * invDet;
+  const bool rej = (fabsf(det) < FSPT_EPSILON) || (u < 0.0f || u > 1.0f) || (v < 0.0f || u + v > 1.0f);
+  return (!rej && dist > FSPT_EPSILON) ? dist : FSPT_MAX_T;
 }
 
 // The same test for two triangles at once: every f32 operation of tri_test, in the same order, once per half of the
@@ -289,7 +312,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
         st_path_w(A.ps.sd(slot), __int_as_float((ibest == -1) ? 2 : 3));
       }
       if (WRITE_COUNT) A.count_out[slot] = cnt_exact;
-      if (A.hit_index && !kind) A.hit_index[slot] = ibest;  // continuation rays: slot = queue position
+      if (A.hit_flag && !kind) A.hit_flag[slot] = (ibest != -1);  // continuation rays: slot = queue position
       n_nodes += cnt & 0xffffu;
       n_leaves += cnt >> 16;
       have = false;
@@ -456,7 +479,11 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const float4 q0 = __ldg(tp + 3 * k), q1 = __ldg(tp + 3 * k + 1), q2 = __ldg(tp + 3 * k + 2);
+#if TRACE_TRI_BRANCHLESS
+            const float res = tri_test_nb(q0, q1, q2, ox, oy, oz, dx, dy, dz);
+#else
             const float res = tri_test(q0, q1, q2, ox, oy, oz, dx, dy, dz);
+#endif
             if (res < tbest) { ibest = first + k; tbest = res; }
           }
 #endif

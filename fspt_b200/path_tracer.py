@@ -22,7 +22,8 @@ class PathTracer:
         self.pingpong = 0                      # main.js:25
         self.scene = scene_arrays
         self.ctx = capi.Context(self.resolution[0], self.resolution[1], device)
-        self.upload_bytes = self.ctx.scene_upload(scene_arrays)
+        # scene_arrays None: the scene arrives later (fspt_scene_broadcast from the rank that compiled it)
+        self.upload_bytes = self.ctx.scene_upload(scene_arrays) if scene_arrays is not None else 0
         self._seed = seed
         self._rand = scenes.rand_bases
 
