@@ -91,7 +91,7 @@ struct Ctx {
   size_t wave_paths = 0;
   PathState ps{};             // = ps2[0] (debug entry points)
   PathState ps2[2]{};         // dense path-record arrays, ping-pong: shade reads one, compacts survivors into the other
-  int* d_list = nullptr;      // shadow list: record positions
+  float4* d_shadow = nullptr; // shadow rays of the current bounce, dense: origin | record position, direction | -
   int* d_counts = nullptr;    // set k at [2k, 2k+1] = (#continuation, #shadow), [32] fetch cursor (own cache line)
   int* d_count_out = nullptr; // per-slot visit count (debug)
   unsigned char* d_hit_flag = nullptr;  // hit / miss per record position
@@ -198,7 +198,7 @@ int alloc_wave(Ctx* c) {
   const size_t W = c->wave_paths;
   for (int k = 0; k < 2; ++k) CK(cudaMalloc(&c->ps2[k].rec, W * 16 * FSPT_PATH_WORDS));
   c->ps = c->ps2[0];
-  CK(cudaMalloc(&c->d_list, W * sizeof(int)));
+  CK(cudaMalloc(&c->d_shadow, W * 32));
   CK(cudaMalloc(&c->d_counts, 64 * sizeof(int)));  // [0..3] the two count pairs; [32] the fetch cursor, on its own 128-byte
                                                    // line: every warp's atomicAdd hits it, nothing else should
   CK(cudaMemset(c->d_counts, 0, 64 * sizeof(int)));
@@ -252,7 +252,7 @@ __global__ void k_set_counts(int* counts, int n_cont, int n_shadow) {
 }
 
 // Traverses the continuation ray of every record of array `which` (d_counts[2*which] of them) + d_counts[2*which+1]
-// shadow rays (positions in d_list); results go into the records, plus one hit/miss byte per position (for k_shade).
+// shadow rays (d_shadow); results go into the records, plus one hit/miss byte per position (for k_shade).
 int launch_trace(Ctx* c, int which, bool hit_flags, bool write_count, const FrameParams* cam = nullptr,
                  const float* rb_cam = nullptr, int n_samples = 1) {
   TraceArgs A;
@@ -261,7 +261,7 @@ int launch_trace(Ctx* c, int which, bool hit_flags, bool write_count, const Fram
   A.anyhit = c->anyhit;
   A.nodes = c->sc.nodes; A.tris = c->sc.tris; A.leaves = c->sc.leaves; A.root_ref = c->sc.root_ref; A.nodes_tex = c->nodes_tex;
   A.ps = c->ps2[which];
-  A.list_shadow = c->d_list;
+  A.shadow_rays = c->d_shadow;
   A.counts = c->d_counts + 2 * which;
   A.next = c->d_counts + 32;
   A.stats = c->d_stats;
@@ -345,7 +345,7 @@ int render_wave(Ctx* c, const FrameParams& fp, uint32_t first_tick, int S, const
   A.sc = c->sc; A.f = fp;
   A.rb_trace = rb_trace;
   A.hit_flag = c->d_hit_flag;
-  A.list_shadow_out = c->d_list;
+  A.shadow_rays_out = c->d_shadow;
   A.sample_color = c->d_sample_color;
   A.capped = c->d_stats + 3;
   A.n_samples = S;
@@ -551,7 +551,7 @@ void fspt_destroy(fspt_ctx* ctx) {
   free_scene(c);
   dfree(c->d_fb); dfree(c->d_last_color); dfree(c->d_sample_color); dfree(c->d_cam_pos); dfree(c->d_cam_dir); dfree(c->d_rgba8);
   dfree(c->ps2[0].rec); dfree(c->ps2[1].rec);
-  dfree(c->d_list);
+  dfree(c->d_shadow);
   dfree(c->d_counts); dfree(c->d_count_out); dfree(c->d_hit_flag); dfree(c->d_stats); dfree(c->d_rb);
   if (c->h_rb) cudaFreeHost(c->h_rb);
   if (c->h_poll) cudaFreeHost(c->h_poll);

@@ -227,7 +227,9 @@ struct ShadeArgs {
   FrameParams f;
   const float* rb_trace;      // per sample-in-wave
   const int* counts_in;       // [0] = number of records in ps
-  int* list_shadow_out;       // positions (in ps_out) of the paths that also cast a shadow ray
+  float4* shadow_rays_out;    // shadow rays of the paths that cast one, dense, 2 words each: origin | position in ps_out,
+                              // direction | -.  (A list of record positions made the traversal kernel's shadow-ray
+                              // fetch two dependent gathers over two sectors; this is one contiguous 32-byte read.)
   int* counts_out;            // [0] continuation, [1] shadow
   float4* sample_color;       // [pixel][sample-in-wave] final un-clamped path colour
   unsigned long long* capped; // paths stopped by the refraction cap
@@ -577,7 +579,11 @@ __global__ void __launch_bounds__(SHADE_THREADS, SHADE_MIN_BLOCKS) k_shade(const
 #pragma unroll
         for (int w = 0; w < 6; ++w) st_path(dst[w], rec.w[w]);
       }
-      if (shadow) A.list_shadow_out[s_base[1] + s_ws[warp] + __popc(ms & lt2)] = pos_out;
+      if (shadow) {
+        float4* sr = A.shadow_rays_out + 2 * (size_t)(s_base[1] + s_ws[warp] + __popc(ms & lt2));
+        sr[0] = make_float4(rec.w[0].x, rec.w[0].y, rec.w[0].z, __int_as_float(pos_out));
+        sr[1] = rec.w[2];
+      }
 #else
       const int pos_out = append_pos(cont, A.counts_out + 0);
       if (cont) {
@@ -585,7 +591,14 @@ __global__ void __launch_bounds__(SHADE_THREADS, SHADE_MIN_BLOCKS) k_shade(const
 #pragma unroll
         for (int w = 0; w < 6; ++w) st_path(dst[w], rec.w[w]);
       }
-      append(shadow, pos_out, A.list_shadow_out, A.counts_out + 1);
+      {
+        const int j = append_pos(shadow, A.counts_out + 1);
+        if (shadow) {  // origin = the continuation ray's (tracer.fs:501), direction = the sampled environment direction
+          float4* sr = A.shadow_rays_out + 2 * (size_t)j;
+          st_path(sr[0], make_float4(rec.w[0].x, rec.w[0].y, rec.w[0].z, __int_as_float(pos_out)));
+          st_path(sr[1], rec.w[2]);
+        }
+      }
 #endif
       nh -= take;
       __syncthreads();

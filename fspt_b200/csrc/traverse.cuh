@@ -31,8 +31,6 @@
 //   - BROADCAST OPERANDS: ray origin / direction / inverse direction are kept as scalars and packed at the use
 //     site; ptxas folds `mov.b64 {x, x}` into the `.F32` scalar-broadcast operand of FADD2/FMUL2, which frees the
 //     nine registers the materialised (x, x) pairs occupied.
-//   - WORK POOLS: a warp reserves TRACE_POOL consecutive queue items with one atomicAdd and hands them to its
-//     idle lanes at later refills (no atomic round trip on most refills; a warp's rays are consecutive records).
 #pragma once
 #include "camera.cuh"
 #include "device_common.cuh"
@@ -44,7 +42,7 @@ struct TraceArgs {
   cudaTextureObject_t nodes_tex;  // the node array again as a linear texture (second L1 data pipe)
   int root_ref;
   PathState ps;           // rays in, hits out (words 0..2 of the path record)
-  const int* list_shadow; // record positions of the paths that cast a shadow ray (continuation rays: every record)
+  const float4* shadow_rays;  // shadow rays, dense, 2 words each: origin | record position, direction | - (written by k_shade)
   const int* counts;      // counts[0] = #continuation, counts[1] = #shadow
   int* next;              // work-fetch cursor (zeroed before launch)
   unsigned long long* stats;  // [0] rays, [1] node visits, [2] leaf visits
@@ -92,8 +90,11 @@ struct TraceArgs {
 #ifndef TRACE_TRI_BRANCHLESS
 #define TRACE_TRI_BRANCHLESS 0
 #endif
-#ifndef TRACE_POOL
-#define TRACE_POOL 0         /* queue items a warp reserves per atomicAdd (0 = one atomicAdd per refill) */
+#ifndef TRACE_EARLY_FETCH
+#define TRACE_EARLY_FETCH 0  /* 1: rays are requested with cp.async one short run before they are started */
+#endif
+#ifndef TRACE_EARLY_STEPS
+#define TRACE_EARLY_STEPS 6  /* iterations of the short run between requesting and starting rays */
 #endif
 #ifndef TRACE_MIN_BLOCKS
 #define TRACE_MIN_BLOCKS 9   /* resident CTAs per SM the register allocation is held to (9 x 128 threads = 56 registers) */
@@ -292,13 +293,53 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
   unsigned n_nodes = 0, n_leaves = 0;  // per thread and launch: far below 2^32 (touched at retirement only)
   bool drained = false;
   bool boolean_ray = false;  // only hit-or-miss is consumed (tracer.fs:502, :509 at the last bounce)
-#if TRACE_POOL
-  int pool_next = 0, pool_end = 0;  // warp-uniform: queue items reserved by this warp and not handed out yet
-  bool exhausted = false;           // the global queue has no item beyond this warp's run
+#if TRACE_EARLY_FETCH
+  // EARLY FETCH: the ray of an idle lane is requested with cp.async (global -> shared, no registers, nothing waits) when
+  // the warp leaves a full run, the warp then keeps traversing for a few iterations with the lanes it still has, and
+  // only then are the new rays started -- the ray fetch (a DRAM round trip: path records stream) no longer stalls the
+  // lanes that still have work.  Stage 1 = retire + request, short run; stage 0 = start the requested rays, full run.
+  constexpr bool EARLY = !CAMERA;
+  __shared__ float4 s_fetch[EARLY ? 2 * TRACE_THREADS : 2];  // [thread][2]: word 0 = origin | position, word 1 = direction | mark
+  bool pending = false;
+  int stage = 1;
+#else
+  constexpr bool EARLY = false;
+  const bool pending = false;
+  const int stage = 1;
 #endif
 
+  // start the ray whose two words are o4 / d4 on this lane
+  auto start_ray = [&](const float4 o4, const float4 d4, int slot) {
+    ox = o4.x; oy = o4.y; oz = o4.z;
+    const float dx = d4.x, dy = d4.y, dz = d4.z;
+    RAY_SLOT = slot;
+    RAY_DX = dx; RAY_DY = dy; RAY_DZ = dz;
+    const float ix = 1.0f / dx, iy = 1.0f / dy, iz = 1.0f / dz;  // `vec3 inverse = 1.0 / ray.dir`, tracer.fs:318
+#if TRACE_BCAST
+    RAY_IX = ix; RAY_IY = iy; RAY_IZ = iz;
+#else
+    ox2 = pack2(ox, ox); oy2 = pack2(oy, oy); oz2 = pack2(oz, oz);
+    ix2 = pack2(ix, ix); iy2 = pack2(iy, iy); iz2 = pack2(iz, iz);
+#endif
+    have = true;
+    tbest = FSPT_MAX_T; ibest = -1; cnt = 0; cnt_exact = 0;
+    sp = sp0;
+    STACK_PUSH(FSPT_SENTINEL);
+    cur = A.root_ref;
+  };
+
   for (;;) {
-    const bool need = (cur == FSPT_SENTINEL);
+#if TRACE_EARLY_FETCH
+    if (EARLY && stage == 0 && pending) {  // the requested rays have had a short run's time to arrive
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      const float4 o4 = s_fetch[2 * threadIdx.x], d4 = s_fetch[2 * threadIdx.x + 1];
+      // shadow rays always; continuation rays when k_shade marked the path's last bounce (index word = -2)
+      boolean_ray = A.anyhit && (kind || __float_as_int(d4.w) == -2);
+      start_ray(o4, d4, kind ? __float_as_int(o4.w) : RAY_SLOT);
+      pending = false;
+    }
+#endif
+    const bool need = (cur == FSPT_SENTINEL) && !pending;
     const bool retire = need && have;
     if (retire) {  // retire the finished ray
       const int slot = RAY_SLOT;
@@ -317,83 +358,55 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
       n_leaves += cnt >> 16;
       have = false;
     }
-    if (!drained) {
+    if (!drained && stage == 1) {
       const unsigned m = __ballot_sync(FULL, need);
       if (m) {
         const int n_cont = s_counts[0], total = n_cont + s_counts[1];  // shared memory: two fewer live registers
         const int want = __popc(m);
         const int rank = __popc(m & ((1u << lane) - 1u));
-        int my;
-#if TRACE_POOL
-        const int left = pool_end - pool_next;
-        if (left < want && !exhausted) {
-          // not enough reserved items for every idle lane: the lowest-ranked lanes take what is left of the old run
-          // (no item is skipped), the others start a new run reserved with one atomicAdd
-          int base = 0;
-          if (lane == 0) base = atomicAdd(A.next, TRACE_POOL);
-          base = __shfl_sync(FULL, base, 0);
-          my = rank < left ? pool_next + rank : base + (rank - left);
-          exhausted = base + TRACE_POOL >= total;  // every later reservation starts beyond the queue
-          pool_end = exhausted ? total : base + TRACE_POOL;
-          pool_next = base + (want - left);
-          if (pool_next > pool_end) pool_next = pool_end;
-          if (base >= total) pool_next = pool_end = 0;
-        } else {
-          my = rank < left ? pool_next + rank : total;
-          pool_next += want < left ? want : left;
-        }
-        if (exhausted && pool_next >= pool_end) drained = true;
-#else
         const int leader = __ffs(m) - 1;
         int base = 0;
         if ((int)lane == leader) base = atomicAdd(A.next, want);
         base = __shfl_sync(FULL, base, leader);
         if (base + want >= total) drained = true;
-        my = base + rank;
-#endif
-        if (need) {
-          if (my < total) {
-            float dx, dy, dz;
-            int slot;
-            if (CAMERA) {
-              kind = false;
-              slot = my;
-              v3 o, d;
-              int px, py;
-              camera_ray(A.f, A.rb_cam, A.n_samples, my, o, d, px, py);
-              ox = o.x; oy = o.y; oz = o.z;
-              dx = d.x; dy = d.y; dz = d.z;
-            } else {
-              kind = my >= n_cont;
-              slot = kind ? ld_list(A.list_shadow + (my - n_cont)) : my;
-              const float4 o4 = ld_path(A.ps.ro(slot));
-              const float4 d4 = ld_path(kind ? A.ps.sd(slot) : A.ps.rd(slot));
-              ox = o4.x; oy = o4.y; oz = o4.z;
-              dx = d4.x; dy = d4.y; dz = d4.z;
-              // shadow rays always; continuation rays when k_shade marked the path's last bounce (index word = -2)
-              boolean_ray = A.anyhit && (kind || __float_as_int(d4.w) == -2);
-            }
-            RAY_SLOT = slot;
-            RAY_DX = dx; RAY_DY = dy; RAY_DZ = dz;
-            const float ix = 1.0f / dx, iy = 1.0f / dy, iz = 1.0f / dz;  // `vec3 inverse = 1.0 / ray.dir`, tracer.fs:318
-#if TRACE_BCAST
-            RAY_IX = ix; RAY_IY = iy; RAY_IZ = iz;
+        const int my = base + rank;
+        if (need && my < total) {
+          if (CAMERA) {
+            kind = false;
+            v3 o, d;
+            int px, py;
+            camera_ray(A.f, A.rb_cam, A.n_samples, my, o, d, px, py);
+            start_ray(make_float4(o.x, o.y, o.z, 0.0f), make_float4(d.x, d.y, d.z, 0.0f), my);
+          } else {
+            // continuation rays: words 0 / 1 of record `my`; shadow rays: their own dense array written by k_shade
+            // (origin | record position, direction | -), no indirection through a list
+            kind = my >= n_cont;
+            const float4* src = kind ? A.shadow_rays + 2 * (size_t)(my - n_cont) : &A.ps.ro(my);
+#if TRACE_EARLY_FETCH
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_fetch[2 * threadIdx.x]);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16u), "l"(src + 1) : "memory");
+            RAY_SLOT = my;  // continuation rays: the record position; shadow rays take theirs from word 0 at the start
+            pending = true;
 #else
-            ox2 = pack2(ox, ox); oy2 = pack2(oy, oy); oz2 = pack2(oz, oz);
-            ix2 = pack2(ix, ix); iy2 = pack2(iy, iy); iz2 = pack2(iz, iz);
+            const float4 o4 = ld_path(src[0]), d4 = ld_path(src[1]);
+            boolean_ray = A.anyhit && (kind || __float_as_int(d4.w) == -2);
+            start_ray(o4, d4, kind ? __float_as_int(o4.w) : my);
 #endif
-            have = true;
-            tbest = FSPT_MAX_T; ibest = -1; cnt = 0; cnt_exact = 0;
-            sp = sp0;
-            STACK_PUSH(FSPT_SENTINEL);
-            cur = A.root_ref;
           }
         }
       }
     }
-    if (__ballot_sync(FULL, cur != FSPT_SENTINEL) == 0u) break;
+    if (__ballot_sync(FULL, cur != FSPT_SENTINEL || pending) == 0u) break;
 
+#if TRACE_EARLY_FETCH
+    // stage 1 (rays requested, not started): a short run with whatever lanes are left; stage 0: a full run
+    const int refill = (drained || (EARLY && stage == 1)) ? 1 : TRACE_REFILL;
+    int budget = (EARLY && stage == 1 && !drained) ? TRACE_EARLY_STEPS : 0x7fffffff;
+    if (EARLY) stage ^= 1;
+#else
     const int refill = drained ? 1 : TRACE_REFILL;
+#endif
     for (;;) {
       // Warp-level phase scheduling: every iteration runs ONE step for the larger group of lanes -- those
       // standing on an interior node or those standing on a leaf -- and the other group waits.  (A classic
@@ -402,6 +415,9 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
       const bool is_leaf = !is_int && cur != FSPT_SENTINEL;
       const int ni = __popc(__ballot_sync(FULL, is_int)), nl = __popc(__ballot_sync(FULL, is_leaf));
       if (ni + nl < refill) break;
+#if TRACE_EARLY_FETCH
+      if (EARLY && --budget < 0) break;
+#endif
       if (ni * TRACE_INT_WEIGHT >= nl * TRACE_LEAF_WEIGHT) {
         // ---- interior node: both child boxes from one 64-byte record --------------------------------
         if (is_int) {
