@@ -240,7 +240,8 @@ struct ShadeArgs {
   const unsigned char* hit_flag;  // hit / miss per record position, written by k_trace.  (Measured and dropped: a 4-byte hit
                                   // INDEX per position carried through the queues, so that the shading records are requested
                                   // together with the path record -- shade +2.4 %: wider reads and queues cost more than
-                                  // the shorter dependent chain saves at 32 warps/SM.)
+                                  // the shorter dependent chain saves at 32 warps/SM.  Also measured and dropped: requesting
+                                  // the NEXT tile's bytes before this tile's groups are shaded, +0.5 %.)
 };
 
 // Warp-aggregated append: one atomicAdd per warp per list (ballot + popc prefix); call with all 32 lanes

@@ -90,12 +90,6 @@ struct TraceArgs {
 #ifndef TRACE_TRI_BRANCHLESS
 #define TRACE_TRI_BRANCHLESS 0
 #endif
-#ifndef TRACE_EARLY_FETCH
-#define TRACE_EARLY_FETCH 0  /* 1: rays are requested with cp.async one short run before they are started */
-#endif
-#ifndef TRACE_EARLY_STEPS
-#define TRACE_EARLY_STEPS 6  /* iterations of the short run between requesting and starting rays */
-#endif
 #ifndef TRACE_MIN_BLOCKS
 #define TRACE_MIN_BLOCKS 9   /* resident CTAs per SM the register allocation is held to (9 x 128 threads = 56 registers) */
 #endif
@@ -229,60 +223,67 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
   if (threadIdx.x == 0) { s_counts[0] = A.counts[0]; s_counts[1] = A.counts[1]; }
   __syncthreads();
 
+  // Per-lane on-chip state, ONE shared array laid out [row][thread] (bank = lane for any per-lane row: conflict-free):
+  //   rows 0..6  (TRACE_SMEM_RAY) ray values that only one phase reads -- d (leaf steps), 1/d (interior steps), record
+  //              position (retirement) -- so they stay out of the register file; their loads overlap the node /
+  //              triangle fetch of the same step;
+  //   rows 7..   (TRACE_SMEM_STACK) the first entries of the traversal stack; deeper entries spill to local memory.
+  // `lane_addr` is the 32-bit shared-window address of the thread's column, `sp` the BYTE offset of its next free stack
+  // entry inside the column (row * 4 * TRACE_THREADS), so one register is the depth and (plus lane_addr) the address, and
+  // "still in shared memory" is a comparison with a constant.  Every access is an explicit ld.shared / st.shared on
+  // [lane_addr + offset]: when the arrays were indexed through C++ pointers ptxas rebuilt the shared-window base
+  // (S2R SR_CgaCtaId + 3 instructions) in front of every push and pop, on the pop -> node-fetch dependency chain.  The
+  // address is passed through an opaque `mov` once so that it lives in one register instead of being rematerialised.
+  constexpr int RAY_ROWS = TRACE_SMEM_RAY ? 7 : 0;
+  constexpr unsigned ROW = 4u * TRACE_THREADS;
+#if TRACE_SMEM_RAY || TRACE_SMEM_STACK
+  __shared__ int s_lane[(RAY_ROWS + TRACE_SMEM_STACK) * TRACE_THREADS];
+  unsigned lane_addr;
+  asm volatile("mov.u32 %0, %1;" : "=r"(lane_addr) : "r"((unsigned)__cvta_generic_to_shared(s_lane) + 4u * threadIdx.x));
+#define LANE_LD(dst, off) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(dst) : "r"(lane_addr + (off)))
+#define LANE_ST(off, v) asm volatile("st.shared.b32 [%0], %1;" ::"r"(lane_addr + (off)), "r"(v))
+#endif
 #if TRACE_SMEM_STACK
-  // [depth][thread]: bank = lane whatever the per-lane depth.  `sp` is the BYTE offset of the thread's next free entry
-  // (depth * 4 * TRACE_THREADS + 4 * thread), so one register is both the depth and the address.
-  __shared__ int s_stack[TRACE_SMEM_STACK * TRACE_THREADS];
   int spill[FSPT_STACK - TRACE_SMEM_STACK];
-  constexpr unsigned ROW = 4u * TRACE_THREADS, SMEM_END = ROW * TRACE_SMEM_STACK;
-  const unsigned sp0 = 4u * threadIdx.x;
-#define STACK_AT(off) (*reinterpret_cast<int*>(reinterpret_cast<char*>(s_stack) + (off)))
+  constexpr unsigned SP0 = ROW * RAY_ROWS, SMEM_END = ROW * (RAY_ROWS + TRACE_SMEM_STACK);
 #define STACK_PUSH(v)                                                              \
   do {                                                                             \
-    if (sp < SMEM_END) STACK_AT(sp) = (v);                                         \
-    else spill[(sp - SMEM_END) / ROW] = (v);                                       \
+    const int v_ = (v);                                                            \
+    if (sp < SMEM_END) LANE_ST(sp, v_);                                            \
+    else spill[(sp - SMEM_END) / ROW] = v_;                                        \
     sp += ROW;                                                                     \
   } while (0)
 #define STACK_POP(dst)                                                             \
   do {                                                                             \
     sp -= ROW;                                                                     \
-    if (sp < SMEM_END) dst = STACK_AT(sp);                                         \
+    if (sp < SMEM_END) LANE_LD(dst, sp);                                           \
     else dst = spill[(sp - SMEM_END) / ROW];                                       \
   } while (0)
 #else
   int stack[FSPT_STACK];
-  const unsigned sp0 = 0;
+  constexpr unsigned SP0 = 0;
 #define STACK_PUSH(v) do { stack[sp++] = (v); } while (0)
 #define STACK_POP(dst) do { dst = stack[--sp]; } while (0)
 #endif
   int cur = FSPT_SENTINEL;
-  unsigned sp = sp0;
+  unsigned sp = SP0;
   unsigned cnt = 0;  // visits of the current ray: low 16 bits all nodes, high 16 bits leaves (statistics; the bvh_test
                      // count of the WRITE_COUNT variant is kept separately and exact)
   int cnt_exact = 0;
   bool kind = false, have = false;
 #if TRACE_SMEM_RAY
-  // ray values that only one phase reads stay out of the register file: 1/d (interior steps), d (leaf steps), slot
-  // (retirement).  [value][thread]: conflict-free.  The loads overlap the node / leaf-block fetch of the same step.
-  __shared__ float s_ray[7 * TRACE_THREADS];
-  float* const my_ray = s_ray + threadIdx.x;
-#define RAY_DX my_ray[0 * TRACE_THREADS]
-#define RAY_DY my_ray[1 * TRACE_THREADS]
-#define RAY_DZ my_ray[2 * TRACE_THREADS]
-#define RAY_IX my_ray[3 * TRACE_THREADS]
-#define RAY_IY my_ray[4 * TRACE_THREADS]
-#define RAY_IZ my_ray[5 * TRACE_THREADS]
-#define RAY_SLOT (reinterpret_cast<int*>(my_ray)[6 * TRACE_THREADS])
+  enum { R_DX = 0, R_DY = 1, R_DZ = 2, R_IX = 3, R_IY = 4, R_IZ = 5, R_SLOT = 6 };
+#define RAY_GET(row) ([&] { int v_; LANE_LD(v_, (row) * ROW); return v_; }())
+#define RAY_GETF(row) __int_as_float(RAY_GET(row))
+#define RAY_SET(row, v) LANE_ST((row) * ROW, (int)(v))
+#define RAY_SETF(row, v) LANE_ST((row) * ROW, __float_as_int(v))
 #else
-  float r_dx = 0, r_dy = 0, r_dz = 0, r_ix = 0, r_iy = 0, r_iz = 0;
-  int r_slot = -1;
-#define RAY_DX r_dx
-#define RAY_DY r_dy
-#define RAY_DZ r_dz
-#define RAY_IX r_ix
-#define RAY_IY r_iy
-#define RAY_IZ r_iz
-#define RAY_SLOT r_slot
+  enum { R_DX = 0, R_DY = 1, R_DZ = 2, R_IX = 3, R_IY = 4, R_IZ = 5, R_SLOT = 6 };
+  int r_val[7] = {0, 0, 0, 0, 0, 0, -1};  // constant indices only: registers
+#define RAY_GET(row) r_val[row]
+#define RAY_GETF(row) __int_as_float(r_val[row])
+#define RAY_SET(row, v) (r_val[row] = (int)(v))
+#define RAY_SETF(row, v) (r_val[row] = __float_as_int(v))
 #endif
   float ox = 0, oy = 0, oz = 0;
 #if !TRACE_BCAST
@@ -293,59 +294,35 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
   unsigned n_nodes = 0, n_leaves = 0;  // per thread and launch: far below 2^32 (touched at retirement only)
   bool drained = false;
   bool boolean_ray = false;  // only hit-or-miss is consumed (tracer.fs:502, :509 at the last bounce)
-#if TRACE_EARLY_FETCH
-  // EARLY FETCH: the ray of an idle lane is requested with cp.async (global -> shared, no registers, nothing waits) when
-  // the warp leaves a full run, the warp then keeps traversing for a few iterations with the lanes it still has, and
-  // only then are the new rays started -- the ray fetch (a DRAM round trip: path records stream) no longer stalls the
-  // lanes that still have work.  Stage 1 = retire + request, short run; stage 0 = start the requested rays, full run.
-  constexpr bool EARLY = !CAMERA;
-  __shared__ float4 s_fetch[EARLY ? 2 * TRACE_THREADS : 2];  // [thread][2]: word 0 = origin | position, word 1 = direction | mark
-  bool pending = false;
-  int stage = 1;
-#else
-  constexpr bool EARLY = false;
-  const bool pending = false;
-  const int stage = 1;
-#endif
 
   // start the ray whose two words are o4 / d4 on this lane
   auto start_ray = [&](const float4 o4, const float4 d4, int slot) {
     ox = o4.x; oy = o4.y; oz = o4.z;
     const float dx = d4.x, dy = d4.y, dz = d4.z;
-    RAY_SLOT = slot;
-    RAY_DX = dx; RAY_DY = dy; RAY_DZ = dz;
+    RAY_SET(R_SLOT, slot);
+    RAY_SETF(R_DX, dx); RAY_SETF(R_DY, dy); RAY_SETF(R_DZ, dz);
     const float ix = 1.0f / dx, iy = 1.0f / dy, iz = 1.0f / dz;  // `vec3 inverse = 1.0 / ray.dir`, tracer.fs:318
 #if TRACE_BCAST
-    RAY_IX = ix; RAY_IY = iy; RAY_IZ = iz;
+    RAY_SETF(R_IX, ix); RAY_SETF(R_IY, iy); RAY_SETF(R_IZ, iz);
 #else
     ox2 = pack2(ox, ox); oy2 = pack2(oy, oy); oz2 = pack2(oz, oz);
     ix2 = pack2(ix, ix); iy2 = pack2(iy, iy); iz2 = pack2(iz, iz);
 #endif
     have = true;
     tbest = FSPT_MAX_T; ibest = -1; cnt = 0; cnt_exact = 0;
-    sp = sp0;
+    sp = SP0;
     STACK_PUSH(FSPT_SENTINEL);
     cur = A.root_ref;
   };
 
   for (;;) {
-#if TRACE_EARLY_FETCH
-    if (EARLY && stage == 0 && pending) {  // the requested rays have had a short run's time to arrive
-      asm volatile("cp.async.wait_all;" ::: "memory");
-      const float4 o4 = s_fetch[2 * threadIdx.x], d4 = s_fetch[2 * threadIdx.x + 1];
-      // shadow rays always; continuation rays when k_shade marked the path's last bounce (index word = -2)
-      boolean_ray = A.anyhit && (kind || __float_as_int(d4.w) == -2);
-      start_ray(o4, d4, kind ? __float_as_int(o4.w) : RAY_SLOT);
-      pending = false;
-    }
-#endif
-    const bool need = (cur == FSPT_SENTINEL) && !pending;
+    const bool need = (cur == FSPT_SENTINEL);
     const bool retire = need && have;
     if (retire) {  // retire the finished ray
-      const int slot = RAY_SLOT;
+      const int slot = RAY_GET(R_SLOT);
       if (CAMERA) {
         st_path(A.ps.ro(slot), make_float4(ox, oy, oz, tbest));
-        st_path(A.ps.rd(slot), make_float4(RAY_DX, RAY_DY, RAY_DZ, __int_as_float(ibest)));
+        st_path(A.ps.rd(slot), make_float4(RAY_GETF(R_DX), RAY_GETF(R_DY), RAY_GETF(R_DZ), __int_as_float(ibest)));
       } else if (!kind) {
         st_path_w(A.ps.ro(slot), tbest);
         st_path_w(A.ps.rd(slot), __int_as_float(ibest));
@@ -358,7 +335,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
       n_leaves += cnt >> 16;
       have = false;
     }
-    if (!drained && stage == 1) {
+    if (!drained) {
       const unsigned m = __ballot_sync(FULL, need);
       if (m) {
         const int n_cont = s_counts[0], total = n_cont + s_counts[1];  // shared memory: two fewer live registers
@@ -382,31 +359,17 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
             // (origin | record position, direction | -), no indirection through a list
             kind = my >= n_cont;
             const float4* src = kind ? A.shadow_rays + 2 * (size_t)(my - n_cont) : &A.ps.ro(my);
-#if TRACE_EARLY_FETCH
-            const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_fetch[2 * threadIdx.x]);
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16u), "l"(src + 1) : "memory");
-            RAY_SLOT = my;  // continuation rays: the record position; shadow rays take theirs from word 0 at the start
-            pending = true;
-#else
             const float4 o4 = ld_path(src[0]), d4 = ld_path(src[1]);
+            // shadow rays always; continuation rays when k_shade marked the path's last bounce (index word = -2)
             boolean_ray = A.anyhit && (kind || __float_as_int(d4.w) == -2);
             start_ray(o4, d4, kind ? __float_as_int(o4.w) : my);
-#endif
           }
         }
       }
     }
-    if (__ballot_sync(FULL, cur != FSPT_SENTINEL || pending) == 0u) break;
+    if (__ballot_sync(FULL, cur != FSPT_SENTINEL) == 0u) break;
 
-#if TRACE_EARLY_FETCH
-    // stage 1 (rays requested, not started): a short run with whatever lanes are left; stage 0: a full run
-    const int refill = (drained || (EARLY && stage == 1)) ? 1 : TRACE_REFILL;
-    int budget = (EARLY && stage == 1 && !drained) ? TRACE_EARLY_STEPS : 0x7fffffff;
-    if (EARLY) stage ^= 1;
-#else
     const int refill = drained ? 1 : TRACE_REFILL;
-#endif
     for (;;) {
       // Warp-level phase scheduling: every iteration runs ONE step for the larger group of lanes -- those
       // standing on an interior node or those standing on a leaf -- and the other group waits.  (A classic
@@ -415,9 +378,6 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
       const bool is_leaf = !is_int && cur != FSPT_SENTINEL;
       const int ni = __popc(__ballot_sync(FULL, is_int)), nl = __popc(__ballot_sync(FULL, is_leaf));
       if (ni + nl < refill) break;
-#if TRACE_EARLY_FETCH
-      if (EARLY && --budget < 0) break;
-#endif
       if (ni * TRACE_INT_WEIGHT >= nl * TRACE_LEAF_WEIGHT) {
         // ---- interior node: both child boxes from one 64-byte record --------------------------------
         if (is_int) {
@@ -433,7 +393,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
           const int cl = __float_as_int(df.x), cr = __float_as_int(df.y);
           float lh, rh;
 #if TRACE_BCAST
-          slab_pair(a, b, c, bc2(ox), bc2(oy), bc2(oz), bc2(RAY_IX), bc2(RAY_IY), bc2(RAY_IZ), lh, rh);
+          slab_pair(a, b, c, bc2(ox), bc2(oy), bc2(oz), bc2(RAY_GETF(R_IX)), bc2(RAY_GETF(R_IY)), bc2(RAY_GETF(R_IZ)), lh, rh);
 #else
           slab_pair(a, b, c, ox2, oy2, oz2, ix2, iy2, iz2, lh, rh);
 #endif
@@ -453,7 +413,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
         if (is_leaf) {
           if (WRITE_COUNT) cnt_exact++;
           cnt += 0x10001u;
-          const float dx = RAY_DX, dy = RAY_DY, dz = RAY_DZ;
+          const float dx = RAY_GETF(R_DX), dy = RAY_GETF(R_DY), dz = RAY_GETF(R_DZ);
 #if TRACE_LEAF_BLOCKS
           // block words: w0 = {first, -, -, -}; pair A (triangles 0,1) = w1..w4 + w5.xy; pair B (2,3) = w5.zw + w6..w9;
           // each pair component-major: (c.t0, c.t1) for c = v1.xyz, e1.xyz, e2.xyz
@@ -524,11 +484,10 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(A.stats + 0, (unsigned long long)(A.counts[0] + A.counts[1]));
 #undef STACK_PUSH
 #undef STACK_POP
-#undef RAY_DX
-#undef RAY_DY
-#undef RAY_DZ
-#undef RAY_IX
-#undef RAY_IY
-#undef RAY_IZ
-#undef RAY_SLOT
+#undef LANE_LD
+#undef LANE_ST
+#undef RAY_GET
+#undef RAY_GETF
+#undef RAY_SET
+#undef RAY_SETF
 }

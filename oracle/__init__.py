@@ -15,7 +15,7 @@ _LIB = os.path.join(_HERE, "libfspt_oracle.so")
 
 
 def build(force=False):
-    srcs = [os.path.join(_HERE, f) for f in ("fspt_oracle.cpp", "fspt_oracle_host.cpp", "oracle_math.h", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("fspt_oracle.cpp", "fspt_oracle_host.cpp", "oracle_math.h", "oracle_texunit.h", "Makefile")]
     if force or not os.path.exists(_LIB) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in srcs if os.path.exists(s)):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _LIB

@@ -24,6 +24,7 @@
 #include <vector>
 
 #include "oracle_math.h"
+#include "oracle_texunit.h"
 
 using namespace om;
 
@@ -168,59 +169,12 @@ Hit intersectScene(const OScene& s, v3 ro, v3 rd, Counters& c, int* countOut) {
   return result;
 }
 
-/* ---- texture units ------------------------------------------------------ */
-inline long long coordToInt(float f) { /* guard NaN/huge so CPU and GPU agree */
-  if (!(f >= -1.0e9f && f <= 1.0e9f)) f = 0.0f;
-  return (long long)f;
+/* ---- texture units: the GL sampling model lives in oracle_texunit.h (shared with oracle/glsl_cpu) ---- */
+inline long long coordToInt(float f) { return tu_coord_to_int(f); }
+inline v4 textureAtlas(const OScene& s, float u, float v, float layerf) {
+  return tu_texture_array(s.atlas, s.atlas_res, s.atlas_layers, u, v, layerf);
 }
-inline int wrapRepeat(long long i, int size) {
-  long long m = i % size;
-  if (m < 0) m += size;
-  return (int)m;
-}
-inline int wrapClamp(long long i, int size) { return (int)(i < 0 ? 0 : (i >= size ? size - 1 : i)); }
-inline v4 texel8(const uint8_t* p) {
-  v4 r = {(float)p[0] / 255.0f, (float)p[1] / 255.0f, (float)p[2] / 255.0f, (float)p[3] / 255.0f};
-  return r;
-}
-/* GL ES 3.0 3.8.10 LINEAR: tau = (1-a)(1-b)t00 + a(1-b)t10 + (1-a)b t01 + ab t11 */
-inline v4 bilerp(v4 t00, v4 t10, v4 t01, v4 t11, float a, float b) {
-  float w00 = (1.0f - a) * (1.0f - b), w10 = a * (1.0f - b), w01 = (1.0f - a) * b, w11 = a * b;
-  v4 r;
-  r.x = w00 * t00.x + w10 * t10.x + w01 * t01.x + w11 * t11.x;
-  r.y = w00 * t00.y + w10 * t10.y + w01 * t01.y + w11 * t11.y;
-  r.z = w00 * t00.z + w10 * t10.z + w01 * t01.z + w11 * t11.z;
-  r.w = w00 * t00.w + w10 * t10.w + w01 * t01.w + w11 * t11.w;
-  return r;
-}
-/* texture(texArray, vec3(uv, layer)): REPEAT/REPEAT, LINEAR, no mips (main.js:551-555) */
-v4 textureAtlas(const OScene& s, float u, float v, float layerf) {
-  int R = s.atlas_res;
-  long long Lq = coordToInt(floorf(layerf + 0.5f));
-  int L = (int)(Lq < 0 ? 0 : (Lq >= s.atlas_layers ? s.atlas_layers - 1 : Lq));
-  float x = u * (float)R - 0.5f, y = v * (float)R - 0.5f;
-  float fx = floorf(x), fy = floorf(y);
-  float a = x - fx, b = y - fy;
-  long long ix = coordToInt(fx), iy = coordToInt(fy);
-  int i0 = wrapRepeat(ix, R), i1 = wrapRepeat(ix + 1, R);
-  int j0 = wrapRepeat(iy, R), j1 = wrapRepeat(iy + 1, R);
-  const uint8_t* base = s.atlas + (size_t)L * R * R * 4;
-  return bilerp(texel8(base + ((size_t)j0 * R + i0) * 4), texel8(base + ((size_t)j0 * R + i1) * 4),
-                texel8(base + ((size_t)j1 * R + i0) * 4), texel8(base + ((size_t)j1 * R + i1) * 4), a, b);
-}
-/* texture(envTex, c): S REPEAT, T CLAMP_TO_EDGE, LINEAR, RGBA8 (main.js:170-180) */
-v4 textureEnv(const OScene& s, float u, float v) {
-  int W = s.env_w, H = s.env_h;
-  float x = u * (float)W - 0.5f, y = v * (float)H - 0.5f;
-  float fx = floorf(x), fy = floorf(y);
-  float a = x - fx, b = y - fy;
-  long long ix = coordToInt(fx), iy = coordToInt(fy);
-  int i0 = wrapRepeat(ix, W), i1 = wrapRepeat(ix + 1, W);
-  int j0 = wrapClamp(iy, H), j1 = wrapClamp(iy + 1, H);
-  const uint8_t* base = s.env;
-  return bilerp(texel8(base + ((size_t)j0 * W + i0) * 4), texel8(base + ((size_t)j0 * W + i1) * 4),
-                texel8(base + ((size_t)j1 * W + i0) * 4), texel8(base + ((size_t)j1 * W + i1) * 4), a, b);
-}
+inline v4 textureEnv(const OScene& s, float u, float v) { return tu_texture_env(s.env, s.env_w, s.env_h, u, v); }
 
 /* envColor, tracer.fs:410-414: RGBE decode AFTER filtering the encoded texel */
 v3 envColor(const OScene& s, float cx, float cy) {
