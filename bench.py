@@ -172,10 +172,12 @@ def find_browser():
 
 def run_reference(args, rank):
     """--impl reference: the reference's own algorithm on the host CPU, all host threads, one 1-spp pass per step.
-    Preferred: the unmodified shaders in headless Chromium on SwiftShader (oracle/swiftshader/run_harness.py), used when
-    a browser AND a copy of the reference are present at run time.  Neither exists on the GPU box (probed below), so the
-    arm that actually runs is the repo's C++ restatement of the shaders (oracle/, kind "port"), with the scene compiled
-    by the oracle's own host code -- the product library is not loaded in this arm."""
+    In order of preference: (1) the unmodified reference in headless Chromium on SwiftShader
+    (oracle/swiftshader/run_harness.py), when a browser AND a copy of the reference are present at run time -- neither
+    exists on the GPU box (probed below); (2) the reference's own camera.fs + tracer.fs compiled for the CPU
+    (oracle/_ref/libfspt_ref.so, kind "reference": built where the reference tree exists, travels with the snapshot);
+    (3) the repo's C++ restatement of the shaders (kind "port").  The scene is compiled by the oracle's own host code:
+    the product library is not loaded in this arm."""
     if rank != 0:
         return
     import oracle
@@ -201,36 +203,58 @@ def run_reference(args, rank):
             }))
             return
         except Exception as e:  # fall through to the port, say why
-            sys.stderr.write("SwiftShader harness failed (%s); timing the C++ port instead\n" % e)
+            sys.stderr.write("SwiftShader harness failed (%s); timing the CPU build of the shaders instead\n" % e)
     oracle.build()
     sa, cam = build_scene(args, host=oracle if CONFIGS[args.config]["scene"] == "bunny" else None)
-    O = oracle.Oracle(sa)
-    rc, rt = scenes.rand_bases(args.steps + args.warmup, 1)
+    tracer, camera, kind = cpu_path(sa)
+    rc, rt = scenes.rand_bases(args.steps + args.warmup + 1, 1)
     lens = scenes.lens_features(cam)
 
-    def one(k):
-        pos, d = oracle.camera(W, H, cam["eye"], cam["dir"], cam["fov_scale"], lens, rc[k])
-        fb, st = O.trace(pos, d, W, H, k, rt[k], cam["env_theta"])
-        return st
+    def one(k, trace=None, cam_fn=None):
+        pos, d = (cam_fn or camera)(W, H, cam["eye"], cam["dir"], cam["fov_scale"], lens, rc[k])
+        (trace or tracer)(pos, d, W, H, k, rt[k], cam["env_theta"])
     for k in range(args.warmup):
         one(k)
-    rays = 0
     t0 = time.perf_counter()
     for k in range(args.steps):
-        rays += one(args.warmup + k)["rays"]
+        one(args.warmup + k)
     dt = time.perf_counter() - t0
     val = args.steps * W * H / dt / 1e6
     sample = "%d x (drawCamera + drawTracer) 1-spp passes of the %dx%d frame (of %d spp)" % (args.steps, W, H, args.spp)
+    base = {"value": val, "unit": "Mpath-samples/s", "cores": cores, "kind": kind, "sample": sample,
+            "what": CPU_KINDS[kind],
+            "browser_probe": browser or "none found (chromium / google-chrome / chrome / headless_shell)"}
+    if kind == "reference":  # the repo's restatement beside it, one pass: it is the faster of the two
+        O = oracle.Oracle(sa)
+        t1 = time.perf_counter()
+        one(args.warmup + args.steps, trace=O.trace, cam_fn=oracle.camera)
+        base["port_value"] = W * H / (time.perf_counter() - t1) / 1e6
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "Mpath-samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "mrays_per_s": rays / dt / 1e6,
         "config": workload_config(args, sa, 1, "host CPU, %d threads" % cores),
-        "cpu_baseline": {"value": val, "unit": "Mpath-samples/s", "cores": cores, "kind": "port", "sample": sample,
-                         "browser_probe": browser or "none found (chromium / google-chrome / chrome / headless_shell)"},
+        "cpu_baseline": base,
         "e2e": {"value": val, "unit": "Mpath-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+CPU_KINDS = {
+    "reference": "the reference's own camera.fs + tracer.fs, compiled for the CPU from /root/reference/shader by "
+                 "`make -C oracle ref` (oracle/_ref/libfspt_ref.so, prebuilt where the reference tree exists), all host threads",
+    "port": "oracle/fspt_oracle.cpp, the repo's C++ restatement of the shaders (oracle/_ref was not shipped with this "
+            "snapshot), all host threads",
+}
+
+
+def cpu_path(sa):
+    """(trace, camera, kind) of the CPU baseline: the reference's shaders compiled for the CPU when that library is
+    present (it is built where /root/reference exists and travels with the snapshot), else the oracle port."""
+    import oracle
+    from oracle import reference_shaders
+    if reference_shaders.available():
+        return reference_shaders.Reference(sa).trace, reference_shaders.camera, "reference"
+    return oracle.Oracle(sa).trace, oracle.camera, "port"
 
 
 def verify_parity(rank, world, local_rank, comm_ok):
@@ -500,11 +524,12 @@ def main():
 
 
 def cpu_baseline(args, sa, cam):
-    """The oracle (kind "port": C++ restatement of the reference shaders) on the GPU box's host cores, bounded sample."""
+    """The CPU implementation of the same frame on the GPU box's host cores, bounded sample: the reference's shaders
+    compiled for the CPU (kind "reference") when oracle/_ref travelled with the snapshot, else the oracle (kind "port")."""
     import oracle
     from fspt_b200 import scenes
     oracle.build()
-    O = oracle.Oracle(sa)
+    tracer, camera, kind = cpu_path(sa)
     W, H = args.width, args.height
     cores = os.cpu_count() or 1
     rc, rt = scenes.rand_bases(64, 1)
@@ -512,13 +537,20 @@ def cpu_baseline(args, sa, cam):
     n, t_total, k = 0, 0.0, 0
     while t_total < 10.0 and k < 64:
         t0 = time.perf_counter()
-        pos, d = oracle.camera(W, H, cam["eye"], cam["dir"], cam["fov_scale"], lens, rc[k])
-        O.trace(pos, d, W, H, k, rt[k], cam["env_theta"])
+        pos, d = camera(W, H, cam["eye"], cam["dir"], cam["fov_scale"], lens, rc[k])
+        tracer(pos, d, W, H, k, rt[k], cam["env_theta"])
         t_total += time.perf_counter() - t0
         n += 1
         k += 1
-    return {"value": n * W * H / t_total / 1e6, "unit": "Mpath-samples/s", "cores": cores, "kind": "port",
-            "sample": "%d of %d spp of the same %dx%d frame (%.1f s of CPU work, all %d host threads)" % (n, args.spp, W, H, t_total, cores)}
+    out = {"value": n * W * H / t_total / 1e6, "unit": "Mpath-samples/s", "cores": cores, "kind": kind, "what": CPU_KINDS[kind],
+           "sample": "%d of %d spp of the same %dx%d frame (%.1f s of CPU work, all %d host threads)" % (n, args.spp, W, H, t_total, cores)}
+    if kind == "reference":
+        O = oracle.Oracle(sa)
+        t0 = time.perf_counter()
+        pos, d = oracle.camera(W, H, cam["eye"], cam["dir"], cam["fov_scale"], lens, rc[0])
+        O.trace(pos, d, W, H, 0, rt[0], cam["env_theta"])
+        out["port_value"] = W * H / (time.perf_counter() - t0) / 1e6
+    return out
 
 
 if __name__ == "__main__":

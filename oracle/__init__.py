@@ -1,8 +1,9 @@
 """CPU oracle for the FSPT hot path -- TEST INFRASTRUCTURE, never imported by fspt_b200/.
 
 ctypes front-end of oracle/libfspt_oracle.so (sources: fspt_oracle.cpp, fspt_oracle_host.cpp,
-oracle_math.h; recipe: oracle/Makefile).  PARITY UNPINNED: the reference ships no golden
-vectors and cannot run in this image; see fspt_oracle.cpp.
+oracle_math.h, oracle_texunit.h; recipe: oracle/Makefile).  The shader restatement is pinned bit for bit to the
+reference's own shader sources executed on the CPU (oracle/reference_shaders.py, tests/test_reference_pin.py); see the
+header of fspt_oracle.cpp for what that covers.
 """
 import ctypes as C
 import os

@@ -1,11 +1,15 @@
 /*
  * oracle/fspt_oracle.cpp -- TEST INFRASTRUCTURE.  CPU restatement of the FSPT hot path.
  *
- * PARITY UNPINNED: the reference (apbodnar/FSPT) ships no tests, golden vectors or
- * known-answer data, and neither its JavaScript host nor its GLSL can execute in this
- * image (no browser / Node / GLSL compiler), so this restatement cannot be checked
- * against outputs of the reference itself.  It is pinned instead by hand-derived
- * known-answer cases, brute-force equivalence and analytic furnace tests (tests/).
+ * PARITY PIN: the reference (apbodnar/FSPT) ships no tests, golden vectors or known-answer data, and no browser /
+ * Node / GLSL compiler exists in this image.  What this restatement IS checked against is the reference's own shader
+ * text: `make -C oracle ref` compiles /root/reference/shader/{camera,tracer,bvh_test,draw}.fs for the CPU behind a GLSL
+ * subset (oracle/glsl_cpu/, output oracle/_ref/libfspt_ref.so), and tests/test_reference_pin.py demands bit-identical
+ * camera rays, (index, t, count) records, accumulation targets over several ticks and RGBA8 frames from the two, on
+ * four scenes; tests/golden/*.npz hold outputs of those shaders.  What remains a model on BOTH sides is what GLSL
+ * leaves to the platform -- built-in function precision (oracle_math.h, "FSPT-DM2") and texture filtering arithmetic
+ * (oracle_texunit.h) -- and the two deliberate guards listed in DESIGN.md section 2 (refraction cap, NaN sanitising,
+ * both switchable off and off in those tests).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
  * legs may load this library.  The product (fspt_b200/) never does.

@@ -8,7 +8,8 @@
  * per tree node, index lists copied per split, like the JS) -- the product has its own
  * fast builder (fspt_b200/csrc/bvh_builder.cpp) which tests compare against this one.
  *
- * PARITY UNPINNED (see fspt_oracle.cpp header).
+ * PARITY: the shader restatement next door is pinned to the reference's shader text (fspt_oracle.cpp header); these
+ * JavaScript restatements have no such pin yet where this header says so below (no JavaScript engine in the image).
  */
 #include <math.h>
 #include <stdint.h>

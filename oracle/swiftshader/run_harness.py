@@ -233,7 +233,7 @@ def main():
     browser = find_browser(a.browser)
     if not browser:
         print("no Chromium-family browser found (%s); install one or pass --browser.  This image has none and no network: "
-              "the oracle stays 'parity unpinned' (DESIGN.md section 2)." % ", ".join(BROWSERS))
+              "the pin that exists is the shaders compiled for the CPU, oracle/glsl_cpu (DESIGN.md section 2)." % ", ".join(BROWSERS))
         return 3
     if not os.path.isfile(os.path.join(a.reference, "main.js")):
         print("reference tree not found at %s" % a.reference)

@@ -1,5 +1,7 @@
-"""Committed golden fixtures (tests/golden/*.npz, made by tests/golden/make_golden.py with the oracle):
-CPU: the oracle still reproduces them bit for bit;  GPU: the CUDA path reproduces them bit for bit."""
+"""Committed golden fixtures (tests/golden/*.npz).  bunny_small / pbr_refractive_small / quad_kat hold OUTPUTS OF THE
+REFERENCE'S OWN SHADERS (camera.fs, bvh_test.fs, tracer.fs, draw.fs run on the CPU through oracle/glsl_cpu where the
+reference tree exists; generator tests/golden/make_golden.py, provenance recorded inside each file).
+CPU: the oracle reproduces them bit for bit;  GPU: the CUDA path reproduces them bit for bit."""
 import glob
 import os
 import types
@@ -22,6 +24,13 @@ def beq(a, b):
     if a.dtype.kind == "f":
         return bool(np.all((a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))))
     return bool(np.array_equal(a, b))
+
+
+def test_shader_fixtures_say_where_they_come_from():
+    made = [p for p in GOLDEN if os.path.basename(p) in ("bunny_small.npz", "pbr_refractive_small.npz", "quad_kat.npz")]
+    assert len(made) == 3
+    for p in made:
+        assert "outputs of /root/reference/shader" in str(np.load(p)["provenance"])
 
 
 def post_kwargs(z):

@@ -1,6 +1,6 @@
 """CPU suite: pins the oracle (hand-derived KATs, brute force, analytic furnace), the FSPT-DM2 arithmetic,
 the native host-side compilers against the oracle's literal restatements, and the C ABI surface.
-No GPU needed.  PARITY UNPINNED against the reference itself (it ships no vectors and cannot run here)."""
+No GPU needed.  (The pin of the oracle to the reference's own shader sources is tests/test_reference_pin.py.)"""
 import ctypes as C
 import os
 import re
