@@ -8,8 +8,10 @@
  * per tree node, index lists copied per split, like the JS) -- the product has its own
  * fast builder (fspt_b200/csrc/bvh_builder.cpp) which tests compare against this one.
  *
- * PARITY: the shader restatement next door is pinned to the reference's shader text (fspt_oracle.cpp header); these
- * JavaScript restatements have no such pin yet where this header says so below (no JavaScript engine in the image).
+ * PARITY PIN: tests/test_reference_js_pin.py runs the reference's own bvh.js / env_sampler.js in a real ECMAScript
+ * engine (oracle/reference_js.py: Qt's QJSEngine through ctypes) and demands the same nodes, triangle order, depth and
+ * bins, bit for bit, from this file and from the product's native builder.  oracle_pack_layer (the WebGL blit of
+ * texture_packer.js) has no such pin.
  */
 #include <math.h>
 #include <stdint.h>
