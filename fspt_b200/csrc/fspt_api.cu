@@ -48,9 +48,6 @@ struct Ctx {
   bool has_scene = false, has_dielectric = false;
   DeviceScene sc{};
   void *d_nodes = nullptr, *d_tris = nullptr, *d_shade = nullptr, *d_bins = nullptr, *d_layer_info = nullptr;
-  void* d_leaves = nullptr;
-  size_t cap_leaves = 0;
-  int n_leaves = 0;
   cudaArray_t atlas_arr = nullptr, env_arr = nullptr, mat_arr = nullptr;
   int mat_R = 0, mat_L = 0;
   bool mat_surface = false;           // mat_arr was created with cudaArraySurfaceLoadStore (GPU-side interleave)
@@ -116,7 +113,7 @@ struct Ctx {
   void* d_lin = nullptr;      // linear staging of the environment + atlas arrays for fspt_scene_broadcast
   size_t cap_lin = 0;
   void* d_hdr = nullptr;      // broadcast header
-  size_t bytes_nodes = 0, bytes_tris = 0, bytes_shade = 0, bytes_leaves = 0, bytes_bins = 0, bytes_layer_info = 0,
+  size_t bytes_nodes = 0, bytes_tris = 0, bytes_shade = 0, bytes_bins = 0, bytes_layer_info = 0,
          bytes_mat_info = 0;
   int trace_blocks = 0, trace_blocks_cnt = 0, trace_blocks_cam = 0, shade_blocks = 0;
   int trace_blocks_nt = 0, trace_blocks_cnt_nt = 0, trace_blocks_cam_nt = 0;  // NODE_TEX = false instantiations
@@ -164,8 +161,8 @@ void free_scene(Ctx* c) {
   c->mat_R = c->mat_L = 0;
   dfree(c->d_mat_info); c->cap_mat_info = 0;
   c->atlas_R = c->atlas_L = c->env_W = c->env_H = 0;
-  dfree(c->d_nodes); dfree(c->d_tris); dfree(c->d_shade); dfree(c->d_bins); dfree(c->d_layer_info); dfree(c->d_leaves);
-  c->cap_nodes = c->cap_tris = c->cap_shade = c->cap_bins = c->cap_layer_info = c->cap_leaves = 0;
+  dfree(c->d_nodes); dfree(c->d_tris); dfree(c->d_shade); dfree(c->d_bins); dfree(c->d_layer_info);
+  c->cap_nodes = c->cap_tris = c->cap_shade = c->cap_bins = c->cap_layer_info = 0;
   if (c->h_stage) cudaFreeHost(c->h_stage);
   c->h_stage = nullptr; c->stage_bytes = 0;
   if (c->h_geo) cudaFreeHost(c->h_geo);
@@ -259,7 +256,7 @@ int launch_trace(Ctx* c, int which, bool hit_flags, bool write_count, const Fram
   if (cam) A.f = *cam; else memset(&A.f, 0, sizeof A.f);
   A.rb_cam = rb_cam; A.n_samples = n_samples;
   A.anyhit = c->anyhit;
-  A.nodes = c->sc.nodes; A.tris = c->sc.tris; A.leaves = c->sc.leaves; A.root_ref = c->sc.root_ref; A.nodes_tex = c->nodes_tex;
+  A.nodes = c->sc.nodes; A.tris = c->sc.tris; A.root_ref = c->sc.root_ref; A.nodes_tex = c->nodes_tex;
   A.ps = c->ps2[which];
   A.shadow_rays = c->d_shadow;
   A.counts = c->d_counts + 2 * which;
@@ -451,8 +448,8 @@ void comm_free(Ctx* c) {
 
 // what a receiving rank has to know before the buffers of fspt_scene_broadcast arrive
 struct SceneHeader {
-  uint64_t bytes_nodes, bytes_tris, bytes_shade, bytes_leaves, bytes_bins, bytes_layer_info, bytes_mat_info, scene_bytes;
-  int32_t root_ref, n_tris, n_interior, n_leaves, atlas_res, atlas_layers, env_w, env_h, n_bins;
+  uint64_t bytes_nodes, bytes_tris, bytes_shade, bytes_bins, bytes_layer_info, bytes_mat_info, scene_bytes;
+  int32_t root_ref, n_tris, n_interior, atlas_res, atlas_layers, env_w, env_h, n_bins;
   int32_t mat_R, mat_L, use_mat_tex, has_dielectric, magic;
 };
 
@@ -634,22 +631,15 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
   // ---- serial pre-pass over the nodes (own thread): reference node i = [left,right,triIndex | min | max] -> child references
   std::vector<int32_t> ref((size_t)N);   // child reference of node i
   std::vector<int32_t> interior_of;      // reference node index of interior record k
-  std::vector<int32_t> leaf_first;       // first triangle of leaf k (leaves in node order = pre-order)
   auto ibits = [&](int node, int k) { int32_t v; memcpy(&v, s->bvh + (size_t)node * 9 + k, 4); return v; };
   int bad_node = -1, bad_tri = 0;
   std::thread node_thread([&]() {
     interior_of.reserve((size_t)N / 2 + 1);
-    leaf_first.reserve((size_t)N / 2 + 1);
     for (int i = 0; i < N; ++i) {
       const int32_t tri = ibits(i, 2);
       if (tri > -1) {  // `current.triangles > -1`, tracer.fs:379
         if (tri >= T) { bad_node = i; bad_tri = tri; return; }
-#if TRACE_LEAF_BLOCKS
-        ref[i] = ~(int32_t)leaf_first.size();
-        leaf_first.push_back(tri);
-#else
         ref[i] = ~tri;
-#endif
       } else {
         ref[i] = (int32_t)interior_of.size();
         interior_of.push_back(i);
@@ -688,13 +678,12 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
   node_thread.join();
   if (bad_node >= 0) return fail(c, FSPT_E_INVALID, "node %d: triangle index %d out of range", bad_node, bad_tri);
   const size_t NI = interior_of.size();
-  const size_t NL = std::max<size_t>(1, leaf_first.size());  // (no leaf blocks in this build: one dummy block)
   lap("node + material pre-pass");
   // ---- host staging block (pinned, kept between uploads): every copy below is a true async DMA and the user's
   // buffers are no longer referenced when this function returns.  Very large scenes stage in pageable memory.
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
   const size_t o_nodes = 0, o_tris = o_nodes + al(std::max<size_t>(NI, 1) * 64), o_shade = o_tris + al((size_t)(T + 3) * 48),
-               o_leaves = o_shade + al((size_t)T * 192), o_bins = o_leaves + al(NL * 160), o_layer = o_bins + al((size_t)s->env_bins * 16),
+               o_bins = o_shade + al((size_t)T * 192), o_layer = o_bins + al((size_t)s->env_bins * 16),
                o_mat = o_layer + al((size_t)L * 8), o_matsrc = o_mat + al(std::max<size_t>(32, mats.size() * 32)),
                o_env = o_matsrc + al(std::max<size_t>(32, mats.size() * sizeof(MatSrc))),
                geo_bytes = o_env + al((size_t)s->env_width * s->env_height * 4);
@@ -715,7 +704,6 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
   float* nodes = reinterpret_cast<float*>(hg + o_nodes);
   float* tris = reinterpret_cast<float*>(hg + o_tris);
   float* shade = reinterpret_cast<float*>(hg + o_shade);
-  float* leaves = reinterpret_cast<float*>(hg + o_leaves);
   float* bins = reinterpret_cast<float*>(hg + o_bins);
   uint32_t* layer_info = reinterpret_cast<uint32_t*>(hg + o_layer);
   int32_t* mat_info = reinterpret_cast<int32_t*>(hg + o_mat);
@@ -787,23 +775,6 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
       e = v[3] - v[0]; o[3] = e; e = v[4] - v[1]; o[4] = e; e = v[5] - v[2]; o[5] = e;
       e = v[6] - v[0]; o[6] = e; e = v[7] - v[1]; o[7] = e; e = v[8] - v[2]; o[8] = e;
     };
-    // LeafBlock160 per leaf: the four triangles a leaf visit tests as two component-major pairs (device_common.cuh)
-    if (leaf_first.empty()) memset(leaves, 0, 160);  // TRACE_LEAF_BLOCKS == 0: leaf_first stays empty, nothing is built
-    const int leaf_chunks = (int)((leaf_first.size() + 16383) / 16384);
-    parallel(leaf_chunks, geo_workers, [&](int ch) {
-      const size_t k1 = std::min(leaf_first.size(), (size_t)(ch + 1) * 16384);
-      for (size_t k = (size_t)ch * 16384; k < k1; ++k) {
-        const int first = leaf_first[k];
-        float* o = leaves + k * 40;
-        for (int j = 0; j < 4; ++j) {
-          float t9[9];
-          tri9(first + j, t9);
-          for (int comp = 0; comp < 9; ++comp) o[(j < 2 ? 4 : 22) + 2 * comp + (j & 1)] = t9[comp];
-        }
-        memcpy(o, &first, 4);
-        o[1] = o[2] = o[3] = 0.0f;
-      }
-    });
     const int tri_chunks = (T + 3 + 16383) / 16384;
     parallel(tri_chunks, geo_workers, [&](int ch) {
       const int t1 = std::min(T + 3, (ch + 1) * 16384);
@@ -1041,20 +1012,18 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
   lap("join geometry thread");
   int rc_;
   const size_t nodes_bytes = std::max<size_t>(NI, 1) * 64, tris_bytes = (size_t)(T + 3) * 48, shade_bytes = (size_t)T * 192,
-               bins_bytes = (size_t)s->env_bins * 16, leaves_bytes = NL * 160;
+               bins_bytes = (size_t)s->env_bins * 16;
   if ((rc_ = ensure(c, c->d_layer_info, c->cap_layer_info, (size_t)L * 8))) return rc_;
   if ((rc_ = ensure(c, c->d_mat_info, c->cap_mat_info, n_mat_info * 4))) return rc_;
   if ((rc_ = ensure(c, c->d_nodes, c->cap_nodes, nodes_bytes))) return rc_;
   if ((rc_ = ensure(c, c->d_tris, c->cap_tris, tris_bytes))) return rc_;
   if ((rc_ = ensure(c, c->d_shade, c->cap_shade, shade_bytes))) return rc_;
-  if ((rc_ = ensure(c, c->d_leaves, c->cap_leaves, leaves_bytes))) return rc_;
   if ((rc_ = ensure(c, c->d_bins, c->cap_bins, bins_bytes))) return rc_;
   CK(cudaMemcpyAsync(c->d_layer_info, layer_info, (size_t)L * 8, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->d_mat_info, mat_info, n_mat_info * 4, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->d_nodes, nodes, nodes_bytes, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->d_tris, tris, tris_bytes, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->d_shade, shade, shade_bytes, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->d_leaves, leaves, leaves_bytes, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->d_bins, bins, bins_bytes, cudaMemcpyHostToDevice, c->stream));
   lap("malloc + enqueue geometry");
   // ---- environment: 2D array, RGBA8 RGBE (main.js:170-180) ----------------------------------------------------
@@ -1091,12 +1060,10 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
   c->sc.nodes = reinterpret_cast<const float4*>(c->d_nodes);
   c->sc.tris = reinterpret_cast<const float4*>(c->d_tris);
   c->sc.shade = reinterpret_cast<const float4*>(c->d_shade);
-  c->sc.leaves = reinterpret_cast<const float4*>(c->d_leaves);
-  c->n_leaves = (int)leaf_first.size();
   c->sc.bins = reinterpret_cast<const float4*>(c->d_bins);
   c->sc.layer_info = reinterpret_cast<const uint2*>(c->d_layer_info);
   c->sc.mat_info = reinterpret_cast<const int4*>(c->d_mat_info);
-  c->bytes_nodes = nodes_bytes; c->bytes_tris = tris_bytes; c->bytes_shade = shade_bytes; c->bytes_leaves = leaves_bytes;
+  c->bytes_nodes = nodes_bytes; c->bytes_tris = tris_bytes; c->bytes_shade = shade_bytes;
   c->bytes_bins = bins_bytes; c->bytes_layer_info = (size_t)L * 8; c->bytes_mat_info = n_mat_info * 4;
   c->sc.root_ref = ref[0];
   c->sc.n_tris = T; c->sc.n_interior = (int)NI;
@@ -1446,10 +1413,10 @@ int fspt_scene_broadcast(fspt_ctx* ctx, int32_t root) {
   memset(&h, 0, sizeof h);
   static_assert(sizeof(SceneHeader) <= 256, "header buffer");
   if (is_root) {
-    h.bytes_nodes = c->bytes_nodes; h.bytes_tris = c->bytes_tris; h.bytes_shade = c->bytes_shade; h.bytes_leaves = c->bytes_leaves;
+    h.bytes_nodes = c->bytes_nodes; h.bytes_tris = c->bytes_tris; h.bytes_shade = c->bytes_shade;
     h.bytes_bins = c->bytes_bins; h.bytes_layer_info = c->bytes_layer_info; h.bytes_mat_info = c->bytes_mat_info;
     h.scene_bytes = c->scene_bytes;
-    h.root_ref = c->sc.root_ref; h.n_tris = c->sc.n_tris; h.n_interior = c->sc.n_interior; h.n_leaves = c->n_leaves;
+    h.root_ref = c->sc.root_ref; h.n_tris = c->sc.n_tris; h.n_interior = c->sc.n_interior;
     h.atlas_res = c->sc.atlas_res; h.atlas_layers = c->sc.atlas_layers; h.env_w = c->sc.env_w; h.env_h = c->sc.env_h;
     h.n_bins = c->sc.n_bins;
     h.use_mat_tex = c->sc.mat_tex ? 1 : 0;
@@ -1489,7 +1456,6 @@ int fspt_scene_broadcast(fspt_ctx* ctx, int32_t root) {
     if ((rc = ensure(c, c->d_nodes, c->cap_nodes, h.bytes_nodes))) return rc;
     if ((rc = ensure(c, c->d_tris, c->cap_tris, h.bytes_tris))) return rc;
     if ((rc = ensure(c, c->d_shade, c->cap_shade, h.bytes_shade))) return rc;
-    if ((rc = ensure(c, c->d_leaves, c->cap_leaves, h.bytes_leaves))) return rc;
     if ((rc = ensure(c, c->d_bins, c->cap_bins, h.bytes_bins))) return rc;
     if ((rc = ensure(c, c->d_layer_info, c->cap_layer_info, h.bytes_layer_info))) return rc;
     if ((rc = ensure(c, c->d_mat_info, c->cap_mat_info, h.bytes_mat_info))) return rc;
@@ -1547,7 +1513,6 @@ int fspt_scene_broadcast(fspt_ctx* ctx, int32_t root) {
   NK(N->Broadcast(c->d_nodes, c->d_nodes, h.bytes_nodes, ncclUint8, root, c->comm, c->stream));
   NK(N->Broadcast(c->d_tris, c->d_tris, h.bytes_tris, ncclUint8, root, c->comm, c->stream));
   NK(N->Broadcast(c->d_shade, c->d_shade, h.bytes_shade, ncclUint8, root, c->comm, c->stream));
-  NK(N->Broadcast(c->d_leaves, c->d_leaves, h.bytes_leaves, ncclUint8, root, c->comm, c->stream));
   NK(N->Broadcast(c->d_bins, c->d_bins, h.bytes_bins, ncclUint8, root, c->comm, c->stream));
   NK(N->Broadcast(c->d_layer_info, c->d_layer_info, h.bytes_layer_info, ncclUint8, root, c->comm, c->stream));
   NK(N->Broadcast(c->d_mat_info, c->d_mat_info, h.bytes_mat_info, ncclUint8, root, c->comm, c->stream));
@@ -1573,16 +1538,15 @@ int fspt_scene_broadcast(fspt_ctx* ctx, int32_t root) {
       nt.readMode = cudaReadModeElementType;
       CK(cudaCreateTextureObject(&c->nodes_tex, &nr, &nt, nullptr));
     }
-    c->bytes_nodes = h.bytes_nodes; c->bytes_tris = h.bytes_tris; c->bytes_shade = h.bytes_shade; c->bytes_leaves = h.bytes_leaves;
+    c->bytes_nodes = h.bytes_nodes; c->bytes_tris = h.bytes_tris; c->bytes_shade = h.bytes_shade;
     c->bytes_bins = h.bytes_bins; c->bytes_layer_info = h.bytes_layer_info; c->bytes_mat_info = h.bytes_mat_info;
     c->sc.nodes = reinterpret_cast<const float4*>(c->d_nodes);
     c->sc.tris = reinterpret_cast<const float4*>(c->d_tris);
     c->sc.shade = reinterpret_cast<const float4*>(c->d_shade);
-    c->sc.leaves = reinterpret_cast<const float4*>(c->d_leaves);
     c->sc.bins = reinterpret_cast<const float4*>(c->d_bins);
     c->sc.layer_info = reinterpret_cast<const uint2*>(c->d_layer_info);
     c->sc.mat_info = reinterpret_cast<const int4*>(c->d_mat_info);
-    c->sc.root_ref = h.root_ref; c->sc.n_tris = h.n_tris; c->sc.n_interior = h.n_interior; c->n_leaves = h.n_leaves;
+    c->sc.root_ref = h.root_ref; c->sc.n_tris = h.n_tris; c->sc.n_interior = h.n_interior;
     c->sc.atlas_res = h.atlas_res; c->sc.atlas_layers = h.atlas_layers; c->sc.env_w = h.env_w; c->sc.env_h = h.env_h;
     c->sc.n_bins = h.n_bins;
     c->has_dielectric = h.has_dielectric != 0;

@@ -23,11 +23,6 @@
 //     was 71-78 % (it competes with nodes and triangles), so every fourth pop waited for L2 before the dependent
 //     node fetch could issue.  The first TRACE_SMEM_STACK entries now sit in shared memory, laid out
 //     [depth][thread] (bank = lane for every per-lane depth: conflict-free), deeper entries spill to local memory.
-//   - LEAF BLOCKS: a leaf visit used to run four serialised load -> Moller-Trumbore rounds (4 dependent memory
-//     round trips, 294 warp instructions).  The upload now writes one 160-byte block per leaf (five whole
-//     sectors) holding its four test triangles component-major -- word c = component c of triangles 0..3 -- so
-//     the visit reads 160 contiguous bytes and evaluates the four tests as two packed f32x2 streams (FADD2/FMUL2:
-//     two independent IEEE f32 operations per instruction, bit-identical per lane), triangles (0,1) then (2,3).
 //   - BROADCAST OPERANDS: ray origin / direction / inverse direction are kept as scalars and packed at the use
 //     site; ptxas folds `mov.b64 {x, x}` into the `.F32` scalar-broadcast operand of FADD2/FMUL2, which frees the
 //     nine registers the materialised (x, x) pairs occupied.
@@ -38,7 +33,6 @@
 struct TraceArgs {
   const float4* nodes;
   const float4* tris;
-  const float4* leaves;   // LeafBlock160: 10 x float4 per leaf (device_common.cuh)
   cudaTextureObject_t nodes_tex;  // the node array again as a linear texture (second L1 data pipe)
   int root_ref;
   PathState ps;           // rays in, hits out (words 0..2 of the path record)
@@ -66,18 +60,8 @@ struct TraceArgs {
 #define TRACE_REFILL 16      /* a warp fetches new rays when fewer lanes than this still hold one (with 36 warps/SM:
                                 16 is 2.3 % faster than 12 on the 82 k-triangle scene, 1.8 % slower on 1 M triangles) */
 #endif
-#ifndef TRACE_INT_WEIGHT
-#define TRACE_INT_WEIGHT 1
-#define TRACE_LEAF_WEIGHT 1
-#endif
 #ifndef TRACE_SMEM_STACK
 #define TRACE_SMEM_STACK 12  /* stack entries per thread held in shared memory (0 = all in local memory) */
-#endif
-#ifndef TRACE_LEAF_BLOCKS
-#define TRACE_LEAF_BLOCKS 0  /* 1: leaf refs are ~leaf ordinal and index LeafBlock160; 0: ~first triangle, Tri48 */
-#endif
-#ifndef TRACE_LEAF_ROUNDS
-#define TRACE_LEAF_ROUNDS 2  /* 1: all ten loads of a leaf block up front (36 live data registers); 2: one pair per round */
 #endif
 #ifndef TRACE_BCAST
 #define TRACE_BCAST 1        /* 1: ray origin / inverse direction are scalars, packed at the use site (ptxas folds the (x, x)
@@ -86,9 +70,6 @@ struct TraceArgs {
 #ifndef TRACE_SMEM_RAY
 #define TRACE_SMEM_RAY 1     /* 1: per-ray values used by one phase only (1/d: interior steps, d: leaf steps, slot: retirement)
                                 live in shared memory [value][thread] instead of registers */
-#endif
-#ifndef TRACE_TRI_BRANCHLESS
-#define TRACE_TRI_BRANCHLESS 0
 #endif
 #ifndef TRACE_MIN_BLOCKS
 #define TRACE_MIN_BLOCKS 9   /* resident CTAs per SM the register allocation is held to (9 x 128 threads = 56 registers) */
@@ -150,62 +131,6 @@ __device__ __forceinline__ float tri_test(const float4 q0, const float4 q1, cons
   if (v < 0.0f || u + v > 1.0f) return FSPT_MAX_T;
   const float dist = (e2x * qx + e2y * qy + e2z * qz) * invDet;
   return dist > FSPT_EPSILON ? dist : FSPT_MAX_T;
-}
-
-// Branch-free form of tri_test: the reference's early returns (tracer.fs:305,309,312) become one predicate.  A rejected
-// test yields MAX_T whatever the later (then meaningless, possibly NaN / inf) values are, so evaluating all of them is
-// the same function; in a divergent warp some lane nearly always needs the full test anyway, and the four
-// branch + reconvergence pairs per triangle disappear.
-__device__ __forceinline__ float tri_test_nb(const float4 q0, const float4 q1, const float4 q2, float ox, float oy,
-                                             float oz, float dx, float dy, float dz) {
-  const float e1x = q0.w, e1y = q1.x, e1z = q1.y, e2x = q1.z, e2y = q1.w, e2z = q2.x;
-  const float px = dy * e2z - e2y * dz, py = dz * e2x - e2z * dx, pz = dx * e2y - e2x * dy;  // cross(dir,e2)
-  const float det = e1x * px + e1y * py + e1z * pz;
-  const float invDet = 1.0f / det;
-  const float tx = ox - q0.x, ty = oy - q0.y, tz = oz - q0.z;
-  const float u = (tx * px + ty * py + tz * pz) * invDet;
-  const float qx = ty * e1z - e1y * tz, qy = tz * e1x - e1z * tx, qz = tx * e1y - e1x * ty;  // cross(t,e1)
-  const float v = (dx * qx + dy * qy + dz * qz) * invDet;
-  const float dist = (e2x * qx + e2y * qy + e2z * qz) * invDet;
-  const bool rej = (fabsf(det) < FSPT_EPSILON) || (u < 0.0f || u > 1.0f) || (v < 0.0f || u + v > 1.0f);
-  return (!rej && dist > FSPT_EPSILON) ? dist : FSPT_MAX_T;
-}
-
-// The same test for two triangles at once: every f32 operation of tri_test, in the same order, once per half of the
-// pair.  PRODUCTS run on the packed pipe (FMUL2: two IEEE multiplications per instruction); SUMS and DIFFERENCES of
-// products stay scalar FADDs on purpose: ptxas 12.9 contracts `mul.rn.f32x2` + `add.rn.f32x2` into FFMA2 even with
-// -fmad=false and explicit .rn (measured: the hit distances moved by an ulp), and it does not fuse across the
-// packed / scalar boundary.  The early returns become one predicate per triangle: a rejected test yields MAX_T
-// whatever the later (then meaningless) values are, so evaluating all of them changes nothing (tracer.fs:300-315).
-struct f2 { float a, b; };
-__device__ __forceinline__ f2 prod2(f32x2 x, f32x2 y) { f2 r; unpack2(mul2(x, y), r.a, r.b); return r; }
-__device__ __forceinline__ f32x2 pk(f2 v) { return pack2(v.a, v.b); }
-__device__ __forceinline__ f2 dif(f2 x, f2 y) { f2 r; r.a = x.a - y.a; r.b = x.b - y.b; return r; }
-__device__ __forceinline__ f2 sum3(f2 x, f2 y, f2 z) { f2 r; r.a = x.a + y.a + z.a; r.b = x.b + y.b + z.b; return r; }
-__device__ __forceinline__ void tri_test2(f32x2 v1x, f32x2 v1y, f32x2 v1z, f32x2 e1x, f32x2 e1y, f32x2 e1z, f32x2 e2x,
-                                          f32x2 e2y, f32x2 e2z, float ox, float oy, float oz, float dx, float dy, float dz,
-                                          float& r0, float& r1) {
-  const f32x2 DX = bc2(dx), DY = bc2(dy), DZ = bc2(dz);
-  // cross(dir, e2)
-  const f2 px = dif(prod2(DY, e2z), prod2(e2y, DZ)), py = dif(prod2(DZ, e2x), prod2(e2z, DX)), pz = dif(prod2(DX, e2y), prod2(e2x, DY));
-  const f32x2 PX = pk(px), PY = pk(py), PZ = pk(pz);
-  const f2 det = sum3(prod2(e1x, PX), prod2(e1y, PY), prod2(e1z, PZ));
-  const f32x2 inv = pack2(1.0f / det.a, 1.0f / det.b);
-  f2 t;  // t = origin - v1 (a difference of non-products: nothing to contract)
-  unpack2(sub2(bc2(ox), v1x), t.a, t.b); const f32x2 TX = pk(t);
-  unpack2(sub2(bc2(oy), v1y), t.a, t.b); const f32x2 TY = pk(t);
-  unpack2(sub2(bc2(oz), v1z), t.a, t.b); const f32x2 TZ = pk(t);
-  const f2 u = prod2(pk(sum3(prod2(TX, PX), prod2(TY, PY), prod2(TZ, PZ))), inv);
-  // cross(t, e1)
-  const f2 qx = dif(prod2(TY, e1z), prod2(e1y, TZ)), qy = dif(prod2(TZ, e1x), prod2(e1z, TX)), qz = dif(prod2(TX, e1y), prod2(e1x, TY));
-  const f32x2 QX = pk(qx), QY = pk(qy), QZ = pk(qz);
-  const f2 v = prod2(pk(sum3(prod2(DX, QX), prod2(DY, QY), prod2(DZ, QZ))), inv);
-  const f2 dist = prod2(pk(sum3(prod2(e2x, QX), prod2(e2y, QY), prod2(e2z, QZ))), inv);
-  const float uv0 = u.a + v.a, uv1 = u.b + v.b;
-  const bool rej0 = (fabsf(det.a) < FSPT_EPSILON) || (u.a < 0.0f || u.a > 1.0f) || (v.a < 0.0f || uv0 > 1.0f);
-  const bool rej1 = (fabsf(det.b) < FSPT_EPSILON) || (u.b < 0.0f || u.b > 1.0f) || (v.b < 0.0f || uv1 > 1.0f);
-  r0 = (!rej0 && dist.a > FSPT_EPSILON) ? dist.a : FSPT_MAX_T;
-  r1 = (!rej1 && dist.b > FSPT_EPSILON) ? dist.b : FSPT_MAX_T;
 }
 
 // CAMERA = the primary launch of a render wave: the ray of slot `my` is generated on the fly (camera.fs) and the whole
@@ -378,7 +303,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
       const bool is_leaf = !is_int && cur != FSPT_SENTINEL;
       const int ni = __popc(__ballot_sync(FULL, is_int)), nl = __popc(__ballot_sync(FULL, is_leaf));
       if (ni + nl < refill) break;
-      if (ni * TRACE_INT_WEIGHT >= nl * TRACE_LEAF_WEIGHT) {
+      if (ni >= nl) {
         // ---- interior node: both child boxes from one 64-byte record --------------------------------
         if (is_int) {
           if (WRITE_COUNT) cnt_exact++;
@@ -414,55 +339,14 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
           if (WRITE_COUNT) cnt_exact++;
           cnt += 0x10001u;
           const float dx = RAY_GETF(R_DX), dy = RAY_GETF(R_DY), dz = RAY_GETF(R_DZ);
-#if TRACE_LEAF_BLOCKS
-          // block words: w0 = {first, -, -, -}; pair A (triangles 0,1) = w1..w4 + w5.xy; pair B (2,3) = w5.zw + w6..w9;
-          // each pair component-major: (c.t0, c.t1) for c = v1.xyz, e1.xyz, e2.xyz
-          const float4* lp = A.leaves + 10 * (size_t)(~cur);
-          const int first = __float_as_int(__ldg(&lp[0].x));
-          const float4 w1 = __ldg(lp + 1), w2 = __ldg(lp + 2), w3 = __ldg(lp + 3), w4 = __ldg(lp + 4), w5 = __ldg(lp + 5);
-#if TRACE_LEAF_ROUNDS == 2
-          // second pair in a second round trip (18 fewer live registers); its two remaining sectors are requested now.
-          // Measured: the CCTL.PF1 prefetches cost +25 % traversal time -- kept as a documented dead end.
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(lp + 6));
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(lp + 8));
-#endif
-#if TRACE_LEAF_ROUNDS == 3
-          // one word of each of the second pair's two remaining sectors is loaded now (8 registers instead of 18): the
-          // second round's other two loads then hit L1
-          const float4 w6 = __ldg(lp + 6), w8 = __ldg(lp + 8);
-#endif
-          float r0, r1, r2, r3;
-          tri_test2(pack2(w1.x, w1.y), pack2(w1.z, w1.w), pack2(w2.x, w2.y), pack2(w2.z, w2.w), pack2(w3.x, w3.y),
-                    pack2(w3.z, w3.w), pack2(w4.x, w4.y), pack2(w4.z, w4.w), pack2(w5.x, w5.y), ox, oy, oz, dx, dy, dz, r0, r1);
-#if TRACE_LEAF_ROUNDS == 2
-          asm volatile("" ::: "memory");
-#endif
-#if TRACE_LEAF_ROUNDS == 3
-          asm volatile("" ::: "memory");
-          const float4 w7 = __ldg(lp + 7), w9 = __ldg(lp + 9);
-#else
-          const float4 w6 = __ldg(lp + 6), w7 = __ldg(lp + 7), w8 = __ldg(lp + 8), w9 = __ldg(lp + 9);
-#endif
-          tri_test2(pack2(w5.z, w5.w), pack2(w6.x, w6.y), pack2(w6.z, w6.w), pack2(w7.x, w7.y), pack2(w7.z, w7.w),
-                    pack2(w8.x, w8.y), pack2(w8.z, w8.w), pack2(w9.x, w9.y), pack2(w9.z, w9.w), ox, oy, oz, dx, dy, dz, r2, r3);
-          if (r0 < tbest) { ibest = first; tbest = r0; }      // in triangle order, strict `<`: tracer.fs:357-362
-          if (r1 < tbest) { ibest = first + 1; tbest = r1; }
-          if (r2 < tbest) { ibest = first + 2; tbest = r2; }
-          if (r3 < tbest) { ibest = first + 3; tbest = r3; }
-#else
           const int first = ~cur;
           const float4* tp = A.tris + 3 * (size_t)first;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const float4 q0 = __ldg(tp + 3 * k), q1 = __ldg(tp + 3 * k + 1), q2 = __ldg(tp + 3 * k + 2);
-#if TRACE_TRI_BRANCHLESS
-            const float res = tri_test_nb(q0, q1, q2, ox, oy, oz, dx, dy, dz);
-#else
             const float res = tri_test(q0, q1, q2, ox, oy, oz, dx, dy, dz);
-#endif
             if (res < tbest) { ibest = first + k; tbest = res; }
           }
-#endif
           STACK_POP(cur);
           if (!CAMERA && boolean_ray && ibest != -1) cur = FSPT_SENTINEL;  // any hit settles it
         }

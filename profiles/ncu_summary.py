@@ -20,7 +20,7 @@ WANT = [
     'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
     'lts__t_sector_hit_rate.pct', 'lts__t_bytes.sum', 'lts__throughput.avg.pct_of_peak_sustained_elapsed',
     'l1tex__t_sector_hit_rate.pct', 'l1tex__t_bytes.sum', 'l1tex__throughput.avg.pct_of_peak_sustained_elapsed',
-    # L1 data pipes: the node records go through the texture pipe, leaf blocks / path records through the LSU
+    # L1 data pipes: half of every node record goes through the texture pipe, the other half, triangles and path records through the LSU
     'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed',
     'l1tex__data_pipe_tex_wavefronts.avg.pct_of_peak_sustained_elapsed',
     'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',

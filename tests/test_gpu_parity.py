@@ -212,7 +212,7 @@ def test_ten_million_triangles_at_4k_bit_exact(oracle_mod):
     """BASELINE configs[4] geometry and resolution: 10 M triangles (subdiv-8 icosphere + 8.69 M soup, seed 4321) at
     3840x2160, 1 sample: camera rays (gl_FragCoord seeds beyond 2^22, where `seed += 0.2113` stalls in f32,
     camera.fs:19,38), primary (index, t, count), the accumulator with and without any-hit, and the device V / L counters
-    against the CPU oracle.  The BVH (0.7 GB of nodes + leaf blocks + triangles) no longer fits the L2."""
+    against the CPU oracle.  The BVH (0.7 GB of nodes + triangles) no longer fits the L2."""
     sa, cam = scenes.sphere_soup(subdiv=8, n_soup=10000000 - 1310720, seed=4321)
     assert sa.n_tris == 10000000 and sa.depth <= 64
     _full_frame_check(oracle_mod, sa, cam, 3840, 2160, 1, 17)
