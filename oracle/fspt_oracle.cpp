@@ -6,7 +6,7 @@
  * text: `make -C oracle ref` compiles /root/reference/shader/{camera,tracer,bvh_test,draw}.fs for the CPU behind a GLSL
  * subset (oracle/glsl_cpu/, output oracle/_ref/libfspt_ref.so), and tests/test_reference_pin.py demands bit-identical
  * camera rays, (index, t, count) records, accumulation targets over several ticks and RGBA8 frames from the two, on
- * four scenes; tests/golden/*.npz hold outputs of those shaders.  What remains a model on BOTH sides is what GLSL
+ * four scenes; the fixtures under tests/golden hold outputs of those shaders.  What remains a model on BOTH sides is what GLSL
  * leaves to the platform -- built-in function precision (oracle_math.h, "FSPT-DM2") and texture filtering arithmetic
  * (oracle_texunit.h) -- and the two deliberate guards listed in DESIGN.md section 2 (refraction cap, NaN sanitising,
  * both switchable off and off in those tests).

@@ -11,7 +11,7 @@
  * PARITY PIN: tests/test_reference_js_pin.py runs the reference's own bvh.js / env_sampler.js in a real ECMAScript
  * engine (oracle/reference_js.py: Qt's QJSEngine through ctypes) and demands the same nodes, triangle order, depth and
  * bins, bit for bit, from this file and from the product's native builder.  oracle_pack_layer (the WebGL blit of
- * texture_packer.js) has no such pin.
+ * texture_packer.js) is compared with the blit shader's own text compiled for the CPU (tests/test_reference_pin.py).
  */
 #include <math.h>
 #include <stdint.h>
@@ -20,6 +20,8 @@
 #include <algorithm>
 #include <memory>
 #include <vector>
+
+#include "oracle_texunit.h"
 
 namespace {
 
@@ -252,36 +254,17 @@ int oracle_env_bins(const uint8_t* data, int width, int height, uint16_t* boxes_
  * (texture_packer.js:103-121) on a texture uploaded by setAndDrawTexture (:159-176) and read back by getPixels
  * (:178-184).  rgba8: w*h*4, row 0 = image top.  out: res*res*4, row y = gl_FragCoord.y. */
 void oracle_pack_layer(const uint8_t* rgba8, int w, int h, int res, int corrected, const int32_t* swizzle, uint8_t* out) {
-  auto texel = [&](long long i, long long j, float* c) { /* texelFetch after wrap; sRGB decode per texel (SRGB8_ALPHA8) */
-    long long ii = i % w; if (ii < 0) ii += w;                     /* TEXTURE_WRAP_S = REPEAT, :91 */
-    long long jj = j < 0 ? 0 : (j >= h ? h - 1 : j);               /* TEXTURE_WRAP_T = CLAMP_TO_EDGE, :92 */
-    const uint8_t* p = rgba8 + ((size_t)jj * w + (size_t)ii) * 4;
-    for (int k = 0; k < 4; ++k) {
-      float v = (float)p[k] / 255.0f;
-      if (corrected && k < 3) v = v <= 0.04045f ? v / 12.92f : (float)pow(((double)v + 0.055) / 1.055, 2.4);
-      c[k] = v;
-    }
-  };
   for (int y = 0; y < res; ++y)
     for (int x = 0; x < res; ++x) {
       float u = ((float)x + 0.5f) / (float)res, v = ((float)y + 0.5f) / (float)res; /* gl_FragCoord.xy / dims */
       v = 1.0f - v;                                                                /* uv.y = 1.0 - uv.y */
-      float fx = u * (float)w - 0.5f, fy = v * (float)h - 0.5f;                    /* LINEAR, GL ES 3.0 3.8.10 */
-      float flx = floorf(fx), fly = floorf(fy);
-      float a = fx - flx, b = fy - fly;
-      float t00[4], t10[4], t01[4], t11[4], c[4];
-      texel((long long)flx, (long long)fly, t00); texel((long long)flx + 1, (long long)fly, t10);
-      texel((long long)flx, (long long)fly + 1, t01); texel((long long)flx + 1, (long long)fly + 1, t11);
-      float w00 = (1.0f - a) * (1.0f - b), w10 = a * (1.0f - b), w01 = (1.0f - a) * b, w11 = a * b;
-      for (int k = 0; k < 4; ++k) c[k] = w00 * t00[k] + w10 * t10[k] + w01 * t01[k] + w11 * t11[k];
+      const om::v4 t = om::tu_texture_2d(rgba8, w, h, corrected, u, v);            /* texture(tex, uv), oracle_texunit.h */
+      const float c[4] = {t.x, t.y, t.z, t.w};
       float sc[4];
       for (int k = 0; k < 4; ++k) sc[k] = c[swizzle ? swizzle[k] : k];             /* c[k] = copy[swizzle[k]] */
       float rgb[3] = {sc[0] * sc[3], sc[1] * sc[3], sc[2] * sc[3]};                /* vec4(c.rgb * c.a, 1.0) */
       uint8_t* o = out + ((size_t)y * res + x) * 4;
-      for (int k = 0; k < 3; ++k) {
-        float q = rgb[k];
-        o[k] = !(q > 0.0f) ? 0 : (q >= 1.0f ? 255 : (uint8_t)(int)floorf(q * 255.0f + 0.5f));
-      }
+      for (int k = 0; k < 3; ++k) o[k] = om::tu_quant8(rgb[k]);
       o[3] = 255;
     }
 }

@@ -4,6 +4,10 @@
 Lexical adapter GLSL ES 3.00 -> C++ for the reference's fragment shaders, run at BUILD time by oracle/Makefile:
 
     python oracle/glsl_cpu/glsl2cpp.py /root/reference/shader/tracer.fs oracle/_ref/tracer.gen.inc
+    python oracle/glsl_cpu/glsl2cpp.py /root/reference/texture_packer.js oracle/_ref/blit.gen.inc --js-template fsStr
+
+(the second form takes the GLSL out of a JavaScript template string, ``let fsStr = `...`;``: the atlas blit shader of
+texture_packer.js:103-121 lives there)
 
 The output (git-ignored, never committed: it is derived from the reference's source) is #included inside a namespace
 behind glsl_body.inc and compiled by g++.  Nothing about the shader's logic is touched -- no statement is added,
@@ -103,6 +107,14 @@ def convert(src):
 
 if __name__ == "__main__":
     text = open(sys.argv[1]).read()
+    if "--js-template" in sys.argv:
+        name = sys.argv[sys.argv.index("--js-template") + 1]
+        m = re.search(r"\blet\s+%s\s*=\s*`(.*?)`\s*;" % re.escape(name), text, re.S)
+        assert m, "no template string %s in %s" % (name, sys.argv[1])
+        body = m.group(1).split("\n")          # the string's lines share the JavaScript code's indentation: remove it
+        ind = min(len(l) - len(l.lstrip(" ")) for l in body[1:] if l.strip())
+        body = [body[0]] + [l[ind:] if l.strip() else "" for l in body[1:]]
+        text = "\n" * text[:m.start(1)].count("\n") + "\n".join(body)   # keep the JavaScript file's line numbers
     out = convert(text)
     assert out.count("\n") == text.count("\n")
     with open(sys.argv[2], "w") as f:

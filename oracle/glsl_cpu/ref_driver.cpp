@@ -1,7 +1,8 @@
 /*
  * oracle/glsl_cpu/ref_driver.cpp -- TEST INFRASTRUCTURE.  The reference's own fragment shaders, executed on the CPU.
  *
- * Compiles /root/reference/shader/{camera,tracer,bvh_test,draw}.fs -- adapted lexically by glsl2cpp.py into
+ * Compiles /root/reference/shader/{camera,tracer,bvh_test,draw}.fs and the atlas blit shader embedded in
+ * /root/reference/texture_packer.js -- adapted lexically by glsl2cpp.py into
  * oracle/_ref/*.gen.inc at build time, never copied into the repository -- behind the GLSL subset of glsl_body.inc,
  * one namespace per shader, and runs their main() once per fragment the way main.js's draw calls do
  * (main.js:728-807: camera pass -> tracer pass with ping-ponged accumulation targets -> draw pass).  The entry points
@@ -67,11 +68,7 @@ void pad_dims(long long n_floats, int per_element, int channels, int& width, int
   height = width > 0 ? (int)ceil(num_pixels / width) : 0;
 }
 
-uint8_t quant8(float v) { /* RGBA8 framebuffer write: clamp, round to nearest (GL ES 3.0 section 2.1.6.1) */
-  if (!(v > 0.0f)) return 0;
-  if (v >= 1.0f) return 255;
-  return (uint8_t)(int)floorf(v * 255.0f + 0.5f);
-}
+uint8_t quant8(float v) { return om::tu_quant8(v); } /* RGBA8 colour-buffer write */
 
 }  // namespace
 
@@ -242,4 +239,26 @@ extern "C" void ref_draw(const float* fb, int W, int H, float exposure, float sa
   });
 }
 
-extern "C" int ref_abi_version() { return 1; }
+/* ------------------------------------------------------------------------------------------------------------------ */
+namespace blit_fs { /* the fragment shader inside texture_packer.js (:103-121, template string fsStr) */
+#include "glsl_body.inc"
+#include "blit.gen.inc"
+}  // namespace blit_fs
+
+/* One image layer of TexturePacker.getPixels(): setAndDrawTexture(img) (texture_packer.js:159-176) + readPixels (:178-184).
+ * rgba8: w*h*4, row 0 = image top (texImage2D without FLIP_Y: texture row 0).  out: res*res*4, row y = gl_FragCoord.y. */
+extern "C" void ref_pack_layer(const uint8_t* rgba8, int w, int h, int res, int corrected, const int32_t* swz, uint8_t* out) {
+  using namespace blit_fs;
+  tex.u8 = rgba8; tex.w = w; tex.h = h; tex.ch = 4; tex.srgb = corrected;
+  dims = vec2((float)res, (float)res);
+  swizzle = swz ? uvec4{(uint)swz[0], (uint)swz[1], (uint)swz[2], (uint)swz[3]} : uvec4{0u, 1u, 2u, 3u}; /* :173 */
+  for (int y = 0; y < res; ++y)
+    for (int x = 0; x < res; ++x) {
+      gl_FragCoord = vec4((float)x + 0.5f, (float)y + 0.5f, 0.5f, 1.0f);
+      shader_main();
+      uint8_t* o = out + ((size_t)y * res + x) * 4;
+      o[0] = quant8(fragColor.x); o[1] = quant8(fragColor.y); o[2] = quant8(fragColor.z); o[3] = quant8(fragColor.w);
+    }
+}
+
+extern "C" int ref_abi_version() { return 2; }

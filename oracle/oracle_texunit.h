@@ -61,16 +61,34 @@ static inline v4 tu_texture_array(const uint8_t* atlas, int R, int layers, float
   return tu_bilerp(tu_texel8(base + ((size_t)j0 * R + i0) * 4), tu_texel8(base + ((size_t)j0 * R + i1) * 4),
                    tu_texel8(base + ((size_t)j1 * R + i0) * 4), tu_texel8(base + ((size_t)j1 * R + i1) * 4), a, b);
 }
-/* texture(sampler2D env, vec2(u, v)): RGBA8, S REPEAT, T CLAMP_TO_EDGE, LINEAR (main.js:170-180) */
-static inline v4 tu_texture_env(const uint8_t* env, int W, int H, float u, float v) {
+/* texture(sampler2D, vec2(u, v)) on an RGBA8 or SRGB8_ALPHA8 texture with S REPEAT, T CLAMP_TO_EDGE, LINEAR -- the state
+ * of both 2-D textures the reference samples with filtering: the environment map (main.js:170-180, RGBA8) and the image
+ * being blitted into the atlas (texture_packer.js:88-95,159-165; SRGB8_ALPHA8 when `corrected`).  sRGB texels are
+ * decoded before filtering (GL ES 3.0 section 3.8.16), alpha is linear. */
+static inline v4 tu_texel8_srgb(const uint8_t* p, int srgb) {
+  v4 r = tu_texel8(p);
+  if (srgb) {
+    float* c = &r.x;
+    for (int k = 0; k < 3; ++k) c[k] = c[k] <= 0.04045f ? c[k] / 12.92f : (float)pow(((double)c[k] + 0.055) / 1.055, 2.4);
+  }
+  return r;
+}
+static inline v4 tu_texture_2d(const uint8_t* tex, int W, int H, int srgb, float u, float v) {
   float x = u * (float)W - 0.5f, y = v * (float)H - 0.5f;
   float fx = floorf(x), fy = floorf(y);
   float a = x - fx, b = y - fy;
   long long ix = tu_coord_to_int(fx), iy = tu_coord_to_int(fy);
   int i0 = tu_wrap_repeat(ix, W), i1 = tu_wrap_repeat(ix + 1, W);
   int j0 = tu_wrap_clamp(iy, H), j1 = tu_wrap_clamp(iy + 1, H);
-  return tu_bilerp(tu_texel8(env + ((size_t)j0 * W + i0) * 4), tu_texel8(env + ((size_t)j0 * W + i1) * 4),
-                   tu_texel8(env + ((size_t)j1 * W + i0) * 4), tu_texel8(env + ((size_t)j1 * W + i1) * 4), a, b);
+  return tu_bilerp(tu_texel8_srgb(tex + ((size_t)j0 * W + i0) * 4, srgb), tu_texel8_srgb(tex + ((size_t)j0 * W + i1) * 4, srgb),
+                   tu_texel8_srgb(tex + ((size_t)j1 * W + i0) * 4, srgb), tu_texel8_srgb(tex + ((size_t)j1 * W + i1) * 4, srgb), a, b);
+}
+static inline v4 tu_texture_env(const uint8_t* env, int W, int H, float u, float v) { return tu_texture_2d(env, W, H, 0, u, v); }
+/* RGBA8 colour-buffer write: clamp to [0, 1], round to nearest (GL ES 3.0 section 2.1.6.1) */
+static inline uint8_t tu_quant8(float v) {
+  if (!(v > 0.0f)) return 0;
+  if (v >= 1.0f) return 255;
+  return (uint8_t)(int)floorf(v * 255.0f + 0.5f);
 }
 
 }  // namespace om

@@ -87,3 +87,13 @@ def draw(fb, exposure=1.0, saturation=1.0, denoise=False, max_sigma=2.0, scale=1
     lib().ref_draw(_p(fb), C.c_int(W), C.c_int(H), C.c_float(exposure), C.c_float(saturation),
                    C.c_int(1 if denoise else 0), C.c_float(max_sigma), C.c_float(scale), _p(out), _p(outf), C.c_int(nthreads))
     return (out, outf) if want_float else out
+
+
+def pack_layer(pixels, res, corrected=False, swizzle=None):
+    """One atlas layer by the blit shader inside texture_packer.js (:103-121), GL state of :88-95,159-176."""
+    pixels = np.ascontiguousarray(pixels, dtype=np.uint8)
+    h, w = pixels.shape[0], pixels.shape[1]
+    out = np.empty((res, res, 4), np.uint8)
+    sw = np.asarray(swizzle, np.int32) if swizzle is not None else None
+    lib().ref_pack_layer(_p(pixels), C.c_int(w), C.c_int(h), C.c_int(res), C.c_int(1 if corrected else 0), _p(sw), _p(out))
+    return out

@@ -132,3 +132,17 @@ def test_draw_fs(post, oracle_mod):
     fb[5, 7, :3] = 900.0  # a firefly for the 5x5 filter
     fb[20, 30, :3] = 0.0
     assert beq(oracle_mod.draw(fb, **post), R.draw(fb, **post))
+
+
+@pytest.mark.parametrize("res,corrected,sw", [(64, True, None), (37, False, [2, 1, 0, 3]), (16, False, None),
+                                              (128, True, [0, 0, 0, 3]), (53, True, [3, 2, 1, 0])])
+def test_atlas_blit_shader_of_texture_packer_js(res, corrected, sw, oracle_mod):
+    """The fragment shader inside texture_packer.js (:103-121, a JavaScript template string) with the GL state of
+    :88-95,159-176 (REPEAT / CLAMP_TO_EDGE, LINEAR, SRGB8_ALPHA8 when `corrected`, swizzle uniform, RGBA8 read-back):
+    restatement and the product's native blit against the shader text."""
+    from fspt_b200 import capi
+    rng = np.random.default_rng(2)
+    img = rng.integers(0, 256, (37, 53, 4), dtype=np.uint8)  # odd, non-square, with alpha
+    ref = R.pack_layer(img, res, corrected, sw)
+    assert beq(oracle_mod.pack_layer(img, res, corrected, sw), ref)
+    assert beq(capi.pack_layer(img, res, corrected, sw), ref)
