@@ -452,11 +452,11 @@ def main():
     # ---- end-to-end through the host API with host buffers ---------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        barrier()
-        n_e2e = max(1, min(args.steps, 3))
-        t0 = time.perf_counter()
+        n_e2e = max(1, min(args.steps, 5))
         h2d = 0
-        for _ in range(n_e2e):
+
+        def e2e_step():
+            nonlocal h2d
             if rank == 0:
                 h2d = ctx.scene_upload(sa) + 2 * 4 * len(rc)   # host buffers -> HBM, once per box
             if world > 1:
@@ -464,6 +464,11 @@ def main():
             step()
             if rank == 0:
                 pt.drawQuad(out8)  # post-pass + D2H of the RGBA8 frame
+        e2e_step()  # one untimed pass: the staging threads and pinned blocks of the upload path are warm
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()
         barrier()
         e2e_s = time.perf_counter() - t0
         e2e = {"value": n_e2e * samples_per_step / e2e_s / 1e6, "unit": "Mpath-samples/s",

@@ -57,7 +57,7 @@ struct Ctx {
   size_t cap_raw = 0, cap_mat_src = 0;
   void* d_mat_info = nullptr;
   size_t cap_mat_info = 0;
-  cudaTextureObject_t nodes_tex = 0;
+  cudaTextureObject_t nodes_tex = 0;  // the node array again as a linear texture (second L1 data pipe)
   int atlas_R = 0, atlas_L = 0, env_W = 0, env_H = 0;       // dims of the resident arrays (reused across uploads)
   size_t cap_nodes = 0, cap_tris = 0, cap_shade = 0, cap_bins = 0, cap_layer_info = 0;
   uint8_t* h_stage = nullptr;                               // pinned staging for the atlas (one slot per layer)
@@ -246,6 +246,23 @@ __global__ void __launch_bounds__(256) k_interleave_atlas(cudaSurfaceObject_t su
 
 __global__ void k_set_counts(int* counts, int n_cont, int n_shadow) {
   counts[0] = n_cont; counts[1] = n_shadow; counts[2] = 0; counts[3] = 0; counts[32] = 0;
+}
+
+// A device array of 16-byte words as a linear texture (tex1Dfetch): the second L1 data path next to the LSU.  Arrays
+// beyond the 2^27-texel limit get no texture (0) and are read with plain loads.
+int linear_tex(Ctx* c, cudaTextureObject_t* tex, void* ptr, size_t bytes, bool allowed = true) {
+  if (*tex) cudaDestroyTextureObject(*tex);
+  *tex = 0;
+  if (!allowed || bytes / 16 > ((size_t)1 << 27) || bytes == 0) return FSPT_OK;
+  cudaResourceDesc r = {};
+  r.resType = cudaResourceTypeLinear;
+  r.res.linear.devPtr = ptr;
+  r.res.linear.desc = cudaCreateChannelDesc<float4>();
+  r.res.linear.sizeInBytes = bytes;
+  cudaTextureDesc t = {};
+  t.readMode = cudaReadModeElementType;
+  CK(cudaCreateTextureObject(tex, &r, &t, nullptr));
+  return FSPT_OK;
 }
 
 // Traverses the continuation ray of every record of array `which` (d_counts[2*which] of them) + d_counts[2*which+1]
@@ -828,13 +845,19 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
   bool use_mat_tex = !getenv("FSPT_PLAIN_ATLAS");
   {
     const size_t inter = (size_t)n_tex_mats * layer_texels * 16, plain = (size_t)L * layer_bytes;
-    size_t free_b = 0, total_b = 0;
-    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { (void)cudaGetLastError(); free_b = (size_t)48 << 30; }
-    const size_t resident = c->mat_arr ? (size_t)c->mat_R * c->mat_R * 16 * (size_t)c->mat_L : 0;  // reused when it fits
-    if (inter > std::max<size_t>(4 * plain, (size_t)256 << 20) || inter > ((size_t)48 << 30) || inter > (free_b + resident) / 2)
+    // the array of the previous upload is reused when it has the same shape: then nothing is allocated and the driver is
+    // not asked for the free memory (cudaMemGetInfo is a resource-manager call: usually 0.1 ms, but 20-100 ms every few
+    // dozen calls on the virtualised hosts measured, which showed up as spikes in the end-to-end step time)
+    const bool reuse = c->mat_arr && c->mat_R == R && c->mat_L == std::max(1, n_tex_mats);
+    size_t free_b = (size_t)48 << 30, total_b = 0;
+    if (!reuse && cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { (void)cudaGetLastError(); free_b = (size_t)48 << 30; }
+    const size_t resident = c->mat_arr ? (size_t)c->mat_R * c->mat_R * 16 * (size_t)c->mat_L : 0;  // freed before the new one
+    if (inter > std::max<size_t>(4 * plain, (size_t)256 << 20) || inter > ((size_t)48 << 30) ||
+        (!reuse && inter > (free_b + resident) / 2))
       use_mat_tex = false;
     if (getenv("FSPT_FORCE_MAT_TEX")) use_mat_tex = true;  // test knob: exercise the allocation-failure fallback
   }
+  lap("atlas sizing");
   std::atomic<int> cuda_err(0);
   std::mutex mu;
   bool plain_atlas = !use_mat_tex;
@@ -924,7 +947,11 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
       const int bands = std::max(1, std::min(R, 16));
       std::vector<int> tex_mat_ids;
       for (size_t m = 0; m < mats.size(); ++m) if (mat_info[8 * m] >= 0) tex_mat_ids.push_back((int)m);
+      std::atomic<long long> t_copy_max(0), t_enq_max(0), t_first_max(0);
+      const auto t_par0 = std::chrono::steady_clock::now();
       parallel((int)tex_mat_ids.size() * bands, atlas_workers, [&](int item) {
+        const auto ti0 = std::chrono::steady_clock::now();
+        if (timing) { long long d = std::chrono::duration_cast<std::chrono::microseconds>(ti0 - t_par0).count(); if (item < atlas_workers) { long long o = t_first_max.load(); while (d > o && !t_first_max.compare_exchange_weak(o, d)) {} } }
         const int m = tex_mat_ids[item / bands], band = item % bands;
         const int tl = mat_info[8 * m];
         const int y0 = (int)((long long)R * band / bands), y1 = (int)((long long)R * (band + 1) / bands);
@@ -961,10 +988,18 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
         cp.dstPos = make_cudaPos(0, y0, tl);
         cp.extent = make_cudaExtent(R, y1 - y0, 1);
         cp.kind = cudaMemcpyHostToDevice;
+        const auto ti1 = std::chrono::steady_clock::now();
         std::lock_guard<std::mutex> g(mu);
         cudaError_t e = cudaMemcpy3DAsync(&cp, c->copy_stream);
         if (e != cudaSuccess) cuda_err.store((int)e);
+        if (timing) {
+          const auto ti2 = std::chrono::steady_clock::now();
+          long long dc = std::chrono::duration_cast<std::chrono::microseconds>(ti1 - ti0).count(), de = std::chrono::duration_cast<std::chrono::microseconds>(ti2 - ti1).count();
+          long long o = t_copy_max.load(); while (dc > o && !t_copy_max.compare_exchange_weak(o, dc)) {}
+          o = t_enq_max.load(); while (de > o && !t_enq_max.compare_exchange_weak(o, de)) {}
+        }
       });
+      if (timing) fprintf(stderr, "[fspt upload]   interleave items: slowest copy %.2f ms, slowest enqueue (incl. lock) %.2f ms, last first-item start %.2f ms, %d workers\n", t_copy_max.load() / 1e3, t_enq_max.load() / 1e3, t_first_max.load() / 1e3, atlas_workers);
     }
   }
   if (plain_atlas) {
@@ -1039,20 +1074,8 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
   }
   CK(cudaMemcpy2DToArrayAsync(c->env_arr, 0, 0, hg + o_env, (size_t)s->env_width * 4, (size_t)s->env_width * 4,
                               s->env_height, cudaMemcpyHostToDevice, c->stream));
-  {
-    cudaResourceDesc nr = {};
-    nr.resType = cudaResourceTypeLinear;
-    nr.res.linear.devPtr = c->d_nodes;
-    nr.res.linear.desc = cudaCreateChannelDesc<float4>();
-    nr.res.linear.sizeInBytes = nodes_bytes;
-    cudaTextureDesc nt = {};
-    nt.readMode = cudaReadModeElementType;
-    if (c->nodes_tex) cudaDestroyTextureObject(c->nodes_tex);
-    c->nodes_tex = 0;
-    const size_t max_texels = (size_t)1 << 27;  // linear-texture limit; beyond it the kernels use plain loads
-    if (nodes_bytes / 16 <= max_texels && !getenv("FSPT_NO_NODE_TEX"))  // env: test knob for the LSU-only instantiation
-      CK(cudaCreateTextureObject(&c->nodes_tex, &nr, &nt, nullptr));
-  }
+  // env: test knob for the LSU-only instantiation of k_trace
+  if ((rc_ = linear_tex(c, &c->nodes_tex, c->d_nodes, nodes_bytes, !getenv("FSPT_NO_NODE_TEX")))) return rc_;
   // no synchronisation: everything the DMA engine still reads lives in the context's pinned staging blocks, which the
   // next upload (and destroy) only touch after synchronising the stream; work enqueued by fspt_render waits in order
   if (!pageable_geo.empty() || timing) { CK(cudaStreamSynchronize(c->stream)); CK(cudaStreamSynchronize(c->copy_stream)); }
@@ -1526,18 +1549,7 @@ int fspt_scene_broadcast(fspt_ctx* ctx, int32_t root) {
     cp.dstArray = h.use_mat_tex ? c->mat_arr : c->atlas_arr;
     CK(cudaMemcpy3DAsync(&cp, c->stream));
     CK(cudaEventRecord(c->ev_atlas, c->stream));
-    if (c->nodes_tex) cudaDestroyTextureObject(c->nodes_tex);
-    c->nodes_tex = 0;
-    if (h.bytes_nodes / 16 <= ((size_t)1 << 27)) {
-      cudaResourceDesc nr = {};
-      nr.resType = cudaResourceTypeLinear;
-      nr.res.linear.devPtr = c->d_nodes;
-      nr.res.linear.desc = cudaCreateChannelDesc<float4>();
-      nr.res.linear.sizeInBytes = h.bytes_nodes;
-      cudaTextureDesc nt = {};
-      nt.readMode = cudaReadModeElementType;
-      CK(cudaCreateTextureObject(&c->nodes_tex, &nr, &nt, nullptr));
-    }
+    if ((rc = linear_tex(c, &c->nodes_tex, c->d_nodes, h.bytes_nodes))) return rc;
     c->bytes_nodes = h.bytes_nodes; c->bytes_tris = h.bytes_tris; c->bytes_shade = h.bytes_shade;
     c->bytes_bins = h.bytes_bins; c->bytes_layer_info = h.bytes_layer_info; c->bytes_mat_info = h.bytes_mat_info;
     c->sc.nodes = reinterpret_cast<const float4*>(c->d_nodes);
