@@ -53,7 +53,7 @@ EXPORTS = [
     "fspt_accum_device_ptr", "fspt_set_accum_samples", "fspt_debug_primary", "fspt_debug_trace",
     "fspt_debug_last_color", "fspt_debug_math", "fspt_debug_read_bandwidth", "fspt_get_stats", "fspt_synchronize", "fspt_bvh_build", "fspt_bvh_build2",
     "fspt_env_bins", "fspt_pack_layer", "fspt_set_param", "fspt_set_tile", "fspt_comm_unique_id", "fspt_comm_init",
-    "fspt_comm_destroy", "fspt_reduce_accum", "fspt_scene_broadcast",
+    "fspt_comm_destroy", "fspt_reduce_accum", "fspt_scene_broadcast", "fspt_scene_upload_async", "fspt_scene_upload_wait",
 ]
 PARAM_ANYHIT, PARAM_MAX_REFRACTIONS, PARAM_SANITIZE_NAN = 1, 2, 3
 
@@ -182,7 +182,10 @@ class Context:
         except Exception:
             pass
 
-    def scene_upload(self, sa):
+    def scene_upload(self, sa, wait=True):
+        """fspt_scene_upload; wait=False: fspt_scene_upload_async -- returns once everything but the atlas has been
+        consumed, the atlas is staged in the background (the arrays are kept alive here until upload_wait / the next
+        upload) and the next render's primary traversal overlaps it."""
         d = SceneDesc()
         keep = dict(
             bvh=f32(sa.bvh), tris=f32(sa.tris), mats=f32(sa.mats), norms=f32(sa.norms), uvs=f32(sa.uvs),
@@ -205,8 +208,21 @@ class Context:
         d.env_height, d.env_width = keep["env"].shape[0], keep["env"].shape[1]
         d.env_bins = keep["bins"].size // 4
         d.leaf_size = getattr(sa, "leaf_size", 4)
-        self._ck(self.lib.fspt_scene_upload(self.h, C.byref(d)))
+        if wait:
+            self._ck(self.lib.fspt_scene_upload(self.h, C.byref(d)))
+            self._keep = None
+        else:
+            self._keep = None  # (the library joins the previous staging thread before it touches anything)
+            self._ck(self.lib.fspt_scene_upload_async(self.h, C.byref(d)))
+            self._keep = keep
         return sum(v.nbytes for v in keep.values())
+
+    def upload_wait(self):
+        """fspt_scene_upload_wait: the atlas of the last asynchronous upload has been staged; its buffers are released."""
+        try:
+            self._ck(self.lib.fspt_scene_upload_wait(self.h))
+        finally:
+            self._keep = None
 
     @staticmethod
     def frame(eye, dir_, fov_scale, lens_features, env_theta):

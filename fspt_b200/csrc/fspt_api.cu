@@ -63,6 +63,11 @@ struct Ctx {
   uint8_t* h_stage = nullptr;                               // pinned staging for the atlas (one slot per layer)
   cudaStream_t copy_stream = nullptr;                       // atlas DMA, overlaps the primary traversal
   cudaEvent_t ev_atlas = nullptr;
+  // fspt_scene_upload_async: the atlas is staged (host interleave into pinned memory + band-wise DMA) by this thread
+  // after the call has returned; joined before the first shading launch and by everything that touches scene state
+  std::thread atlas_thread;
+  std::atomic<int> atlas_err{0};  // first cudaError_t of a staging item (atlas_mu serialises the enqueues)
+  std::mutex atlas_mu;
   uint8_t* h_geo = nullptr;                                 // pinned staging for geometry records, bins, env
   size_t geo_stage_bytes = 0;
   size_t stage_bytes = 0;
@@ -210,6 +215,27 @@ int alloc_wave(Ctx* c) {
   for (auto& e : c->ev_rb) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   CK(cudaMallocHost(&c->h_poll, Ctx::POLL_SLOTS * sizeof(int)));
   for (auto& e : c->ev_poll) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  return FSPT_OK;
+}
+
+// n_items work items handed to at most max_workers host threads (each bound to `device`)
+void parallel_for(int device, int n_items, int max_workers, const std::function<void(int)>& fn) {
+  std::atomic<int> next_item(0);
+  const int n_workers = std::max(1, std::min(n_items, max_workers));
+  std::vector<std::thread> workers;
+  for (int w = 0; w < n_workers; ++w)
+    workers.emplace_back([&]() {
+      cudaSetDevice(device);
+      for (;;) { const int i = next_item.fetch_add(1); if (i >= n_items) break; fn(i); }
+    });
+  for (auto& t : workers) t.join();
+}
+
+// Waits for the atlas staging of the last fspt_scene_upload_async (no-op otherwise) and reports its outcome.
+int atlas_join(Ctx* c) {
+  if (c->atlas_thread.joinable()) c->atlas_thread.join();
+  const int e = c->atlas_err.exchange(0);
+  if (e) { c->has_scene = false; return fail(c, FSPT_E_CUDA, "atlas upload failed: %s", cudaGetErrorString((cudaError_t)e)); }
   return FSPT_OK;
 }
 
@@ -366,7 +392,11 @@ int render_wave(Ctx* c, const FrameParams& fp, uint32_t first_tick, int S, const
   A.max_refractions = c->max_refractions;
   A.anyhit = c->anyhit;
   const int hard_cap = FSPT_NUM_BOUNCES + 1 + (c->has_dielectric ? c->max_refractions + 2 : 0);
-  CK(cudaStreamWaitEvent(c->stream, c->ev_atlas, 0));  // atlas DMA of the last upload (no-op once it has completed)
+  // atlas of the last upload: an asynchronous upload's staging thread is joined HERE, with the primary traversal already
+  // running on the GPU (the event it records has to exist before the stream can be made to wait on it); then the DMA
+  // itself is waited for on the device (no-op once it has completed)
+  if ((rc = atlas_join(c))) return rc;
+  CK(cudaStreamWaitEvent(c->stream, c->ev_atlas, 0));
   int cur = 0;
   for (int b = 0; b < hard_cap; ++b) {
     const int nxt = cur ^ 1;
@@ -560,6 +590,7 @@ void fspt_destroy(fspt_ctx* ctx) {
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
   if (!c) return;
   cudaSetDevice(c->device);
+  if (c->atlas_thread.joinable()) c->atlas_thread.join();
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
   free_scene(c);
@@ -584,7 +615,10 @@ void fspt_destroy(fspt_ctx* ctx) {
   delete c;
 }
 
-int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
+// fspt_scene_upload / fspt_scene_upload_async.  async_atlas: the atlas staging (the largest part: interleave into pinned
+// memory + DMA) continues on a thread of the context after the function has returned; everything else -- every geometry
+// buffer, the environment, the tables -- has been consumed by then.
+static int scene_upload_impl(fspt_ctx* ctx, const fspt_scene_desc* s, bool async_atlas) {
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
   const bool timing = getenv("FSPT_TIMING") != nullptr;
   auto t_prev = std::chrono::steady_clock::now();
@@ -602,6 +636,7 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
     return fail(c, FSPT_E_INVALID, "scene_upload: non-positive size (an environment with >= 1 bin is mandatory, main.js:303-308)");
   if (s->leaf_size != 4) return fail(c, FSPT_E_INVALID, "scene_upload: LEAF_SIZE must be 4 (main.js:45), got %d", s->leaf_size);
   CK(cudaSetDevice(c->device));
+  (void)atlas_join(c);  // a staging thread of the previous upload still reads the pinned block and the arrays
   CK(cudaStreamSynchronize(c->stream));
   CK(cudaStreamSynchronize(c->copy_stream));
   c->has_scene = false;  // device buffers, arrays and texture objects of the previous scene are reused when they fit
@@ -613,17 +648,8 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
   // (dist.share_host_threads sets FSPT_UPLOAD_THREADS = cores / processes on this node)
   int hw = (int)std::max(4u, std::min(32u, std::thread::hardware_concurrency()));
   if (const char* e = getenv("FSPT_UPLOAD_THREADS")) hw = std::max(4, std::min(64, atoi(e)));
-  auto parallel = [&](int n_items, int max_workers, const std::function<void(int)>& fn) {
-    std::atomic<int> next_item(0);
-    const int n_workers = std::max(1, std::min(n_items, max_workers));
-    std::vector<std::thread> workers;
-    for (int w = 0; w < n_workers; ++w)
-      workers.emplace_back([&]() {
-        cudaSetDevice(c->device);
-        for (;;) { const int i = next_item.fetch_add(1); if (i >= n_items) break; fn(i); }
-      });
-    for (auto& t : workers) t.join();
-  };
+  const int device = c->device;
+  auto parallel = [&](int n_items, int max_workers, const std::function<void(int)>& fn) { parallel_for(device, n_items, max_workers, fn); };
   struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } };
   // ---- constant-colour layers (exact: every texel compared), scanned in the background while the pre-passes run.
   // constant <=> every texel equals its successor; work item = (layer, band), abandoned once the layer is known varied
@@ -858,8 +884,11 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
     if (getenv("FSPT_FORCE_MAT_TEX")) use_mat_tex = true;  // test knob: exercise the allocation-failure fallback
   }
   lap("atlas sizing");
-  std::atomic<int> cuda_err(0);
-  std::mutex mu;
+  // The staging itself is a job (everything it needs captured by value: it may outlive this call) that runs here or,
+  // for fspt_scene_upload_async, on the context's staging thread.
+  std::function<void()> atlas_job;
+  const uint8_t* const atlas_src = s->atlas;
+  c->atlas_err.store(0);
   bool plain_atlas = !use_mat_tex;
   if (use_mat_tex) {
     if (c->sc.atlas) { cudaDestroyTextureObject(c->sc.atlas); c->sc.atlas = 0; }
@@ -927,79 +956,74 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
       if ((rc2 = ensure(c, c->d_mat_src, c->cap_mat_src, sizeof(MatSrc) * (size_t)ML))) return rc2;
       // work item = (raw layer, band of rows): copy into the pinned block, DMA the band
       const int bands = std::max(1, std::min(R, 16));
-      parallel((int)raw_layers.size() * bands, atlas_workers, [&](int item) {
-        const int ri = item / bands, band = item % bands;
-        const size_t y0 = (size_t)R * band / bands, y1 = (size_t)R * (band + 1) / bands;
-        const size_t off = (size_t)ri * layer_bytes + y0 * R * 4, bytes = (y1 - y0) * R * 4;
-        memcpy(c->h_stage + off, s->atlas + (size_t)raw_layers[ri] * layer_bytes + y0 * R * 4, bytes);
-        std::lock_guard<std::mutex> g(mu);
-        cudaError_t e = cudaMemcpyAsync(reinterpret_cast<uint8_t*>(c->d_raw) + off, c->h_stage + off, bytes, cudaMemcpyHostToDevice, c->copy_stream);
-        if (e != cudaSuccess) cuda_err.store((int)e);
-      });
-      CK(cudaMemcpyAsync(c->d_mat_src, mat_src, sizeof(MatSrc) * (size_t)n_tex_mats, cudaMemcpyHostToDevice, c->copy_stream));
-      const dim3 blk(32, 8), grd((R + 31) / 32, (R + 7) / 8, n_tex_mats);
-      k_interleave_atlas<<<grd, blk, 0, c->copy_stream>>>(c->mat_surf, reinterpret_cast<const uint32_t*>(c->d_raw),
-                                                          reinterpret_cast<const MatSrc*>(c->d_mat_src), R, layer_texels);
       c->stats.kernel_launches++;
-      CK(cudaGetLastError());
+      atlas_job = [c, device, atlas_src, raw_layers, bands, atlas_workers, R, layer_bytes, layer_texels, mat_src, n_tex_mats]() {
+        parallel_for(device, (int)raw_layers.size() * bands, atlas_workers, [&](int item) {
+          const int ri = item / bands, band = item % bands;
+          const size_t y0 = (size_t)R * band / bands, y1 = (size_t)R * (band + 1) / bands;
+          const size_t off = (size_t)ri * layer_bytes + y0 * R * 4, bytes = (y1 - y0) * R * 4;
+          memcpy(c->h_stage + off, atlas_src + (size_t)raw_layers[ri] * layer_bytes + y0 * R * 4, bytes);
+          std::lock_guard<std::mutex> g(c->atlas_mu);
+          cudaError_t e = cudaMemcpyAsync(reinterpret_cast<uint8_t*>(c->d_raw) + off, c->h_stage + off, bytes, cudaMemcpyHostToDevice, c->copy_stream);
+          if (e != cudaSuccess) c->atlas_err.store((int)e);
+        });
+        cudaError_t e = cudaMemcpyAsync(c->d_mat_src, mat_src, sizeof(MatSrc) * (size_t)n_tex_mats, cudaMemcpyHostToDevice, c->copy_stream);
+        if (e != cudaSuccess) c->atlas_err.store((int)e);
+        const dim3 blk(32, 8), grd((R + 31) / 32, (R + 7) / 8, n_tex_mats);
+        k_interleave_atlas<<<grd, blk, 0, c->copy_stream>>>(c->mat_surf, reinterpret_cast<const uint32_t*>(c->d_raw),
+                                                            reinterpret_cast<const MatSrc*>(c->d_mat_src), R, layer_texels);
+        if ((e = cudaGetLastError()) != cudaSuccess) c->atlas_err.store((int)e);
+      };
     } else {
       // work item = (textured material, band of rows): interleave the four source layers, DMA the band
       const int bands = std::max(1, std::min(R, 16));
-      std::vector<int> tex_mat_ids;
-      for (size_t m = 0; m < mats.size(); ++m) if (mat_info[8 * m] >= 0) tex_mat_ids.push_back((int)m);
-      std::atomic<long long> t_copy_max(0), t_enq_max(0), t_first_max(0);
-      const auto t_par0 = std::chrono::steady_clock::now();
-      parallel((int)tex_mat_ids.size() * bands, atlas_workers, [&](int item) {
-        const auto ti0 = std::chrono::steady_clock::now();
-        if (timing) { long long d = std::chrono::duration_cast<std::chrono::microseconds>(ti0 - t_par0).count(); if (item < atlas_workers) { long long o = t_first_max.load(); while (d > o && !t_first_max.compare_exchange_weak(o, d)) {} } }
-        const int m = tex_mat_ids[item / bands], band = item % bands;
-        const int tl = mat_info[8 * m];
-        const int y0 = (int)((long long)R * band / bands), y1 = (int)((long long)R * (band + 1) / bands);
-        const uint32_t* src[4];
-        for (int k = 0; k < 4; ++k) src[k] = reinterpret_cast<const uint32_t*>(s->atlas) + (size_t)mats[m][k] * layer_texels;
-        uint32_t* dst = reinterpret_cast<uint32_t*>(c->h_stage) + ((size_t)tl * layer_texels + (size_t)y0 * R) * 4;
-        const size_t i0 = (size_t)y0 * R, n = (size_t)(y1 - y0) * R;
-        size_t i = 0;
+      std::vector<int> tex_layer;                  // per textured material: its layer of the material array
+      std::vector<std::array<int, 4>> tex_src;     // ... and its four source layers of the atlas
+      for (size_t m = 0; m < mats.size(); ++m)
+        if (mat_info[8 * m] >= 0) { tex_layer.push_back(mat_info[8 * m]); tex_src.push_back(mats[m]); }
+      atlas_job = [c, device, atlas_src, tex_layer, tex_src, bands, atlas_workers, R, layer_texels]() {
+        parallel_for(device, (int)tex_layer.size() * bands, atlas_workers, [&](int item) {
+          const int tm = item / bands, band = item % bands;
+          const int tl = tex_layer[tm];
+          const int y0 = (int)((long long)R * band / bands), y1 = (int)((long long)R * (band + 1) / bands);
+          const uint32_t* src[4];
+          for (int k = 0; k < 4; ++k) src[k] = reinterpret_cast<const uint32_t*>(atlas_src) + (size_t)tex_src[tm][k] * layer_texels;
+          uint32_t* dst = reinterpret_cast<uint32_t*>(c->h_stage) + ((size_t)tl * layer_texels + (size_t)y0 * R) * 4;
+          const size_t i0 = (size_t)y0 * R, n = (size_t)(y1 - y0) * R;
+          size_t i = 0;
 #if defined(__SSE2__)
-        // 4x4 transpose of 32-bit texels, written with non-temporal stores: the staging block is only read by the DMA
-        // engine, so it should neither be fetched for ownership nor displace the source layers from the CPU caches
-        for (; i + 4 <= n; i += 4) {
-          const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src[0] + i0 + i));
-          const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src[1] + i0 + i));
-          const __m128i c2 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src[2] + i0 + i));
-          const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src[3] + i0 + i));
-          const __m128i ab_lo = _mm_unpacklo_epi32(a, b), ab_hi = _mm_unpackhi_epi32(a, b);
-          const __m128i cd_lo = _mm_unpacklo_epi32(c2, d), cd_hi = _mm_unpackhi_epi32(c2, d);
-          __m128i* o = reinterpret_cast<__m128i*>(dst + 4 * i);  // 16-byte aligned: pinned block + multiples of 16
-          _mm_stream_si128(o + 0, _mm_unpacklo_epi64(ab_lo, cd_lo));
-          _mm_stream_si128(o + 1, _mm_unpackhi_epi64(ab_lo, cd_lo));
-          _mm_stream_si128(o + 2, _mm_unpacklo_epi64(ab_hi, cd_hi));
-          _mm_stream_si128(o + 3, _mm_unpackhi_epi64(ab_hi, cd_hi));
-        }
-        _mm_sfence();
+          // 4x4 transpose of 32-bit texels, written with non-temporal stores: the staging block is only read by the DMA
+          // engine, so it should neither be fetched for ownership nor displace the source layers from the CPU caches
+          for (; i + 4 <= n; i += 4) {
+            const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src[0] + i0 + i));
+            const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src[1] + i0 + i));
+            const __m128i c2 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src[2] + i0 + i));
+            const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src[3] + i0 + i));
+            const __m128i ab_lo = _mm_unpacklo_epi32(a, b), ab_hi = _mm_unpackhi_epi32(a, b);
+            const __m128i cd_lo = _mm_unpacklo_epi32(c2, d), cd_hi = _mm_unpackhi_epi32(c2, d);
+            __m128i* o = reinterpret_cast<__m128i*>(dst + 4 * i);  // 16-byte aligned: pinned block + multiples of 16
+            _mm_stream_si128(o + 0, _mm_unpacklo_epi64(ab_lo, cd_lo));
+            _mm_stream_si128(o + 1, _mm_unpackhi_epi64(ab_lo, cd_lo));
+            _mm_stream_si128(o + 2, _mm_unpacklo_epi64(ab_hi, cd_hi));
+            _mm_stream_si128(o + 3, _mm_unpackhi_epi64(ab_hi, cd_hi));
+          }
+          _mm_sfence();
 #endif
-        for (; i < n; ++i) {
-          dst[4 * i + 0] = src[0][i0 + i]; dst[4 * i + 1] = src[1][i0 + i];
-          dst[4 * i + 2] = src[2][i0 + i]; dst[4 * i + 3] = src[3][i0 + i];
-        }
-        cudaMemcpy3DParms cp = {};
-        cp.srcPtr = make_cudaPitchedPtr(dst, (size_t)R * 16, R, y1 - y0);
-        cp.dstArray = c->mat_arr;
-        cp.dstPos = make_cudaPos(0, y0, tl);
-        cp.extent = make_cudaExtent(R, y1 - y0, 1);
-        cp.kind = cudaMemcpyHostToDevice;
-        const auto ti1 = std::chrono::steady_clock::now();
-        std::lock_guard<std::mutex> g(mu);
-        cudaError_t e = cudaMemcpy3DAsync(&cp, c->copy_stream);
-        if (e != cudaSuccess) cuda_err.store((int)e);
-        if (timing) {
-          const auto ti2 = std::chrono::steady_clock::now();
-          long long dc = std::chrono::duration_cast<std::chrono::microseconds>(ti1 - ti0).count(), de = std::chrono::duration_cast<std::chrono::microseconds>(ti2 - ti1).count();
-          long long o = t_copy_max.load(); while (dc > o && !t_copy_max.compare_exchange_weak(o, dc)) {}
-          o = t_enq_max.load(); while (de > o && !t_enq_max.compare_exchange_weak(o, de)) {}
-        }
-      });
-      if (timing) fprintf(stderr, "[fspt upload]   interleave items: slowest copy %.2f ms, slowest enqueue (incl. lock) %.2f ms, last first-item start %.2f ms, %d workers\n", t_copy_max.load() / 1e3, t_enq_max.load() / 1e3, t_first_max.load() / 1e3, atlas_workers);
+          for (; i < n; ++i) {
+            dst[4 * i + 0] = src[0][i0 + i]; dst[4 * i + 1] = src[1][i0 + i];
+            dst[4 * i + 2] = src[2][i0 + i]; dst[4 * i + 3] = src[3][i0 + i];
+          }
+          cudaMemcpy3DParms cp = {};
+          cp.srcPtr = make_cudaPitchedPtr(dst, (size_t)R * 16, R, y1 - y0);
+          cp.dstArray = c->mat_arr;
+          cp.dstPos = make_cudaPos(0, y0, tl);
+          cp.extent = make_cudaExtent(R, y1 - y0, 1);
+          cp.kind = cudaMemcpyHostToDevice;
+          std::lock_guard<std::mutex> g(c->atlas_mu);
+          cudaError_t e = cudaMemcpy3DAsync(&cp, c->copy_stream);
+          if (e != cudaSuccess) c->atlas_err.store((int)e);
+        });
+      };
     }
   }
   if (plain_atlas) {
@@ -1023,25 +1047,45 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
       CK(cudaMallocHost(&c->h_stage, layer_bytes * L));
       c->stage_bytes = layer_bytes * L;
     }
-    parallel(L, atlas_workers, [&](int l) {
-      uint8_t* dst = c->h_stage + (size_t)l * layer_bytes;
-      memcpy(dst, s->atlas + (size_t)l * layer_bytes, layer_bytes);
-      cudaMemcpy3DParms cp = {};
-      cp.srcPtr = make_cudaPitchedPtr(dst, (size_t)R * 4, R, R);
-      cp.dstArray = c->atlas_arr;
-      cp.dstPos = make_cudaPos(0, 0, l);
-      cp.extent = make_cudaExtent(R, R, 1);
-      cp.kind = cudaMemcpyHostToDevice;
-      std::lock_guard<std::mutex> g(mu);
-      cudaError_t e = cudaMemcpy3DAsync(&cp, c->copy_stream);
-      if (e != cudaSuccess) cuda_err.store((int)e);
-    });
+    atlas_job = [c, device, atlas_src, L, atlas_workers, R, layer_bytes]() {
+      parallel_for(device, L, atlas_workers, [&](int l) {
+        uint8_t* dst = c->h_stage + (size_t)l * layer_bytes;
+        memcpy(dst, atlas_src + (size_t)l * layer_bytes, layer_bytes);
+        cudaMemcpy3DParms cp = {};
+        cp.srcPtr = make_cudaPitchedPtr(dst, (size_t)R * 4, R, R);
+        cp.dstArray = c->atlas_arr;
+        cp.dstPos = make_cudaPos(0, 0, l);
+        cp.extent = make_cudaExtent(R, R, 1);
+        cp.kind = cudaMemcpyHostToDevice;
+        std::lock_guard<std::mutex> g(c->atlas_mu);
+        cudaError_t e = cudaMemcpy3DAsync(&cp, c->copy_stream);
+        if (e != cudaSuccess) c->atlas_err.store((int)e);
+      });
+    };
   }
-  if (cuda_err.load()) return fail(c, FSPT_E_CUDA, "atlas upload failed: %s", cudaGetErrorString((cudaError_t)cuda_err.load()));
-  // the atlas travels on its own stream: only k_shade needs it, so the camera + primary traversal launch of the next
-  // render overlaps the tail of this DMA (render_wave waits on the event before its first k_shade)
-  CK(cudaEventRecord(c->ev_atlas, c->copy_stream));
-  lap("atlas stage + scan + enqueue");
+  // The atlas travels on its own stream: only k_shade needs it, so the camera + primary traversal launch of the next
+  // render overlaps the tail of this DMA (render_wave waits on the event before its first k_shade).  Asynchronous upload:
+  // the staging job itself moves to the context's thread, which records the event when its last band is enqueued;
+  // render_wave joins it after it has launched the primary traversal.  (A scene staged through a pageable block -- more
+  // than 1 GB of geometry -- keeps this call synchronous: the job's tables live in that block.)
+  auto run_atlas_job = [c, device, atlas_job]() {
+    cudaSetDevice(device);
+    if (atlas_job) atlas_job();
+    cudaError_t e = cudaEventRecord(c->ev_atlas, c->copy_stream);
+    if (e != cudaSuccess) c->atlas_err.store((int)e);
+  };
+  struct StagingGuard {  // an error return below must not leave the staging thread reading the caller's atlas
+    Ctx* c; bool ok = false;
+    ~StagingGuard() { if (!ok && c->atlas_thread.joinable()) c->atlas_thread.join(); }
+  } staging_guard{c};
+  if (async_atlas && pageable_geo.empty()) {
+    c->atlas_thread = std::thread(run_atlas_job);
+    lap("atlas job handed to the staging thread");
+  } else {
+    run_atlas_job();
+    if (int rcj = atlas_join(c)) return rcj;
+    lap("atlas stage + scan + enqueue");
+  }
   geo_thread.join();
   if (geo.code != FSPT_OK) return fail(c, geo.code, "%s", geo.msg);
   lap("join geometry thread");
@@ -1078,7 +1122,7 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
   if ((rc_ = linear_tex(c, &c->nodes_tex, c->d_nodes, nodes_bytes, !getenv("FSPT_NO_NODE_TEX")))) return rc_;
   // no synchronisation: everything the DMA engine still reads lives in the context's pinned staging blocks, which the
   // next upload (and destroy) only touch after synchronising the stream; work enqueued by fspt_render waits in order
-  if (!pageable_geo.empty() || timing) { CK(cudaStreamSynchronize(c->stream)); CK(cudaStreamSynchronize(c->copy_stream)); }
+  if (!pageable_geo.empty() || (timing && !async_atlas)) { CK(cudaStreamSynchronize(c->stream)); CK(cudaStreamSynchronize(c->copy_stream)); }
   lap("env + textures (+ sync when timing)");
   c->sc.nodes = reinterpret_cast<const float4*>(c->d_nodes);
   c->sc.tris = reinterpret_cast<const float4*>(c->d_tris);
@@ -1096,7 +1140,16 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) {
   c->has_scene = true;
   c->scene_bytes = (size_t)N * 36 + (size_t)T * (36 + 48 + 108 + 24) + (size_t)s->atlas_res * s->atlas_res * 4 * s->atlas_layers +
                    (size_t)s->env_width * s->env_height * 4 + (size_t)s->env_bins * 8;
+  staging_guard.ok = true;
   return FSPT_OK;
+}
+
+int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) { return scene_upload_impl(ctx, s, false); }
+int fspt_scene_upload_async(fspt_ctx* ctx, const fspt_scene_desc* s) { return scene_upload_impl(ctx, s, true); }
+int fspt_scene_upload_wait(fspt_ctx* ctx) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  if (!c) return FSPT_E_INVALID;
+  return atlas_join(c);
 }
 
 int fspt_clear(fspt_ctx* ctx) {
@@ -1148,6 +1201,7 @@ int fspt_synchronize(fspt_ctx* ctx) {
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
   if (!c) return FSPT_E_INVALID;
   CK(cudaSetDevice(c->device));
+  if (int rc = atlas_join(c)) return rc;
   CK(cudaStreamSynchronize(c->stream));
   CK(cudaStreamSynchronize(c->copy_stream));
   return FSPT_OK;
@@ -1431,6 +1485,7 @@ int fspt_scene_broadcast(fspt_ctx* ctx, int32_t root) {
   const bool is_root = c->comm_rank == root;
   if (is_root && !c->has_scene) return fail(c, FSPT_E_STATE, "fspt_scene_broadcast: the root has no scene (fspt_scene_upload first)");
   CK(cudaSetDevice(c->device));
+  if (int rcj = atlas_join(c)) return rcj;  // the root's atlas array is read below
   NcclApi* N = nccl_api();
   SceneHeader h;
   memset(&h, 0, sizeof h);

@@ -96,10 +96,14 @@ napi_value Create(napi_env env, napi_callback_info info) {
   return ext;
 }
 
+// sceneUpload(ctx, scene[, 1]): a third argument of 1 selects fspt_scene_upload_async -- the host keeps scene.atlas
+// alive and untouched until sceneUploadWait(ctx) (typed arrays are borrowed, not copied).
 napi_value SceneUpload(napi_env env, napi_callback_info info) {
-  size_t argc = 2;
-  napi_value argv[2];
+  size_t argc = 3;
+  napi_value argv[3];
   NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+  int32_t async_atlas = 0;
+  if (argc > 2) napi_get_value_int32(env, argv[2], &async_atlas);
   fspt_ctx* ctx = Unwrap(env, argv[0]);
   fspt_scene_desc d;
   std::memset(&d, 0, sizeof d);
@@ -124,8 +128,18 @@ napi_value SceneUpload(napi_env env, napi_callback_info info) {
   d.env_height = (int32_t)NumProp(env, argv[1], "envHeight", 0);
   d.env_bins = (int32_t)(nbins / 4);
   d.leaf_size = (int32_t)NumProp(env, argv[1], "leafSize", 4);
-  int rc = fspt_scene_upload(ctx, &d);
+  int rc = async_atlas ? fspt_scene_upload_async(ctx, &d) : fspt_scene_upload(ctx, &d);
   if (rc) return Throw(env, ctx, rc);
+  return nullptr;
+}
+
+napi_value SceneUploadWait(napi_env env, napi_callback_info info) {
+  size_t argc = 1;
+  napi_value argv[1];
+  NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+  fspt_ctx* ctx = Unwrap(env, argv[0]);
+  int r = fspt_scene_upload_wait(ctx);
+  if (r) return Throw(env, ctx, r);
   return nullptr;
 }
 
@@ -305,7 +319,7 @@ napi_value SceneBroadcast(napi_env env, napi_callback_info info) {  // sceneBroa
 
 napi_value Init(napi_env env, napi_value exports) {
   const struct { const char* name; napi_callback fn; } fns[] = {
-      {"create", Create}, {"sceneUpload", SceneUpload}, {"render", Render}, {"clear", Clear},
+      {"create", Create}, {"sceneUpload", SceneUpload}, {"sceneUploadWait", SceneUploadWait}, {"render", Render}, {"clear", Clear},
       {"resolve", Resolve}, {"readAccum", ReadAccum}, {"bvhBuild", BvhBuild},
       {"setTile", SetTile}, {"setAccumMode", SetAccumMode}, {"commUniqueId", CommUniqueId}, {"commInit", CommInit},
       {"reduceAccum", ReduceAccum}, {"sceneBroadcast", SceneBroadcast}};

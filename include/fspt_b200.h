@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define FSPT_ABI_VERSION 2
+#define FSPT_ABI_VERSION 3
 
 enum {
   FSPT_OK = 0,
@@ -105,6 +105,14 @@ const char* fspt_last_error(const fspt_ctx* ctx); /* ctx may be NULL: error of t
 
 /* The texImage2D/3D uploads of initBVH()/initAtlas() (main.js:408-437,548-560,170-180). */
 int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* scene);
+/* The same upload, returning as soon as every buffer EXCEPT scene->atlas has been consumed (texImage3D of the atlas,
+ * main.js:556-559, is by far the largest transfer and only the shading pass reads it): the atlas is staged and DMA'd
+ * by a thread of the context while the caller goes on -- typically into fspt_render, whose camera + primary traversal
+ * launch then overlaps the atlas transfer; the library waits for the staging itself before its first shading launch.
+ * scene->atlas must stay valid and unchanged until fspt_scene_upload_wait (or fspt_synchronize, the next upload, or
+ * fspt_destroy) has returned; errors of the staging are reported by whichever call joins it. */
+int fspt_scene_upload_async(fspt_ctx* ctx, const fspt_scene_desc* scene);
+int fspt_scene_upload_wait(fspt_ctx* ctx);
 
 /* clear() (main.js:826-836): zero the accumulation target, pingpong = 0. */
 int fspt_clear(fspt_ctx* ctx);

@@ -319,3 +319,44 @@ def test_collectives_need_a_communicator(small_bunny):
             assert e.value.code == -3  # FSPT_E_STATE
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("mode", ["cpu", "gpu", "plain"])
+def test_asynchronous_upload_equals_the_synchronous_one(monkeypatch, mode):
+    """fspt_scene_upload_async returns before the atlas has been staged; a render enqueued right behind it starts its
+    primary traversal at once and waits for the staging before its first shading launch.  Same bits as the synchronous
+    upload for every staging path (host interleave, GPU interleave, plain layers), across scene swaps without a render
+    in between, and with the source atlas overwritten as soon as fspt_scene_upload_wait has returned."""
+    if mode == "plain":
+        monkeypatch.setenv("FSPT_PLAIN_ATLAS", "1")
+    else:
+        monkeypatch.setenv("FSPT_ATLAS_INTERLEAVE", mode)
+    sa, cam = scenes.pbr_scene(atlas_res=256, subdiv=2, env_size=(128, 64))
+    sb, _ = scenes.pbr_scene(atlas_res=64, subdiv=2, env_size=(128, 64))
+    W, H = 96, 64
+    rc, rt = scenes.rand_bases(3, 31)
+    ctx = capi.Context(W, H)
+    try:
+        ctx.scene_upload(sa)
+        fr = _frame(ctx, cam)
+        ctx.render(fr, 0, rc, rt)
+        ref = ctx.read_accum().copy()
+        assert float(ref[..., :3].max()) > 0.0
+        for _ in range(3):
+            ctx.scene_upload(sb, wait=False)       # replaced before anything used it: the next upload joins the staging
+            ctx.scene_upload(sa, wait=False)
+            ctx.clear()
+            ctx.render(fr, 0, rc, rt)              # joins the staging thread behind the primary traversal launch
+            assert np.array_equal(ref.view(np.uint32), ctx.read_accum().view(np.uint32))
+        # the borrow ends at upload_wait: scribbling over a COPY of the atlas afterwards must not reach the device
+        import copy
+        sc = copy.copy(sa)
+        sc.atlas = np.array(sa.atlas, copy=True)
+        ctx.scene_upload(sc, wait=False)
+        ctx.upload_wait()
+        sc.atlas[...] = 0
+        ctx.clear()
+        ctx.render(fr, 0, rc, rt)
+        assert np.array_equal(ref.view(np.uint32), ctx.read_accum().view(np.uint32))
+    finally:
+        ctx.close()

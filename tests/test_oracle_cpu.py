@@ -282,7 +282,7 @@ def test_c_abi_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert sorted(declared) == sorted(capi.EXPORTS)
-    assert lib.fspt_abi_version() == 2
+    assert lib.fspt_abi_version() == 3
 
 
 def test_no_silent_cpu_fallback():

@@ -1,4 +1,5 @@
-"""Per-step wall time of the e2e leg (upload + clear + render + resolve), with and without torch in the process."""
+"""Per-step wall time of the e2e leg (upload + clear + render + resolve), with and without torch in the process;
+--async: fspt_scene_upload_async (the atlas transfer overlaps the primary traversal)."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -17,7 +18,7 @@ out8 = np.empty((720, 1280, 4), np.uint8)
 ts = []
 for i in range(24):
     t0 = time.perf_counter()
-    pt.ctx.scene_upload(sa)
+    pt.ctx.scene_upload(sa, wait="--async" not in sys.argv)
     t1 = time.perf_counter()
     pt.clear(); pt.ctx.render(pt._frame(), 0, rc, rt); pt.stats()
     t2 = time.perf_counter()
