@@ -17,6 +17,7 @@
 #include <atomic>
 #include <map>
 #include <chrono>
+#include <condition_variable>
 #include <functional>
 #include <mutex>
 #include <thread>
@@ -25,6 +26,7 @@
 
 #include "../../include/fspt_b200.h"
 #include "device_common.cuh"
+#include "host_pool.h"
 #include "shade.cuh"
 #include "traverse.cuh"
 
@@ -63,11 +65,17 @@ struct Ctx {
   uint8_t* h_stage = nullptr;                               // pinned staging for the atlas (one slot per layer)
   cudaStream_t copy_stream = nullptr;                       // atlas DMA, overlaps the primary traversal
   cudaEvent_t ev_atlas = nullptr;
-  // fspt_scene_upload_async: the atlas is staged (host interleave into pinned memory + band-wise DMA) by this thread
-  // after the call has returned; joined before the first shading launch and by everything that touches scene state
+  // fspt_scene_upload_async: the atlas part of the upload (constant-layer scan, host interleave into pinned memory,
+  // band-wise DMA) runs on this thread after the call has returned; joined before the first shading launch and by
+  // everything that touches scene state
   std::thread atlas_thread;
-  std::atomic<int> atlas_err{0};  // first cudaError_t of a staging item (atlas_mu serialises the enqueues)
-  std::mutex atlas_mu;
+  std::atomic<uint64_t> atlas_launches{0};  // kernels launched by the atlas part (folded into stats.kernel_launches)
+  int atlas_rc = 0;            // outcome of the atlas part (written by the atlas thread, read after joining it)
+  std::string atlas_error;
+  HostPool* pool = nullptr;    // host workers of fspt_scene_upload (created at the first upload)
+  uint8_t* h_ring = nullptr;   // pinned ring the geometry records are staged through, chunk by chunk
+  size_t ring_bytes = 0;
+  std::vector<cudaEvent_t> ev_ring;  // per ring slot: the copies that read it have completed
   uint8_t* h_geo = nullptr;                                 // pinned staging for geometry records, bins, env
   size_t geo_stage_bytes = 0;
   size_t stage_bytes = 0;
@@ -218,27 +226,6 @@ int alloc_wave(Ctx* c) {
   return FSPT_OK;
 }
 
-// n_items work items handed to at most max_workers host threads (each bound to `device`)
-void parallel_for(int device, int n_items, int max_workers, const std::function<void(int)>& fn) {
-  std::atomic<int> next_item(0);
-  const int n_workers = std::max(1, std::min(n_items, max_workers));
-  std::vector<std::thread> workers;
-  for (int w = 0; w < n_workers; ++w)
-    workers.emplace_back([&]() {
-      cudaSetDevice(device);
-      for (;;) { const int i = next_item.fetch_add(1); if (i >= n_items) break; fn(i); }
-    });
-  for (auto& t : workers) t.join();
-}
-
-// Waits for the atlas staging of the last fspt_scene_upload_async (no-op otherwise) and reports its outcome.
-int atlas_join(Ctx* c) {
-  if (c->atlas_thread.joinable()) c->atlas_thread.join();
-  const int e = c->atlas_err.exchange(0);
-  if (e) { c->has_scene = false; return fail(c, FSPT_E_CUDA, "atlas upload failed: %s", cudaGetErrorString((cudaError_t)e)); }
-  return FSPT_OK;
-}
-
 // ---- traversal launch helpers ---------------------------------------------------------------------------
 void record_trace_begin(Ctx* c, int tag = 0) {
   if (c->ev_trace_used + 2 > c->ev_trace.size()) {
@@ -272,6 +259,314 @@ __global__ void __launch_bounds__(256) k_interleave_atlas(cudaSurfaceObject_t su
 
 __global__ void k_set_counts(int* counts, int n_cont, int n_shadow) {
   counts[0] = n_cont; counts[1] = n_shadow; counts[2] = 0; counts[3] = 0; counts[32] = 0;
+}
+
+// Waits for the atlas part of the last fspt_scene_upload_async (no-op otherwise) and reports its outcome.
+int atlas_join(Ctx* c) {
+  if (c->atlas_thread.joinable()) c->atlas_thread.join();
+  const int rc = c->atlas_rc;
+  c->atlas_rc = FSPT_OK;
+  if (rc) { c->has_scene = false; c->error = c->atlas_error; }
+  return rc;
+}
+
+// ---- the atlas part of a scene upload (main.js:548-560) ------------------------------------------------------
+// Constant-colour layers are detected (exact: every texel compared), then the atlas is re-interleaved per material into
+// 16-byte texels (device_common.cuh "MatTexel") in pinned memory by the host workers and DMA'd band by band as the bands
+// land; a scene with so many layer combinations that this would not fit falls back to the plain RGBA8 layered array.
+// Everything travels on the copy stream and ends with ev_atlas: only k_shade reads what this function uploads, so a
+// render's camera + primary traversal launch overlaps it.  Runs inline (fspt_scene_upload) or on the context's atlas
+// thread (fspt_scene_upload_async); every input is held by value or lives in the context's pinned blocks.
+struct AtlasJob {
+  const uint8_t* atlas;                     // caller's layers, RGBA8, L x R x R
+  int L, R;
+  std::vector<std::array<int, 4>> mats;     // distinct layer quadruples (diffuse, emission, metallic-roughness, normal)
+  uint32_t* layer_info;                     // pinned: per layer {constant?, first texel}
+  int32_t* mat_info;                        // pinned: per material 2 x int4
+  size_t n_mat_info;                        // ints
+  MatSrc* mat_src;                          // pinned: per textured material (GPU-side interleave)
+  std::vector<uint8_t> varied;               // per layer: 1 = not a constant colour (scanned next to the geometry staging)
+  int workers;
+  bool timing;
+};
+
+// constant-colour layers: constant <=> every texel equals its successor (exact: every texel compared); work item =
+// (layer, band), abandoned once the layer is known to vary
+constexpr int SCAN_BANDS = 8;
+inline void scan_layer_band(const uint8_t* atlas, size_t layer_texels, int item, std::atomic<int>* varied) {
+  const int l = item / SCAN_BANDS, band = item % SCAN_BANDS;
+  if (varied[l].load(std::memory_order_relaxed)) return;
+  const uint32_t* px = reinterpret_cast<const uint32_t*>(atlas) + (size_t)l * layer_texels;
+  const size_t i0 = layer_texels * band / SCAN_BANDS, i1 = std::min(layer_texels - 1, layer_texels * (band + 1) / SCAN_BANDS);
+  for (size_t i = i0; i < i1;) {
+    const size_t n = std::min<size_t>(i1 - i, 16384);
+    if (memcmp(px + i, px + i + 1, n * 4) != 0) { varied[l].store(1, std::memory_order_relaxed); return; }
+    i += n;
+  }
+}
+
+int stage_atlas(Ctx* c, const AtlasJob& J) {
+  auto afail = [&](int code, const char* what, cudaError_t e) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "atlas upload: %s failed: %s", what, cudaGetErrorString(e));
+    c->atlas_error = buf;
+    return code;
+  };
+#define ACK(call)                                                         \
+  do {                                                                    \
+    cudaError_t e_ = (call);                                              \
+    if (e_ != cudaSuccess) return afail(FSPT_E_CUDA, #call, e_);          \
+  } while (0)
+  auto t_prev = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!J.timing) return;
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[fspt upload]   atlas: %-24s %7.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+    t_prev = now;
+  };
+  const int L = J.L, R = J.R;
+  const size_t layer_texels = (size_t)R * R, layer_bytes = layer_texels * 4;
+  const std::vector<std::array<int, 4>>& mats = J.mats;
+  uint32_t* layer_info = J.layer_info;
+  int32_t* mat_info = J.mat_info;
+  HostPool& pool = *c->pool;
+  for (int l = 0; l < L; ++l) {
+    layer_info[2 * l] = J.varied[l] ? 0u : 1u;
+    memcpy(&layer_info[2 * l + 1], J.atlas + (size_t)l * layer_bytes, 4);
+  }
+  memset(mat_info, 0, J.n_mat_info * 4);
+  int n_tex_mats = 0;
+  for (size_t m = 0; m < mats.size(); ++m) {
+    bool all_const = true;
+    for (int k = 0; k < 4; ++k) all_const = all_const && layer_info[2 * mats[m][k]];
+    mat_info[8 * m] = all_const ? -1 : n_tex_mats++;
+    for (int k = 0; k < 4; ++k) mat_info[8 * m + 1 + k] = (int32_t)layer_info[2 * mats[m][k] + 1];
+  }
+  // The interleaved atlas costs res^2 * 16 bytes per TEXTURED MATERIAL (distinct layer quadruple) and the same again in
+  // pinned staging; quadruples can outnumber layers, so it is bounded against the plain atlas (4 x its bytes, at least
+  // 256 MB) and against the free device memory, and any allocation failure falls back to the plain RGBA8 array.
+  bool use_mat_tex = !getenv("FSPT_PLAIN_ATLAS");
+  {
+    const size_t inter = (size_t)n_tex_mats * layer_texels * 16, plain = (size_t)L * layer_bytes;
+    // the array of the previous upload is reused when it has the same shape: then nothing is allocated and the driver is
+    // not asked for the free memory (cudaMemGetInfo is a resource-manager call: usually 0.1 ms, but 20-100 ms every few
+    // dozen calls on the virtualised hosts measured, which showed up as spikes in the end-to-end step time)
+    const bool reuse = c->mat_arr && c->mat_R == R && c->mat_L == std::max(1, n_tex_mats);
+    size_t free_b = (size_t)48 << 30, total_b = 0;
+    if (!reuse && cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { (void)cudaGetLastError(); free_b = (size_t)48 << 30; }
+    const size_t resident = c->mat_arr ? (size_t)c->mat_R * c->mat_R * 16 * (size_t)c->mat_L : 0;  // freed before the new one
+    if (inter > std::max<size_t>(4 * plain, (size_t)256 << 20) || inter > ((size_t)48 << 30) ||
+        (!reuse && inter > (free_b + resident) / 2))
+      use_mat_tex = false;
+    if (getenv("FSPT_FORCE_MAT_TEX")) use_mat_tex = true;  // test knob: exercise the allocation-failure fallback
+  }
+  lap("tables + sizing");
+  cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
+  cudaResourceDesc rd = {};
+  rd.resType = cudaResourceTypeArray;
+  cudaTextureDesc td = {};
+  td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+  td.filterMode = cudaFilterModePoint;
+  td.readMode = cudaReadModeElementType;
+  td.normalizedCoords = 0;
+  std::atomic<int> cuda_err(0);
+  std::mutex mu;  // serialises the enqueues of the staging items
+  bool plain_atlas = !use_mat_tex;
+  if (use_mat_tex) {
+    if (c->sc.atlas) { cudaDestroyTextureObject(c->sc.atlas); c->sc.atlas = 0; }
+    if (c->atlas_arr) { cudaFreeArray(c->atlas_arr); c->atlas_arr = nullptr; c->atlas_R = c->atlas_L = 0; }
+    const int ML = std::max(1, n_tex_mats);
+    // Where the interleave runs.  On the host (default): the 16-byte texels are built in pinned memory and DMA'd.  On the
+    // GPU: only the DISTINCT varying layers cross PCIe as raw RGBA8 and k_interleave_atlas builds the texels through a
+    // surface -- a material with one image map and three colours then costs 1 layer of staging and DMA instead of 4.
+    // Measured break-even (bench scene, 7 varying layers behind 2 materials: GPU path 20 % slower): chosen when the raw
+    // layers are at most half of the interleaved bytes.  FSPT_ATLAS_INTERLEAVE=gpu|cpu overrides.
+    std::vector<int> raw_of((size_t)L, -1), raw_layers;
+    MatSrc* mat_src = J.mat_src;
+    for (size_t m = 0; m < mats.size(); ++m) {
+      const int tl = mat_info[8 * m];
+      if (tl < 0) continue;
+      for (int k = 0; k < 4; ++k) {
+        const int l = mats[m][k];
+        if (!layer_info[2 * l] && raw_of[l] < 0) { raw_of[l] = (int)raw_layers.size(); raw_layers.push_back(l); }
+        mat_src[tl].raw[k] = layer_info[2 * l] ? -1 : raw_of[l];
+        mat_src[tl].cst[k] = layer_info[2 * l + 1];
+      }
+    }
+    bool gpu_interleave = n_tex_mats > 0 && raw_layers.size() * 2 <= (size_t)n_tex_mats * 4;
+    if (const char* e = getenv("FSPT_ATLAS_INTERLEAVE")) gpu_interleave = n_tex_mats > 0 && !strcmp(e, "gpu");
+    if (!c->mat_arr || c->mat_R != R || c->mat_L != ML || c->mat_surface != gpu_interleave) {
+      if (c->sc.mat_tex) cudaDestroyTextureObject(c->sc.mat_tex);
+      c->sc.mat_tex = 0;
+      if (c->mat_surf) cudaDestroySurfaceObject(c->mat_surf);
+      c->mat_surf = 0;
+      if (c->mat_arr) cudaFreeArray(c->mat_arr);
+      c->mat_arr = nullptr;
+      cudaChannelFormatDesc fmt4 = cudaCreateChannelDesc<uint4>();
+      c->mat_R = c->mat_L = 0;
+      const size_t max_ml = getenv("FSPT_FORCE_MAT_TEX") ? (size_t)atoi(getenv("FSPT_FORCE_MAT_TEX")) : (size_t)1 << 30;
+      if ((size_t)ML > max_ml ||  // (test knob: pretend the device cannot hold more than that many material layers)
+          cudaMalloc3DArray(&c->mat_arr, &fmt4, make_cudaExtent(R, R, ML),
+                            cudaArrayLayered | (gpu_interleave ? cudaArraySurfaceLoadStore : 0)) != cudaSuccess) {
+        (void)cudaGetLastError();
+        c->mat_arr = nullptr;
+        plain_atlas = true;
+      } else {
+        rd.res.array.array = c->mat_arr;
+        ACK(cudaCreateTextureObject(&c->sc.mat_tex, &rd, &td, nullptr));
+        if (gpu_interleave) ACK(cudaCreateSurfaceObject(&c->mat_surf, &rd));
+        c->mat_R = R; c->mat_L = ML; c->mat_surface = gpu_interleave;
+      }
+    }
+    const size_t need = gpu_interleave ? layer_bytes * raw_layers.size() : layer_texels * 16 * (size_t)ML;
+    if (!plain_atlas && c->stage_bytes < need) {
+      if (c->h_stage) cudaFreeHost(c->h_stage);
+      c->h_stage = nullptr; c->stage_bytes = 0;
+      if (cudaMallocHost(&c->h_stage, need) != cudaSuccess) {
+        (void)cudaGetLastError();
+        c->h_stage = nullptr;
+        plain_atlas = true;
+      } else {
+        c->stage_bytes = need;
+      }
+    }
+    lap("arrays + pinned block");
+    if (plain_atlas) {
+      // could not hold the interleaved atlas: every material becomes "plain" (the tables are not consulted by k_shade<false>)
+    } else if (gpu_interleave) {
+      if (!(c->d_raw && c->cap_raw >= need)) {
+        if (c->d_raw) cudaFree(c->d_raw);
+        c->d_raw = nullptr; c->cap_raw = 0;
+        ACK(cudaMalloc(&c->d_raw, need));
+        c->cap_raw = need;
+      }
+      if (!(c->d_mat_src && c->cap_mat_src >= sizeof(MatSrc) * (size_t)ML)) {
+        if (c->d_mat_src) cudaFree(c->d_mat_src);
+        c->d_mat_src = nullptr; c->cap_mat_src = 0;
+        ACK(cudaMalloc(&c->d_mat_src, sizeof(MatSrc) * (size_t)ML));
+        c->cap_mat_src = sizeof(MatSrc) * (size_t)ML;
+      }
+      // work item = (raw layer, band of rows): copy into the pinned block, DMA the band
+      const int bands = std::max(1, std::min(R, 16));
+      pool.run((int)raw_layers.size() * bands, J.workers, [&](int item) {
+        const int ri = item / bands, band = item % bands;
+        const size_t y0 = (size_t)R * band / bands, y1 = (size_t)R * (band + 1) / bands;
+        const size_t off = (size_t)ri * layer_bytes + y0 * R * 4, bytes = (y1 - y0) * R * 4;
+        memcpy(c->h_stage + off, J.atlas + (size_t)raw_layers[ri] * layer_bytes + y0 * R * 4, bytes);
+        std::lock_guard<std::mutex> g(mu);
+        cudaError_t e = cudaMemcpyAsync(reinterpret_cast<uint8_t*>(c->d_raw) + off, c->h_stage + off, bytes, cudaMemcpyHostToDevice, c->copy_stream);
+        if (e != cudaSuccess) cuda_err.store((int)e);
+      });
+      ACK(cudaMemcpyAsync(c->d_mat_src, mat_src, sizeof(MatSrc) * (size_t)n_tex_mats, cudaMemcpyHostToDevice, c->copy_stream));
+      const dim3 blk(32, 8), grd((R + 31) / 32, (R + 7) / 8, n_tex_mats);
+      k_interleave_atlas<<<grd, blk, 0, c->copy_stream>>>(c->mat_surf, reinterpret_cast<const uint32_t*>(c->d_raw),
+                                                          reinterpret_cast<const MatSrc*>(c->d_mat_src), R, layer_texels);
+      c->atlas_launches.fetch_add(1);
+      ACK(cudaGetLastError());
+    } else {
+      // work item = (textured material, band of rows): interleave the four source layers, DMA the band
+      const int bands = std::max(1, std::min(R, 16));
+      std::vector<int> tex_mat_ids;
+      for (size_t m = 0; m < mats.size(); ++m) if (mat_info[8 * m] >= 0) tex_mat_ids.push_back((int)m);
+      pool.run((int)tex_mat_ids.size() * bands, J.workers, [&](int item) {
+        const int m = tex_mat_ids[item / bands], band = item % bands;
+        const int tl = mat_info[8 * m];
+        const int y0 = (int)((long long)R * band / bands), y1 = (int)((long long)R * (band + 1) / bands);
+        const uint32_t* src[4];
+        for (int k = 0; k < 4; ++k) src[k] = reinterpret_cast<const uint32_t*>(J.atlas) + (size_t)mats[m][k] * layer_texels;
+        uint32_t* dst = reinterpret_cast<uint32_t*>(c->h_stage) + ((size_t)tl * layer_texels + (size_t)y0 * R) * 4;
+        const size_t i0 = (size_t)y0 * R, n = (size_t)(y1 - y0) * R;
+        size_t i = 0;
+#if defined(__SSE2__)
+        // 4x4 transpose of 32-bit texels, written with non-temporal stores: the staging block is only read by the DMA
+        // engine, so it should neither be fetched for ownership nor displace the source layers from the CPU caches
+        for (; i + 4 <= n; i += 4) {
+          const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src[0] + i0 + i));
+          const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src[1] + i0 + i));
+          const __m128i c2 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src[2] + i0 + i));
+          const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src[3] + i0 + i));
+          const __m128i ab_lo = _mm_unpacklo_epi32(a, b), ab_hi = _mm_unpackhi_epi32(a, b);
+          const __m128i cd_lo = _mm_unpacklo_epi32(c2, d), cd_hi = _mm_unpackhi_epi32(c2, d);
+          __m128i* o = reinterpret_cast<__m128i*>(dst + 4 * i);  // 16-byte aligned: pinned block + multiples of 16
+          _mm_stream_si128(o + 0, _mm_unpacklo_epi64(ab_lo, cd_lo));
+          _mm_stream_si128(o + 1, _mm_unpackhi_epi64(ab_lo, cd_lo));
+          _mm_stream_si128(o + 2, _mm_unpacklo_epi64(ab_hi, cd_hi));
+          _mm_stream_si128(o + 3, _mm_unpackhi_epi64(ab_hi, cd_hi));
+        }
+        _mm_sfence();
+#endif
+        for (; i < n; ++i) {
+          dst[4 * i + 0] = src[0][i0 + i]; dst[4 * i + 1] = src[1][i0 + i];
+          dst[4 * i + 2] = src[2][i0 + i]; dst[4 * i + 3] = src[3][i0 + i];
+        }
+        cudaMemcpy3DParms cp = {};
+        cp.srcPtr = make_cudaPitchedPtr(dst, (size_t)R * 16, R, y1 - y0);
+        cp.dstArray = c->mat_arr;
+        cp.dstPos = make_cudaPos(0, y0, tl);
+        cp.extent = make_cudaExtent(R, y1 - y0, 1);
+        cp.kind = cudaMemcpyHostToDevice;
+        std::lock_guard<std::mutex> g(mu);
+        cudaError_t e = cudaMemcpy3DAsync(&cp, c->copy_stream);
+        if (e != cudaSuccess) cuda_err.store((int)e);
+      });
+    }
+  }
+  if (plain_atlas) {
+    if (c->sc.mat_tex) { cudaDestroyTextureObject(c->sc.mat_tex); c->sc.mat_tex = 0; }
+    if (c->mat_surf) { cudaDestroySurfaceObject(c->mat_surf); c->mat_surf = 0; }
+    c->mat_surface = false;
+    if (c->mat_arr) { cudaFreeArray(c->mat_arr); c->mat_arr = nullptr; c->mat_R = c->mat_L = 0; }
+    if (!c->atlas_arr || c->atlas_R != R || c->atlas_L != L) {
+      if (c->sc.atlas) cudaDestroyTextureObject(c->sc.atlas);
+      c->sc.atlas = 0;
+      if (c->atlas_arr) cudaFreeArray(c->atlas_arr);
+      c->atlas_arr = nullptr;
+      ACK(cudaMalloc3DArray(&c->atlas_arr, &fmt, make_cudaExtent(R, R, L), cudaArrayLayered));
+      rd.res.array.array = c->atlas_arr;
+      ACK(cudaCreateTextureObject(&c->sc.atlas, &rd, &td, nullptr));
+      c->atlas_R = R; c->atlas_L = L;
+    }
+    if (c->stage_bytes < layer_bytes * L) {
+      if (c->h_stage) cudaFreeHost(c->h_stage);
+      c->h_stage = nullptr; c->stage_bytes = 0;
+      ACK(cudaMallocHost(&c->h_stage, layer_bytes * L));
+      c->stage_bytes = layer_bytes * L;
+    }
+    pool.run(L, J.workers, [&](int l) {
+      uint8_t* dst = c->h_stage + (size_t)l * layer_bytes;
+      memcpy(dst, J.atlas + (size_t)l * layer_bytes, layer_bytes);
+      cudaMemcpy3DParms cp = {};
+      cp.srcPtr = make_cudaPitchedPtr(dst, (size_t)R * 4, R, R);
+      cp.dstArray = c->atlas_arr;
+      cp.dstPos = make_cudaPos(0, 0, l);
+      cp.extent = make_cudaExtent(R, R, 1);
+      cp.kind = cudaMemcpyHostToDevice;
+      std::lock_guard<std::mutex> g(mu);
+      cudaError_t e = cudaMemcpy3DAsync(&cp, c->copy_stream);
+      if (e != cudaSuccess) cuda_err.store((int)e);
+    });
+  }
+  if (cuda_err.load()) return afail(FSPT_E_CUDA, "a staging copy", (cudaError_t)cuda_err.load());
+  lap("stage + enqueue");
+  // the two small tables k_shade reads next to the texels: same stream, so the same event covers them
+  auto grow = [&](void*& p, size_t& cap, size_t bytes) -> cudaError_t {
+    if (p && cap >= bytes) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  };
+  ACK(grow(c->d_layer_info, c->cap_layer_info, (size_t)L * 8));
+  ACK(grow(c->d_mat_info, c->cap_mat_info, J.n_mat_info * 4));
+  ACK(cudaMemcpyAsync(c->d_layer_info, layer_info, (size_t)L * 8, cudaMemcpyHostToDevice, c->copy_stream));
+  ACK(cudaMemcpyAsync(c->d_mat_info, mat_info, J.n_mat_info * 4, cudaMemcpyHostToDevice, c->copy_stream));
+  c->sc.layer_info = reinterpret_cast<const uint2*>(c->d_layer_info);
+  c->sc.mat_info = reinterpret_cast<const int4*>(c->d_mat_info);
+  c->bytes_layer_info = (size_t)L * 8; c->bytes_mat_info = J.n_mat_info * 4;
+  ACK(cudaEventRecord(c->ev_atlas, c->copy_stream));
+  return FSPT_OK;
+#undef ACK
 }
 
 // A device array of 16-byte words as a linear texture (tex1Dfetch): the second L1 data path next to the LSU.  Arrays
@@ -382,7 +677,7 @@ int render_wave(Ctx* c, const FrameParams& fp, uint32_t first_tick, int S, const
   rc = launch_trace(c, 0, true, false, &fp, rb_cam, S);  // camera.fs + primary rays (tracer.fs:440), fused
   if (rc) return rc;
   ShadeArgs A;
-  A.sc = c->sc; A.f = fp;
+  A.f = fp;
   A.rb_trace = rb_trace;
   A.hit_flag = c->d_hit_flag;
   A.shadow_rays_out = c->d_shadow;
@@ -396,6 +691,7 @@ int render_wave(Ctx* c, const FrameParams& fp, uint32_t first_tick, int S, const
   // running on the GPU (the event it records has to exist before the stream can be made to wait on it); then the DMA
   // itself is waited for on the device (no-op once it has completed)
   if ((rc = atlas_join(c))) return rc;
+  A.sc = c->sc;  // (the atlas part sets the texture objects and table pointers)
   CK(cudaStreamWaitEvent(c->stream, c->ev_atlas, 0));
   int cur = 0;
   for (int b = 0; b < hard_cap; ++b) {
@@ -593,6 +889,10 @@ void fspt_destroy(fspt_ctx* ctx) {
   if (c->atlas_thread.joinable()) c->atlas_thread.join();
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+  delete c->pool;
+  c->pool = nullptr;
+  if (c->h_ring) cudaFreeHost(c->h_ring);
+  for (auto e : c->ev_ring) cudaEventDestroy(e);
   free_scene(c);
   dfree(c->d_fb); dfree(c->d_last_color); dfree(c->d_sample_color); dfree(c->d_cam_pos); dfree(c->d_cam_dir); dfree(c->d_rgba8);
   dfree(c->ps2[0].rec); dfree(c->ps2[1].rec);
@@ -615,9 +915,16 @@ void fspt_destroy(fspt_ctx* ctx) {
   delete c;
 }
 
-// fspt_scene_upload / fspt_scene_upload_async.  async_atlas: the atlas staging (the largest part: interleave into pinned
-// memory + DMA) continues on a thread of the context after the function has returned; everything else -- every geometry
-// buffer, the environment, the tables -- has been consumed by then.
+// fspt_scene_upload / fspt_scene_upload_async.
+// Order of work (round 2, second half: the geometry used to be staged next to the atlas by a quarter of the host
+// threads and DMA'd only when all of it was ready, which put ~3 ms between the call and the first traversal launch):
+//   1. pre-passes over nodes and triangles (parallel): interior-record numbering, material ids;
+//   2. geometry records (Node64 / Tri48 / ShadeRec), bins and environment: built chunk by chunk by ALL host workers into
+//      a ring of pinned slots, every chunk DMA'd the moment it is complete -- the traversal kernel's inputs are on
+//      their way before anything else is touched, and a 10 M-triangle scene (2.6 GB of records) streams through
+//      256 MB of pinned memory instead of a pageable copy;
+//   3. the atlas part (stage_atlas): inline, or -- async_atlas -- on the context's atlas thread after this function has
+//      returned; every other buffer of the scene has been consumed by then.
 static int scene_upload_impl(fspt_ctx* ctx, const fspt_scene_desc* s, bool async_atlas) {
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
   const bool timing = getenv("FSPT_TIMING") != nullptr;
@@ -636,164 +943,264 @@ static int scene_upload_impl(fspt_ctx* ctx, const fspt_scene_desc* s, bool async
     return fail(c, FSPT_E_INVALID, "scene_upload: non-positive size (an environment with >= 1 bin is mandatory, main.js:303-308)");
   if (s->leaf_size != 4) return fail(c, FSPT_E_INVALID, "scene_upload: LEAF_SIZE must be 4 (main.js:45), got %d", s->leaf_size);
   CK(cudaSetDevice(c->device));
-  (void)atlas_join(c);  // a staging thread of the previous upload still reads the pinned block and the arrays
+  (void)atlas_join(c);  // the atlas thread of the previous upload still reads the pinned blocks and the arrays
   CK(cudaStreamSynchronize(c->stream));
   CK(cudaStreamSynchronize(c->copy_stream));
   c->has_scene = false;  // device buffers, arrays and texture objects of the previous scene are reused when they fit
   lap("sync");
   const int N = s->n_nodes, T = s->n_triangles;
-  const int R = s->atlas_res, L = s->atlas_layers;
-  const size_t layer_texels = (size_t)R * R, layer_bytes = layer_texels * 4;
+  const int L = s->atlas_layers;
   // host threads for staging: all cores of a single-process host; one process per GPU shares them
   // (dist.share_host_threads sets FSPT_UPLOAD_THREADS = cores / processes on this node)
   int hw = (int)std::max(4u, std::min(32u, std::thread::hardware_concurrency()));
   if (const char* e = getenv("FSPT_UPLOAD_THREADS")) hw = std::max(4, std::min(64, atoi(e)));
-  const int device = c->device;
-  auto parallel = [&](int n_items, int max_workers, const std::function<void(int)>& fn) { parallel_for(device, n_items, max_workers, fn); };
-  struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } };
-  // ---- constant-colour layers (exact: every texel compared), scanned in the background while the pre-passes run.
-  // constant <=> every texel equals its successor; work item = (layer, band), abandoned once the layer is known varied
-  const int atlas_workers = std::max(2, hw - hw / 4);
-  std::vector<std::atomic<int>> varied((size_t)L);
-  for (auto& v : varied) v.store(0);
-  std::thread scan_thread([&]() {
-    const int bands = 8;
-    parallel(L * bands, atlas_workers, [&](int item) {
-      const int l = item / bands, band = item % bands;
-      if (varied[l].load(std::memory_order_relaxed)) return;
-      const uint32_t* px = reinterpret_cast<const uint32_t*>(s->atlas) + (size_t)l * layer_texels;
-      const size_t i0 = layer_texels * band / bands, i1 = std::min(layer_texels - 1, layer_texels * (band + 1) / bands);
-      for (size_t i = i0; i < i1;) {
-        const size_t n = std::min<size_t>(i1 - i, 16384);
-        if (memcmp(px + i, px + i + 1, n * 4) != 0) { varied[l].store(1, std::memory_order_relaxed); return; }
-        i += n;
-      }
-    });
-  });
-  Joiner scan_join{scan_thread};
-  // ---- serial pre-pass over the nodes (own thread): reference node i = [left,right,triIndex | min | max] -> child references
-  std::vector<int32_t> ref((size_t)N);   // child reference of node i
-  std::vector<int32_t> interior_of;      // reference node index of interior record k
+  if (!c->pool) { const int device = c->device; c->pool = new HostPool([device]() { cudaSetDevice(device); }); }
+  HostPool& pool = *c->pool;
   auto ibits = [&](int node, int k) { int32_t v; memcpy(&v, s->bvh + (size_t)node * 9 + k, 4); return v; };
-  int bad_node = -1, bad_tri = 0;
-  std::thread node_thread([&]() {
-    interior_of.reserve((size_t)N / 2 + 1);
-    for (int i = 0; i < N; ++i) {
-      const int32_t tri = ibits(i, 2);
-      if (tri > -1) {  // `current.triangles > -1`, tracer.fs:379
-        if (tri >= T) { bad_node = i; bad_tri = tri; return; }
-        ref[i] = ~tri;
-      } else {
-        ref[i] = (int32_t)interior_of.size();
-        interior_of.push_back(i);
-      }
-    }
-  });
-  Joiner node_join{node_thread};
-  // ---- serial pre-pass over the triangles: materials = distinct quadruples of atlas layers (diffuse, emission,
-  // metallic-roughness, normal), tracer.fs:453-456
+
+  // ---- pre-passes, two parallel regions around a short serial step.
+  // Nodes: reference node i = [left, right, triIndex | min | max] -> child references; interior nodes are numbered in
+  // node order (count per chunk, prefix sum over the chunks, assign).
+  // Triangles: materials = distinct quadruples of atlas layers (diffuse, emission, metallic-roughness, normal),
+  // tracer.fs:453-456, numbered in order of first appearance (local numbering per chunk, serial merge of the few keys,
+  // then the chunks rewrite their ids if the merge changed any).
+  std::vector<int32_t> ref((size_t)N);   // child reference of node i: >= 0 interior record, < 0 ~first triangle
+  std::vector<int32_t> interior_of;      // reference node index of interior record k
   std::vector<int32_t> mat_id((size_t)T);
   std::vector<std::array<int, 4>> mats;
   bool dielectric = false;
-  {
+  const int PRE_CHUNK = 8192;
+  const int n_nchunks = (N + PRE_CHUNK - 1) / PRE_CHUNK, n_tchunks = (T + PRE_CHUNK - 1) / PRE_CHUNK;
+  std::vector<int> chunk_interiors((size_t)n_nchunks + 1, 0);
+  std::atomic<int> bad_node(-1);
+  std::vector<std::vector<std::array<int, 4>>> local_keys((size_t)n_tchunks);
+  std::vector<int> local_diel((size_t)n_tchunks, 0);
+  auto layer_of = [&](float lf) {  // texture(texArray, vec3(uv, layer)): layer = clamp(floor(l + 0.5), 0, d - 1)
+    float f = floorf(lf + 0.5f);
+    if (!(f >= -1.0e9f && f <= 1.0e9f)) f = 0.0f;
+    long long q = (long long)f;
+    return (int)(q < 0 ? 0 : (q >= s->atlas_layers ? s->atlas_layers - 1 : q));
+  };
+  pool.run(n_nchunks + n_tchunks, hw, [&](int item) {
+    if (item < n_nchunks) {
+      const int ch = item, i1 = std::min(N, (ch + 1) * PRE_CHUNK);
+      int n_int = 0;
+      for (int i = ch * PRE_CHUNK; i < i1; ++i) {
+        const int32_t tri = ibits(i, 2);
+        if (tri > -1) {  // `current.triangles > -1`, tracer.fs:379
+          if (tri >= T) { int exp = -1; bad_node.compare_exchange_strong(exp, i); }
+        } else {
+          ++n_int;
+        }
+      }
+      chunk_interiors[ch + 1] = n_int;
+      return;
+    }
+    const int ch = item - n_nchunks, t0 = ch * PRE_CHUNK, t1 = std::min(T, (ch + 1) * PRE_CHUNK);
     std::map<std::array<int, 4>, int> ids;
+    std::vector<std::array<int, 4>>& keys = local_keys[ch];
     std::array<int, 4> last = {-1, -1, -1, -1};
-    int last_id = -1;
-    auto layer_of = [&](float lf) {  // texture(texArray, vec3(uv, layer)): layer = clamp(floor(l + 0.5), 0, d - 1)
-      float f = floorf(lf + 0.5f);
-      if (!(f >= -1.0e9f && f <= 1.0e9f)) f = 0.0f;
-      long long q = (long long)f;
-      return (int)(q < 0 ? 0 : (q >= s->atlas_layers ? s->atlas_layers - 1 : q));
-    };
-    for (int t = 0; t < T; ++t) {
+    int last_id = -1, diel = 0;
+    for (int t = t0; t < t1; ++t) {
       const float* o = s->materials + (size_t)t * 12;
-      if (o[10] >= 0.0f) dielectric = true;
-      if (t > 0 && memcmp(o, o - 12, 16) == 0) { mat_id[t] = last_id; continue; }  // same four layer floats as the previous triangle
+      if (o[10] >= 0.0f) diel = 1;
+      if (t > t0 && memcmp(o, o - 12, 16) == 0) { mat_id[t] = last_id; continue; }  // same four layer floats as the previous triangle
       const std::array<int, 4> key = {layer_of(o[0]), layer_of(o[1]), layer_of(o[3]), layer_of(o[2])};
       if (key != last) {
         auto it = ids.find(key);
-        if (it == ids.end()) { it = ids.emplace(key, (int)mats.size()).first; mats.push_back(key); }
+        if (it == ids.end()) { it = ids.emplace(key, (int)keys.size()).first; keys.push_back(key); }
         last = key; last_id = it->second;
       }
       mat_id[t] = last_id;
     }
-  }
-  node_thread.join();
-  if (bad_node >= 0) return fail(c, FSPT_E_INVALID, "node %d: triangle index %d out of range", bad_node, bad_tri);
-  const size_t NI = interior_of.size();
-  lap("node + material pre-pass");
-  // ---- host staging block (pinned, kept between uploads): every copy below is a true async DMA and the user's
-  // buffers are no longer referenced when this function returns.  Very large scenes stage in pageable memory.
-  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-  const size_t o_nodes = 0, o_tris = o_nodes + al(std::max<size_t>(NI, 1) * 64), o_shade = o_tris + al((size_t)(T + 3) * 48),
-               o_bins = o_shade + al((size_t)T * 192), o_layer = o_bins + al((size_t)s->env_bins * 16),
-               o_mat = o_layer + al((size_t)L * 8), o_matsrc = o_mat + al(std::max<size_t>(32, mats.size() * 32)),
-               o_env = o_matsrc + al(std::max<size_t>(32, mats.size() * sizeof(MatSrc))),
-               geo_bytes = o_env + al((size_t)s->env_width * s->env_height * 4);
-  std::vector<uint8_t> pageable_geo;
-  uint8_t* hg;
-  if (geo_bytes <= ((size_t)1 << 30)) {
-    if (c->geo_stage_bytes < geo_bytes) {
-      if (c->h_geo) cudaFreeHost(c->h_geo);
-      c->h_geo = nullptr; c->geo_stage_bytes = 0;
-      CK(cudaMallocHost(&c->h_geo, geo_bytes));
-      c->geo_stage_bytes = geo_bytes;
+    local_diel[ch] = diel;
+  });
+  if (bad_node.load() >= 0)
+    return fail(c, FSPT_E_INVALID, "node %d: triangle index %d out of range", bad_node.load(), ibits(bad_node.load(), 2));
+  for (int ch = 0; ch < n_nchunks; ++ch) chunk_interiors[ch + 1] += chunk_interiors[ch];
+  const size_t NI = (size_t)chunk_interiors[n_nchunks];
+  interior_of.resize(NI);
+  std::vector<std::vector<int>> remap((size_t)n_tchunks);
+  bool identity = true;
+  {
+    std::map<std::array<int, 4>, int> ids;
+    for (int ch = 0; ch < n_tchunks; ++ch) {
+      dielectric = dielectric || local_diel[ch];
+      remap[ch].resize(local_keys[ch].size());
+      for (size_t k = 0; k < local_keys[ch].size(); ++k) {
+        auto it = ids.find(local_keys[ch][k]);
+        if (it == ids.end()) { it = ids.emplace(local_keys[ch][k], (int)mats.size()).first; mats.push_back(local_keys[ch][k]); }
+        remap[ch][k] = it->second;
+        identity = identity && it->second == (int)k;
+      }
     }
-    hg = c->h_geo;
-  } else {
-    pageable_geo.resize(geo_bytes);
-    hg = pageable_geo.data();
   }
-  float* nodes = reinterpret_cast<float*>(hg + o_nodes);
-  float* tris = reinterpret_cast<float*>(hg + o_tris);
-  float* shade = reinterpret_cast<float*>(hg + o_shade);
+  pool.run(n_nchunks + (identity ? 0 : n_tchunks), hw, [&](int item) {
+    if (item < n_nchunks) {
+      const int ch = item, i1 = std::min(N, (ch + 1) * PRE_CHUNK);
+      int k = chunk_interiors[ch];
+      for (int i = ch * PRE_CHUNK; i < i1; ++i) {
+        const int32_t tri = ibits(i, 2);
+        if (tri > -1) ref[i] = ~tri;
+        else { ref[i] = k; interior_of[(size_t)k++] = i; }
+      }
+      return;
+    }
+    const int ch = item - n_nchunks, t1 = std::min(T, (ch + 1) * PRE_CHUNK);
+    const std::vector<int>& r = remap[ch];
+    for (int t = ch * PRE_CHUNK; t < t1; ++t) mat_id[t] = r[mat_id[t]];
+  });
+  lap("node + material pre-pass");
+
+  // ---- pinned block for the small tables and the environment (kept between uploads)
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t env_bytes = (size_t)s->env_width * s->env_height * 4;
+  const size_t o_bins = 0, o_layer = o_bins + al((size_t)s->env_bins * 16), o_mat = o_layer + al((size_t)L * 8),
+               o_matsrc = o_mat + al(std::max<size_t>(32, mats.size() * 32)),
+               o_env = o_matsrc + al(std::max<size_t>(32, mats.size() * sizeof(MatSrc))), small_bytes = o_env + al(env_bytes);
+  if (c->geo_stage_bytes < small_bytes) {
+    if (c->h_geo) cudaFreeHost(c->h_geo);
+    c->h_geo = nullptr; c->geo_stage_bytes = 0;
+    CK(cudaMallocHost(&c->h_geo, small_bytes));
+    c->geo_stage_bytes = small_bytes;
+  }
+  uint8_t* hg = c->h_geo;
   float* bins = reinterpret_cast<float*>(hg + o_bins);
-  uint32_t* layer_info = reinterpret_cast<uint32_t*>(hg + o_layer);
-  int32_t* mat_info = reinterpret_cast<int32_t*>(hg + o_mat);
   const size_t n_mat_info = std::max<size_t>(8, mats.size() * 8);
-  // ---- geometry records: built by a background thread (which fans out) while this thread stages the atlas ------
+  // ---- device buffers, environment array
+  int rc_;
+  const size_t nodes_bytes = std::max<size_t>(NI, 1) * 64, tris_bytes = (size_t)(T + 3) * 48, shade_bytes = (size_t)T * 192,
+               bins_bytes = (size_t)s->env_bins * 16;
+  if ((rc_ = ensure(c, c->d_nodes, c->cap_nodes, nodes_bytes))) return rc_;
+  if ((rc_ = ensure(c, c->d_tris, c->cap_tris, tris_bytes))) return rc_;
+  if ((rc_ = ensure(c, c->d_shade, c->cap_shade, shade_bytes))) return rc_;
+  if ((rc_ = ensure(c, c->d_bins, c->cap_bins, bins_bytes))) return rc_;
+  if (!c->env_arr || c->env_W != s->env_width || c->env_H != s->env_height) {  // 2D array, RGBA8 RGBE (main.js:170-180)
+    cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
+    cudaResourceDesc rd = {};
+    rd.resType = cudaResourceTypeArray;
+    cudaTextureDesc td = {};
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+    td.filterMode = cudaFilterModePoint;
+    td.readMode = cudaReadModeElementType;
+    td.normalizedCoords = 0;
+    if (c->sc.env) cudaDestroyTextureObject(c->sc.env);
+    c->sc.env = 0;
+    if (c->env_arr) cudaFreeArray(c->env_arr);
+    c->env_arr = nullptr;
+    CK(cudaMallocArray(&c->env_arr, &fmt, s->env_width, s->env_height));
+    rd.res.array.array = c->env_arr;
+    CK(cudaCreateTextureObject(&c->sc.env, &rd, &td, nullptr));
+    c->env_W = s->env_width; c->env_H = s->env_height;
+  }
+  // ---- work items of the staging region: bands of the environment (+ the bins), node chunks, triangle chunks -- each
+  // DMA'd the moment it is complete -- and, behind them, the constant-layer scan of the atlas, which the workers that
+  // run out of geometry pick up.  Chunks are sized so that a small scene still gives every worker a few items; each
+  // geometry chunk owns one slot of the pinned ring.
+  const int workers = hw;
+  const int tri_chunk = (int)std::max<size_t>(1024, std::min<size_t>(16384, ((size_t)T + 3) / (4 * (size_t)workers) + 1));
+  const int node_chunk = (int)std::max<size_t>(4096, std::min<size_t>(65536, NI / (4 * (size_t)workers) + 1));
+  const int n_node_items = NI ? (int)((NI + node_chunk - 1) / node_chunk) : 1;
+  const int n_tri_items = (T + 3 + tri_chunk - 1) / tri_chunk;
+  const int n_env_items = std::max(1, std::min(s->env_height, (int)(env_bytes >> 20)));  // ~1 MB of rows each
+  const int n_geo_items = n_node_items + n_tri_items;
+  const int n_scan_items = L * SCAN_BANDS;
+  const int n_items = n_env_items + n_geo_items + n_scan_items;
+  const size_t layer_texels = (size_t)s->atlas_res * s->atlas_res;
+  std::vector<std::atomic<int>> varied((size_t)L);
+  for (auto& v : varied) v.store(0);
+  const size_t slot_bytes = al(std::max<size_t>((size_t)node_chunk * 64, (size_t)tri_chunk * (48 + 192)));
+  int n_slots = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_geo_items, std::max<size_t>(2 * (size_t)workers, ((size_t)256 << 20) / slot_bytes)));
+  if (const char* e = getenv("FSPT_RING_SLOTS")) n_slots = std::max(1, std::min(n_slots, atoi(e)));  // test knob: force slot reuse
+  if (c->ring_bytes < slot_bytes * (size_t)n_slots) {
+    if (c->h_ring) cudaFreeHost(c->h_ring);
+    c->h_ring = nullptr; c->ring_bytes = 0;
+    CK(cudaMallocHost(&c->h_ring, slot_bytes * (size_t)n_slots));
+    c->ring_bytes = slot_bytes * (size_t)n_slots;
+  }
+  while ((int)c->ev_ring.size() < n_slots) {
+    cudaEvent_t e;
+    CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->ev_ring.push_back(e);
+  }
+  lap("buffers + pinned ring");
   struct GeoStatus { int code = FSPT_OK; char msg[192] = {0}; } geo;
   std::mutex geo_mu;
   auto geo_fail = [&](int code, const char* fmt, int a0, int a1, int a2) {
     std::lock_guard<std::mutex> g(geo_mu);
     if (geo.code == FSPT_OK) { geo.code = code; snprintf(geo.msg, sizeof geo.msg, fmt, a0, a1, a2); }
   };
-  const int geo_workers = std::max(2, hw / 4);
-  std::thread geo_thread([&]() {
-    std::thread env_thread([&]() {
-      for (size_t i = 0; i < (size_t)s->env_bins * 4; ++i) bins[i] = (float)s->radiance_bins[i];  // vec4(radianceBins[idx]), tracer.fs:424
-      memcpy(hg + o_env, s->env, (size_t)s->env_width * s->env_height * 4);
-    });
-    // depth / stack bound check (the reference has int stack[64], tracer.fs:368): iterative DFS; child indices out
-    // of range end it silently, the node loop below reports them
-    std::thread dfs_thread([&]() {
-      std::vector<std::pair<int, int>> st;
-      st.reserve(256);
-      st.push_back({0, 1});
-      int max_depth = 0;
-      size_t visited = 0;
-      while (!st.empty()) {
-        auto [n, d] = st.back(); st.pop_back();
-        if (++visited > (size_t)N) { geo_fail(FSPT_E_INVALID, "BVH is not a tree (cycle or shared node)", 0, 0, 0); return; }
-        max_depth = std::max(max_depth, d);
-        if (ibits(n, 2) > -1) continue;
-        const int32_t l = ibits(n, 0), r = ibits(n, 1);
-        if (l < 0 || l >= N || r < 0 || r >= N) return;
-        st.push_back({l, d + 1});
-        st.push_back({r, d + 1});
-      }
-      if (max_depth + 1 > FSPT_STACK)
-        geo_fail(FSPT_E_LIMIT, "BVH depth %d exceeds the traversal stack (%d, as in tracer.fs:368)", max_depth, FSPT_STACK, 0);
-    });
-    // Node64 per interior node: (left, right) pairs per component, the operand layout of the packed f32x2 slab test
-    if (NI == 0) memset(nodes, 0, 64);
-    const int node_chunks = (int)((NI + 16383) / 16384);
-    parallel(node_chunks, geo_workers, [&](int ch) {
-      const size_t k1 = std::min(NI, (size_t)(ch + 1) * 16384);
-      for (size_t k = (size_t)ch * 16384; k < k1; ++k) {
+  // depth / stack bound check (the reference has int stack[64], tracer.fs:368): iterative DFS on its own thread; child
+  // indices out of range end it silently, the node items below report them
+  struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } };
+  std::thread dfs_thread([&]() {
+    std::vector<std::pair<int, int>> st;
+    st.reserve(256);
+    st.push_back({0, 1});
+    int max_depth = 0;
+    size_t visited = 0;
+    while (!st.empty()) {
+      auto [n, d] = st.back(); st.pop_back();
+      if (++visited > (size_t)N) { geo_fail(FSPT_E_INVALID, "BVH is not a tree (cycle or shared node)", 0, 0, 0); return; }
+      max_depth = std::max(max_depth, d);
+      if (ibits(n, 2) > -1) continue;
+      const int32_t l = ibits(n, 0), r = ibits(n, 1);
+      if (l < 0 || l >= N || r < 0 || r >= N) return;
+      st.push_back({l, d + 1});
+      st.push_back({r, d + 1});
+    }
+    if (max_depth + 1 > FSPT_STACK)
+      geo_fail(FSPT_E_LIMIT, "BVH depth %d exceeds the traversal stack (%d, as in tracer.fs:368)", max_depth, FSPT_STACK, 0);
+  });
+  Joiner dfs_join{dfs_thread};
+  std::atomic<int> dma_err(0);
+  std::mutex dma_mu;  // serialises the enqueues on the context's stream
+  std::vector<std::atomic<int>> slot_done((size_t)n_slots);  // last item whose copies have been enqueued from the slot
+  for (auto& v : slot_done) v.store(-1);
+  auto tri9 = [&](int t, float* o) {  // v1 | e1 | e2 of triangle t (t >= T: padBuffer's -1 fill, main.js:143-154)
+    float v[9];
+    if (t < T) memcpy(v, s->triangles + (size_t)t * 9, sizeof v);
+    else for (float& x : v) x = -1.0f;
+    o[0] = v[0]; o[1] = v[1]; o[2] = v[2];
+    volatile float e;  // keep these as single f32 subtractions
+    e = v[3] - v[0]; o[3] = e; e = v[4] - v[1]; o[4] = e; e = v[5] - v[2]; o[5] = e;
+    e = v[6] - v[0]; o[6] = e; e = v[7] - v[1]; o[7] = e; e = v[8] - v[2]; o[8] = e;
+  };
+  pool.run(n_items, workers, [&](int item) {
+    if (item < n_env_items) {  // a band of environment rows (+ the bins): their own pinned block
+      if (item == 0)
+        for (size_t i = 0; i < (size_t)s->env_bins * 4; ++i) bins[i] = (float)s->radiance_bins[i];  // vec4(radianceBins[idx]), tracer.fs:424
+      const size_t pitch = (size_t)s->env_width * 4;
+      const int y0 = (int)((long long)s->env_height * item / n_env_items), y1 = (int)((long long)s->env_height * (item + 1) / n_env_items);
+      memcpy(hg + o_env + y0 * pitch, s->env + y0 * pitch, (size_t)(y1 - y0) * pitch);
+      std::lock_guard<std::mutex> g(dma_mu);
+      cudaError_t e = item == 0 ? cudaMemcpyAsync(c->d_bins, bins, bins_bytes, cudaMemcpyHostToDevice, c->stream) : cudaSuccess;
+      if (e == cudaSuccess)
+        e = cudaMemcpy2DToArrayAsync(c->env_arr, 0, y0, hg + o_env + y0 * pitch, pitch, pitch, y1 - y0, cudaMemcpyHostToDevice, c->stream);
+      if (e != cudaSuccess) dma_err.store((int)e);
+      return;
+    }
+    if (item >= n_env_items + n_geo_items) {  // atlas: constant-layer scan
+      scan_layer_band(s->atlas, layer_texels, item - n_env_items - n_geo_items, varied.data());
+      return;
+    }
+    // ring slot of this chunk: free once the copies of the chunk that used it last have completed
+    const int ring_item = item - n_env_items, slot = ring_item % n_slots;
+    if (ring_item >= n_slots) {
+      while (slot_done[slot].load(std::memory_order_acquire) != ring_item - n_slots) std::this_thread::yield();
+      cudaEventSynchronize(c->ev_ring[slot]);
+    }
+    uint8_t* hs = c->h_ring + (size_t)slot * slot_bytes;
+    cudaError_t e = cudaSuccess;
+    if (ring_item < n_node_items) {
+      // Node64 per interior node: (left, right) pairs per component, the operand layout of the packed f32x2 slab test
+      const size_t k0 = (size_t)ring_item * node_chunk, k1 = std::min(NI, k0 + node_chunk);
+      float* nodes = reinterpret_cast<float*>(hs);
+      if (NI == 0) memset(nodes, 0, 64);
+      for (size_t k = k0; k < k1; ++k) {
         const int i = interior_of[k];
         const int32_t l = ibits(i, 0), r = ibits(i, 1);
-        float* o = nodes + k * 16;
+        float* o = nodes + (k - k0) * 16;
         if (l < 0 || l >= N || r < 0 || r >= N || l == i || r == i) {
           geo_fail(FSPT_E_INVALID, "node %d: child index out of range (%d, %d)", i, l, r);
           memset(o, 0, 64);
@@ -806,27 +1213,22 @@ static int scene_upload_impl(fspt_ctx* ctx, const fspt_scene_desc* s, bool async
         memcpy(o + 12, &lr, 4); memcpy(o + 13, &rr, 4);
         o[14] = o[15] = 0.0f;
       }
-    });
-    // triangles: v1, e1, e2 (tracer.fs:301-302) + LEAF_SIZE-1 padBuffer-style (-1,-1,-1) tail records; shading
-    // records: material (12) | uvs (6) | material id | pad | normals (27) | pad
-    auto tri9 = [&](int t, float* o) {  // v1 | e1 | e2 of triangle t (t >= T: padBuffer's -1 fill, main.js:143-154)
-      float v[9];
-      if (t < T) memcpy(v, s->triangles + (size_t)t * 9, sizeof v);
-      else for (float& x : v) x = -1.0f;
-      o[0] = v[0]; o[1] = v[1]; o[2] = v[2];
-      volatile float e;  // keep these as single f32 subtractions
-      e = v[3] - v[0]; o[3] = e; e = v[4] - v[1]; o[4] = e; e = v[5] - v[2]; o[5] = e;
-      e = v[6] - v[0]; o[6] = e; e = v[7] - v[1]; o[7] = e; e = v[8] - v[2]; o[8] = e;
-    };
-    const int tri_chunks = (T + 3 + 16383) / 16384;
-    parallel(tri_chunks, geo_workers, [&](int ch) {
-      const int t1 = std::min(T + 3, (ch + 1) * 16384);
-      for (int t = ch * 16384; t < t1; ++t) {
-        float* o = tris + (size_t)t * 12;
+      const size_t bytes = NI ? (k1 - k0) * 64 : 64;
+      std::lock_guard<std::mutex> g(dma_mu);
+      e = cudaMemcpyAsync(reinterpret_cast<uint8_t*>(c->d_nodes) + k0 * 64, nodes, bytes, cudaMemcpyHostToDevice, c->stream);
+      if (e == cudaSuccess) e = cudaEventRecord(c->ev_ring[slot], c->stream);
+    } else {
+      // triangles: v1, e1, e2 (tracer.fs:301-302) + LEAF_SIZE-1 padBuffer-style (-1,-1,-1) tail records; shading
+      // records: material (12) | uvs (6) | material id | pad | normals (27) | pad
+      const int t0 = (ring_item - n_node_items) * tri_chunk, t1 = std::min(T + 3, t0 + tri_chunk), ts = std::min(T, t1);
+      float* tris = reinterpret_cast<float*>(hs);
+      float* shade = reinterpret_cast<float*>(hs + (size_t)tri_chunk * 48);
+      for (int t = t0; t < t1; ++t) {
+        float* o = tris + (size_t)(t - t0) * 12;
         tri9(t, o);
         o[9] = o[10] = o[11] = 0.0f;
         if (t >= T) continue;
-        float* h = shade + (size_t)t * 48;
+        float* h = shade + (size_t)(t - t0) * 48;
         memcpy(h, s->materials + (size_t)t * 12, 48);
         memcpy(h + 12, s->uvs + (size_t)t * 6, 24);
         memcpy(h + 18, &mat_id[t], 4);  // material id in the record's padding
@@ -834,312 +1236,66 @@ static int scene_upload_impl(fspt_ctx* ctx, const fspt_scene_desc* s, bool async
         memcpy(h + 20, s->normals + (size_t)t * 27, 108);
         h[47] = 0.0f;
       }
-    });
-    env_thread.join();
-    dfs_thread.join();
+      std::lock_guard<std::mutex> g(dma_mu);
+      e = cudaMemcpyAsync(reinterpret_cast<uint8_t*>(c->d_tris) + (size_t)t0 * 48, tris, (size_t)(t1 - t0) * 48, cudaMemcpyHostToDevice, c->stream);
+      if (e == cudaSuccess && ts > t0)
+        e = cudaMemcpyAsync(reinterpret_cast<uint8_t*>(c->d_shade) + (size_t)t0 * 192, shade, (size_t)(ts - t0) * 192, cudaMemcpyHostToDevice, c->stream);
+      if (e == cudaSuccess) e = cudaEventRecord(c->ev_ring[slot], c->stream);
+    }
+    if (e != cudaSuccess) dma_err.store((int)e);
+    slot_done[slot].store(ring_item, std::memory_order_release);
   });
-  Joiner geo_join{geo_thread};
-  // ---- atlas (main.js:548-560).  Constant-colour layers are detected (exact: every texel compared), then the atlas
-  // is re-interleaved per material into 16-byte texels (device_common.cuh "MatTexel") in pinned memory by a few host
-  // threads and DMA'd layer by layer as the layers land; a scene with so many layer combinations that this would not
-  // fit falls back to the plain RGBA8 layered array.
-  cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
-  cudaResourceDesc rd = {};
-  rd.resType = cudaResourceTypeArray;
-  cudaTextureDesc td = {};
-  td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
-  td.filterMode = cudaFilterModePoint;
-  td.readMode = cudaReadModeElementType;
-  td.normalizedCoords = 0;
-  scan_thread.join();
-  for (int l = 0; l < L; ++l) {
-    layer_info[2 * l] = varied[l].load() ? 0u : 1u;
-    memcpy(&layer_info[2 * l + 1], s->atlas + (size_t)l * layer_bytes, 4);
-  }
-  lap("constant-layer scan");
-  memset(mat_info, 0, n_mat_info * 4);
-  int n_tex_mats = 0;
-  for (size_t m = 0; m < mats.size(); ++m) {
-    bool all_const = true;
-    for (int k = 0; k < 4; ++k) all_const = all_const && layer_info[2 * mats[m][k]];
-    mat_info[8 * m] = all_const ? -1 : n_tex_mats++;
-    for (int k = 0; k < 4; ++k) mat_info[8 * m + 1 + k] = (int32_t)layer_info[2 * mats[m][k] + 1];
-  }
-  // The interleaved atlas costs res^2 * 16 bytes per TEXTURED MATERIAL (distinct layer quadruple) and the same again in
-  // pinned staging; quadruples can outnumber layers, so it is bounded against the plain atlas (4 x its bytes, at least
-  // 256 MB) and against the free device memory, and any allocation failure falls back to the plain RGBA8 array.
-  bool use_mat_tex = !getenv("FSPT_PLAIN_ATLAS");
-  {
-    const size_t inter = (size_t)n_tex_mats * layer_texels * 16, plain = (size_t)L * layer_bytes;
-    // the array of the previous upload is reused when it has the same shape: then nothing is allocated and the driver is
-    // not asked for the free memory (cudaMemGetInfo is a resource-manager call: usually 0.1 ms, but 20-100 ms every few
-    // dozen calls on the virtualised hosts measured, which showed up as spikes in the end-to-end step time)
-    const bool reuse = c->mat_arr && c->mat_R == R && c->mat_L == std::max(1, n_tex_mats);
-    size_t free_b = (size_t)48 << 30, total_b = 0;
-    if (!reuse && cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { (void)cudaGetLastError(); free_b = (size_t)48 << 30; }
-    const size_t resident = c->mat_arr ? (size_t)c->mat_R * c->mat_R * 16 * (size_t)c->mat_L : 0;  // freed before the new one
-    if (inter > std::max<size_t>(4 * plain, (size_t)256 << 20) || inter > ((size_t)48 << 30) ||
-        (!reuse && inter > (free_b + resident) / 2))
-      use_mat_tex = false;
-    if (getenv("FSPT_FORCE_MAT_TEX")) use_mat_tex = true;  // test knob: exercise the allocation-failure fallback
-  }
-  lap("atlas sizing");
-  // The staging itself is a job (everything it needs captured by value: it may outlive this call) that runs here or,
-  // for fspt_scene_upload_async, on the context's staging thread.
-  std::function<void()> atlas_job;
-  const uint8_t* const atlas_src = s->atlas;
-  c->atlas_err.store(0);
-  bool plain_atlas = !use_mat_tex;
-  if (use_mat_tex) {
-    if (c->sc.atlas) { cudaDestroyTextureObject(c->sc.atlas); c->sc.atlas = 0; }
-    if (c->atlas_arr) { cudaFreeArray(c->atlas_arr); c->atlas_arr = nullptr; c->atlas_R = c->atlas_L = 0; }
-    const int ML = std::max(1, n_tex_mats);
-    // Where the interleave runs.  On the host (default): the 16-byte texels are built in pinned memory and DMA'd.  On the
-    // GPU: only the DISTINCT varying layers cross PCIe as raw RGBA8 and k_interleave_atlas builds the texels through a
-    // surface -- a material with one image map and three colours then costs 1 layer of staging and DMA instead of 4.
-    // Measured break-even (bench scene, 7 varying layers behind 2 materials: GPU path 20 % slower): chosen when the raw
-    // layers are at most half of the interleaved bytes.  FSPT_ATLAS_INTERLEAVE=gpu|cpu overrides.
-    std::vector<int> raw_of((size_t)L, -1), raw_layers;
-    MatSrc* mat_src = reinterpret_cast<MatSrc*>(hg + o_matsrc);
-    for (size_t m = 0; m < mats.size(); ++m) {
-      const int tl = mat_info[8 * m];
-      if (tl < 0) continue;
-      for (int k = 0; k < 4; ++k) {
-        const int l = mats[m][k];
-        if (!layer_info[2 * l] && raw_of[l] < 0) { raw_of[l] = (int)raw_layers.size(); raw_layers.push_back(l); }
-        mat_src[tl].raw[k] = layer_info[2 * l] ? -1 : raw_of[l];
-        mat_src[tl].cst[k] = layer_info[2 * l + 1];
-      }
-    }
-    bool gpu_interleave = n_tex_mats > 0 && raw_layers.size() * 2 <= (size_t)n_tex_mats * 4;
-    if (const char* e = getenv("FSPT_ATLAS_INTERLEAVE")) gpu_interleave = n_tex_mats > 0 && !strcmp(e, "gpu");
-    if (!c->mat_arr || c->mat_R != R || c->mat_L != ML || c->mat_surface != gpu_interleave) {
-      if (c->sc.mat_tex) cudaDestroyTextureObject(c->sc.mat_tex);
-      c->sc.mat_tex = 0;
-      if (c->mat_surf) cudaDestroySurfaceObject(c->mat_surf);
-      c->mat_surf = 0;
-      if (c->mat_arr) cudaFreeArray(c->mat_arr);
-      c->mat_arr = nullptr;
-      cudaChannelFormatDesc fmt4 = cudaCreateChannelDesc<uint4>();
-      c->mat_R = c->mat_L = 0;
-      const size_t max_ml = getenv("FSPT_FORCE_MAT_TEX") ? (size_t)atoi(getenv("FSPT_FORCE_MAT_TEX")) : (size_t)1 << 30;
-      if ((size_t)ML > max_ml ||  // (test knob: pretend the device cannot hold more than that many material layers)
-          cudaMalloc3DArray(&c->mat_arr, &fmt4, make_cudaExtent(R, R, ML),
-                            cudaArrayLayered | (gpu_interleave ? cudaArraySurfaceLoadStore : 0)) != cudaSuccess) {
-        (void)cudaGetLastError();
-        c->mat_arr = nullptr;
-        plain_atlas = true;
-      } else {
-        rd.res.array.array = c->mat_arr;
-        CK(cudaCreateTextureObject(&c->sc.mat_tex, &rd, &td, nullptr));
-        if (gpu_interleave) CK(cudaCreateSurfaceObject(&c->mat_surf, &rd));
-        c->mat_R = R; c->mat_L = ML; c->mat_surface = gpu_interleave;
-      }
-    }
-    const size_t need = gpu_interleave ? layer_bytes * raw_layers.size() : layer_texels * 16 * (size_t)ML;
-    if (!plain_atlas && c->stage_bytes < need) {
-      if (c->h_stage) cudaFreeHost(c->h_stage);
-      c->h_stage = nullptr; c->stage_bytes = 0;
-      if (cudaMallocHost(&c->h_stage, need) != cudaSuccess) {
-        (void)cudaGetLastError();
-        c->h_stage = nullptr;
-        plain_atlas = true;
-      } else {
-        c->stage_bytes = need;
-      }
-    }
-    if (plain_atlas) {
-      // could not hold the interleaved atlas: every material becomes "plain" (mat_info is rebuilt below)
-    } else if (gpu_interleave) {
-      int rc2;
-      if ((rc2 = ensure(c, c->d_raw, c->cap_raw, need))) return rc2;
-      if ((rc2 = ensure(c, c->d_mat_src, c->cap_mat_src, sizeof(MatSrc) * (size_t)ML))) return rc2;
-      // work item = (raw layer, band of rows): copy into the pinned block, DMA the band
-      const int bands = std::max(1, std::min(R, 16));
-      c->stats.kernel_launches++;
-      atlas_job = [c, device, atlas_src, raw_layers, bands, atlas_workers, R, layer_bytes, layer_texels, mat_src, n_tex_mats]() {
-        parallel_for(device, (int)raw_layers.size() * bands, atlas_workers, [&](int item) {
-          const int ri = item / bands, band = item % bands;
-          const size_t y0 = (size_t)R * band / bands, y1 = (size_t)R * (band + 1) / bands;
-          const size_t off = (size_t)ri * layer_bytes + y0 * R * 4, bytes = (y1 - y0) * R * 4;
-          memcpy(c->h_stage + off, atlas_src + (size_t)raw_layers[ri] * layer_bytes + y0 * R * 4, bytes);
-          std::lock_guard<std::mutex> g(c->atlas_mu);
-          cudaError_t e = cudaMemcpyAsync(reinterpret_cast<uint8_t*>(c->d_raw) + off, c->h_stage + off, bytes, cudaMemcpyHostToDevice, c->copy_stream);
-          if (e != cudaSuccess) c->atlas_err.store((int)e);
-        });
-        cudaError_t e = cudaMemcpyAsync(c->d_mat_src, mat_src, sizeof(MatSrc) * (size_t)n_tex_mats, cudaMemcpyHostToDevice, c->copy_stream);
-        if (e != cudaSuccess) c->atlas_err.store((int)e);
-        const dim3 blk(32, 8), grd((R + 31) / 32, (R + 7) / 8, n_tex_mats);
-        k_interleave_atlas<<<grd, blk, 0, c->copy_stream>>>(c->mat_surf, reinterpret_cast<const uint32_t*>(c->d_raw),
-                                                            reinterpret_cast<const MatSrc*>(c->d_mat_src), R, layer_texels);
-        if ((e = cudaGetLastError()) != cudaSuccess) c->atlas_err.store((int)e);
-      };
-    } else {
-      // work item = (textured material, band of rows): interleave the four source layers, DMA the band
-      const int bands = std::max(1, std::min(R, 16));
-      std::vector<int> tex_layer;                  // per textured material: its layer of the material array
-      std::vector<std::array<int, 4>> tex_src;     // ... and its four source layers of the atlas
-      for (size_t m = 0; m < mats.size(); ++m)
-        if (mat_info[8 * m] >= 0) { tex_layer.push_back(mat_info[8 * m]); tex_src.push_back(mats[m]); }
-      atlas_job = [c, device, atlas_src, tex_layer, tex_src, bands, atlas_workers, R, layer_texels]() {
-        parallel_for(device, (int)tex_layer.size() * bands, atlas_workers, [&](int item) {
-          const int tm = item / bands, band = item % bands;
-          const int tl = tex_layer[tm];
-          const int y0 = (int)((long long)R * band / bands), y1 = (int)((long long)R * (band + 1) / bands);
-          const uint32_t* src[4];
-          for (int k = 0; k < 4; ++k) src[k] = reinterpret_cast<const uint32_t*>(atlas_src) + (size_t)tex_src[tm][k] * layer_texels;
-          uint32_t* dst = reinterpret_cast<uint32_t*>(c->h_stage) + ((size_t)tl * layer_texels + (size_t)y0 * R) * 4;
-          const size_t i0 = (size_t)y0 * R, n = (size_t)(y1 - y0) * R;
-          size_t i = 0;
-#if defined(__SSE2__)
-          // 4x4 transpose of 32-bit texels, written with non-temporal stores: the staging block is only read by the DMA
-          // engine, so it should neither be fetched for ownership nor displace the source layers from the CPU caches
-          for (; i + 4 <= n; i += 4) {
-            const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src[0] + i0 + i));
-            const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src[1] + i0 + i));
-            const __m128i c2 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src[2] + i0 + i));
-            const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src[3] + i0 + i));
-            const __m128i ab_lo = _mm_unpacklo_epi32(a, b), ab_hi = _mm_unpackhi_epi32(a, b);
-            const __m128i cd_lo = _mm_unpacklo_epi32(c2, d), cd_hi = _mm_unpackhi_epi32(c2, d);
-            __m128i* o = reinterpret_cast<__m128i*>(dst + 4 * i);  // 16-byte aligned: pinned block + multiples of 16
-            _mm_stream_si128(o + 0, _mm_unpacklo_epi64(ab_lo, cd_lo));
-            _mm_stream_si128(o + 1, _mm_unpackhi_epi64(ab_lo, cd_lo));
-            _mm_stream_si128(o + 2, _mm_unpacklo_epi64(ab_hi, cd_hi));
-            _mm_stream_si128(o + 3, _mm_unpackhi_epi64(ab_hi, cd_hi));
-          }
-          _mm_sfence();
-#endif
-          for (; i < n; ++i) {
-            dst[4 * i + 0] = src[0][i0 + i]; dst[4 * i + 1] = src[1][i0 + i];
-            dst[4 * i + 2] = src[2][i0 + i]; dst[4 * i + 3] = src[3][i0 + i];
-          }
-          cudaMemcpy3DParms cp = {};
-          cp.srcPtr = make_cudaPitchedPtr(dst, (size_t)R * 16, R, y1 - y0);
-          cp.dstArray = c->mat_arr;
-          cp.dstPos = make_cudaPos(0, y0, tl);
-          cp.extent = make_cudaExtent(R, y1 - y0, 1);
-          cp.kind = cudaMemcpyHostToDevice;
-          std::lock_guard<std::mutex> g(c->atlas_mu);
-          cudaError_t e = cudaMemcpy3DAsync(&cp, c->copy_stream);
-          if (e != cudaSuccess) c->atlas_err.store((int)e);
-        });
-      };
-    }
-  }
-  if (plain_atlas) {
-    if (c->sc.mat_tex) { cudaDestroyTextureObject(c->sc.mat_tex); c->sc.mat_tex = 0; }
-    if (c->mat_surf) { cudaDestroySurfaceObject(c->mat_surf); c->mat_surf = 0; }
-    c->mat_surface = false;
-    if (c->mat_arr) { cudaFreeArray(c->mat_arr); c->mat_arr = nullptr; c->mat_R = c->mat_L = 0; }
-    if (!c->atlas_arr || c->atlas_R != R || c->atlas_L != L) {
-      if (c->sc.atlas) cudaDestroyTextureObject(c->sc.atlas);
-      c->sc.atlas = 0;
-      if (c->atlas_arr) cudaFreeArray(c->atlas_arr);
-      c->atlas_arr = nullptr;
-      CK(cudaMalloc3DArray(&c->atlas_arr, &fmt, make_cudaExtent(R, R, L), cudaArrayLayered));
-      rd.res.array.array = c->atlas_arr;
-      CK(cudaCreateTextureObject(&c->sc.atlas, &rd, &td, nullptr));
-      c->atlas_R = R; c->atlas_L = L;
-    }
-    if (c->stage_bytes < layer_bytes * L) {
-      if (c->h_stage) cudaFreeHost(c->h_stage);
-      c->h_stage = nullptr; c->stage_bytes = 0;
-      CK(cudaMallocHost(&c->h_stage, layer_bytes * L));
-      c->stage_bytes = layer_bytes * L;
-    }
-    atlas_job = [c, device, atlas_src, L, atlas_workers, R, layer_bytes]() {
-      parallel_for(device, L, atlas_workers, [&](int l) {
-        uint8_t* dst = c->h_stage + (size_t)l * layer_bytes;
-        memcpy(dst, atlas_src + (size_t)l * layer_bytes, layer_bytes);
-        cudaMemcpy3DParms cp = {};
-        cp.srcPtr = make_cudaPitchedPtr(dst, (size_t)R * 4, R, R);
-        cp.dstArray = c->atlas_arr;
-        cp.dstPos = make_cudaPos(0, 0, l);
-        cp.extent = make_cudaExtent(R, R, 1);
-        cp.kind = cudaMemcpyHostToDevice;
-        std::lock_guard<std::mutex> g(c->atlas_mu);
-        cudaError_t e = cudaMemcpy3DAsync(&cp, c->copy_stream);
-        if (e != cudaSuccess) c->atlas_err.store((int)e);
-      });
-    };
-  }
-  // The atlas travels on its own stream: only k_shade needs it, so the camera + primary traversal launch of the next
-  // render overlaps the tail of this DMA (render_wave waits on the event before its first k_shade).  Asynchronous upload:
-  // the staging job itself moves to the context's thread, which records the event when its last band is enqueued;
-  // render_wave joins it after it has launched the primary traversal.  (A scene staged through a pageable block -- more
-  // than 1 GB of geometry -- keeps this call synchronous: the job's tables live in that block.)
-  auto run_atlas_job = [c, device, atlas_job]() {
-    cudaSetDevice(device);
-    if (atlas_job) atlas_job();
-    cudaError_t e = cudaEventRecord(c->ev_atlas, c->copy_stream);
-    if (e != cudaSuccess) c->atlas_err.store((int)e);
-  };
-  struct StagingGuard {  // an error return below must not leave the staging thread reading the caller's atlas
-    Ctx* c; bool ok = false;
-    ~StagingGuard() { if (!ok && c->atlas_thread.joinable()) c->atlas_thread.join(); }
-  } staging_guard{c};
-  if (async_atlas && pageable_geo.empty()) {
-    c->atlas_thread = std::thread(run_atlas_job);
-    lap("atlas job handed to the staging thread");
-  } else {
-    run_atlas_job();
-    if (int rcj = atlas_join(c)) return rcj;
-    lap("atlas stage + scan + enqueue");
-  }
-  geo_thread.join();
-  if (geo.code != FSPT_OK) return fail(c, geo.code, "%s", geo.msg);
-  lap("join geometry thread");
-  int rc_;
-  const size_t nodes_bytes = std::max<size_t>(NI, 1) * 64, tris_bytes = (size_t)(T + 3) * 48, shade_bytes = (size_t)T * 192,
-               bins_bytes = (size_t)s->env_bins * 16;
-  if ((rc_ = ensure(c, c->d_layer_info, c->cap_layer_info, (size_t)L * 8))) return rc_;
-  if ((rc_ = ensure(c, c->d_mat_info, c->cap_mat_info, n_mat_info * 4))) return rc_;
-  if ((rc_ = ensure(c, c->d_nodes, c->cap_nodes, nodes_bytes))) return rc_;
-  if ((rc_ = ensure(c, c->d_tris, c->cap_tris, tris_bytes))) return rc_;
-  if ((rc_ = ensure(c, c->d_shade, c->cap_shade, shade_bytes))) return rc_;
-  if ((rc_ = ensure(c, c->d_bins, c->cap_bins, bins_bytes))) return rc_;
-  CK(cudaMemcpyAsync(c->d_layer_info, layer_info, (size_t)L * 8, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->d_mat_info, mat_info, n_mat_info * 4, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->d_nodes, nodes, nodes_bytes, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->d_tris, tris, tris_bytes, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->d_shade, shade, shade_bytes, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->d_bins, bins, bins_bytes, cudaMemcpyHostToDevice, c->stream));
-  lap("malloc + enqueue geometry");
-  // ---- environment: 2D array, RGBA8 RGBE (main.js:170-180) ----------------------------------------------------
-  if (!c->env_arr || c->env_W != s->env_width || c->env_H != s->env_height) {
-    if (c->sc.env) cudaDestroyTextureObject(c->sc.env);
-    c->sc.env = 0;
-    if (c->env_arr) cudaFreeArray(c->env_arr);
-    c->env_arr = nullptr;
-    CK(cudaMallocArray(&c->env_arr, &fmt, s->env_width, s->env_height));
-    rd.res.array.array = c->env_arr;
-    CK(cudaCreateTextureObject(&c->sc.env, &rd, &td, nullptr));
-    c->env_W = s->env_width; c->env_H = s->env_height;
-  }
-  CK(cudaMemcpy2DToArrayAsync(c->env_arr, 0, 0, hg + o_env, (size_t)s->env_width * 4, (size_t)s->env_width * 4,
-                              s->env_height, cudaMemcpyHostToDevice, c->stream));
+  if (dma_err.load()) return fail(c, FSPT_E_CUDA, "geometry upload failed: %s", cudaGetErrorString((cudaError_t)dma_err.load()));
+  lap("geometry + env + layer scan");
   // env: test knob for the LSU-only instantiation of k_trace
   if ((rc_ = linear_tex(c, &c->nodes_tex, c->d_nodes, nodes_bytes, !getenv("FSPT_NO_NODE_TEX")))) return rc_;
-  // no synchronisation: everything the DMA engine still reads lives in the context's pinned staging blocks, which the
-  // next upload (and destroy) only touch after synchronising the stream; work enqueued by fspt_render waits in order
-  if (!pageable_geo.empty() || (timing && !async_atlas)) { CK(cudaStreamSynchronize(c->stream)); CK(cudaStreamSynchronize(c->copy_stream)); }
-  lap("env + textures (+ sync when timing)");
   c->sc.nodes = reinterpret_cast<const float4*>(c->d_nodes);
   c->sc.tris = reinterpret_cast<const float4*>(c->d_tris);
   c->sc.shade = reinterpret_cast<const float4*>(c->d_shade);
   c->sc.bins = reinterpret_cast<const float4*>(c->d_bins);
-  c->sc.layer_info = reinterpret_cast<const uint2*>(c->d_layer_info);
-  c->sc.mat_info = reinterpret_cast<const int4*>(c->d_mat_info);
-  c->bytes_nodes = nodes_bytes; c->bytes_tris = tris_bytes; c->bytes_shade = shade_bytes;
-  c->bytes_bins = bins_bytes; c->bytes_layer_info = (size_t)L * 8; c->bytes_mat_info = n_mat_info * 4;
+  c->bytes_nodes = nodes_bytes; c->bytes_tris = tris_bytes; c->bytes_shade = shade_bytes; c->bytes_bins = bins_bytes;
   c->sc.root_ref = ref[0];
   c->sc.n_tris = T; c->sc.n_interior = (int)NI;
   c->sc.atlas_res = s->atlas_res; c->sc.atlas_layers = s->atlas_layers; c->sc.env_w = s->env_width; c->sc.env_h = s->env_height;
   c->sc.n_bins = s->env_bins;
   c->has_dielectric = dielectric;
-  c->has_scene = true;
   c->scene_bytes = (size_t)N * 36 + (size_t)T * (36 + 48 + 108 + 24) + (size_t)s->atlas_res * s->atlas_res * 4 * s->atlas_layers +
-                   (size_t)s->env_width * s->env_height * 4 + (size_t)s->env_bins * 8;
+                   env_bytes + (size_t)s->env_bins * 8;
+  // ---- the atlas part: here, or on the context's atlas thread (the caller's atlas stays borrowed until it is joined)
+  AtlasJob job;
+  job.atlas = s->atlas; job.L = L; job.R = s->atlas_res;
+  job.mats = std::move(mats);
+  job.layer_info = reinterpret_cast<uint32_t*>(hg + o_layer);
+  job.mat_info = reinterpret_cast<int32_t*>(hg + o_mat);
+  job.n_mat_info = n_mat_info;
+  job.mat_src = reinterpret_cast<MatSrc*>(hg + o_matsrc);
+  job.varied.resize((size_t)L);
+  for (int l = 0; l < L; ++l) job.varied[l] = (uint8_t)varied[l].load();
+  job.workers = hw;
+  job.timing = timing;
+  c->atlas_rc = FSPT_OK;
+  struct StagingGuard {  // an error return below must not leave the atlas thread reading the caller's buffer
+    Ctx* c; bool ok = false;
+    ~StagingGuard() { if (!ok && c->atlas_thread.joinable()) c->atlas_thread.join(); }
+  } staging_guard{c};
+  if (async_atlas) {
+    const int device = c->device;
+    c->atlas_thread = std::thread([c, device, job = std::move(job)]() {
+      cudaSetDevice(device);
+      c->atlas_rc = stage_atlas(c, job);
+    });
+    lap("atlas part handed to its thread");
+  } else {
+    if ((rc_ = stage_atlas(c, job))) { c->error = c->atlas_error; return rc_; }
+    lap("atlas part");
+  }
+  dfs_thread.join();
+  if (geo.code != FSPT_OK) return fail(c, geo.code, "%s", geo.msg);
+  lap("join depth check");
+  // no synchronisation: everything the DMA engines still read lives in the context's pinned blocks, which the next
+  // upload (and destroy) only touch after synchronising the streams; work enqueued by fspt_render waits in order
+  if (timing && !async_atlas) { CK(cudaStreamSynchronize(c->stream)); CK(cudaStreamSynchronize(c->copy_stream)); lap("sync (timing only)"); }
+  c->has_scene = true;
   staging_guard.ok = true;
   return FSPT_OK;
 }
@@ -1656,6 +1812,7 @@ int fspt_get_stats(fspt_ctx* ctx, fspt_stats* out) {
   (void)cudaGetLastError();  // event queries must not leave a sticky status for the next launch check
   c->stats.trace_ms = tr;
   *out = c->stats;
+  out->kernel_launches += c->atlas_launches.load();
   return FSPT_OK;
 }
 

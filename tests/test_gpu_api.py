@@ -360,3 +360,29 @@ def test_asynchronous_upload_equals_the_synchronous_one(monkeypatch, mode):
         assert np.array_equal(ref.view(np.uint32), ctx.read_accum().view(np.uint32))
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("slots,threads", [("1", "4"), ("3", "16"), (None, "5")])
+def test_geometry_ring_reuse_and_worker_counts_are_bit_identical(small_bunny, monkeypatch, slots, threads):
+    """The geometry records are staged chunk by chunk through a ring of pinned slots by the context's host workers;
+    a slot is rewritten only after the copies that read it have completed.  Forcing the ring down to one or three slots
+    (every chunk then reuses a slot) and changing the number of workers must not change a bit of the render."""
+    sa, cam = small_bunny
+    W, H = 64, 48
+    rc, rt = scenes.rand_bases(2, 41)
+    ctx = capi.Context(W, H)
+    try:
+        ctx.scene_upload(sa)
+        fr = _frame(ctx, cam)
+        ctx.render(fr, 0, rc, rt)
+        ref = ctx.read_accum().copy()
+        if slots:
+            monkeypatch.setenv("FSPT_RING_SLOTS", slots)
+        monkeypatch.setenv("FSPT_UPLOAD_THREADS", threads)
+        for wait in (True, False):
+            ctx.scene_upload(sa, wait=wait)
+            ctx.clear()
+            ctx.render(fr, 0, rc, rt)
+            assert np.array_equal(ref.view(np.uint32), ctx.read_accum().view(np.uint32)), (slots, threads, wait)
+    finally:
+        ctx.close()
