@@ -981,7 +981,54 @@ static int scene_upload_impl(fspt_ctx* ctx, const fspt_scene_desc* s, bool async
     long long q = (long long)f;
     return (int)(q < 0 ? 0 : (q >= s->atlas_layers ? s->atlas_layers - 1 : q));
   };
-  pool.run(n_nchunks + n_tchunks, hw, [&](int item) {
+  // Depth / stack bound check (the reference has int stack[64], tracer.fs:368), also part of the first region: the top
+  // of the tree is walked here until there are a few subtrees per worker, each subtree is then an item (iterative DFS).
+  // Child indices out of range end a walk silently; the node chunks of the staging region report them.
+  struct Sub { int node, depth; };
+  std::vector<Sub> subtrees;
+  int top_depth = 0;
+  size_t top_visited = 0;
+  {
+    std::vector<Sub> frontier{{0, 1}}, next;
+    while (!frontier.empty() && frontier.size() < (size_t)(8 * hw) && top_visited <= (size_t)N) {
+      next.clear();
+      for (const Sub& f : frontier) {
+        ++top_visited;
+        top_depth = std::max(top_depth, f.depth);
+        if (ibits(f.node, 2) > -1) continue;
+        const int32_t l = ibits(f.node, 0), r = ibits(f.node, 1);
+        if (l < 0 || l >= N || r < 0 || r >= N) continue;
+        next.push_back({l, f.depth + 1});
+        next.push_back({r, f.depth + 1});
+      }
+      frontier.swap(next);
+    }
+    subtrees.swap(frontier);
+  }
+  const int n_sub = (int)subtrees.size();
+  std::vector<int> sub_depth((size_t)n_sub, 0);
+  std::vector<size_t> sub_visited((size_t)n_sub, 0);
+  pool.run(n_nchunks + n_tchunks + n_sub, hw, [&](int item) {
+    if (item >= n_nchunks + n_tchunks) {
+      const int k = item - n_nchunks - n_tchunks;
+      std::vector<Sub> st;
+      st.reserve(128);
+      st.push_back(subtrees[k]);
+      int max_depth = 0;
+      size_t visited = 0;
+      while (!st.empty()) {
+        const Sub n = st.back(); st.pop_back();
+        if (++visited > (size_t)N) break;  // more visits than nodes: not a tree
+        max_depth = std::max(max_depth, n.depth);
+        if (ibits(n.node, 2) > -1) continue;
+        const int32_t l = ibits(n.node, 0), r = ibits(n.node, 1);
+        if (l < 0 || l >= N || r < 0 || r >= N) continue;
+        st.push_back({l, n.depth + 1});
+        st.push_back({r, n.depth + 1});
+      }
+      sub_depth[k] = max_depth; sub_visited[k] = visited;
+      return;
+    }
     if (item < n_nchunks) {
       const int ch = item, i1 = std::min(N, (ch + 1) * PRE_CHUNK);
       int n_int = 0;
@@ -1017,6 +1064,14 @@ static int scene_upload_impl(fspt_ctx* ctx, const fspt_scene_desc* s, bool async
   });
   if (bad_node.load() >= 0)
     return fail(c, FSPT_E_INVALID, "node %d: triangle index %d out of range", bad_node.load(), ibits(bad_node.load(), 2));
+  {
+    int max_depth = top_depth;
+    size_t visited = top_visited;
+    for (int k = 0; k < n_sub; ++k) { max_depth = std::max(max_depth, sub_depth[k]); visited += sub_visited[k]; }
+    if (visited > (size_t)N) return fail(c, FSPT_E_INVALID, "BVH is not a tree (cycle or shared node)");
+    if (max_depth + 1 > FSPT_STACK)
+      return fail(c, FSPT_E_LIMIT, "BVH depth %d exceeds the traversal stack (%d, as in tracer.fs:368)", max_depth, FSPT_STACK);
+  }
   for (int ch = 0; ch < n_nchunks; ++ch) chunk_interiors[ch + 1] += chunk_interiors[ch];
   const size_t NI = (size_t)chunk_interiors[n_nchunks];
   interior_of.resize(NI);
@@ -1130,29 +1185,6 @@ static int scene_upload_impl(fspt_ctx* ctx, const fspt_scene_desc* s, bool async
     std::lock_guard<std::mutex> g(geo_mu);
     if (geo.code == FSPT_OK) { geo.code = code; snprintf(geo.msg, sizeof geo.msg, fmt, a0, a1, a2); }
   };
-  // depth / stack bound check (the reference has int stack[64], tracer.fs:368): iterative DFS on its own thread; child
-  // indices out of range end it silently, the node items below report them
-  struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } };
-  std::thread dfs_thread([&]() {
-    std::vector<std::pair<int, int>> st;
-    st.reserve(256);
-    st.push_back({0, 1});
-    int max_depth = 0;
-    size_t visited = 0;
-    while (!st.empty()) {
-      auto [n, d] = st.back(); st.pop_back();
-      if (++visited > (size_t)N) { geo_fail(FSPT_E_INVALID, "BVH is not a tree (cycle or shared node)", 0, 0, 0); return; }
-      max_depth = std::max(max_depth, d);
-      if (ibits(n, 2) > -1) continue;
-      const int32_t l = ibits(n, 0), r = ibits(n, 1);
-      if (l < 0 || l >= N || r < 0 || r >= N) return;
-      st.push_back({l, d + 1});
-      st.push_back({r, d + 1});
-    }
-    if (max_depth + 1 > FSPT_STACK)
-      geo_fail(FSPT_E_LIMIT, "BVH depth %d exceeds the traversal stack (%d, as in tracer.fs:368)", max_depth, FSPT_STACK, 0);
-  });
-  Joiner dfs_join{dfs_thread};
   std::atomic<int> dma_err(0);
   std::mutex dma_mu;  // serialises the enqueues on the context's stream
   std::vector<std::atomic<int>> slot_done((size_t)n_slots);  // last item whose copies have been enqueued from the slot
@@ -1261,7 +1293,11 @@ static int scene_upload_impl(fspt_ctx* ctx, const fspt_scene_desc* s, bool async
   c->has_dielectric = dielectric;
   c->scene_bytes = (size_t)N * 36 + (size_t)T * (36 + 48 + 108 + 24) + (size_t)s->atlas_res * s->atlas_res * 4 * s->atlas_layers +
                    env_bytes + (size_t)s->env_bins * 8;
-  // ---- the atlas part: here, or on the context's atlas thread (the caller's atlas stays borrowed until it is joined)
+  // ---- the atlas part: here, or on the context's atlas thread (the caller's atlas stays borrowed until it is joined).
+  // Measured alternatives (e2e step of the bench scene, asynchronous upload, 29.4 ms as built): the layer scan inside the
+  // atlas part instead of the staging region 29.8 (the upload returns 0.2 ms earlier but the atlas lands 0.7 ms later, and
+  // the first shading launch waits for that); the whole atlas part started before the geometry staging on workers of
+  // its own 32.5 (32 threads on 16 cores: the geometry, which the first traversal launch waits for, takes 3 ms).
   AtlasJob job;
   job.atlas = s->atlas; job.L = L; job.R = s->atlas_res;
   job.mats = std::move(mats);
@@ -1289,9 +1325,7 @@ static int scene_upload_impl(fspt_ctx* ctx, const fspt_scene_desc* s, bool async
     if ((rc_ = stage_atlas(c, job))) { c->error = c->atlas_error; return rc_; }
     lap("atlas part");
   }
-  dfs_thread.join();
   if (geo.code != FSPT_OK) return fail(c, geo.code, "%s", geo.msg);
-  lap("join depth check");
   // no synchronisation: everything the DMA engines still read lives in the context's pinned blocks, which the next
   // upload (and destroy) only touch after synchronising the streams; work enqueued by fspt_render waits in order
   if (timing && !async_atlas) { CK(cudaStreamSynchronize(c->stream)); CK(cudaStreamSynchronize(c->copy_stream)); lap("sync (timing only)"); }

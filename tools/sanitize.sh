@@ -10,10 +10,13 @@ ctx.scene_upload(sa)
 fr = ctx.frame(cam["eye"], cam["dir"], cam["fov_scale"], scenes.lens_features(cam), cam["env_theta"])
 rc, rt = scenes.rand_bases(3, 1)
 ctx.clear(); ctx.render(fr, 0, rc, rt); img = ctx.resolve(denoise=True)
+ctx.scene_upload(sa, wait=False)   # asynchronous upload: atlas thread + ring reuse (FSPT_RING_SLOTS=2 below)
+ctx.clear(); ctx.render(fr, 0, rc, rt); img2 = ctx.resolve(denoise=True)
+assert (img == img2).all()
 idx, t, cnt, pos, d = ctx.debug_primary(fr, 5.0)
 print("ok", img.mean(), (idx >= 0).mean(), ctx.stats()["rays"])
 ctx.close()
 PY
 for tool in memcheck racecheck initcheck; do
-  echo "== $tool"; compute-sanitizer --tool $tool --error-exitcode 3 python /tmp/fspt_san.py 2>&1 | tail -2
+  echo "== $tool"; FSPT_RING_SLOTS=2 compute-sanitizer --tool $tool --error-exitcode 3 python /tmp/fspt_san.py 2>&1 | tail -2
 done
