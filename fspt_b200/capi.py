@@ -54,6 +54,7 @@ EXPORTS = [
     "fspt_debug_last_color", "fspt_debug_math", "fspt_debug_read_bandwidth", "fspt_get_stats", "fspt_synchronize", "fspt_bvh_build", "fspt_bvh_build2",
     "fspt_env_bins", "fspt_pack_layer", "fspt_set_param", "fspt_set_tile", "fspt_comm_unique_id", "fspt_comm_init",
     "fspt_comm_destroy", "fspt_reduce_accum", "fspt_scene_broadcast", "fspt_scene_upload_async", "fspt_scene_upload_wait",
+    "fspt_host_register", "fspt_host_unregister",
 ]
 PARAM_ANYHIT, PARAM_MAX_REFRACTIONS, PARAM_SANITIZE_NAN = 1, 2, 3
 
@@ -97,6 +98,23 @@ def comm_unique_id():
     if rc != FSPT_OK:
         raise FsptError(rc, (lib.fspt_last_error(None) or b"").decode())
     return bytes(buf)
+
+
+def host_register(a):
+    """fspt_host_register: page-lock a C-contiguous numpy array in place (uploads then DMA it from where it lies)."""
+    lib = load()
+    assert a.flags["C_CONTIGUOUS"]
+    rc = lib.fspt_host_register(a.ctypes.data_as(C.c_void_p), C.c_uint64(a.nbytes))
+    if rc != FSPT_OK:
+        raise FsptError(rc, (lib.fspt_last_error(None) or b"").decode())
+    return a
+
+
+def host_unregister(a):
+    lib = load()
+    rc = lib.fspt_host_unregister(a.ctypes.data_as(C.c_void_p))
+    if rc != FSPT_OK:
+        raise FsptError(rc, (lib.fspt_last_error(None) or b"").decode())
 
 
 def ptr(a):

@@ -261,6 +261,13 @@ __global__ void k_set_counts(int* counts, int n_cont, int n_shadow) {
   counts[0] = n_cont; counts[1] = n_shadow; counts[2] = 0; counts[3] = 0; counts[32] = 0;
 }
 
+// true when `p` points into page-locked host memory (cudaHostRegister / cudaMallocHost, by whoever): DMA can read it in place
+bool host_is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
 // Waits for the atlas part of the last fspt_scene_upload_async (no-op otherwise) and reports its outcome.
 int atlas_join(Ctx* c) {
   if (c->atlas_thread.joinable()) c->atlas_thread.join();
@@ -285,7 +292,9 @@ struct AtlasJob {
   int32_t* mat_info;                        // pinned: per material 2 x int4
   size_t n_mat_info;                        // ints
   MatSrc* mat_src;                          // pinned: per textured material (GPU-side interleave)
-  std::vector<uint8_t> varied;               // per layer: 1 = not a constant colour (scanned next to the geometry staging)
+  std::vector<uint8_t> varied;               // per layer: 1 = not a constant colour (scanned next to the geometry staging);
+                                             // empty: the atlas part scans the layers itself
+  bool src_pinned;                           // the caller's atlas is page-locked (fspt_host_register): no staging copy
   int workers;
   bool timing;
 };
@@ -330,9 +339,17 @@ int stage_atlas(Ctx* c, const AtlasJob& J) {
   uint32_t* layer_info = J.layer_info;
   int32_t* mat_info = J.mat_info;
   HostPool& pool = *c->pool;
-  for (int l = 0; l < L; ++l) {
-    layer_info[2 * l] = J.varied[l] ? 0u : 1u;
-    memcpy(&layer_info[2 * l + 1], J.atlas + (size_t)l * layer_bytes, 4);
+  {
+    std::vector<std::atomic<int>> varied((size_t)L);
+    if (J.varied.empty()) {
+      for (auto& v : varied) v.store(0);
+      pool.run(L * SCAN_BANDS, J.workers, [&](int item) { scan_layer_band(J.atlas, layer_texels, item, varied.data()); });
+      lap("constant-layer scan");
+    }
+    for (int l = 0; l < L; ++l) {
+      layer_info[2 * l] = (J.varied.empty() ? varied[l].load() : J.varied[l]) ? 0u : 1u;
+      memcpy(&layer_info[2 * l + 1], J.atlas + (size_t)l * layer_bytes, 4);
+    }
   }
   memset(mat_info, 0, J.n_mat_info * 4);
   int n_tex_mats = 0;
@@ -393,8 +410,11 @@ int stage_atlas(Ctx* c, const AtlasJob& J) {
         mat_src[tl].cst[k] = layer_info[2 * l + 1];
       }
     }
-    bool gpu_interleave = n_tex_mats > 0 && raw_layers.size() * 2 <= (size_t)n_tex_mats * 4;
+    // A page-locked source (the host registered its atlas, fspt_host_register) needs no staging at all on the GPU path:
+    // the distinct varying layers are DMA'd from where they lie, the host does nothing but enqueue the copies.
+    bool gpu_interleave = n_tex_mats > 0 && (J.src_pinned || raw_layers.size() * 2 <= (size_t)n_tex_mats * 4);
     if (const char* e = getenv("FSPT_ATLAS_INTERLEAVE")) gpu_interleave = n_tex_mats > 0 && !strcmp(e, "gpu");
+    const bool direct = gpu_interleave && J.src_pinned;
     if (!c->mat_arr || c->mat_R != R || c->mat_L != ML || c->mat_surface != gpu_interleave) {
       if (c->sc.mat_tex) cudaDestroyTextureObject(c->sc.mat_tex);
       c->sc.mat_tex = 0;
@@ -419,7 +439,7 @@ int stage_atlas(Ctx* c, const AtlasJob& J) {
       }
     }
     const size_t need = gpu_interleave ? layer_bytes * raw_layers.size() : layer_texels * 16 * (size_t)ML;
-    if (!plain_atlas && c->stage_bytes < need) {
+    if (!plain_atlas && !direct && c->stage_bytes < need) {
       if (c->h_stage) cudaFreeHost(c->h_stage);
       c->h_stage = nullptr; c->stage_bytes = 0;
       if (cudaMallocHost(&c->h_stage, need) != cudaSuccess) {
@@ -446,9 +466,14 @@ int stage_atlas(Ctx* c, const AtlasJob& J) {
         ACK(cudaMalloc(&c->d_mat_src, sizeof(MatSrc) * (size_t)ML));
         c->cap_mat_src = sizeof(MatSrc) * (size_t)ML;
       }
+      if (direct) {
+        for (size_t ri = 0; ri < raw_layers.size(); ++ri)
+          ACK(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(c->d_raw) + ri * layer_bytes, J.atlas + (size_t)raw_layers[ri] * layer_bytes,
+                              layer_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+      }
       // work item = (raw layer, band of rows): copy into the pinned block, DMA the band
       const int bands = std::max(1, std::min(R, 16));
-      pool.run((int)raw_layers.size() * bands, J.workers, [&](int item) {
+      pool.run(direct ? 0 : (int)raw_layers.size() * bands, J.workers, [&](int item) {
         const int ri = item / bands, band = item % bands;
         const size_t y0 = (size_t)R * band / bands, y1 = (size_t)R * (band + 1) / bands;
         const size_t off = (size_t)ri * layer_bytes + y0 * R * 4, bytes = (y1 - y0) * R * 4;
@@ -1159,7 +1184,11 @@ static int scene_upload_impl(fspt_ctx* ctx, const fspt_scene_desc* s, bool async
   const int n_tri_items = (T + 3 + tri_chunk - 1) / tri_chunk;
   const int n_env_items = std::max(1, std::min(s->env_height, (int)(env_bytes >> 20)));  // ~1 MB of rows each
   const int n_geo_items = n_node_items + n_tri_items;
-  const int n_scan_items = L * SCAN_BANDS;
+  // (a page-locked atlas under an asynchronous upload: the scan is all the host work the atlas part has left, and it
+  // should not hold up this function's return -- it moves to the atlas thread)
+  const bool atlas_pinned = host_is_pinned(s->atlas);
+  const bool scan_here = !(async_atlas && atlas_pinned);
+  const int n_scan_items = scan_here ? L * SCAN_BANDS : 0;
   const int n_items = n_env_items + n_geo_items + n_scan_items;
   const size_t layer_texels = (size_t)s->atlas_res * s->atlas_res;
   std::vector<std::atomic<int>> varied((size_t)L);
@@ -1167,6 +1196,7 @@ static int scene_upload_impl(fspt_ctx* ctx, const fspt_scene_desc* s, bool async
   const size_t slot_bytes = al(std::max<size_t>((size_t)node_chunk * 64, (size_t)tri_chunk * (48 + 192)));
   int n_slots = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_geo_items, std::max<size_t>(2 * (size_t)workers, ((size_t)256 << 20) / slot_bytes)));
   if (const char* e = getenv("FSPT_RING_SLOTS")) n_slots = std::max(1, std::min(n_slots, atoi(e)));  // test knob: force slot reuse
+  const bool ring_wraps = n_geo_items > n_slots;  // otherwise every chunk has a slot of its own and no event is needed
   if (c->ring_bytes < slot_bytes * (size_t)n_slots) {
     if (c->h_ring) cudaFreeHost(c->h_ring);
     c->h_ring = nullptr; c->ring_bytes = 0;
@@ -1186,7 +1216,10 @@ static int scene_upload_impl(fspt_ctx* ctx, const fspt_scene_desc* s, bool async
     if (geo.code == FSPT_OK) { geo.code = code; snprintf(geo.msg, sizeof geo.msg, fmt, a0, a1, a2); }
   };
   std::atomic<int> dma_err(0);
-  std::mutex dma_mu;  // serialises the enqueues on the context's stream
+  // (No lock around the enqueues: the runtime is thread-safe, and a slot's event only has to follow the slot's own copies,
+  // which the recording thread enqueued itself.  A mutex held across the two or three calls of an item serialised ~60
+  // items x ~12 us on the bench scene -- most of the region's 1.4 ms.)
+  const bool src_env_pinned = host_is_pinned(s->env);
   std::vector<std::atomic<int>> slot_done((size_t)n_slots);  // last item whose copies have been enqueued from the slot
   for (auto& v : slot_done) v.store(-1);
   auto tri9 = [&](int t, float* o) {  // v1 | e1 | e2 of triangle t (t >= T: padBuffer's -1 fill, main.js:143-154)
@@ -1204,11 +1237,11 @@ static int scene_upload_impl(fspt_ctx* ctx, const fspt_scene_desc* s, bool async
         for (size_t i = 0; i < (size_t)s->env_bins * 4; ++i) bins[i] = (float)s->radiance_bins[i];  // vec4(radianceBins[idx]), tracer.fs:424
       const size_t pitch = (size_t)s->env_width * 4;
       const int y0 = (int)((long long)s->env_height * item / n_env_items), y1 = (int)((long long)s->env_height * (item + 1) / n_env_items);
-      memcpy(hg + o_env + y0 * pitch, s->env + y0 * pitch, (size_t)(y1 - y0) * pitch);
-      std::lock_guard<std::mutex> g(dma_mu);
+      const uint8_t* src = s->env + y0 * pitch;   // page-locked by the caller (fspt_host_register): DMA'd where it lies
+      if (!src_env_pinned) { memcpy(hg + o_env + y0 * pitch, src, (size_t)(y1 - y0) * pitch); src = hg + o_env + y0 * pitch; }
       cudaError_t e = item == 0 ? cudaMemcpyAsync(c->d_bins, bins, bins_bytes, cudaMemcpyHostToDevice, c->stream) : cudaSuccess;
       if (e == cudaSuccess)
-        e = cudaMemcpy2DToArrayAsync(c->env_arr, 0, y0, hg + o_env + y0 * pitch, pitch, pitch, y1 - y0, cudaMemcpyHostToDevice, c->stream);
+        e = cudaMemcpy2DToArrayAsync(c->env_arr, 0, y0, src, pitch, pitch, y1 - y0, cudaMemcpyHostToDevice, c->stream);
       if (e != cudaSuccess) dma_err.store((int)e);
       return;
     }
@@ -1246,9 +1279,8 @@ static int scene_upload_impl(fspt_ctx* ctx, const fspt_scene_desc* s, bool async
         o[14] = o[15] = 0.0f;
       }
       const size_t bytes = NI ? (k1 - k0) * 64 : 64;
-      std::lock_guard<std::mutex> g(dma_mu);
       e = cudaMemcpyAsync(reinterpret_cast<uint8_t*>(c->d_nodes) + k0 * 64, nodes, bytes, cudaMemcpyHostToDevice, c->stream);
-      if (e == cudaSuccess) e = cudaEventRecord(c->ev_ring[slot], c->stream);
+      if (e == cudaSuccess && ring_wraps) e = cudaEventRecord(c->ev_ring[slot], c->stream);
     } else {
       // triangles: v1, e1, e2 (tracer.fs:301-302) + LEAF_SIZE-1 padBuffer-style (-1,-1,-1) tail records; shading
       // records: material (12) | uvs (6) | material id | pad | normals (27) | pad
@@ -1268,11 +1300,10 @@ static int scene_upload_impl(fspt_ctx* ctx, const fspt_scene_desc* s, bool async
         memcpy(h + 20, s->normals + (size_t)t * 27, 108);
         h[47] = 0.0f;
       }
-      std::lock_guard<std::mutex> g(dma_mu);
       e = cudaMemcpyAsync(reinterpret_cast<uint8_t*>(c->d_tris) + (size_t)t0 * 48, tris, (size_t)(t1 - t0) * 48, cudaMemcpyHostToDevice, c->stream);
       if (e == cudaSuccess && ts > t0)
         e = cudaMemcpyAsync(reinterpret_cast<uint8_t*>(c->d_shade) + (size_t)t0 * 192, shade, (size_t)(ts - t0) * 192, cudaMemcpyHostToDevice, c->stream);
-      if (e == cudaSuccess) e = cudaEventRecord(c->ev_ring[slot], c->stream);
+      if (e == cudaSuccess && ring_wraps) e = cudaEventRecord(c->ev_ring[slot], c->stream);
     }
     if (e != cudaSuccess) dma_err.store((int)e);
     slot_done[slot].store(ring_item, std::memory_order_release);
@@ -1305,8 +1336,11 @@ static int scene_upload_impl(fspt_ctx* ctx, const fspt_scene_desc* s, bool async
   job.mat_info = reinterpret_cast<int32_t*>(hg + o_mat);
   job.n_mat_info = n_mat_info;
   job.mat_src = reinterpret_cast<MatSrc*>(hg + o_matsrc);
-  job.varied.resize((size_t)L);
-  for (int l = 0; l < L; ++l) job.varied[l] = (uint8_t)varied[l].load();
+  if (scan_here) {
+    job.varied.resize((size_t)L);
+    for (int l = 0; l < L; ++l) job.varied[l] = (uint8_t)varied[l].load();
+  }
+  job.src_pinned = atlas_pinned;
   job.workers = hw;
   job.timing = timing;
   c->atlas_rc = FSPT_OK;
@@ -1336,6 +1370,20 @@ static int scene_upload_impl(fspt_ctx* ctx, const fspt_scene_desc* s, bool async
 
 int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) { return scene_upload_impl(ctx, s, false); }
 int fspt_scene_upload_async(fspt_ctx* ctx, const fspt_scene_desc* s) { return scene_upload_impl(ctx, s, true); }
+int fspt_host_register(void* p, uint64_t bytes) {
+  if (!p || !bytes) return FSPT_E_INVALID;
+  cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) { (void)cudaGetLastError(); return FSPT_OK; }
+  if (e != cudaSuccess) { (void)cudaGetLastError(); g_create_error = std::string("cudaHostRegister: ") + cudaGetErrorString(e); return FSPT_E_CUDA; }
+  return FSPT_OK;
+}
+int fspt_host_unregister(void* p) {
+  if (!p) return FSPT_E_INVALID;
+  cudaError_t e = cudaHostUnregister(p);
+  if (e != cudaSuccess) { (void)cudaGetLastError(); g_create_error = std::string("cudaHostUnregister: ") + cudaGetErrorString(e); return FSPT_E_CUDA; }
+  return FSPT_OK;
+}
+
 int fspt_scene_upload_wait(fspt_ctx* ctx) {
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
   if (!c) return FSPT_E_INVALID;

@@ -113,6 +113,13 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* scene);
  * fspt_destroy) has returned; errors of the staging are reported by whichever call joins it. */
 int fspt_scene_upload_async(fspt_ctx* ctx, const fspt_scene_desc* scene);
 int fspt_scene_upload_wait(fspt_ctx* ctx);
+/* Optional: page-lock a host buffer the caller keeps across uploads (cudaHostRegister; no reference counterpart --
+ * WebGL copies out of JS memory).  fspt_scene_upload(_async) recognises page-locked memory by itself, whoever locked it:
+ * a page-locked `atlas` is DMA'd from where it lies (only its distinct non-constant layers cross PCIe; the per-material
+ * texels are built on the GPU) and a page-locked `env` likewise; the geometry buffers are always repacked through the
+ * library's own staging.  Errors of these two calls are reported through fspt_last_error(NULL). */
+int fspt_host_register(void* ptr, uint64_t bytes);
+int fspt_host_unregister(void* ptr);
 
 /* clear() (main.js:826-836): zero the accumulation target, pingpong = 0. */
 int fspt_clear(fspt_ctx* ctx);

@@ -386,3 +386,43 @@ def test_geometry_ring_reuse_and_worker_counts_are_bit_identical(small_bunny, mo
             assert np.array_equal(ref.view(np.uint32), ctx.read_accum().view(np.uint32)), (slots, threads, wait)
     finally:
         ctx.close()
+
+
+def test_page_locked_atlas_and_env_are_uploaded_in_place(monkeypatch):
+    """fspt_host_register: a page-locked atlas is DMA'd from where it lies (distinct non-constant layers only, per-material
+    texels built by k_interleave_atlas) and a page-locked environment likewise -- same bits as the staged upload, in the
+    synchronous and the asynchronous call, and again after the buffers have been unlocked."""
+    import copy
+    sa0, cam = scenes.pbr_scene(atlas_res=128, subdiv=2, env_size=(128, 64))
+    sa = copy.copy(sa0)
+    sa.atlas = np.array(sa0.atlas, copy=True)
+    sa.env = np.array(sa0.env, copy=True)
+    W, H = 96, 64
+    rc, rt = scenes.rand_bases(3, 51)
+    ctx = capi.Context(W, H)
+    try:
+        ctx.scene_upload(sa0)
+        fr = _frame(ctx, cam)
+        ctx.render(fr, 0, rc, rt)
+        ref = ctx.read_accum().copy()
+        assert float(ref[..., :3].max()) > 0.0
+        capi.host_register(sa.atlas)
+        capi.host_register(sa.env)
+        capi.host_register(sa.env)      # registering twice is not an error
+        try:
+            for wait in (True, False, False):
+                ctx.scene_upload(sa, wait=wait)
+                ctx.clear()
+                ctx.render(fr, 0, rc, rt)
+                assert np.array_equal(ref.view(np.uint32), ctx.read_accum().view(np.uint32)), wait
+            ctx.upload_wait()
+        finally:
+            ctx.synchronize()
+            capi.host_unregister(sa.atlas)
+            capi.host_unregister(sa.env)
+        ctx.scene_upload(sa, wait=False)
+        ctx.clear()
+        ctx.render(fr, 0, rc, rt)
+        assert np.array_equal(ref.view(np.uint32), ctx.read_accum().view(np.uint32))
+    finally:
+        ctx.close()

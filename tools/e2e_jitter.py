@@ -1,5 +1,6 @@
 """Per-step wall time of the e2e leg (upload + clear + render + resolve), with and without torch in the process;
---async: fspt_scene_upload_async (the atlas transfer overlaps the primary traversal)."""
+--async: fspt_scene_upload_async (the atlas transfer overlaps the primary traversal); --pinned: atlas and environment
+page-locked in place (fspt_host_register)."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -13,6 +14,9 @@ from fspt_b200 import scenes
 from fspt_b200.path_tracer import PathTracer
 sa, cam = scenes.bunny_class(subdiv=6, atlas_res=2048)
 pt = PathTracer(sa, (1280, 720), cam, device=0)
+if "--pinned" in sys.argv:
+    from fspt_b200 import capi
+    pt.ctx.synchronize(); capi.host_register(sa.atlas); capi.host_register(sa.env)
 rc, rt = scenes.rand_bases(64, 1)
 out8 = np.empty((720, 1280, 4), np.uint8)
 ts = []

@@ -4,6 +4,8 @@ from fspt_b200 import scenes, capi
 ASYNC = "--async" in sys.argv   # fspt_scene_upload_async: time to return, then the time until everything has landed
 sa, cam = scenes.sphere_soup() if "--soup" in sys.argv else scenes.bunny_class(subdiv=6, atlas_res=2048)
 ctx = capi.Context(1280, 720)
+if "--pinned" in sys.argv:
+    capi.host_register(sa.atlas); capi.host_register(sa.env)
 for i in range(4):
     t0 = time.perf_counter(); n = ctx.scene_upload(sa, wait=not ASYNC); t1 = time.perf_counter(); ctx.synchronize(); dt = time.perf_counter() - t0
     print("upload returned after %.2f ms, landed after %.1f ms for %.1f MB -> %.1f GB/s" % ((t1 - t0) * 1e3, dt * 1e3, n / 1e6, n / dt / 1e9))
