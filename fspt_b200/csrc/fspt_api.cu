@@ -125,7 +125,11 @@ struct Ctx {
   bool reduce_timed = false;
   void* d_lin = nullptr;      // linear staging of the environment + atlas arrays for fspt_scene_broadcast
   size_t cap_lin = 0;
-  void* d_hdr = nullptr;      // broadcast header
+  void* d_hdr = nullptr;      // broadcast headers
+  void* d_lin_env = nullptr;  // linear staging of the environment array (phase 1 of the broadcast)
+  size_t cap_lin_env = 0;
+  int bcast_pending_root = -1;  // >= 0: phase 2 of fspt_scene_broadcast (the atlas) has not been issued yet
+  cudaEvent_t ev_bcast = nullptr;  // end of phase 1 on the context's stream
   size_t bytes_nodes = 0, bytes_tris = 0, bytes_shade = 0, bytes_bins = 0, bytes_layer_info = 0,
          bytes_mat_info = 0;
   int trace_blocks = 0, trace_blocks_cnt = 0, trace_blocks_cam = 0, shade_blocks = 0;
@@ -135,6 +139,7 @@ struct Ctx {
 };
 
 void comm_free(Ctx* c);
+int broadcast_phase2(Ctx* c);
 
 int fail(Ctx* c, int code, const char* fmt, ...) {
   char buf[512];
@@ -716,6 +721,7 @@ int render_wave(Ctx* c, const FrameParams& fp, uint32_t first_tick, int S, const
   // running on the GPU (the event it records has to exist before the stream can be made to wait on it); then the DMA
   // itself is waited for on the device (no-op once it has completed)
   if ((rc = atlas_join(c))) return rc;
+  if ((rc = broadcast_phase2(c))) return rc;  // multi-GPU: the atlas travels to the other ranks now, behind the traversal
   A.sc = c->sc;  // (the atlas part sets the texture objects and table pointers)
   CK(cudaStreamWaitEvent(c->stream, c->ev_atlas, 0));
   int cur = 0;
@@ -821,6 +827,131 @@ struct SceneHeader {
   int32_t mat_R, mat_L, use_mat_tex, has_dielectric, magic;
 };
 
+// what a receiving rank has to know before the atlas part of fspt_scene_broadcast arrives (phase 2)
+struct SceneHeader2 {
+  uint64_t bytes_layer_info, bytes_mat_info;
+  int32_t mat_R, mat_L, use_mat_tex, magic;
+};
+
+// The scene resident on `root` -> every other rank, device to device over NVLink: the records fspt_scene_upload built
+// (Node64, Tri48, ShadeRec, bins, layer / material tables) and linear copies of the environment and atlas arrays.  One
+// host stages and uploads a scene once instead of every rank repeating the same 200 MB of host work.
+//
+// Two phases, like the upload itself.  Phase 1 (here, on the context's stream): what the traversal kernel needs -- and
+// the environment.  Phase 2 (the atlas and its tables, on the copy stream) is DEFERRED to the point where the root's
+// atlas is needed anyway: the first shading launch of the next fspt_render, behind its primary traversal launch (or the
+// next fspt_synchronize / fspt_reduce_accum / upload / broadcast, whichever comes first -- every rank reaches one of them,
+// in the same order relative to the other collectives).  An asynchronous upload on the root therefore overlaps its atlas
+// transfer with the primary traversal on EVERY rank, and the root's host is not held in the broadcast call.
+int broadcast_phase2(Ctx* c) {
+  if (c->bcast_pending_root < 0) return FSPT_OK;
+  const int root = c->bcast_pending_root;
+  c->bcast_pending_root = -1;
+  const bool is_root = c->comm_rank == root;
+  NcclApi* N = nccl_api();
+  SceneHeader2 h;
+  memset(&h, 0, sizeof h);
+  static_assert(sizeof(SceneHeader2) <= 128, "header buffer");
+  uint8_t* d_hdr2 = reinterpret_cast<uint8_t*>(c->d_hdr) + 256;
+  // the collectives of one communicator run one after the other: this one starts behind phase 1 (its last collective
+  // recorded the event), not behind the traversal launch that may have been enqueued since
+  CK(cudaStreamWaitEvent(c->copy_stream, c->ev_bcast, 0));
+  if (is_root) {
+    int rcj = atlas_join(c);  // (normally already joined by the caller)
+    if (rcj) h.magic = -1;    // the ranks must not wait for an atlas that will not come
+    else {
+      h.bytes_layer_info = c->bytes_layer_info; h.bytes_mat_info = c->bytes_mat_info;
+      h.use_mat_tex = c->sc.mat_tex ? 1 : 0;
+      h.mat_R = h.use_mat_tex ? c->mat_R : c->atlas_R;
+      h.mat_L = h.use_mat_tex ? c->mat_L : c->atlas_L;
+      h.magic = 0x46535032;
+    }
+    CK(cudaMemcpyAsync(d_hdr2, &h, sizeof h, cudaMemcpyHostToDevice, c->copy_stream));
+    NK(N->Broadcast(d_hdr2, d_hdr2, sizeof h, ncclUint8, root, c->comm, c->copy_stream));
+    if (rcj) return rcj;
+  } else {
+    NK(N->Broadcast(d_hdr2, d_hdr2, sizeof h, ncclUint8, root, c->comm, c->copy_stream));
+    CK(cudaMemcpyAsync(&h, d_hdr2, sizeof h, cudaMemcpyDeviceToHost, c->copy_stream));
+    CK(cudaStreamSynchronize(c->copy_stream));
+    if (h.magic != 0x46535032) { c->has_scene = false; return fail(c, FSPT_E_NCCL, "fspt_scene_broadcast: rank %d has no atlas to send (its upload failed)", root); }
+  }
+  const size_t texel = h.use_mat_tex ? 16 : 4;
+  const size_t atlas_bytes = (size_t)h.mat_R * h.mat_R * texel * (size_t)h.mat_L;
+  int rc;
+  if ((rc = ensure(c, c->d_lin, c->cap_lin, atlas_bytes))) return rc;
+  uint8_t* lin = reinterpret_cast<uint8_t*>(c->d_lin);
+  cudaMemcpy3DParms cp = {};
+  cp.extent = make_cudaExtent(h.mat_R, h.mat_R, h.mat_L);
+  cp.kind = cudaMemcpyDeviceToDevice;
+  if (is_root) {
+    // the atlas DMA of the upload runs on this same stream (in order)
+    cp.srcArray = h.use_mat_tex ? c->mat_arr : c->atlas_arr;
+    cp.dstPtr = make_cudaPitchedPtr(lin, (size_t)h.mat_R * texel, h.mat_R, h.mat_R);
+    CK(cudaMemcpy3DAsync(&cp, c->copy_stream));
+  } else {
+    // storage on the receiving side: same reuse rules as fspt_scene_upload
+    if ((rc = ensure(c, c->d_layer_info, c->cap_layer_info, h.bytes_layer_info))) return rc;
+    if ((rc = ensure(c, c->d_mat_info, c->cap_mat_info, h.bytes_mat_info))) return rc;
+    cudaResourceDesc rd = {};
+    rd.resType = cudaResourceTypeArray;
+    cudaTextureDesc td = {};
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+    td.filterMode = cudaFilterModePoint;
+    td.readMode = cudaReadModeElementType;
+    cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
+    if (h.use_mat_tex) {
+      if (c->sc.atlas) { cudaDestroyTextureObject(c->sc.atlas); c->sc.atlas = 0; }
+      if (c->atlas_arr) { cudaFreeArray(c->atlas_arr); c->atlas_arr = nullptr; c->atlas_R = c->atlas_L = 0; }
+      if (!c->mat_arr || c->mat_R != h.mat_R || c->mat_L != h.mat_L) {
+        if (c->sc.mat_tex) cudaDestroyTextureObject(c->sc.mat_tex);
+        c->sc.mat_tex = 0;
+        if (c->mat_surf) cudaDestroySurfaceObject(c->mat_surf);
+        c->mat_surf = 0; c->mat_surface = false;
+        if (c->mat_arr) cudaFreeArray(c->mat_arr);
+        c->mat_arr = nullptr;
+        cudaChannelFormatDesc fmt4 = cudaCreateChannelDesc<uint4>();
+        CK(cudaMalloc3DArray(&c->mat_arr, &fmt4, make_cudaExtent(h.mat_R, h.mat_R, h.mat_L), cudaArrayLayered));
+        rd.res.array.array = c->mat_arr;
+        CK(cudaCreateTextureObject(&c->sc.mat_tex, &rd, &td, nullptr));
+        c->mat_R = h.mat_R; c->mat_L = h.mat_L;
+      }
+    } else {
+      if (c->sc.mat_tex) { cudaDestroyTextureObject(c->sc.mat_tex); c->sc.mat_tex = 0; }
+      if (c->mat_surf) { cudaDestroySurfaceObject(c->mat_surf); c->mat_surf = 0; }
+      c->mat_surface = false;
+      if (c->mat_arr) { cudaFreeArray(c->mat_arr); c->mat_arr = nullptr; c->mat_R = c->mat_L = 0; }
+      if (!c->atlas_arr || c->atlas_R != h.mat_R || c->atlas_L != h.mat_L) {
+        if (c->sc.atlas) cudaDestroyTextureObject(c->sc.atlas);
+        c->sc.atlas = 0;
+        if (c->atlas_arr) cudaFreeArray(c->atlas_arr);
+        c->atlas_arr = nullptr;
+        CK(cudaMalloc3DArray(&c->atlas_arr, &fmt, make_cudaExtent(h.mat_R, h.mat_R, h.mat_L), cudaArrayLayered));
+        rd.res.array.array = c->atlas_arr;
+        CK(cudaCreateTextureObject(&c->sc.atlas, &rd, &td, nullptr));
+        c->atlas_R = h.mat_R; c->atlas_L = h.mat_L;
+      }
+    }
+  }
+  NK(N->GroupStart());
+  NK(N->Broadcast(c->d_layer_info, c->d_layer_info, h.bytes_layer_info, ncclUint8, root, c->comm, c->copy_stream));
+  NK(N->Broadcast(c->d_mat_info, c->d_mat_info, h.bytes_mat_info, ncclUint8, root, c->comm, c->copy_stream));
+  NK(N->Broadcast(lin, lin, atlas_bytes, ncclUint8, root, c->comm, c->copy_stream));
+  NK(N->GroupEnd());
+  c->stats.kernel_launches += 4;
+  if (!is_root) {
+    cp.srcPtr = make_cudaPitchedPtr(lin, (size_t)h.mat_R * texel, h.mat_R, h.mat_R);
+    cp.dstArray = h.use_mat_tex ? c->mat_arr : c->atlas_arr;
+    CK(cudaMemcpy3DAsync(&cp, c->copy_stream));
+    c->bytes_layer_info = h.bytes_layer_info; c->bytes_mat_info = h.bytes_mat_info;
+    c->sc.layer_info = reinterpret_cast<const uint2*>(c->d_layer_info);
+    c->sc.mat_info = reinterpret_cast<const int4*>(c->d_mat_info);
+  }
+  // what the first shading launch waits for; later collectives on the context's stream come behind it as well
+  CK(cudaEventRecord(c->ev_atlas, c->copy_stream));
+  CK(cudaStreamWaitEvent(c->stream, c->ev_atlas, 0));
+  return FSPT_OK;
+}
+
 int pull_stats(Ctx* c) {
   unsigned long long h[8];
   CK(cudaMemcpy(h, c->d_stats, sizeof h, cudaMemcpyDeviceToHost));
@@ -912,6 +1043,7 @@ void fspt_destroy(fspt_ctx* ctx) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->atlas_thread.joinable()) c->atlas_thread.join();
+  c->bcast_pending_root = -1;  // (no collective in a destructor)
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
   delete c->pool;
@@ -930,7 +1062,8 @@ void fspt_destroy(fspt_ctx* ctx) {
   comm_free(c);
   if (c->ev_red0) cudaEventDestroy(c->ev_red0);
   if (c->ev_red1) cudaEventDestroy(c->ev_red1);
-  dfree(c->d_lin); dfree(c->d_hdr);
+  dfree(c->d_lin); dfree(c->d_hdr); dfree(c->d_lin_env);
+  if (c->ev_bcast) cudaEventDestroy(c->ev_bcast);
   for (auto e : c->ev_trace) cudaEventDestroy(e);
   if (c->ev_begin) cudaEventDestroy(c->ev_begin);
   if (c->ev_end) cudaEventDestroy(c->ev_end);
@@ -969,6 +1102,7 @@ static int scene_upload_impl(fspt_ctx* ctx, const fspt_scene_desc* s, bool async
   if (s->leaf_size != 4) return fail(c, FSPT_E_INVALID, "scene_upload: LEAF_SIZE must be 4 (main.js:45), got %d", s->leaf_size);
   CK(cudaSetDevice(c->device));
   (void)atlas_join(c);  // the atlas thread of the previous upload still reads the pinned blocks and the arrays
+  if (int rcb = broadcast_phase2(c)) return rcb;  // (a broadcast nobody rendered from: finish it before its source goes away)
   CK(cudaStreamSynchronize(c->stream));
   CK(cudaStreamSynchronize(c->copy_stream));
   c->has_scene = false;  // device buffers, arrays and texture objects of the previous scene are reused when they fit
@@ -1440,6 +1574,7 @@ int fspt_synchronize(fspt_ctx* ctx) {
   if (!c) return FSPT_E_INVALID;
   CK(cudaSetDevice(c->device));
   if (int rc = atlas_join(c)) return rc;
+  if (int rc = broadcast_phase2(c)) return rc;
   CK(cudaStreamSynchronize(c->stream));
   CK(cudaStreamSynchronize(c->copy_stream));
   return FSPT_OK;
@@ -1679,7 +1814,7 @@ int fspt_comm_init(fspt_ctx* ctx, const uint8_t* id_bytes, int32_t rank, int32_t
   memcpy(&id, id_bytes, sizeof id);
   NK(N->CommInitRank(&c->comm, world, id, rank));
   c->comm_rank = rank; c->comm_world = world;
-  if (!c->d_hdr) CK(cudaMalloc(&c->d_hdr, 256));
+  if (!c->d_hdr) CK(cudaMalloc(&c->d_hdr, 512));  // [0, 256) geometry header, [256, 512) atlas header
   return FSPT_OK;
 }
 
@@ -1702,6 +1837,7 @@ int fspt_reduce_accum(fspt_ctx* ctx, int32_t root) {
   if (root < 0 || root >= c->comm_world) return fail(c, FSPT_E_INVALID, "fspt_reduce_accum: root %d of %d ranks", root, c->comm_world);
   if (c->accum_mode != 1) return fail(c, FSPT_E_STATE, "fspt_reduce_accum needs the sum accumulation mode (fspt_set_accum_mode(ctx, 1))");
   CK(cudaSetDevice(c->device));
+  if (int rc = broadcast_phase2(c)) return rc;  // (a rank that rendered nothing since the broadcast)
   NcclApi* N = nccl_api();
   if (!c->ev_red0) { CK(cudaEventCreate(&c->ev_red0)); CK(cudaEventCreate(&c->ev_red1)); }
   CK(cudaEventRecord(c->ev_red0, c->stream));
@@ -1712,9 +1848,6 @@ int fspt_reduce_accum(fspt_ctx* ctx, int32_t root) {
   return FSPT_OK;
 }
 
-// The scene resident on `root` -> every other rank, device to device over NVLink: the records fspt_scene_upload built
-// (Node64, Tri48, LeafBlock160, ShadeRec, bins, layer / material tables) and linear copies of the environment and atlas
-// arrays.  One host stages and uploads a scene once instead of every rank repeating the same 200 MB of host work.
 int fspt_scene_broadcast(fspt_ctx* ctx, int32_t root) {
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
   if (!c) return FSPT_E_INVALID;
@@ -1723,28 +1856,27 @@ int fspt_scene_broadcast(fspt_ctx* ctx, int32_t root) {
   const bool is_root = c->comm_rank == root;
   if (is_root && !c->has_scene) return fail(c, FSPT_E_STATE, "fspt_scene_broadcast: the root has no scene (fspt_scene_upload first)");
   CK(cudaSetDevice(c->device));
-  if (int rcj = atlas_join(c)) return rcj;  // the root's atlas array is read below
+  int rc;
+  if ((rc = broadcast_phase2(c))) return rc;  // (a previous broadcast nobody rendered from)
+  if (!is_root && (rc = atlas_join(c))) return rc;
   NcclApi* N = nccl_api();
   SceneHeader h;
   memset(&h, 0, sizeof h);
   static_assert(sizeof(SceneHeader) <= 256, "header buffer");
+  if (!c->ev_bcast) CK(cudaEventCreateWithFlags(&c->ev_bcast, cudaEventDisableTiming));
   if (is_root) {
     h.bytes_nodes = c->bytes_nodes; h.bytes_tris = c->bytes_tris; h.bytes_shade = c->bytes_shade;
-    h.bytes_bins = c->bytes_bins; h.bytes_layer_info = c->bytes_layer_info; h.bytes_mat_info = c->bytes_mat_info;
+    h.bytes_bins = c->bytes_bins;
     h.scene_bytes = c->scene_bytes;
     h.root_ref = c->sc.root_ref; h.n_tris = c->sc.n_tris; h.n_interior = c->sc.n_interior;
     h.atlas_res = c->sc.atlas_res; h.atlas_layers = c->sc.atlas_layers; h.env_w = c->sc.env_w; h.env_h = c->sc.env_h;
     h.n_bins = c->sc.n_bins;
-    h.use_mat_tex = c->sc.mat_tex ? 1 : 0;
-    h.mat_R = h.use_mat_tex ? c->mat_R : c->atlas_R;
-    h.mat_L = h.use_mat_tex ? c->mat_L : c->atlas_L;
     h.has_dielectric = c->has_dielectric ? 1 : 0;
     h.magic = 0x46535054;
     CK(cudaMemcpyAsync(c->d_hdr, &h, sizeof h, cudaMemcpyHostToDevice, c->stream));
   } else {
-    CK(cudaStreamSynchronize(c->stream));  // buffers of the previous scene may be in use
+    CK(cudaStreamSynchronize(c->stream));  // nothing of the previous scene may still be in flight
     CK(cudaStreamSynchronize(c->copy_stream));
-    c->has_scene = false;
   }
   NK(N->Broadcast(c->d_hdr, c->d_hdr, sizeof h, ncclUint8, root, c->comm, c->stream));
   if (!is_root) {
@@ -1752,37 +1884,27 @@ int fspt_scene_broadcast(fspt_ctx* ctx, int32_t root) {
     CK(cudaStreamSynchronize(c->stream));
     if (h.magic != 0x46535054) return fail(c, FSPT_E_NCCL, "fspt_scene_broadcast: bad header from rank %d", root);
   }
-  const size_t texel = h.use_mat_tex ? 16 : 4;
-  const size_t env_bytes = (size_t)h.env_w * h.env_h * 4, atlas_bytes = (size_t)h.mat_R * h.mat_R * texel * (size_t)h.mat_L;
-  int rc;
-  if ((rc = ensure(c, c->d_lin, c->cap_lin, env_bytes + atlas_bytes))) return rc;
-  uint8_t* lin = reinterpret_cast<uint8_t*>(c->d_lin);
-  cudaMemcpy3DParms cp = {};
-  cp.extent = make_cudaExtent(h.mat_R, h.mat_R, h.mat_L);
-  cp.kind = cudaMemcpyDeviceToDevice;
+  const size_t env_bytes = (size_t)h.env_w * h.env_h * 4;
+  if ((rc = ensure(c, c->d_lin_env, c->cap_lin_env, env_bytes))) return rc;
+  uint8_t* lin = reinterpret_cast<uint8_t*>(c->d_lin_env);
   if (is_root) {
-    CK(cudaStreamWaitEvent(c->stream, c->ev_atlas, 0));  // the atlas DMA of the upload runs on its own stream
     CK(cudaMemcpy2DFromArrayAsync(lin, (size_t)h.env_w * 4, c->env_arr, 0, 0, (size_t)h.env_w * 4, h.env_h,
                                   cudaMemcpyDeviceToDevice, c->stream));
-    cp.srcArray = h.use_mat_tex ? c->mat_arr : c->atlas_arr;
-    cp.dstPtr = make_cudaPitchedPtr(lin + env_bytes, (size_t)h.mat_R * texel, h.mat_R, h.mat_R);
-    CK(cudaMemcpy3DAsync(&cp, c->stream));
   } else {
     // storage on the receiving side: same reuse rules as fspt_scene_upload
+    c->has_scene = false;
     if ((rc = ensure(c, c->d_nodes, c->cap_nodes, h.bytes_nodes))) return rc;
     if ((rc = ensure(c, c->d_tris, c->cap_tris, h.bytes_tris))) return rc;
     if ((rc = ensure(c, c->d_shade, c->cap_shade, h.bytes_shade))) return rc;
     if ((rc = ensure(c, c->d_bins, c->cap_bins, h.bytes_bins))) return rc;
-    if ((rc = ensure(c, c->d_layer_info, c->cap_layer_info, h.bytes_layer_info))) return rc;
-    if ((rc = ensure(c, c->d_mat_info, c->cap_mat_info, h.bytes_mat_info))) return rc;
-    cudaResourceDesc rd = {};
-    rd.resType = cudaResourceTypeArray;
-    cudaTextureDesc td = {};
-    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
-    td.filterMode = cudaFilterModePoint;
-    td.readMode = cudaReadModeElementType;
-    cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
     if (!c->env_arr || c->env_W != h.env_w || c->env_H != h.env_h) {
+      cudaResourceDesc rd = {};
+      rd.resType = cudaResourceTypeArray;
+      cudaTextureDesc td = {};
+      td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+      td.filterMode = cudaFilterModePoint;
+      td.readMode = cudaReadModeElementType;
+      cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
       if (c->sc.env) cudaDestroyTextureObject(c->sc.env);
       c->sc.env = 0;
       if (c->env_arr) cudaFreeArray(c->env_arr);
@@ -1792,65 +1914,25 @@ int fspt_scene_broadcast(fspt_ctx* ctx, int32_t root) {
       CK(cudaCreateTextureObject(&c->sc.env, &rd, &td, nullptr));
       c->env_W = h.env_w; c->env_H = h.env_h;
     }
-    if (h.use_mat_tex) {
-      if (c->sc.atlas) { cudaDestroyTextureObject(c->sc.atlas); c->sc.atlas = 0; }
-      if (c->atlas_arr) { cudaFreeArray(c->atlas_arr); c->atlas_arr = nullptr; c->atlas_R = c->atlas_L = 0; }
-      if (!c->mat_arr || c->mat_R != h.mat_R || c->mat_L != h.mat_L) {
-        if (c->sc.mat_tex) cudaDestroyTextureObject(c->sc.mat_tex);
-        c->sc.mat_tex = 0;
-        if (c->mat_surf) cudaDestroySurfaceObject(c->mat_surf);
-        c->mat_surf = 0; c->mat_surface = false;
-        if (c->mat_arr) cudaFreeArray(c->mat_arr);
-        c->mat_arr = nullptr;
-        cudaChannelFormatDesc fmt4 = cudaCreateChannelDesc<uint4>();
-        CK(cudaMalloc3DArray(&c->mat_arr, &fmt4, make_cudaExtent(h.mat_R, h.mat_R, h.mat_L), cudaArrayLayered));
-        rd.res.array.array = c->mat_arr;
-        CK(cudaCreateTextureObject(&c->sc.mat_tex, &rd, &td, nullptr));
-        c->mat_R = h.mat_R; c->mat_L = h.mat_L;
-      }
-    } else {
-      if (c->sc.mat_tex) { cudaDestroyTextureObject(c->sc.mat_tex); c->sc.mat_tex = 0; }
-      if (c->mat_surf) { cudaDestroySurfaceObject(c->mat_surf); c->mat_surf = 0; }
-      c->mat_surface = false;
-      if (c->mat_arr) { cudaFreeArray(c->mat_arr); c->mat_arr = nullptr; c->mat_R = c->mat_L = 0; }
-      if (!c->atlas_arr || c->atlas_R != h.mat_R || c->atlas_L != h.mat_L) {
-        if (c->sc.atlas) cudaDestroyTextureObject(c->sc.atlas);
-        c->sc.atlas = 0;
-        if (c->atlas_arr) cudaFreeArray(c->atlas_arr);
-        c->atlas_arr = nullptr;
-        CK(cudaMalloc3DArray(&c->atlas_arr, &fmt, make_cudaExtent(h.mat_R, h.mat_R, h.mat_L), cudaArrayLayered));
-        rd.res.array.array = c->atlas_arr;
-        CK(cudaCreateTextureObject(&c->sc.atlas, &rd, &td, nullptr));
-        c->atlas_R = h.mat_R; c->atlas_L = h.mat_L;
-      }
-    }
   }
   NK(N->GroupStart());
   NK(N->Broadcast(c->d_nodes, c->d_nodes, h.bytes_nodes, ncclUint8, root, c->comm, c->stream));
   NK(N->Broadcast(c->d_tris, c->d_tris, h.bytes_tris, ncclUint8, root, c->comm, c->stream));
   NK(N->Broadcast(c->d_shade, c->d_shade, h.bytes_shade, ncclUint8, root, c->comm, c->stream));
   NK(N->Broadcast(c->d_bins, c->d_bins, h.bytes_bins, ncclUint8, root, c->comm, c->stream));
-  NK(N->Broadcast(c->d_layer_info, c->d_layer_info, h.bytes_layer_info, ncclUint8, root, c->comm, c->stream));
-  NK(N->Broadcast(c->d_mat_info, c->d_mat_info, h.bytes_mat_info, ncclUint8, root, c->comm, c->stream));
-  NK(N->Broadcast(lin, lin, env_bytes + atlas_bytes, ncclUint8, root, c->comm, c->stream));
+  NK(N->Broadcast(lin, lin, env_bytes, ncclUint8, root, c->comm, c->stream));
   NK(N->GroupEnd());
-  c->stats.kernel_launches += 8;
+  c->stats.kernel_launches += 6;
   if (!is_root) {
     CK(cudaMemcpy2DToArrayAsync(c->env_arr, 0, 0, lin, (size_t)h.env_w * 4, (size_t)h.env_w * 4, h.env_h,
                                 cudaMemcpyDeviceToDevice, c->stream));
-    cp.srcPtr = make_cudaPitchedPtr(lin + env_bytes, (size_t)h.mat_R * texel, h.mat_R, h.mat_R);
-    cp.dstArray = h.use_mat_tex ? c->mat_arr : c->atlas_arr;
-    CK(cudaMemcpy3DAsync(&cp, c->stream));
-    CK(cudaEventRecord(c->ev_atlas, c->stream));
     if ((rc = linear_tex(c, &c->nodes_tex, c->d_nodes, h.bytes_nodes))) return rc;
     c->bytes_nodes = h.bytes_nodes; c->bytes_tris = h.bytes_tris; c->bytes_shade = h.bytes_shade;
-    c->bytes_bins = h.bytes_bins; c->bytes_layer_info = h.bytes_layer_info; c->bytes_mat_info = h.bytes_mat_info;
+    c->bytes_bins = h.bytes_bins;
     c->sc.nodes = reinterpret_cast<const float4*>(c->d_nodes);
     c->sc.tris = reinterpret_cast<const float4*>(c->d_tris);
     c->sc.shade = reinterpret_cast<const float4*>(c->d_shade);
     c->sc.bins = reinterpret_cast<const float4*>(c->d_bins);
-    c->sc.layer_info = reinterpret_cast<const uint2*>(c->d_layer_info);
-    c->sc.mat_info = reinterpret_cast<const int4*>(c->d_mat_info);
     c->sc.root_ref = h.root_ref; c->sc.n_tris = h.n_tris; c->sc.n_interior = h.n_interior;
     c->sc.atlas_res = h.atlas_res; c->sc.atlas_layers = h.atlas_layers; c->sc.env_w = h.env_w; c->sc.env_h = h.env_h;
     c->sc.n_bins = h.n_bins;
@@ -1858,6 +1940,8 @@ int fspt_scene_broadcast(fspt_ctx* ctx, int32_t root) {
     c->scene_bytes = h.scene_bytes;
     c->has_scene = true;
   }
+  CK(cudaEventRecord(c->ev_bcast, c->stream));
+  c->bcast_pending_root = root;  // phase 2: the atlas, behind the next primary traversal launch
   return FSPT_OK;
 }
 

@@ -57,6 +57,33 @@ def _worker(rank, world, port, out_dir):
     ctx.reduce_accum(0)
     if rank == 0:
         np.save(os.path.join(out_dir, "sum5.npy"), ctx.read_accum())
+    # (4) asynchronous upload on rank 0 + broadcast: the atlas part of the broadcast is deferred behind the primary
+    # traversal launch of the next render on every rank; same bits as (1)
+    if rank == 0:
+        ctx.scene_upload(sa, wait=False)
+    ctx.scene_broadcast(0)
+    ctx.clear()
+    ctx.render(fr, 0, rc[ticks], rt[ticks])
+    ctx.reduce_accum(0)
+    if rank == 0:
+        np.save(os.path.join(out_dir, "sum_async.npy"), ctx.read_accum())
+    # (5) a rank that renders nothing after a broadcast (1 tick over 2 ranks): its reduce issues the deferred atlas part
+    if rank == 0:
+        ctx.scene_upload(sa, wait=False)
+    ctx.scene_broadcast(0)
+    ctx.clear()
+    ticks1 = fdist.shard_ticks(1, rank, world)
+    if len(ticks1):
+        ctx.render(fr, 0, rc[ticks1], rt[ticks1])
+    ctx.reduce_accum(0)
+    if rank == 0:
+        np.save(os.path.join(out_dir, "sum1.npy"), ctx.read_accum())
+    # (6) ... and both ranks render from that scene afterwards
+    ctx.clear()
+    ctx.render(fr, 0, rc[ticks], rt[ticks])
+    ctx.reduce_accum(0)
+    if rank == 0:
+        np.save(os.path.join(out_dir, "sum_after.npy"), ctx.read_accum())
     ctx.close()
     dist.destroy_process_group()
 
@@ -97,3 +124,9 @@ def test_two_gpu_sample_sharding_matches_oracle(tmp_path, oracle_mod):
     ref5 = (((z + cols[0]) + cols[2]) + cols[4]) + ((z + cols[1]) + cols[3])
     sum5 = np.load(tmp_path / "sum5.npy")
     assert np.array_equal(sum5[..., :3].view(np.uint32), ref5.view(np.uint32)) and np.all(sum5[..., 3] == 5)
+    # asynchronous upload + two-phase broadcast: same bits; a rank that only reduces; rendering afterwards
+    first = np.load(tmp_path / "sum.npy")
+    assert np.array_equal(np.load(tmp_path / "sum_async.npy").view(np.uint32), first.view(np.uint32))
+    sum1 = np.load(tmp_path / "sum1.npy")
+    assert np.array_equal(sum1[..., :3].view(np.uint32), (z + cols[0]).view(np.uint32)) and np.all(sum1[..., 3] == 1)
+    assert np.array_equal(np.load(tmp_path / "sum_after.npy").view(np.uint32), first.view(np.uint32))

@@ -1,10 +1,10 @@
 #!/bin/bash
 # 2-GPU box: the multi-rank parity test, the N=2 weak / strong bench lines and the single-GPU config-2 line
 cd "$(dirname "$0")/.."
-python -m pytest tests/test_gpu_multi.py -x -q 2>&1 | tail -3 > gpurun_out/r02b_gputest_multi.log; cat gpurun_out/r02b_gputest_multi.log
+timeout 300 python -m pytest tests/test_gpu_multi.py -x -q 2>&1 | tail -3 > gpurun_out/r02b_gputest_multi.log; cat gpurun_out/r02b_gputest_multi.log
 run() {  # n tag args...
   n=$1; tag=$2; shift 2
-  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29600 + RANDOM % 200)) \
+  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29600 + RANDOM % 200)) \
     bench.py --gpus $n "$@" > gpurun_out/r02b_scale_$tag.json 2> gpurun_out/r02b_scale_$tag.err
   echo "== $tag rc=$?"; grep '^{' gpurun_out/r02b_scale_$tag.json | python -c "
 import sys, json
