@@ -69,6 +69,9 @@ struct Ctx {
   // band-wise DMA) runs on this thread after the call has returned; joined before the first shading launch and by
   // everything that touches scene state
   std::thread atlas_thread;
+  // page-locked sources are DMA'd in place: they stay borrowed until the copies have completed, not just been enqueued
+  bool env_in_place = false, atlas_in_place = false;
+  cudaEvent_t ev_env = nullptr;  // behind the environment copies on the context's stream (recorded when env_in_place)
   std::atomic<uint64_t> atlas_launches{0};  // kernels launched by the atlas part (folded into stats.kernel_launches)
   int atlas_rc = 0;            // outcome of the atlas part (written by the atlas thread, read after joining it)
   std::string atlas_error;
@@ -273,6 +276,14 @@ bool host_is_pinned(const void* p) {
   return a.type == cudaMemoryTypeHost;
 }
 
+// Page-locked sources (fspt_host_register) are read by the copy engines where they lie: the caller gets them back when
+// those copies have completed.  (Staged sources were copied out before the upload returned / the atlas thread ended.)
+int release_borrowed(Ctx* c) {
+  if (c->env_in_place) { CK(cudaEventSynchronize(c->ev_env)); c->env_in_place = false; }
+  if (c->atlas_in_place) { CK(cudaEventSynchronize(c->ev_atlas)); c->atlas_in_place = false; }
+  return FSPT_OK;
+}
+
 // Waits for the atlas part of the last fspt_scene_upload_async (no-op otherwise) and reports its outcome.
 int atlas_join(Ctx* c) {
   if (c->atlas_thread.joinable()) c->atlas_thread.join();
@@ -420,6 +431,7 @@ int stage_atlas(Ctx* c, const AtlasJob& J) {
     bool gpu_interleave = n_tex_mats > 0 && (J.src_pinned || raw_layers.size() * 2 <= (size_t)n_tex_mats * 4);
     if (const char* e = getenv("FSPT_ATLAS_INTERLEAVE")) gpu_interleave = n_tex_mats > 0 && !strcmp(e, "gpu");
     const bool direct = gpu_interleave && J.src_pinned;
+    c->atlas_in_place = direct;
     if (!c->mat_arr || c->mat_R != R || c->mat_L != ML || c->mat_surface != gpu_interleave) {
       if (c->sc.mat_tex) cudaDestroyTextureObject(c->sc.mat_tex);
       c->sc.mat_tex = 0;
@@ -1064,6 +1076,7 @@ void fspt_destroy(fspt_ctx* ctx) {
   if (c->ev_red1) cudaEventDestroy(c->ev_red1);
   dfree(c->d_lin); dfree(c->d_hdr); dfree(c->d_lin_env);
   if (c->ev_bcast) cudaEventDestroy(c->ev_bcast);
+  if (c->ev_env) cudaEventDestroy(c->ev_env);
   for (auto e : c->ev_trace) cudaEventDestroy(e);
   if (c->ev_begin) cudaEventDestroy(c->ev_begin);
   if (c->ev_end) cudaEventDestroy(c->ev_end);
@@ -1443,6 +1456,11 @@ static int scene_upload_impl(fspt_ctx* ctx, const fspt_scene_desc* s, bool async
     slot_done[slot].store(ring_item, std::memory_order_release);
   });
   if (dma_err.load()) return fail(c, FSPT_E_CUDA, "geometry upload failed: %s", cudaGetErrorString((cudaError_t)dma_err.load()));
+  c->env_in_place = src_env_pinned;
+  if (src_env_pinned) {
+    if (!c->ev_env) CK(cudaEventCreateWithFlags(&c->ev_env, cudaEventDisableTiming));
+    CK(cudaEventRecord(c->ev_env, c->stream));
+  }
   lap("geometry + env + layer scan");
   // env: test knob for the LSU-only instantiation of k_trace
   if ((rc_ = linear_tex(c, &c->nodes_tex, c->d_nodes, nodes_bytes, !getenv("FSPT_NO_NODE_TEX")))) return rc_;
@@ -1478,6 +1496,7 @@ static int scene_upload_impl(fspt_ctx* ctx, const fspt_scene_desc* s, bool async
   job.workers = hw;
   job.timing = timing;
   c->atlas_rc = FSPT_OK;
+  c->atlas_in_place = false;
   struct StagingGuard {  // an error return below must not leave the atlas thread reading the caller's buffer
     Ctx* c; bool ok = false;
     ~StagingGuard() { if (!ok && c->atlas_thread.joinable()) c->atlas_thread.join(); }
@@ -1499,6 +1518,10 @@ static int scene_upload_impl(fspt_ctx* ctx, const fspt_scene_desc* s, bool async
   if (timing && !async_atlas) { CK(cudaStreamSynchronize(c->stream)); CK(cudaStreamSynchronize(c->copy_stream)); lap("sync (timing only)"); }
   c->has_scene = true;
   staging_guard.ok = true;
+  if (!async_atlas) {  // a synchronous upload has consumed every buffer when it returns, page-locked ones included
+    int rcw = release_borrowed(c);
+    if (rcw) return rcw;
+  }
   return FSPT_OK;
 }
 
@@ -1521,7 +1544,9 @@ int fspt_host_unregister(void* p) {
 int fspt_scene_upload_wait(fspt_ctx* ctx) {
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
   if (!c) return FSPT_E_INVALID;
-  return atlas_join(c);
+  CK(cudaSetDevice(c->device));
+  if (int rc = atlas_join(c)) return rc;
+  return release_borrowed(c);
 }
 
 int fspt_clear(fspt_ctx* ctx) {

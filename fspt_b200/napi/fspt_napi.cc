@@ -133,6 +133,37 @@ napi_value SceneUpload(napi_env env, napi_callback_info info) {
   return nullptr;
 }
 
+// hostRegister(typedArray) / hostUnregister(typedArray): page-lock the array's backing store in place (fspt_host_register);
+// uploads then DMA a page-locked atlas / env from where it lies.  The host must keep the array alive while registered.
+napi_value HostRegister(napi_env env, napi_callback_info info) {
+  size_t argc = 1;
+  napi_value argv[1];
+  NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+  napi_typedarray_type t;
+  size_t n = 0, off = 0;
+  void* data = nullptr;
+  napi_value ab;
+  NAPI_OK(napi_get_typedarray_info(env, argv[0], &t, &n, &data, &ab, &off));
+  const size_t elem = (t == napi_float32_array || t == napi_int32_array || t == napi_uint32_array) ? 4
+                      : (t == napi_uint16_array || t == napi_int16_array) ? 2 : (t == napi_float64_array) ? 8 : 1;
+  int r = fspt_host_register(data, (uint64_t)(n * elem));
+  if (r) return Throw(env, nullptr, r);
+  return nullptr;
+}
+napi_value HostUnregister(napi_env env, napi_callback_info info) {
+  size_t argc = 1;
+  napi_value argv[1];
+  NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+  napi_typedarray_type t;
+  size_t n = 0, off = 0;
+  void* data = nullptr;
+  napi_value ab;
+  NAPI_OK(napi_get_typedarray_info(env, argv[0], &t, &n, &data, &ab, &off));
+  int r = fspt_host_unregister(data);
+  if (r) return Throw(env, nullptr, r);
+  return nullptr;
+}
+
 napi_value SceneUploadWait(napi_env env, napi_callback_info info) {
   size_t argc = 1;
   napi_value argv[1];
@@ -319,7 +350,8 @@ napi_value SceneBroadcast(napi_env env, napi_callback_info info) {  // sceneBroa
 
 napi_value Init(napi_env env, napi_value exports) {
   const struct { const char* name; napi_callback fn; } fns[] = {
-      {"create", Create}, {"sceneUpload", SceneUpload}, {"sceneUploadWait", SceneUploadWait}, {"render", Render}, {"clear", Clear},
+      {"create", Create}, {"sceneUpload", SceneUpload}, {"sceneUploadWait", SceneUploadWait},
+      {"hostRegister", HostRegister}, {"hostUnregister", HostUnregister}, {"render", Render}, {"clear", Clear},
       {"resolve", Resolve}, {"readAccum", ReadAccum}, {"bvhBuild", BvhBuild},
       {"setTile", SetTile}, {"setAccumMode", SetAccumMode}, {"commUniqueId", CommUniqueId}, {"commInit", CommInit},
       {"reduceAccum", ReduceAccum}, {"sceneBroadcast", SceneBroadcast}};

@@ -109,8 +109,9 @@ int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* scene);
  * main.js:556-559, is by far the largest transfer and only the shading pass reads it): the atlas is staged and DMA'd
  * by a thread of the context while the caller goes on -- typically into fspt_render, whose camera + primary traversal
  * launch then overlaps the atlas transfer; the library waits for the staging itself before its first shading launch.
- * scene->atlas must stay valid and unchanged until fspt_scene_upload_wait (or fspt_synchronize, the next upload, or
- * fspt_destroy) has returned; errors of the staging are reported by whichever call joins it. */
+ * scene->atlas -- and scene->env when it is page-locked, see fspt_host_register -- must stay valid and unchanged until
+ * fspt_scene_upload_wait (or fspt_synchronize, the next upload, or fspt_destroy) has returned; errors of the staging are
+ * reported by whichever call joins it. */
 int fspt_scene_upload_async(fspt_ctx* ctx, const fspt_scene_desc* scene);
 int fspt_scene_upload_wait(fspt_ctx* ctx);
 /* Optional: page-lock a host buffer the caller keeps across uploads (cudaHostRegister; no reference counterpart --

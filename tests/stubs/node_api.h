@@ -5,7 +5,7 @@
 #include <stdint.h>
 typedef struct napi_env__* napi_env; typedef struct napi_value__* napi_value; typedef struct napi_callback_info__* napi_callback_info;
 typedef enum { napi_ok } napi_status;
-typedef enum { napi_uint8_array, napi_uint8_clamped_array, napi_float32_array, napi_int32_array } napi_typedarray_type;
+typedef enum { napi_int8_array, napi_uint8_array, napi_uint8_clamped_array, napi_int16_array, napi_uint16_array, napi_int32_array, napi_uint32_array, napi_float32_array, napi_float64_array, napi_bigint64_array, napi_biguint64_array } napi_typedarray_type;
 typedef napi_value (*napi_callback)(napi_env, napi_callback_info);
 typedef void (*napi_finalize)(napi_env, void*, void*);
 #define NAPI_AUTO_LENGTH SIZE_MAX

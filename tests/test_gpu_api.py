@@ -416,6 +416,21 @@ def test_page_locked_atlas_and_env_are_uploaded_in_place(monkeypatch):
                 ctx.render(fr, 0, rc, rt)
                 assert np.array_equal(ref.view(np.uint32), ctx.read_accum().view(np.uint32)), wait
             ctx.upload_wait()
+            # the borrow of a page-locked buffer ends when its copies have COMPLETED: at the return of the synchronous
+            # call, at fspt_scene_upload_wait for the asynchronous one -- scribbling over it then must not reach the device
+            for wait in (True, False):
+                sa.atlas[...] = sa0.atlas
+                sa.env[...] = sa0.env
+                ctx.scene_upload(sa, wait=wait)
+                if not wait:
+                    ctx.upload_wait()
+                sa.atlas[...] = 0
+                sa.env[...] = 0
+                ctx.clear()
+                ctx.render(fr, 0, rc, rt)
+                assert np.array_equal(ref.view(np.uint32), ctx.read_accum().view(np.uint32)), ("scribble", wait)
+            sa.atlas[...] = sa0.atlas
+            sa.env[...] = sa0.env
         finally:
             ctx.synchronize()
             capi.host_unregister(sa.atlas)
