@@ -533,6 +533,26 @@ def main():
                 "l2_read_peak": l2_gbs, "hbm_read_measured_here": hbm_read_gbs,
             },
         }
+        if world == 1:
+            # "report primary-only (bvh_test mode) and full-path numbers" -- mode=test (main.js:882-884,
+            # bvh_test.fs:224-232): one camera pass + one primary intersectScene with the visit counter per pixel, the
+            # traversal launch timed with CUDA events on the library's stream (1 ray per pixel: a short launch)
+            try:
+                ctx.set_tile(0, 0, W, H)
+                for k in range(2):
+                    ctx.debug_primary(pt._frame(), float(rc_all[0]), want_rays=False)
+                st0 = pt.stats()
+                ctx.debug_primary(pt._frame(), float(rc_all[0]), want_rays=False)
+                stp = pt.stats()
+                line["primary_only"] = {
+                    "mrays_per_s": W * H / (stp["trace_ms"] * 1e-3) / 1e6 if stp["trace_ms"] > 0 else None,
+                    "rays": W * H, "kernel_ms": stp["trace_ms"],
+                    "node_visits_per_ray": (stp["node_visits"] - st0["node_visits"]) / float(W * H),
+                    "leaf_visits_per_ray": (stp["leaf_visits"] - st0["leaf_visits"]) / float(W * H),
+                    "what": "fspt_debug_primary = mode=test of the reference (bvh_test.fs): camera pass + primary closest-hit "
+                            "traversal with the exact visit counter, one ray per pixel"}
+            except Exception as e:  # a measurement aid must not cost the bench line
+                line["primary_only"] = {"error": str(e)}
         if parity is not None and parity[0] is not None:
             line["parity"] = parity[0]
             line["parity_check"] = parity[1]
