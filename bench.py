@@ -422,7 +422,7 @@ def main():
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = pt.stats()["kernel_launches"]
-    dev_ms, trace_ms, shade_ms, alg_bytes, rays = 0.0, 0.0, 0.0, 0, 0
+    dev_ms, trace_ms, shade_ms, alg_bytes, rays, primary_ms = 0.0, 0.0, 0.0, 0, 0, 0.0
     t_wall0 = time.perf_counter()
     for _ in range(args.steps):
         flush.fill_(1)  # L2 flush between timed iterations (outside the event-timed region)
@@ -431,6 +431,7 @@ def main():
         dev_ms += ms
         trace_ms += st["trace_ms"]
         shade_ms += st["shade_ms"]
+        primary_ms += st.get("primary_trace_ms", 0.0)
         rays += st["last_rays"]
         alg_bytes += algorithmic_bytes({"node_visits": st["last_node_visits"], "leaf_visits": st["last_leaf_visits"],
                                         "rays": st["last_rays"]})
@@ -545,6 +546,10 @@ def main():
                 ctx.debug_primary(pt._frame(), float(rc_all[0]), want_rays=False)
                 stp = pt.stats()
                 line["primary_only"] = {
+                    # inside the timed steps: the camera-fused primary launches (spp rays per pixel), CUDA-event timed
+                    "in_render_mrays_per_s": (W * H * float(len(rc)) * args.steps) / (primary_ms * 1e-3) / 1e6 if primary_ms > 0 else None,
+                    "in_render_ms_per_step": primary_ms / args.steps,
+                    # mode=test: one ray per pixel with the exact visit counter (a short launch)
                     "mrays_per_s": W * H / (stp["trace_ms"] * 1e-3) / 1e6 if stp["trace_ms"] > 0 else None,
                     "rays": W * H, "kernel_ms": stp["trace_ms"],
                     "node_visits_per_ray": (stp["node_visits"] - st0["node_visits"]) / float(W * H),

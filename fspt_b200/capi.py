@@ -41,7 +41,8 @@ class Stats(C.Structure):
     _fields_ = [("samples", C.c_uint64), ("rays", C.c_uint64), ("node_visits", C.c_uint64), ("leaf_visits", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("trace_ms", C.c_double), ("render_ms", C.c_double),
                 ("last_rays", C.c_uint64), ("last_node_visits", C.c_uint64), ("last_leaf_visits", C.c_uint64),
-                ("capped_paths", C.c_uint64), ("shade_ms", C.c_double), ("reduce_ms", C.c_double)]
+                ("capped_paths", C.c_uint64), ("shade_ms", C.c_double), ("reduce_ms", C.c_double),
+                ("primary_trace_ms", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

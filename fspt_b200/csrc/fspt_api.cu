@@ -644,7 +644,7 @@ int launch_trace(Ctx* c, int which, bool hit_flags, bool write_count, const Fram
   A.stats = c->d_stats;
   A.count_out = write_count ? c->d_count_out : nullptr;
   A.hit_flag = hit_flags ? c->d_hit_flag : nullptr;
-  record_trace_begin(c);
+  record_trace_begin(c, cam ? 2 : 0);  // tag 2: the camera-fused primary launch of a wave
   if (A.nodes_tex) {
     if (cam) k_trace<false, true, true><<<c->trace_blocks_cam, TRACE_THREADS, 0, c->stream>>>(A);
     else if (write_count) k_trace<true, false, true><<<c->trace_blocks_cnt, TRACE_THREADS, 0, c->stream>>>(A);
@@ -1992,12 +1992,16 @@ int fspt_get_stats(fspt_ctx* ctx, fspt_stats* out) {
   if (rc) return rc;
   float ms = 0.0f;
   if (c->render_timed && cudaEventElapsedTime(&ms, c->ev_begin, c->ev_end) == cudaSuccess) c->stats.render_ms = ms;
-  double tr = 0.0, sh = 0.0;
+  double tr = 0.0, sh = 0.0, pr = 0.0;
   for (size_t i = 0; i + 1 < c->ev_trace_used; i += 2) {
     float t = 0.0f;
-    if (cudaEventElapsedTime(&t, c->ev_trace[i], c->ev_trace[i + 1]) == cudaSuccess) (c->ev_tag[i / 2] ? sh : tr) += t;
+    if (cudaEventElapsedTime(&t, c->ev_trace[i], c->ev_trace[i + 1]) != cudaSuccess) continue;
+    const int tag = c->ev_tag[i / 2];
+    (tag == 1 ? sh : tr) += t;
+    if (tag == 2) pr += t;
   }
   c->stats.shade_ms = sh;
+  c->stats.primary_trace_ms = pr;
   c->stats.reduce_ms = 0.0;
   if (c->reduce_timed && cudaEventElapsedTime(&ms, c->ev_red0, c->ev_red1) == cudaSuccess) c->stats.reduce_ms = ms;
   (void)cudaGetLastError();  // event queries must not leave a sticky status for the next launch check

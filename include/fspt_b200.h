@@ -93,6 +93,8 @@ typedef struct fspt_stats {
   uint64_t capped_paths;  /* paths stopped by the refraction safety cap                              */
   double shade_ms;        /* CUDA-event time spent in shading kernels during the last fspt_render    */
   double reduce_ms;       /* CUDA-event time of the last fspt_reduce_accum (NCCL reduce on the context's stream) */
+  double primary_trace_ms; /* part of trace_ms spent in the camera + primary-ray launches (camera.fs + the first
+                              intersectScene of tracer.fs main, :440) of the last fspt_render */
 } fspt_stats;
 
 int fspt_abi_version(void);
