@@ -68,7 +68,7 @@ def build_scene(args, host=None):
 
 def workload_config(args, sa, n_gpus, parallelism):
     cfg = CONFIGS[args.config]
-    l2 = ("L2 flushed (512 MB write) between timed steps; per-wave path state (2 x 96 B per path, up to 64 Mi paths) "
+    l2 = ("L2 flushed (512 MB write) between timed steps; per-wave path state (2 x 80 B per path, up to 64 Mi paths) "
           "and the atlas exceed the 126 MB L2; BVH nodes + triangles (%.0f MB) %s" %
           ((sa.bvh.shape[0] * 0.5 * 64 + sa.n_tris * 48) / 1e6,
            "stay L2-resident inside a step by design" if args.config != 5 else

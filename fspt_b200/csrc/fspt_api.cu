@@ -204,7 +204,7 @@ int ensure(Ctx* c, void*& p, size_t& cap, size_t bytes) {
 
 int alloc_wave(Ctx* c) {
   // samples in flight: traversal launches amortise their ramp/tail over tens of millions of rays (measured at
-  // 1280x720: 4 -> 16 -> 32 -> 64 samples per wave = +14 % -> +3 % -> +2.7 %); 64 M paths x (2 x 96 B records + lists)
+  // 1280x720: 4 -> 16 -> 32 -> 64 samples per wave = +14 % -> +3 % -> +2.7 %); 64 M paths x (2 x 80 B records + lists)
   // = ~14 GB of 180 GB
   const size_t target_paths = (size_t)64 << 20;
   int S = (int)std::max<size_t>(1, target_paths / (size_t)c->n_pixels);
@@ -214,7 +214,10 @@ int alloc_wave(Ctx* c) {
   c->wave_samples = S;
   c->wave_paths = (size_t)S * c->n_pixels;
   const size_t W = c->wave_paths;
-  for (int k = 0; k < 2; ++k) CK(cudaMalloc(&c->ps2[k].rec, W * 16 * FSPT_PATH_WORDS));
+  for (int k = 0; k < 2; ++k) {
+    CK(cudaMalloc(&c->ps2[k].rec, W * 16 * FSPT_PATH_WORDS));
+    CK(cudaMalloc(&c->ps2[k].sh, W));
+  }
   c->ps = c->ps2[0];
   CK(cudaMalloc(&c->d_shadow, W * 32));
   CK(cudaMalloc(&c->d_counts, 64 * sizeof(int)));  // [0..3] the two count pairs; [32] the fetch cursor, on its own 128-byte
@@ -1064,7 +1067,7 @@ void fspt_destroy(fspt_ctx* ctx) {
   for (auto e : c->ev_ring) cudaEventDestroy(e);
   free_scene(c);
   dfree(c->d_fb); dfree(c->d_last_color); dfree(c->d_sample_color); dfree(c->d_cam_pos); dfree(c->d_cam_dir); dfree(c->d_rgba8);
-  dfree(c->ps2[0].rec); dfree(c->ps2[1].rec);
+  dfree(c->ps2[0].rec); dfree(c->ps2[1].rec); dfree(c->ps2[0].sh); dfree(c->ps2[1].sh);
   dfree(c->d_shadow);
   dfree(c->d_counts); dfree(c->d_count_out); dfree(c->d_hit_flag); dfree(c->d_stats); dfree(c->d_rb);
   if (c->h_rb) cudaFreeHost(c->h_rb);

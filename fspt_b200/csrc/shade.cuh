@@ -288,10 +288,10 @@ __device__ __forceinline__ void shade_miss(const ShadeArgs& A, int pos) {
   if (A.first) {
     color = add(mk3(0.0f, 0.0f, 0.0f), env);  // :443
   } else {
-    const float4 c4 = ld_path(A.ps.col(slot_in)), t4 = ld_path(A.ps.thr(slot_in)), s4 = ld_path(A.ps.sd(slot_in));
+    const float4 c4 = ld_path(A.ps.col(slot_in)), t4 = ld_path(A.ps.thr(slot_in));
     slot = __float_as_int(c4.w);
     color = mk3(c4.x, c4.y, c4.z);
-    if (__float_as_int(s4.w) == 2) {  // shadow.index == -1, :502-504
+    if (A.ps.sh[slot_in] == 2) {  // shadow.index == -1, :502-504
       const float4 p4 = ld_path(A.ps.pend(slot_in));
       color = add(color, mk3(p4.x, p4.y, p4.z));
     }
@@ -302,8 +302,14 @@ __device__ __forceinline__ void shade_miss(const ShadeArgs& A, int pos) {
 }
 
 // One loop iteration of tracer.fs main (:446-513) for a path whose ray HIT, split at the intersectScene calls.
-// Returns true when the path continues; `out` then holds its new 6-word record (continuation ray, shadow ray, state).
+// Returns true when the path continues; `out` then holds its new record (words 0, 1, 3, 4, 5 = the five words of the
+// record in HBM) and, in word 2, the shadow ray's direction for the dense shadow-ray array.
 struct PathRecord { float4 w[6]; };
+__device__ __forceinline__ void store_record(const PathState& ps, int pos, const PathRecord& rec, bool shadow) {
+  float4* dst = ps.rec + FSPT_PATH_WORDS * (size_t)pos;
+  st_path(dst[0], rec.w[0]); st_path(dst[1], rec.w[1]); st_path(dst[2], rec.w[3]); st_path(dst[3], rec.w[4]); st_path(dst[4], rec.w[5]);
+  ps.sh[pos] = shadow ? 1 : 0;  // (every record: a stale 2 of an earlier bounce must not survive at this position)
+}
 template <bool MAT_TEX>
 __device__ __forceinline__ bool shade_hit(const ShadeArgs& A, int pos, bool& shadow, PathRecord& out) {
   const DeviceScene& sc = A.sc;
@@ -320,15 +326,16 @@ __device__ __forceinline__ bool shade_hit(const ShadeArgs& A, int pos, bool& sha
     color = mk3(0.0f, 0.0f, 0.0f);
     reflectance = mk3(1.0f, 1.0f, 1.0f);
   } else {
-    const float4 c4 = ld_path(A.ps.col(pos)), t4 = ld_path(A.ps.thr(pos)), s4 = ld_path(A.ps.sd(pos));
+    const float4 c4 = ld_path(A.ps.col(pos)), t4 = ld_path(A.ps.thr(pos));
     const float4 p4 = ld_path(A.ps.pend(pos));
+    const int shadow_state = A.ps.sh[pos];
     slot = __float_as_int(c4.w);
     color = mk3(c4.x, c4.y, c4.z);
     reflectance = mk3(t4.x, t4.y, t4.z);  // already multiplied by the previous bsdfThroughput (:508), see the store below
     const int packed = __float_as_int(p4.w);
     i = (packed & 0xffff) - 0x100;  // stored biased so that i = -1 survives
     refractions = packed >> 16;
-    if (__float_as_int(s4.w) == 2) color = add(color, mk3(p4.x, p4.y, p4.z));  // shadow.index == -1, :502-504
+    if (shadow_state == 2) color = add(color, mk3(p4.x, p4.y, p4.z));  // shadow.index == -1, :502-504
     ++i;                                                    // for (...; ++i), :446
     if (!(i < FSPT_NUM_BOUNCES)) {
       write_sample(A, slot, color);
@@ -484,7 +491,7 @@ __device__ __forceinline__ bool shade_hit(const ShadeArgs& A, int pos, bool& sha
   out.w[1] = make_float4(rayDir.x, rayDir.y, rayDir.z, __int_as_float(last_bounce ? -2 : -1));
   out.w[2] = make_float4(envDir.x, envDir.y, envDir.z, __int_as_float(shadow ? 1 : 0));
   // accumulatedReflectance *= bsdfThroughput (:508) is a pure product of two values known here: storing it now gives
-  // the same f32 bits as multiplying in the next pass and keeps the record at six words = three 32-byte sectors
+  // the same f32 bits as multiplying in the next pass and keeps the record small (five words in HBM)
   const v3 next_reflectance = mul(reflectance, bsdfThroughput);
   out.w[3] = make_float4(next_reflectance.x, next_reflectance.y, next_reflectance.z, weights.y);
   out.w[4] = make_float4(pend.x, pend.y, pend.z, __int_as_float(((i + 0x100) & 0xffff) | (refractions << 16)));
@@ -575,11 +582,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, SHADE_MIN_BLOCKS) k_shade(const
       __syncthreads();
       const unsigned lt2 = (1u << lane) - 1u;
       const int pos_out = s_base[0] + s_wc[warp] + __popc(mc & lt2);
-      if (cont) {
-        float4* dst = A.ps_out.rec + FSPT_PATH_WORDS * (size_t)pos_out;
-#pragma unroll
-        for (int w = 0; w < 6; ++w) st_path(dst[w], rec.w[w]);
-      }
+      if (cont) store_record(A.ps_out, pos_out, rec, shadow);
       if (shadow) {
         float4* sr = A.shadow_rays_out + 2 * (size_t)(s_base[1] + s_ws[warp] + __popc(ms & lt2));
         sr[0] = make_float4(rec.w[0].x, rec.w[0].y, rec.w[0].z, __int_as_float(pos_out));
@@ -587,11 +590,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, SHADE_MIN_BLOCKS) k_shade(const
       }
 #else
       const int pos_out = append_pos(cont, A.counts_out + 0);
-      if (cont) {
-        float4* dst = A.ps_out.rec + FSPT_PATH_WORDS * (size_t)pos_out;
-#pragma unroll
-        for (int w = 0; w < 6; ++w) st_path(dst[w], rec.w[w]);
-      }
+      if (cont) store_record(A.ps_out, pos_out, rec, shadow);
       {
         const int j = append_pos(shadow, A.counts_out + 1);
         if (shadow) {  // origin = the continuation ray's (tracer.fs:501), direction = the sampled environment direction

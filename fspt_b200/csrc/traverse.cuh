@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
         st_path_w(A.ps.ro(slot), tbest);
         st_path_w(A.ps.rd(slot), __int_as_float(ibest));
       } else {
-        st_path_w(A.ps.sd(slot), __int_as_float((ibest == -1) ? 2 : 3));
+        A.ps.sh[slot] = (ibest == -1) ? 2 : 3;  // the record's shadow-state byte
       }
       if (WRITE_COUNT) A.count_out[slot] = cnt_exact;
       if (A.hit_flag && !kind) A.hit_flag[slot] = (ibest != -1);  // continuation rays: slot = queue position
