@@ -31,3 +31,12 @@ echo "== upload laps (async, config 2 scene)"; FSPT_TIMING=1 timeout 300 python 
 echo "== upload laps (sync, config 3 scene: 1 M triangles)"; FSPT_TIMING=1 timeout 300 python tools/upload_time.py --soup 2>&1 | tail -13 | head -9
 } > gpurun_out/r02b_upload.log 2>&1
 tail -12 gpurun_out/r02b_upload.log
+# ncu evidence of the final kernels (80-byte path records), config 2: launch list + one --set full capture per kernel
+if [ "${NCU:-1}" = "1" ]; then
+  NCUCMD="ncu --clock-control none"
+  BENCH="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-verify"
+  timeout 900 $NCUCMD --metrics gpu__time_duration.sum -c 400 --csv --log-file gpurun_out/r02b_launches.csv $BENCH > gpurun_out/r02b_launches.log 2>&1
+  timeout 1200 $NCUCMD --set full --import-source on -k regex:k_trace --launch-skip 15 --launch-count 3 -f -o gpurun_out/r02b_k_trace $BENCH > gpurun_out/r02b_ncu_trace.log 2>&1
+  timeout 1200 $NCUCMD --set full --import-source on -k regex:k_shade --launch-skip 15 --launch-count 2 -f -o gpurun_out/r02b_k_shade $BENCH > gpurun_out/r02b_ncu_shade.log 2>&1
+  ls -la gpurun_out/ | grep -E "r02b_(k_|launches)"
+fi
