@@ -55,7 +55,7 @@ EXPORTS = [
     "fspt_debug_last_color", "fspt_debug_math", "fspt_debug_read_bandwidth", "fspt_get_stats", "fspt_synchronize", "fspt_bvh_build", "fspt_bvh_build2",
     "fspt_env_bins", "fspt_pack_layer", "fspt_set_param", "fspt_set_tile", "fspt_comm_unique_id", "fspt_comm_init",
     "fspt_comm_destroy", "fspt_reduce_accum", "fspt_scene_broadcast", "fspt_scene_upload_async", "fspt_scene_upload_wait",
-    "fspt_host_register", "fspt_host_unregister",
+    "fspt_host_register", "fspt_host_unregister", "fspt_debug_pack_scene",
 ]
 PARAM_ANYHIT, PARAM_MAX_REFRACTIONS, PARAM_SANITIZE_NAN = 1, 2, 3
 
@@ -174,6 +174,56 @@ def pack_layer(pixels, res, corrected=False, swizzle=None, n_threads=0):
     return out
 
 
+def scene_desc(sa, keep):
+    """fspt_scene_desc over the arrays of a SceneArrays-like object; `keep` receives the (possibly converted) arrays the
+    pointers refer to and must outlive the call that uses the descriptor."""
+    d = SceneDesc()
+    keep.update(
+        bvh=f32(sa.bvh), tris=f32(sa.tris), mats=f32(sa.mats), norms=f32(sa.norms), uvs=f32(sa.uvs),
+        atlas=np.ascontiguousarray(sa.atlas, np.uint8), env=np.ascontiguousarray(sa.env, np.uint8),
+        bins=np.ascontiguousarray(sa.bins, np.uint16))
+    lights = getattr(sa, "lights", None)
+    ranges = getattr(sa, "light_ranges", None)
+    if lights is not None and len(lights):
+        keep["lights"] = f32(lights)
+        keep["ranges"] = f32(ranges)
+        d.lights, d.light_ranges = ptr(keep["lights"]), ptr(keep["ranges"])
+        d.n_light_triangles = keep["lights"].size // 9
+        d.n_light_ranges = keep["ranges"].size // 2
+    d.bvh, d.triangles, d.materials = ptr(keep["bvh"]), ptr(keep["tris"]), ptr(keep["mats"])
+    d.normals, d.uvs, d.atlas, d.env = ptr(keep["norms"]), ptr(keep["uvs"]), ptr(keep["atlas"]), ptr(keep["env"])
+    d.radiance_bins = ptr(keep["bins"])
+    d.n_nodes = keep["bvh"].size // 9
+    d.n_triangles = keep["tris"].size // 9
+    d.atlas_layers, d.atlas_res = keep["atlas"].shape[0], keep["atlas"].shape[1]
+    d.env_height, d.env_width = keep["env"].shape[0], keep["env"].shape[1]
+    d.env_bins = keep["bins"].size // 4
+    d.leaf_size = getattr(sa, "leaf_size", 4)
+    return d
+
+
+def debug_pack_scene(sa, n_threads=0):
+    """fspt_debug_pack_scene: the host half of fspt_scene_upload, no GPU.  Returns a dict with node64 (NI,16) f32,
+    tri48 (T+3,12) f32, shaderec (T,48) f32, mat_id (T,) i32 and the info fields."""
+    lib = load()
+    keep = {}
+    d = scene_desc(sa, keep)
+    info = np.zeros(5, np.int32)
+
+    def ck(rc):
+        if rc != FSPT_OK:
+            raise FsptError(rc, (lib.fspt_last_error(None) or b"").decode())
+    ck(lib.fspt_debug_pack_scene(C.byref(d), None, None, None, None, ptr(info), C.c_int32(n_threads)))
+    ni, T = int(info[0]), d.n_triangles
+    node64 = np.zeros((max(ni, 1), 16), np.float32)
+    tri48 = np.zeros((T + 3, 12), np.float32)
+    shaderec = np.zeros((T, 48), np.float32)
+    mat_id = np.zeros(T, np.int32)
+    ck(lib.fspt_debug_pack_scene(C.byref(d), ptr(node64), ptr(tri48), ptr(shaderec), ptr(mat_id), ptr(info), C.c_int32(n_threads)))
+    return dict(node64=node64[:ni] if ni else node64, tri48=tri48, shaderec=shaderec, mat_id=mat_id, n_interior=ni,
+                n_materials=int(info[1]), root_ref=int(info[2]), dielectric=bool(info[3]), depth=int(info[4]))
+
+
 class Context:
     """Thin RAII wrapper over fspt_ctx."""
 
@@ -205,28 +255,8 @@ class Context:
         """fspt_scene_upload; wait=False: fspt_scene_upload_async -- returns once everything but the atlas has been
         consumed, the atlas is staged in the background (the arrays are kept alive here until upload_wait / the next
         upload) and the next render's primary traversal overlaps it."""
-        d = SceneDesc()
-        keep = dict(
-            bvh=f32(sa.bvh), tris=f32(sa.tris), mats=f32(sa.mats), norms=f32(sa.norms), uvs=f32(sa.uvs),
-            atlas=np.ascontiguousarray(sa.atlas, np.uint8), env=np.ascontiguousarray(sa.env, np.uint8),
-            bins=np.ascontiguousarray(sa.bins, np.uint16))
-        lights = getattr(sa, "lights", None)
-        ranges = getattr(sa, "light_ranges", None)
-        if lights is not None and len(lights):
-            keep["lights"] = f32(lights)
-            keep["ranges"] = f32(ranges)
-            d.lights, d.light_ranges = ptr(keep["lights"]), ptr(keep["ranges"])
-            d.n_light_triangles = keep["lights"].size // 9
-            d.n_light_ranges = keep["ranges"].size // 2
-        d.bvh, d.triangles, d.materials = ptr(keep["bvh"]), ptr(keep["tris"]), ptr(keep["mats"])
-        d.normals, d.uvs, d.atlas, d.env = ptr(keep["norms"]), ptr(keep["uvs"]), ptr(keep["atlas"]), ptr(keep["env"])
-        d.radiance_bins = ptr(keep["bins"])
-        d.n_nodes = keep["bvh"].size // 9
-        d.n_triangles = keep["tris"].size // 9
-        d.atlas_layers, d.atlas_res = keep["atlas"].shape[0], keep["atlas"].shape[1]
-        d.env_height, d.env_width = keep["env"].shape[0], keep["env"].shape[1]
-        d.env_bins = keep["bins"].size // 4
-        d.leaf_size = getattr(sa, "leaf_size", 4)
+        keep = {}
+        d = scene_desc(sa, keep)
         if wait:
             self._ck(self.lib.fspt_scene_upload(self.h, C.byref(d)))
             self._keep = None

@@ -27,6 +27,7 @@
 #include "../../include/fspt_b200.h"
 #include "device_common.cuh"
 #include "host_pool.h"
+#include "scene_pack.h"
 #include "shade.cuh"
 #include "traverse.cuh"
 
@@ -1131,155 +1132,16 @@ static int scene_upload_impl(fspt_ctx* ctx, const fspt_scene_desc* s, bool async
   if (const char* e = getenv("FSPT_UPLOAD_THREADS")) hw = std::max(4, std::min(64, atoi(e)));
   if (!c->pool) { const int device = c->device; c->pool = new HostPool([device]() { cudaSetDevice(device); }); }
   HostPool& pool = *c->pool;
-  auto ibits = [&](int node, int k) { int32_t v; memcpy(&v, s->bvh + (size_t)node * 9 + k, 4); return v; };
-
-  // ---- pre-passes, two parallel regions around a short serial step.
-  // Nodes: reference node i = [left, right, triIndex | min | max] -> child references; interior nodes are numbered in
-  // node order (count per chunk, prefix sum over the chunks, assign).
-  // Triangles: materials = distinct quadruples of atlas layers (diffuse, emission, metallic-roughness, normal),
-  // tracer.fs:453-456, numbered in order of first appearance (local numbering per chunk, serial merge of the few keys,
-  // then the chunks rewrite their ids if the merge changed any).
-  std::vector<int32_t> ref((size_t)N);   // child reference of node i: >= 0 interior record, < 0 ~first triangle
-  std::vector<int32_t> interior_of;      // reference node index of interior record k
-  std::vector<int32_t> mat_id((size_t)T);
-  std::vector<std::array<int, 4>> mats;
-  bool dielectric = false;
-  const int PRE_CHUNK = 8192;
-  const int n_nchunks = (N + PRE_CHUNK - 1) / PRE_CHUNK, n_tchunks = (T + PRE_CHUNK - 1) / PRE_CHUNK;
-  std::vector<int> chunk_interiors((size_t)n_nchunks + 1, 0);
-  std::atomic<int> bad_node(-1);
-  std::vector<std::vector<std::array<int, 4>>> local_keys((size_t)n_tchunks);
-  std::vector<int> local_diel((size_t)n_tchunks, 0);
-  auto layer_of = [&](float lf) {  // texture(texArray, vec3(uv, layer)): layer = clamp(floor(l + 0.5), 0, d - 1)
-    float f = floorf(lf + 0.5f);
-    if (!(f >= -1.0e9f && f <= 1.0e9f)) f = 0.0f;
-    long long q = (long long)f;
-    return (int)(q < 0 ? 0 : (q >= s->atlas_layers ? s->atlas_layers - 1 : q));
-  };
-  // Depth / stack bound check (the reference has int stack[64], tracer.fs:368), also part of the first region: the top
-  // of the tree is walked here until there are a few subtrees per worker, each subtree is then an item (iterative DFS).
-  // Child indices out of range end a walk silently; the node chunks of the staging region report them.
-  struct Sub { int node, depth; };
-  std::vector<Sub> subtrees;
-  int top_depth = 0;
-  size_t top_visited = 0;
+  // ---- pre-passes (scene_pack.h): interior-record numbering, material ids, depth / tree check
+  ScenePrepass pre;
   {
-    std::vector<Sub> frontier{{0, 1}}, next;
-    while (!frontier.empty() && frontier.size() < (size_t)(8 * hw) && top_visited <= (size_t)N) {
-      next.clear();
-      for (const Sub& f : frontier) {
-        ++top_visited;
-        top_depth = std::max(top_depth, f.depth);
-        if (ibits(f.node, 2) > -1) continue;
-        const int32_t l = ibits(f.node, 0), r = ibits(f.node, 1);
-        if (l < 0 || l >= N || r < 0 || r >= N) continue;
-        next.push_back({l, f.depth + 1});
-        next.push_back({r, f.depth + 1});
-      }
-      frontier.swap(next);
-    }
-    subtrees.swap(frontier);
+    const int rcp = scene_prepass(pool, hw, s, pre);
+    if (rcp) return fail(c, rcp, "%s", pre.error.c_str());
   }
-  const int n_sub = (int)subtrees.size();
-  std::vector<int> sub_depth((size_t)n_sub, 0);
-  std::vector<size_t> sub_visited((size_t)n_sub, 0);
-  pool.run(n_nchunks + n_tchunks + n_sub, hw, [&](int item) {
-    if (item >= n_nchunks + n_tchunks) {
-      const int k = item - n_nchunks - n_tchunks;
-      std::vector<Sub> st;
-      st.reserve(128);
-      st.push_back(subtrees[k]);
-      int max_depth = 0;
-      size_t visited = 0;
-      while (!st.empty()) {
-        const Sub n = st.back(); st.pop_back();
-        if (++visited > (size_t)N) break;  // more visits than nodes: not a tree
-        max_depth = std::max(max_depth, n.depth);
-        if (ibits(n.node, 2) > -1) continue;
-        const int32_t l = ibits(n.node, 0), r = ibits(n.node, 1);
-        if (l < 0 || l >= N || r < 0 || r >= N) continue;
-        st.push_back({l, n.depth + 1});
-        st.push_back({r, n.depth + 1});
-      }
-      sub_depth[k] = max_depth; sub_visited[k] = visited;
-      return;
-    }
-    if (item < n_nchunks) {
-      const int ch = item, i1 = std::min(N, (ch + 1) * PRE_CHUNK);
-      int n_int = 0;
-      for (int i = ch * PRE_CHUNK; i < i1; ++i) {
-        const int32_t tri = ibits(i, 2);
-        if (tri > -1) {  // `current.triangles > -1`, tracer.fs:379
-          if (tri >= T) { int exp = -1; bad_node.compare_exchange_strong(exp, i); }
-        } else {
-          ++n_int;
-        }
-      }
-      chunk_interiors[ch + 1] = n_int;
-      return;
-    }
-    const int ch = item - n_nchunks, t0 = ch * PRE_CHUNK, t1 = std::min(T, (ch + 1) * PRE_CHUNK);
-    std::map<std::array<int, 4>, int> ids;
-    std::vector<std::array<int, 4>>& keys = local_keys[ch];
-    std::array<int, 4> last = {-1, -1, -1, -1};
-    int last_id = -1, diel = 0;
-    for (int t = t0; t < t1; ++t) {
-      const float* o = s->materials + (size_t)t * 12;
-      if (o[10] >= 0.0f) diel = 1;
-      if (t > t0 && memcmp(o, o - 12, 16) == 0) { mat_id[t] = last_id; continue; }  // same four layer floats as the previous triangle
-      const std::array<int, 4> key = {layer_of(o[0]), layer_of(o[1]), layer_of(o[3]), layer_of(o[2])};
-      if (key != last) {
-        auto it = ids.find(key);
-        if (it == ids.end()) { it = ids.emplace(key, (int)keys.size()).first; keys.push_back(key); }
-        last = key; last_id = it->second;
-      }
-      mat_id[t] = last_id;
-    }
-    local_diel[ch] = diel;
-  });
-  if (bad_node.load() >= 0)
-    return fail(c, FSPT_E_INVALID, "node %d: triangle index %d out of range", bad_node.load(), ibits(bad_node.load(), 2));
-  {
-    int max_depth = top_depth;
-    size_t visited = top_visited;
-    for (int k = 0; k < n_sub; ++k) { max_depth = std::max(max_depth, sub_depth[k]); visited += sub_visited[k]; }
-    if (visited > (size_t)N) return fail(c, FSPT_E_INVALID, "BVH is not a tree (cycle or shared node)");
-    if (max_depth + 1 > FSPT_STACK)
-      return fail(c, FSPT_E_LIMIT, "BVH depth %d exceeds the traversal stack (%d, as in tracer.fs:368)", max_depth, FSPT_STACK);
-  }
-  for (int ch = 0; ch < n_nchunks; ++ch) chunk_interiors[ch + 1] += chunk_interiors[ch];
-  const size_t NI = (size_t)chunk_interiors[n_nchunks];
-  interior_of.resize(NI);
-  std::vector<std::vector<int>> remap((size_t)n_tchunks);
-  bool identity = true;
-  {
-    std::map<std::array<int, 4>, int> ids;
-    for (int ch = 0; ch < n_tchunks; ++ch) {
-      dielectric = dielectric || local_diel[ch];
-      remap[ch].resize(local_keys[ch].size());
-      for (size_t k = 0; k < local_keys[ch].size(); ++k) {
-        auto it = ids.find(local_keys[ch][k]);
-        if (it == ids.end()) { it = ids.emplace(local_keys[ch][k], (int)mats.size()).first; mats.push_back(local_keys[ch][k]); }
-        remap[ch][k] = it->second;
-        identity = identity && it->second == (int)k;
-      }
-    }
-  }
-  pool.run(n_nchunks + (identity ? 0 : n_tchunks), hw, [&](int item) {
-    if (item < n_nchunks) {
-      const int ch = item, i1 = std::min(N, (ch + 1) * PRE_CHUNK);
-      int k = chunk_interiors[ch];
-      for (int i = ch * PRE_CHUNK; i < i1; ++i) {
-        const int32_t tri = ibits(i, 2);
-        if (tri > -1) ref[i] = ~tri;
-        else { ref[i] = k; interior_of[(size_t)k++] = i; }
-      }
-      return;
-    }
-    const int ch = item - n_nchunks, t1 = std::min(T, (ch + 1) * PRE_CHUNK);
-    const std::vector<int>& r = remap[ch];
-    for (int t = ch * PRE_CHUNK; t < t1; ++t) mat_id[t] = r[mat_id[t]];
-  });
+  const std::vector<int32_t>& ref = pre.ref;
+  std::vector<std::array<int, 4>>& mats = pre.mats;
+  const bool dielectric = pre.dielectric;
+  const size_t NI = pre.NI();
   lap("node + material pre-pass");
 
   // ---- pinned block for the small tables and the environment (kept between uploads)
@@ -1372,15 +1234,6 @@ static int scene_upload_impl(fspt_ctx* ctx, const fspt_scene_desc* s, bool async
   const bool src_env_pinned = host_is_pinned(s->env);
   std::vector<std::atomic<int>> slot_done((size_t)n_slots);  // last item whose copies have been enqueued from the slot
   for (auto& v : slot_done) v.store(-1);
-  auto tri9 = [&](int t, float* o) {  // v1 | e1 | e2 of triangle t (t >= T: padBuffer's -1 fill, main.js:143-154)
-    float v[9];
-    if (t < T) memcpy(v, s->triangles + (size_t)t * 9, sizeof v);
-    else for (float& x : v) x = -1.0f;
-    o[0] = v[0]; o[1] = v[1]; o[2] = v[2];
-    volatile float e;  // keep these as single f32 subtractions
-    e = v[3] - v[0]; o[3] = e; e = v[4] - v[1]; o[4] = e; e = v[5] - v[2]; o[5] = e;
-    e = v[6] - v[0]; o[6] = e; e = v[7] - v[1]; o[7] = e; e = v[8] - v[2]; o[8] = e;
-  };
   pool.run(n_items, workers, [&](int item) {
     if (item < n_env_items) {  // a band of environment rows (+ the bins): their own pinned block
       if (item == 0)
@@ -1408,48 +1261,19 @@ static int scene_upload_impl(fspt_ctx* ctx, const fspt_scene_desc* s, bool async
     uint8_t* hs = c->h_ring + (size_t)slot * slot_bytes;
     cudaError_t e = cudaSuccess;
     if (ring_item < n_node_items) {
-      // Node64 per interior node: (left, right) pairs per component, the operand layout of the packed f32x2 slab test
       const size_t k0 = (size_t)ring_item * node_chunk, k1 = std::min(NI, k0 + node_chunk);
       float* nodes = reinterpret_cast<float*>(hs);
-      if (NI == 0) memset(nodes, 0, 64);
-      for (size_t k = k0; k < k1; ++k) {
-        const int i = interior_of[k];
-        const int32_t l = ibits(i, 0), r = ibits(i, 1);
-        float* o = nodes + (k - k0) * 16;
-        if (l < 0 || l >= N || r < 0 || r >= N || l == i || r == i) {
-          geo_fail(FSPT_E_INVALID, "node %d: child index out of range (%d, %d)", i, l, r);
-          memset(o, 0, 64);
-          continue;
-        }
-        const float* lb = s->bvh + (size_t)l * 9 + 3;
-        const float* rb = s->bvh + (size_t)r * 9 + 3;
-        for (int q = 0; q < 6; ++q) { o[2 * q] = lb[q]; o[2 * q + 1] = rb[q]; }
-        const int32_t lr = ref[l], rr = ref[r];
-        memcpy(o + 12, &lr, 4); memcpy(o + 13, &rr, 4);
-        o[14] = o[15] = 0.0f;
-      }
+      int bl = 0, br = 0;
+      const int bad = pack_node_chunk(s, pre, k0, k1, nodes, &bl, &br);
+      if (bad >= 0) geo_fail(FSPT_E_INVALID, "node %d: child index out of range (%d, %d)", bad, bl, br);
       const size_t bytes = NI ? (k1 - k0) * 64 : 64;
       e = cudaMemcpyAsync(reinterpret_cast<uint8_t*>(c->d_nodes) + k0 * 64, nodes, bytes, cudaMemcpyHostToDevice, c->stream);
       if (e == cudaSuccess && ring_wraps) e = cudaEventRecord(c->ev_ring[slot], c->stream);
     } else {
-      // triangles: v1, e1, e2 (tracer.fs:301-302) + LEAF_SIZE-1 padBuffer-style (-1,-1,-1) tail records; shading
-      // records: material (12) | uvs (6) | material id | pad | normals (27) | pad
       const int t0 = (ring_item - n_node_items) * tri_chunk, t1 = std::min(T + 3, t0 + tri_chunk), ts = std::min(T, t1);
       float* tris = reinterpret_cast<float*>(hs);
       float* shade = reinterpret_cast<float*>(hs + (size_t)tri_chunk * 48);
-      for (int t = t0; t < t1; ++t) {
-        float* o = tris + (size_t)(t - t0) * 12;
-        tri9(t, o);
-        o[9] = o[10] = o[11] = 0.0f;
-        if (t >= T) continue;
-        float* h = shade + (size_t)(t - t0) * 48;
-        memcpy(h, s->materials + (size_t)t * 12, 48);
-        memcpy(h + 12, s->uvs + (size_t)t * 6, 24);
-        memcpy(h + 18, &mat_id[t], 4);  // material id in the record's padding
-        h[19] = 0.0f;
-        memcpy(h + 20, s->normals + (size_t)t * 27, 108);
-        h[47] = 0.0f;
-      }
+      pack_tri_chunk(s, pre, t0, t1, tris, shade);
       e = cudaMemcpyAsync(reinterpret_cast<uint8_t*>(c->d_tris) + (size_t)t0 * 48, tris, (size_t)(t1 - t0) * 48, cudaMemcpyHostToDevice, c->stream);
       if (e == cudaSuccess && ts > t0)
         e = cudaMemcpyAsync(reinterpret_cast<uint8_t*>(c->d_shade) + (size_t)t0 * 192, shade, (size_t)(ts - t0) * 192, cudaMemcpyHostToDevice, c->stream);
@@ -1530,6 +1354,42 @@ static int scene_upload_impl(fspt_ctx* ctx, const fspt_scene_desc* s, bool async
 
 int fspt_scene_upload(fspt_ctx* ctx, const fspt_scene_desc* s) { return scene_upload_impl(ctx, s, false); }
 int fspt_scene_upload_async(fspt_ctx* ctx, const fspt_scene_desc* s) { return scene_upload_impl(ctx, s, true); }
+int fspt_debug_pack_scene(const fspt_scene_desc* s, float* node64_out, float* tri48_out, float* shaderec_out,
+                          int32_t* mat_id_out, int32_t* info_out, int32_t n_threads) {
+  if (!s || !s->bvh || !s->triangles || !s->materials || !s->normals || !s->uvs || !info_out || s->n_nodes <= 0 ||
+      s->n_triangles <= 0 || s->atlas_layers <= 0)
+    return FSPT_E_INVALID;
+  const int hw = std::max(1, std::min(64, n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency()));
+  HostPool pool;
+  ScenePrepass pre;
+  const int rc = scene_prepass(pool, hw, s, pre);
+  if (rc) { g_create_error = pre.error; return rc; }
+  const size_t NI = pre.NI();
+  info_out[0] = (int32_t)NI; info_out[1] = (int32_t)pre.mats.size(); info_out[2] = pre.ref[0];
+  info_out[3] = pre.dielectric ? 1 : 0; info_out[4] = pre.max_depth;
+  if (!node64_out) return FSPT_OK;  // first call: sizes only
+  if (!tri48_out || !shaderec_out) return FSPT_E_INVALID;
+  const int T = s->n_triangles;
+  const size_t node_chunk = 4096;
+  const int tri_chunk = 1024;
+  const int n_node_items = NI ? (int)((NI + node_chunk - 1) / node_chunk) : 1, n_tri_items = (T + 3 + tri_chunk - 1) / tri_chunk;
+  std::atomic<int> bad(-1);
+  pool.run(n_node_items + n_tri_items, hw, [&](int item) {
+    if (item < n_node_items) {
+      const size_t k0 = (size_t)item * node_chunk, k1 = std::min(NI, k0 + node_chunk);
+      int bl = 0, br = 0;
+      const int b = pack_node_chunk(s, pre, k0, k1, node64_out + k0 * 16, &bl, &br);
+      if (b >= 0) { int exp = -1; bad.compare_exchange_strong(exp, b); }
+      return;
+    }
+    const int t0 = (item - n_node_items) * tri_chunk, t1 = std::min(T + 3, t0 + tri_chunk);
+    pack_tri_chunk(s, pre, t0, t1, tri48_out + (size_t)t0 * 12, shaderec_out + (size_t)t0 * 48);
+  });
+  if (bad.load() >= 0) { g_create_error = "node " + std::to_string(bad.load()) + ": child index out of range"; return FSPT_E_INVALID; }
+  if (mat_id_out) memcpy(mat_id_out, pre.mat_id.data(), (size_t)T * 4);
+  return FSPT_OK;
+}
+
 int fspt_host_register(void* p, uint64_t bytes) {
   if (!p || !bytes) return FSPT_E_INVALID;
   cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);

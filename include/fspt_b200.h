@@ -195,6 +195,15 @@ int fspt_debug_last_color(fspt_ctx* ctx, float* rgba32f_out);
  * 5 pow(x,y)); parity aid for the platform built-ins the shaders rely on (tracer.fs:181,412,417). */
 int fspt_debug_math(fspt_ctx* ctx, int32_t fn, const float* x, const float* y, float* out, int32_t n);
 
+/* The host half of fspt_scene_upload without a GPU: pre-passes (interior-record numbering, material ids, depth / tree
+ * check) and the device records the upload DMAs -- Node64 (n_interior x 16 floats), Tri48 ((n_triangles + 3) x 12), ShadeRec
+ * (n_triangles x 48), the material id of every triangle.  info_out[5] = {n_interior, n_materials, root reference,
+ * any dielectric, tree depth}.  Call with node64_out == NULL first to learn n_interior.  Test aid (the CPU suite checks the
+ * records against the reference layout, main.js:360-392); errors are reported like fspt_scene_upload's, text through
+ * fspt_last_error(NULL). */
+int fspt_debug_pack_scene(const fspt_scene_desc* scene, float* node64_out, float* tri48_out, float* shaderec_out,
+                          int32_t* mat_id_out, int32_t* info_out, int32_t n_threads);
+
 /* Streaming-read microbenchmark on the context's device: `iters` passes over a `bytes`-sized buffer with L1-bypassing
  * 16-byte loads from a persistent grid; GB/s out.  With bytes well below the L2 size this is the L2->SM read
  * ceiling that bounds the traversal kernel (SURVEY 8d asks for this denominator); with bytes >> L2 it is the HBM
