@@ -80,7 +80,7 @@ struct Ctx {
   uint8_t* h_ring = nullptr;   // pinned ring the geometry records are staged through, chunk by chunk
   size_t ring_bytes = 0;
   std::vector<cudaEvent_t> ev_ring;  // per ring slot: the copies that read it have completed
-  uint8_t* h_geo = nullptr;                                 // pinned staging for geometry records, bins, env
+  uint8_t* h_geo = nullptr;                                 // pinned block of the small tables (bins, layer / material tables) + env
   size_t geo_stage_bytes = 0;
   size_t stage_bytes = 0;
   size_t scene_bytes = 0;
