@@ -172,9 +172,12 @@ int fspt_comm_destroy(fspt_ctx* ctx);
 /* Sum of every rank's accumulation target -> root's, in place (ncclReduce, f32, 16 bytes/pixel), enqueued on the
  * context's stream after the renders already queued; sum mode only.  Collective. */
 int fspt_reduce_accum(fspt_ctx* ctx, int32_t root);
-/* The scene uploaded on `root` (fspt_scene_upload) -> every other rank, device to device (ncclBroadcast of the
+/* The scene uploaded on `root` (fspt_scene_upload / _async) -> every other rank, device to device (ncclBroadcast of the
  * records the upload built + the environment and atlas texels): replaces the per-GPU repetition of the texImage
- * uploads of initBVH() (main.js:408-437,548-560).  Collective. */
+ * uploads of initBVH() (main.js:408-437,548-560).  Collective, in two phases: the geometry and the environment travel
+ * at the call; the atlas part is issued by the rank's next fspt_render (behind its primary traversal launch, so an
+ * asynchronous upload on the root overlaps on every rank), fspt_synchronize, fspt_reduce_accum, upload or broadcast,
+ * whichever comes first -- like any collective, every rank has to reach one of them. */
 int fspt_scene_broadcast(fspt_ctx* ctx, int32_t root);
 
 /* mode=test (main.js:882-884, bvh_test.fs:224-232): one drawCamera() + primary intersectScene with the
