@@ -353,8 +353,7 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        # (no fdist.share_host_threads(): one rank per box uploads and the others receive the scene over NVLink, so the
-        # uploading rank keeps all host cores for its staging instead of 1/N of them)
+        fdist.share_host_threads()
 
     parity = None
     if not args.no_verify:

@@ -13,9 +13,7 @@ import numpy as np
 
 
 def share_host_threads(local_world=None):
-    """One process per GPU, EVERY process uploading its own copy of the scene: divide the node's cores between the
-    processes' scene-upload staging threads.  (Not for the upload-once + fspt_scene_broadcast flow, where the one
-    uploading rank should keep all cores.)"""
+    """One process per GPU: divide the node's cores between the processes' scene-upload staging threads."""
     if local_world is None:
         local_world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
     n = max(4, (os.cpu_count() or 4) // max(1, local_world))
