@@ -14,7 +14,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "--fmad=false", "--prec-div=true", "--prec-sqrt=true", "--ftz=false",
-    "-Xcompiler", "-fPIC,-ffp-contract=off,-O2", "-Xptxas", "-v",
+    "-Xcompiler", "-fPIC,-ffp-contract=off,-O2,-mssse3", "-Xptxas", "-v",
 ]
 CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-pthread"]
 

@@ -12,6 +12,9 @@
 #if defined(__SSE2__)
 #include <emmintrin.h>
 #endif
+#if defined(__SSSE3__)
+#include <tmmintrin.h>
+#endif
 #include <algorithm>
 #include <array>
 #include <atomic>
@@ -255,17 +258,25 @@ void record_trace_end(Ctx* c) {
 // One texel of a material layer = the RGBA8 texels of its four maps (device_common.cuh "MatTexel"), each taken from an
 // uploaded raw layer or, for a colour layer, from its constant.
 struct MatSrc { int raw[4]; unsigned cst[4]; };
-__global__ void __launch_bounds__(256) k_interleave_atlas(cudaSurfaceObject_t surf, const uint32_t* __restrict__ raw,
+// RGB24: the raw layers travelled without their alpha channel (3 bytes per texel) -- tracer.fs:453-456 reads .rgb / .rg of
+// the four maps, never .a, so alpha cannot influence an image and is not worth a quarter of the PCIe time.
+template <bool RGB24>
+__global__ void __launch_bounds__(256) k_interleave_atlas(cudaSurfaceObject_t surf, const uint8_t* __restrict__ raw,
                                                           const MatSrc* __restrict__ src, int R, size_t layer_texels) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= R || y >= R) return;
   const MatSrc m = src[blockIdx.z];
   const size_t i = (size_t)y * R + x;
+  auto fetch = [&](int k) -> unsigned {
+    if (m.raw[k] < 0) return m.cst[k];
+    if (RGB24) {
+      const uint8_t* p = raw + ((size_t)m.raw[k] * layer_texels + i) * 3;
+      return (unsigned)p[0] | ((unsigned)p[1] << 8) | ((unsigned)p[2] << 16);
+    }
+    return reinterpret_cast<const uint32_t*>(raw)[(size_t)m.raw[k] * layer_texels + i];
+  };
   uint4 v;
-  v.x = m.raw[0] >= 0 ? raw[(size_t)m.raw[0] * layer_texels + i] : m.cst[0];
-  v.y = m.raw[1] >= 0 ? raw[(size_t)m.raw[1] * layer_texels + i] : m.cst[1];
-  v.z = m.raw[2] >= 0 ? raw[(size_t)m.raw[2] * layer_texels + i] : m.cst[2];
-  v.w = m.raw[3] >= 0 ? raw[(size_t)m.raw[3] * layer_texels + i] : m.cst[3];
+  v.x = fetch(0); v.y = fetch(1); v.z = fetch(2); v.w = fetch(3);
   surf2DLayeredwrite(v, surf, x * 16, y, blockIdx.z);
 }
 
@@ -434,8 +445,11 @@ int stage_atlas(Ctx* c, const AtlasJob& J) {
     // the distinct varying layers are DMA'd from where they lie, the host does nothing but enqueue the copies.
     bool gpu_interleave = n_tex_mats > 0 && (J.src_pinned || raw_layers.size() * 2 <= (size_t)n_tex_mats * 4);
     if (const char* e = getenv("FSPT_ATLAS_INTERLEAVE")) gpu_interleave = n_tex_mats > 0 && !strcmp(e, "gpu");
-    const bool direct = gpu_interleave && J.src_pinned;
+    const bool direct = gpu_interleave && J.src_pinned && !getenv("FSPT_ATLAS_NO_DIRECT");
     c->atlas_in_place = direct;
+    // wire format of the staged GPU path: RGB, 3 bytes per texel (the shaders never read alpha, tracer.fs:453-456)
+    const bool rgb24 = gpu_interleave && !direct && !getenv("FSPT_ATLAS_RGBA_WIRE");
+    const size_t wire_layer_bytes = rgb24 ? layer_texels * 3 : layer_bytes;
     if (!c->mat_arr || c->mat_R != R || c->mat_L != ML || c->mat_surface != gpu_interleave) {
       if (c->sc.mat_tex) cudaDestroyTextureObject(c->sc.mat_tex);
       c->sc.mat_tex = 0;
@@ -459,7 +473,7 @@ int stage_atlas(Ctx* c, const AtlasJob& J) {
         c->mat_R = R; c->mat_L = ML; c->mat_surface = gpu_interleave;
       }
     }
-    const size_t need = gpu_interleave ? layer_bytes * raw_layers.size() : layer_texels * 16 * (size_t)ML;
+    const size_t need = gpu_interleave ? wire_layer_bytes * raw_layers.size() : layer_texels * 16 * (size_t)ML;
     if (!plain_atlas && !direct && c->stage_bytes < need) {
       if (c->h_stage) cudaFreeHost(c->h_stage);
       c->h_stage = nullptr; c->stage_bytes = 0;
@@ -497,16 +511,36 @@ int stage_atlas(Ctx* c, const AtlasJob& J) {
       pool.run(direct ? 0 : (int)raw_layers.size() * bands, J.workers, [&](int item) {
         const int ri = item / bands, band = item % bands;
         const size_t y0 = (size_t)R * band / bands, y1 = (size_t)R * (band + 1) / bands;
-        const size_t off = (size_t)ri * layer_bytes + y0 * R * 4, bytes = (y1 - y0) * R * 4;
-        memcpy(c->h_stage + off, J.atlas + (size_t)raw_layers[ri] * layer_bytes + y0 * R * 4, bytes);
+        const size_t bpt = rgb24 ? 3 : 4;
+        const size_t off = (size_t)ri * wire_layer_bytes + y0 * R * bpt, bytes = (y1 - y0) * R * bpt;
+        const uint8_t* src = J.atlas + (size_t)raw_layers[ri] * layer_bytes + y0 * R * 4;
+        if (!rgb24) {
+          memcpy(c->h_stage + off, src, bytes);
+        } else {
+          uint8_t* dst = c->h_stage + off;
+          const size_t n = (y1 - y0) * R;
+          size_t i = 0;
+#if defined(__SSSE3__)
+          // 4 texels (16 bytes) -> 12 bytes per shuffle; the 16-byte store's last 4 bytes are overwritten by the next one
+          const __m128i sh = _mm_setr_epi8(0, 1, 2, 4, 5, 6, 8, 9, 10, 12, 13, 14, -1, -1, -1, -1);
+          for (; i + 8 <= n; i += 4)
+            _mm_storeu_si128(reinterpret_cast<__m128i*>(dst + 3 * i),
+                             _mm_shuffle_epi8(_mm_loadu_si128(reinterpret_cast<const __m128i*>(src + 4 * i)), sh));
+#endif
+          for (; i < n; ++i) { dst[3 * i] = src[4 * i]; dst[3 * i + 1] = src[4 * i + 1]; dst[3 * i + 2] = src[4 * i + 2]; }
+        }
         std::lock_guard<std::mutex> g(mu);
         cudaError_t e = cudaMemcpyAsync(reinterpret_cast<uint8_t*>(c->d_raw) + off, c->h_stage + off, bytes, cudaMemcpyHostToDevice, c->copy_stream);
         if (e != cudaSuccess) cuda_err.store((int)e);
       });
       ACK(cudaMemcpyAsync(c->d_mat_src, mat_src, sizeof(MatSrc) * (size_t)n_tex_mats, cudaMemcpyHostToDevice, c->copy_stream));
       const dim3 blk(32, 8), grd((R + 31) / 32, (R + 7) / 8, n_tex_mats);
-      k_interleave_atlas<<<grd, blk, 0, c->copy_stream>>>(c->mat_surf, reinterpret_cast<const uint32_t*>(c->d_raw),
-                                                          reinterpret_cast<const MatSrc*>(c->d_mat_src), R, layer_texels);
+      if (rgb24)
+        k_interleave_atlas<true><<<grd, blk, 0, c->copy_stream>>>(c->mat_surf, reinterpret_cast<const uint8_t*>(c->d_raw),
+                                                                  reinterpret_cast<const MatSrc*>(c->d_mat_src), R, layer_texels);
+      else
+        k_interleave_atlas<false><<<grd, blk, 0, c->copy_stream>>>(c->mat_surf, reinterpret_cast<const uint8_t*>(c->d_raw),
+                                                                   reinterpret_cast<const MatSrc*>(c->d_mat_src), R, layer_texels);
       c->atlas_launches.fetch_add(1);
       ACK(cudaGetLastError());
     } else {
