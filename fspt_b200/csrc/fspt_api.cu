@@ -673,6 +673,7 @@ int launch_trace(Ctx* c, int which, bool hit_flags, bool write_count, const Fram
   TraceArgs A;
   if (cam) A.f = *cam; else memset(&A.f, 0, sizeof A.f);
   A.rb_cam = rb_cam; A.n_samples = n_samples;
+  A.div_s = make_fastdiv((unsigned)std::max(1, n_samples), c->wave_paths);
   A.anyhit = c->anyhit;
   A.nodes = c->sc.nodes; A.tris = c->sc.tris; A.root_ref = c->sc.root_ref; A.nodes_tex = c->nodes_tex;
   A.ps = c->ps2[which];
@@ -720,6 +721,9 @@ FrameParams make_frame(const Ctx* c, const fspt_frame_params* f, bool whole_fram
   p.rx0 = whole_frame ? 0 : c->rx0; p.ry0 = whole_frame ? 0 : c->ry0;
   p.rw = whole_frame ? c->width : c->rw; p.rh = whole_frame ? c->height : c->rh;
   p.tiled = (p.rw % 8 == 0 && p.rh % 4 == 0) ? 1 : 0;
+  // slot -> pixel: one division by the tiles per row (dividend: a tile index) or by the row width (dividend: a pixel index)
+  p.div_row = p.tiled ? make_fastdiv((unsigned)(p.rw >> 3), ((unsigned long long)p.rw * p.rh) >> 5)
+                      : make_fastdiv((unsigned)p.rw, (unsigned long long)p.rw * p.rh);
   return p;
 }
 
@@ -764,6 +768,7 @@ int render_wave(Ctx* c, const FrameParams& fp, uint32_t first_tick, int S, const
   A.sample_color = c->d_sample_color;
   A.capped = c->d_stats + 3;
   A.n_samples = S;
+  A.div_s = make_fastdiv((unsigned)S, c->wave_paths);
   A.max_refractions = c->max_refractions;
   A.anyhit = c->anyhit;
   const int hard_cap = FSPT_NUM_BOUNCES + 1 + (c->has_dielectric ? c->max_refractions + 2 : 0);
@@ -1575,7 +1580,7 @@ int fspt_debug_primary(fspt_ctx* ctx, const fspt_frame_params* frame, float rand
     int rc0 = stage_rand_bases(c, &rand_base_camera, nullptr, 1);
     if (rc0) return rc0;
   }
-  k_camera<<<(P + 255) / 256, 256, 0, c->stream>>>(fp, c->d_rb, P, 1, c->ps, c->d_cam_pos, c->d_cam_dir);
+  k_camera<<<(P + 255) / 256, 256, 0, c->stream>>>(fp, c->d_rb, P, make_fastdiv(1u, (unsigned long long)P), c->ps, c->d_cam_pos, c->d_cam_dir);
   c->stats.kernel_launches++;
   int rc = set_counts(c, P, 0);
   if (rc) return rc;

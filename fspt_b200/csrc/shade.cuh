@@ -16,13 +16,13 @@
 // camera.fs main as a stand-alone pass (mode=test / fspt_debug_primary; the render loop fuses ray generation into
 // the primary traversal launch, see traverse.cuh).  One thread per path slot.
 __global__ void __launch_bounds__(256) k_camera(const FrameParams f, const float* __restrict__ rb_cam, int n_paths,
-                                                int n_samples, PathState ps, float4* cam_pos_out,
+                                                FastDiv div_s, PathState ps, float4* cam_pos_out,
                                                 float4* cam_dir_out) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_paths) return;
   v3 o, d;
   int x, y;
-  camera_ray(f, rb_cam, n_samples, p, o, d, x, y);
+  camera_ray(f, rb_cam, div_s, p, o, d, x, y);
   st_path(ps.ro(p), make_float4(o.x, o.y, o.z, FSPT_MAX_T));
   st_path(ps.rd(p), make_float4(d.x, d.y, d.z, __int_as_float(-1)));
   if (cam_pos_out) {  // frame-sized targets
@@ -234,6 +234,7 @@ struct ShadeArgs {
   float4* sample_color;       // [pixel][sample-in-wave] final un-clamped path colour
   unsigned long long* capped; // paths stopped by the refraction cap
   int n_samples;              // samples in flight in this wave (slot = pixel * n_samples + sample)
+  FastDiv div_s;              // by n_samples
   int first;                  // 1: slots hold fresh primary rays (tracer.fs:440-445)
   int max_refractions;
   int anyhit;
@@ -269,7 +270,7 @@ __device__ __forceinline__ int append_pos(bool want, int* counter) {
 }
 
 __device__ __forceinline__ void write_sample(const ShadeArgs& A, int slot, v3 color) {
-  const int j = slot / A.n_samples, s = slot - j * A.n_samples;
+  const int j = (int)fast_div((unsigned)slot, A.div_s), s = slot - j * A.n_samples;
   int x, y;
   path_to_pixel(A.f, j, x, y);
   // [pixel][sample]: the samples of a pixel finish in adjacent lanes and land in adjacent 16-byte entries
@@ -342,7 +343,7 @@ __device__ __forceinline__ bool shade_hit(const ShadeArgs& A, int pos, bool& sha
       return false;
     }
   }
-  const float randBase = A.rb_trace[slot % A.n_samples];
+  const float randBase = A.rb_trace[slot - (int)fast_div((unsigned)slot, A.div_s) * A.n_samples];
   // createMaterial / createTriangle / createTexCoords / createNormals, :447-449,460
   const float4* rec = sc.shade + 12 * (size_t)hit_index;
   const float4 m0 = __ldg(rec), m2 = __ldg(rec + 2);

@@ -45,6 +45,7 @@ struct TraceArgs {
   FrameParams f;          // CAMERA mode: primary rays are generated in the fetch instead of being read
   const float* rb_cam;
   int n_samples;
+  FastDiv div_s;          // by n_samples
   int anyhit;             // 1: hit-or-miss rays (shadow rays, marked last-bounce rays) stop at their first intersection
 };
 
@@ -277,7 +278,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
             kind = false;
             v3 o, d;
             int px, py;
-            camera_ray(A.f, A.rb_cam, A.n_samples, my, o, d, px, py);
+            camera_ray(A.f, A.rb_cam, A.div_s, my, o, d, px, py);
             start_ray(make_float4(o.x, o.y, o.z, 0.0f), make_float4(d.x, d.y, d.z, 0.0f), my);
           } else {
             // continuation rays: words 0 / 1 of record `my`; shadow rays: their own dense array written by k_shade
