@@ -81,7 +81,7 @@ __device__ __forceinline__ void texture_atlas4(const DeviceScene& sc, float u, f
   const float x = u * (float)R - 0.5f, y = v * (float)R - 0.5f;
   const float fx = floorf(x), fy = floorf(y);
   const float a = x - fx, b = y - fy;
-  const int ixx = (int)coord_to_int(fx), iyy = (int)coord_to_int(fy);
+  const int ixx = coord_to_i32(fx), iyy = coord_to_i32(fy);
   const float i0 = (float)wrap_repeat(ixx, R) + 0.5f, i1 = (float)wrap_repeat(ixx + 1, R) + 0.5f;
   const float j0 = (float)wrap_repeat(iyy, R) + 0.5f, j1 = (float)wrap_repeat(iyy + 1, R) + 0.5f;
   int L[4];
@@ -115,7 +115,7 @@ __device__ __forceinline__ void texture_material(const DeviceScene& sc, float u,
   const int4 info = __ldg(sc.mat_info + 2 * mat);
   uint4 t00, t10, t01, t11;
   if (info.x >= 0) {
-    const int ixx = (int)coord_to_int(fx), iyy = (int)coord_to_int(fy);
+    const int ixx = coord_to_i32(fx), iyy = coord_to_i32(fy);
     const float i0 = (float)wrap_repeat(ixx, R) + 0.5f, i1 = (float)wrap_repeat(ixx + 1, R) + 0.5f;
     const float j0 = (float)wrap_repeat(iyy, R) + 0.5f, j1 = (float)wrap_repeat(iyy + 1, R) + 0.5f;
     t00 = tex2DLayered<uint4>(sc.mat_tex, i0, j0, info.x);
@@ -137,7 +137,7 @@ __device__ __forceinline__ float4 texture_env(cudaTextureObject_t env, int W, in
   const float x = u * (float)W - 0.5f, y = v * (float)H - 0.5f;
   const float fx = floorf(x), fy = floorf(y);
   const float a = x - fx, b = y - fy;
-  const int ixx = (int)coord_to_int(fx), iyy = (int)coord_to_int(fy);
+  const int ixx = coord_to_i32(fx), iyy = coord_to_i32(fy);
   const float i0 = (float)wrap_repeat(ixx, W) + 0.5f, i1 = (float)wrap_repeat(ixx + 1, W) + 0.5f;
   const float j0 = (float)wrap_clamp(iyy, H) + 0.5f, j1 = (float)wrap_clamp(iyy + 1, H) + 0.5f;
   const uchar4 t00 = tex2D<uchar4>(env, i0, j0), t10 = tex2D<uchar4>(env, i1, j0);
@@ -418,7 +418,7 @@ __device__ __forceinline__ bool shade_hit(const ShadeArgs& A, int pos, bool& sha
   v3 envDir;
   float envPdf;
   {
-    int idx = (int)coord_to_int((float)sc.n_bins * rnd(seed));
+    int idx = coord_to_i32((float)sc.n_bins * rnd(seed));
     if (idx >= sc.n_bins) idx = sc.n_bins - 1;
     if (idx < 0) idx = 0;
     const float4 bin = __ldg(sc.bins + idx);
