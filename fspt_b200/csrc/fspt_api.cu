@@ -1339,6 +1339,7 @@ static int scene_upload_impl(fspt_ctx* ctx, const fspt_scene_desc* s, bool async
   c->sc.n_tris = T; c->sc.n_interior = (int)NI;
   c->sc.atlas_res = s->atlas_res; c->sc.atlas_layers = s->atlas_layers; c->sc.env_w = s->env_width; c->sc.env_h = s->env_height;
   c->sc.n_bins = s->env_bins;
+  set_env_constants(c->sc);
   c->has_dielectric = dielectric;
   c->scene_bytes = (size_t)N * 36 + (size_t)T * (36 + 48 + 108 + 24) + (size_t)s->atlas_res * s->atlas_res * 4 * s->atlas_layers +
                    env_bytes + (size_t)s->env_bins * 8;
@@ -1863,6 +1864,7 @@ int fspt_scene_broadcast(fspt_ctx* ctx, int32_t root) {
     c->sc.root_ref = h.root_ref; c->sc.n_tris = h.n_tris; c->sc.n_interior = h.n_interior;
     c->sc.atlas_res = h.atlas_res; c->sc.atlas_layers = h.atlas_layers; c->sc.env_w = h.env_w; c->sc.env_h = h.env_h;
     c->sc.n_bins = h.n_bins;
+    set_env_constants(c->sc);
     c->has_dielectric = h.has_dielectric != 0;
     c->scene_bytes = h.scene_bytes;
     c->has_scene = true;

@@ -425,15 +425,17 @@ __device__ __forceinline__ bool shade_hit(const ShadeArgs& A, int pos, bool& sha
     const float dimsx = (float)sc.env_w, dimsy = (float)sc.env_h;
     const float r1 = rnd(seed);
     const float r2 = rnd(seed);
-    const float uvx = -envTheta + ((bin.z - bin.x) * r1 + bin.x) / dimsx;
-    const float uvy = 0.0f + ((bin.w - bin.y) * r2 + bin.y) / dimsy;
+    const float qx = (bin.z - bin.x) * r1 + bin.x, qy = (bin.w - bin.y) * r2 + bin.y;
+    // division by a power of two = multiplication by its exact reciprocal, bit for bit (no divide sequence)
+    const float uvx = -envTheta + (sc.env_pow2 ? qx * sc.inv_env_w : qx / dimsx);
+    const float uvy = 0.0f + (sc.env_pow2 ? qy * sc.inv_env_h : qy / dimsy);
     const float theta = uvx * FSPT_TAU;
     const float phi = uvy * FSPT_PI;
     float sinPhi, cosPhi, sinTheta, cosTheta;
     dm::sincosf_(phi, sinPhi, cosPhi);
     dm::sincosf_(theta, sinTheta, cosTheta);
     envDir = mk3(cosTheta * sinPhi, cosPhi, sinTheta * sinPhi);
-    const float nominal = (dimsx * dimsy) / (float)sc.n_bins;
+    const float nominal = sc.env_nominal;  // (dimsx * dimsy) / float(n_bins), evaluated once on the host
     envPdf = nominal / ((bin.z - bin.x) * (bin.w - bin.y) * FSPT_TAU * FSPT_PI * sinPhi);
   }
   const float cosEnv = dot(macroNormal, envDir);  // :474

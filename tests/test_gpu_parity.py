@@ -262,3 +262,12 @@ def test_cuda_against_the_reference_shaders_themselves(small_bunny):
         assert_bit_equal(ctx.resolve(**post), R.draw(fb, **post), "draw.fs RGBA8")
     finally:
         ctx.close()
+
+
+def test_non_power_of_two_atlas_and_environment_bit_exact(oracle_mod):
+    """Texture sizes that are not powers of two: the REPEAT wrap takes the modulo path instead of a mask and sampleEnv's
+    divisions by the environment size stay divisions (for powers of two they are multiplications by the exact
+    reciprocal) -- a 24-texel atlas and a 96x48 environment against the oracle."""
+    sa, cam = scenes.bunny_class(subdiv=3, atlas_res=24, env_size=(96, 48))
+    assert sa.atlas.shape[1] == 24 and sa.env.shape[:2] == (48, 96)
+    _full_frame_check(oracle_mod, sa, cam, 160, 96, 3, 23)
