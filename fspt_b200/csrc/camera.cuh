@@ -31,7 +31,7 @@ __device__ __forceinline__ void camera_ray(const FrameParams& f, const float* __
   const float r = sqrtf(rnd(seed)) * 1.414f;
   float st, ct;
   dm::sincosf_(theta, st, ct);
-  v3 aa = mul(r, add(div(mul(basisX, ct), resx), div(mul(basisY, st), resy)));
+  v3 aa = mul(r, add(div_shared(mul(basisX, ct), resx), div_shared(mul(basisY, st), resy)));  // (one reciprocal per vector)
   aa = mul(aa, f.fov_scale);  // :42
   const float theta2 = rnd(seed) * 3.14159265f * 2.0f;  // getDOF, :32-35
   float st2, ct2;
@@ -39,5 +39,5 @@ __device__ __forceinline__ void camera_ray(const FrameParams& f, const float* __
   const v3 dofDir = add(mul(ct2, basisX), mul(st2, basisY));
   const v3 dof = mul(mul(dofDir, f.lens1), sqrtf(rnd(seed)));
   o = add(P, dof);  // :44
-  d = normalize(sub(add(add(screen, aa), mul(dof, f.lens0)), add(P, dof)));  // :45
+  d = normalize_shared(sub(add(add(screen, aa), mul(dof, f.lens0)), add(P, dof)));  // :45
 }
