@@ -775,8 +775,10 @@ int render_wave(Ctx* c, const FrameParams& fp, uint32_t first_tick, int S, const
   // atlas of the last upload: an asynchronous upload's staging thread is joined HERE, with the primary traversal already
   // running on the GPU (the event it records has to exist before the stream can be made to wait on it); then the DMA
   // itself is waited for on the device (no-op once it has completed)
+  // multi-GPU: the atlas travels to the other ranks now, behind the traversal.  (Phase 2 first: it joins the atlas thread
+  // itself and, should the root's atlas part have failed, tells the other ranks instead of leaving them in the collective.)
+  if ((rc = broadcast_phase2(c))) return rc;
   if ((rc = atlas_join(c))) return rc;
-  if ((rc = broadcast_phase2(c))) return rc;  // multi-GPU: the atlas travels to the other ranks now, behind the traversal
   A.sc = c->sc;  // (the atlas part sets the texture objects and table pointers)
   CK(cudaStreamWaitEvent(c->stream, c->ev_atlas, 0));
   int cur = 0;
@@ -912,7 +914,7 @@ int broadcast_phase2(Ctx* c) {
   // recorded the event), not behind the traversal launch that may have been enqueued since
   CK(cudaStreamWaitEvent(c->copy_stream, c->ev_bcast, 0));
   if (is_root) {
-    int rcj = atlas_join(c);  // (normally already joined by the caller)
+    int rcj = atlas_join(c);  // the root's atlas part ends here at the latest; its outcome travels in the header
     if (rcj) h.magic = -1;    // the ranks must not wait for an atlas that will not come
     else {
       h.bytes_layer_info = c->bytes_layer_info; h.bytes_mat_info = c->bytes_mat_info;
@@ -1157,8 +1159,8 @@ static int scene_upload_impl(fspt_ctx* ctx, const fspt_scene_desc* s, bool async
     return fail(c, FSPT_E_INVALID, "scene_upload: non-positive size (an environment with >= 1 bin is mandatory, main.js:303-308)");
   if (s->leaf_size != 4) return fail(c, FSPT_E_INVALID, "scene_upload: LEAF_SIZE must be 4 (main.js:45), got %d", s->leaf_size);
   CK(cudaSetDevice(c->device));
-  (void)atlas_join(c);  // the atlas thread of the previous upload still reads the pinned blocks and the arrays
   if (int rcb = broadcast_phase2(c)) return rcb;  // (a broadcast nobody rendered from: finish it before its source goes away)
+  (void)atlas_join(c);  // the atlas thread of the previous upload still reads the pinned blocks and the arrays
   CK(cudaStreamSynchronize(c->stream));
   CK(cudaStreamSynchronize(c->copy_stream));
   c->has_scene = false;  // device buffers, arrays and texture objects of the previous scene are reused when they fit
@@ -1501,8 +1503,8 @@ int fspt_synchronize(fspt_ctx* ctx) {
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
   if (!c) return FSPT_E_INVALID;
   CK(cudaSetDevice(c->device));
+  if (int rc = broadcast_phase2(c)) return rc;  // (joins the atlas thread on the root, see render_wave)
   if (int rc = atlas_join(c)) return rc;
-  if (int rc = broadcast_phase2(c)) return rc;
   CK(cudaStreamSynchronize(c->stream));
   CK(cudaStreamSynchronize(c->copy_stream));
   return FSPT_OK;
