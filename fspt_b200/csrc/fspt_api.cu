@@ -1,6 +1,11 @@
 // fspt_api.cu -- context, scene upload (layout repack), wavefront render loop and the extern "C" ABI of
 // libfspt_b200.so (include/fspt_b200.h).  Host side of what main.js does between initBVH() and tick():
 // texImage uploads (main.js:408-437,548-560,170-180), drawCamera/drawTracer/drawQuad (main.js:741-824).
+// Map: Ctx (state of one context) -- stage_atlas (the atlas part of an upload: runs inline or on the context's atlas
+// thread) -- launch_trace / render_wave (one wave of the wavefront) -- NCCL loaded at run time, broadcast_phase2 (the
+// deferred atlas part of fspt_scene_broadcast) -- extern "C": create / destroy, scene_upload_impl (pre-passes and record
+// builders live in scene_pack.h, the worker pool in host_pool.h), render, resolve, accumulation access, debug entry
+// points, tiles and collectives, parameters and statistics.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>  // types only: the library is resolved with dlopen at fspt_comm_init, there is no link-time dependency
