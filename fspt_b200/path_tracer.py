@@ -10,7 +10,7 @@ from . import capi, scenes
 
 class PathTracer:
     def __init__(self, scene_arrays, resolution, camera=None, device=0, seed=1, exposure=1.0, saturation=1.0,
-                 denoise=False, max_sigma=2.0, max_samples=2000, async_upload=True):
+                 denoise=False, max_sigma=2.0, max_samples=2000, async_upload=False):
         self.resolution = (int(resolution[0]), int(resolution[1]))
         cam = dict(eye=[0, 0, 2], dir=[0, 0, -1], fov_scale=0.5, env_theta=0.0, aperture=0.02, focal_depth=2.0)  # main.js:69-74
         cam.update(camera or {})
@@ -23,8 +23,9 @@ class PathTracer:
         self.scene = scene_arrays
         self.ctx = capi.Context(self.resolution[0], self.resolution[1], device)
         # scene_arrays None: the scene arrives later (fspt_scene_broadcast from the rank that compiled it)
-        # asynchronous upload (fspt_scene_upload_async): the atlas is still being staged when this returns and the first
-        # tick's primary traversal overlaps it; self.scene keeps the arrays alive and they must not be modified before then
+        # async_upload=True: fspt_scene_upload_async -- the atlas is still being staged when this returns and the first
+        # tick's primary traversal overlaps it; self.scene keeps the arrays alive and they must not be modified before then.
+        # Default: the synchronous upload, which like texImage2D has consumed every buffer when it returns.
         self.upload_bytes = self.ctx.scene_upload(scene_arrays, wait=not async_upload) if scene_arrays is not None else 0
         self._seed = seed
         self._rand = scenes.rand_bases
